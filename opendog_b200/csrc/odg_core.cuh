@@ -1,0 +1,1147 @@
+// odg_core.cuh — the fused environment step, written once for a 4-lane cooperative group.
+//
+// One environment = 4 lanes (one per leg; 8 environments per warp). Every lane carries the trunk
+// state redundantly and its own leg's joints; quantities that couple legs (composite inertia of the
+// trunk, trunk wrench, the 6x6 Schur complement of the Newton system) are combined with xor-butterfly
+// shuffles inside the 4-lane group, which leave bit-identical values in all 4 lanes.
+//
+// What it replaces (reference, per environment, on the CPU):
+//   mujoco.mj_step x frame_skip           WalkEnvironment.py:58, sim2real/train.py:281-284   [3P wheel]
+//   _get_obs / rewards / is_healthy       WalkEnvironment.py:59-136, reward_calc.py:117-390
+//   ScaleActionWrapper.action             ScaleActionEnvironment.py:21-23
+//   SubprocVecEnv worker auto-reset       train/train.py:81-86                                 [3P SB3]
+//
+// Formulation (differs structurally from oracle/odg_oracle.c on purpose):
+//   * positions are kept relative to the trunk origin O (fp32 stays accurate far from the world origin);
+//   * the trunk's rotational DoFs are handled in the WORLD frame internally (alpha_w = R0 * qacc_rot);
+//   * M and the Newton Hessian H = M + J^T D J are block-arrow (6x6 trunk block + one NJLxNJL block per
+//     leg + couplings), so each lane eliminates its own leg block and the group reduces one 6x6 Schur
+//     complement (21+6 floats) per Newton iteration;
+//   * contact Jacobians are never stored: J*x is evaluated as the acceleration of the contact point.
+//
+// The same source compiles for the host (ODG_HOST_EMU) where 4 std::threads emulate the lanes; that
+// build exists only for tests/ (numerics debugging without a GPU) and is never shipped or loaded by
+// the package.
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+
+#ifdef ODG_HOST_EMU
+#define ODG_DEV inline
+#define ODG_RESTRICT
+struct float4 { float x, y, z, w; };
+float odg_emu_shfl_xor(float v, int m);     // provided by the emulator
+double odg_emu_shfl_xor_d(double v, int m);
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline float odg_fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float odg_fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float odg_fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float odg_fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+#define ODG_UNROLL
+#else
+#define ODG_DEV __device__ __forceinline__
+#define ODG_RESTRICT __restrict__
+#define odg_fmul_rn __fmul_rn
+#define odg_fadd_rn __fadd_rn
+#define odg_fsub_rn __fsub_rn
+#define odg_fdiv_rn __fdiv_rn
+#define ODG_UNROLL _Pragma("unroll")
+#endif
+
+namespace odg {
+
+constexpr int kMaxJL = 3;
+constexpr int kMaxSlot = 8;          // collision geoms per leg
+constexpr int kMaxConLeg = 12;       // contacts per leg (<= 4 per geom)
+constexpr int kMaxNU = 12;
+constexpr int kMaxNQ = 7 + 4 * kMaxJL;
+
+// ---- per-joint, per-leg constants staged in shared memory as s_lc[(j*LC_COUNT + f)*4 + leg]
+enum LegConstField {
+  LC_BP0, LC_BP1, LC_BP2,                       // body_pos
+  LC_BR0, LC_BR1, LC_BR2, LC_BR3, LC_BR4, LC_BR5, LC_BR6, LC_BR7, LC_BR8,   // body_quat as matrix
+  LC_JP0, LC_JP1, LC_JP2,                       // jnt_pos
+  LC_JA0, LC_JA1, LC_JA2,                       // jnt_axis
+  LC_MASS, LC_IP0, LC_IP1, LC_IP2,
+  LC_IXX, LC_IXY, LC_IXZ, LC_IYY, LC_IYZ, LC_IZZ,
+  LC_LO, LC_HI, LC_LIMITED,
+  LC_ARM, LC_FL, LC_RFL, LC_DFL, LC_DAMP, LC_INVW,
+  LC_KP, LC_KV, LC_CLO, LC_CHI, LC_FLO, LC_FHI, LC_HASACT, LC_CLIM, LC_FLIM, LC_UIDX,
+  LC_SLO, LC_SHI,                               // ScaleActionWrapper table (float32 values)
+  LC_HOMEQ,                                     // key_qpos of the joint
+  LC_COUNT
+};
+// per-slot, per-leg constants: s_gc[(slot*GC_COUNT + f)*4 + leg]
+enum GeomConstField { GC_INVW, GC_CX, GC_CY, GC_CZ, GC_COUNT };
+
+struct DevConst {
+  int nleg, njl, nq, nv, nu, nslot, nvert_rows;
+  int body_rot_identity;
+  float h, gx, gy, gz, impratio;
+  // trunk
+  float base_mass, base_ip[3], base_I[6];
+  float base_arm_t[3], base_arm_r;
+  float base_fl[6], base_Rfl[6], base_Dfl[6];
+  float B_fl;                                   // friction-loss rows: aref = -B_fl * vel
+  float K_lim, B_lim, lim_imp[5];
+  // collision slots (identical layout on every leg)
+  int slot_link[kMaxSlot], slot_type[kMaxSlot], slot_nvert[kMaxSlot], slot_vstart[kMaxSlot];
+  int slot_condim[kMaxSlot], slot_isfoot[kMaxSlot];
+  float slot_margin[kMaxSlot], slot_K[kMaxSlot], slot_B[kMaxSlot], slot_imp[kMaxSlot][5];
+  float slot_fri[kMaxSlot], slot_mu[kMaxSlot], slot_radius[kMaxSlot];
+  float tilt_dir[3][3];                         // extra support directions (world)
+  int n_tilt;
+  // env
+  int frame_skip, max_steps, auto_reset, solver_iters, ls_iters, scale_actions, first_env_id;
+  float tol, noise;
+  float key_qpos[kMaxNQ], key_ctrl[kMaxNU];
+  float obs_joint_offset;                       // key_ctrl[0,7:] broadcast quirk (WalkEnvironment.py:116)
+  uint32_t seed_lo, seed_hi;
+};
+
+struct SimPtrs {            // SoA state in HBM: x[i*N + env]
+  int N;
+  float* qpos; float* qvel; float* warm;        // [nq][N], [nv][N], [nv][N]
+  float* last_action;                            // [nu][N]
+  float* desvel;                                 // [3][N]
+  int* step; int* gait_idx; int* gait_cnt; unsigned* episode;   // [N]
+  unsigned char* fresh;                          // [N] last_action is the float64 zeros of reset_model
+};
+
+struct StepArgs {
+  const float* action;      // [N][nu]
+  float* obs;               // [N][obs_dim]
+  float* reward;            // [N]
+  unsigned char* terminated; unsigned char* truncated;
+  int mode;                 // 0 = step, 1 = evaluate (one forward pass, no integration, no auto-reset)
+  int want_info;
+  // info (nullable)
+  float* x_position; float* y_position; float* distance; float* paw_forces; float* patterns_matches;
+  float* lin_vel_reward; float* reward_ctrl; float* terminal_obs; unsigned char* paws_in_ground;
+  int* gait_reward; float* qacc; int* ncon; float* fn_sum; int* solver_iters;
+};
+
+// ---------------------------------------------------------------------------------------------
+struct V3 { float x, y, z; };
+ODG_DEV V3 mk3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+ODG_DEV V3 operator+(V3 a, V3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+ODG_DEV V3 operator-(V3 a, V3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+ODG_DEV V3 operator*(float s, V3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+ODG_DEV V3 operator-(V3 a) { return mk3(-a.x, -a.y, -a.z); }
+ODG_DEV float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+ODG_DEV V3 cross(V3 a, V3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+ODG_DEV float comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+struct M3 { float m[9]; };   // row-major
+ODG_DEV V3 mul(const M3& R, V3 v) {
+  return mk3(R.m[0] * v.x + R.m[1] * v.y + R.m[2] * v.z, R.m[3] * v.x + R.m[4] * v.y + R.m[5] * v.z,
+             R.m[6] * v.x + R.m[7] * v.y + R.m[8] * v.z);
+}
+ODG_DEV V3 tmul(const M3& R, V3 v) {
+  return mk3(R.m[0] * v.x + R.m[3] * v.y + R.m[6] * v.z, R.m[1] * v.x + R.m[4] * v.y + R.m[7] * v.z,
+             R.m[2] * v.x + R.m[5] * v.y + R.m[8] * v.z);
+}
+ODG_DEV M3 mul(const M3& A, const M3& B) {
+  M3 C;
+  ODG_UNROLL for (int i = 0; i < 3; i++)
+    ODG_UNROLL for (int j = 0; j < 3; j++)
+      C.m[i * 3 + j] = A.m[i * 3] * B.m[j] + A.m[i * 3 + 1] * B.m[3 + j] + A.m[i * 3 + 2] * B.m[6 + j];
+  return C;
+}
+ODG_DEV V3 col(const M3& R, int k) { return mk3(R.m[k], R.m[3 + k], R.m[6 + k]); }
+
+// symmetric 3x3: xx xy xz yy yz zz
+struct S3 { float xx, xy, xz, yy, yz, zz; };
+ODG_DEV V3 mul(const S3& A, V3 v) {
+  return mk3(A.xx * v.x + A.xy * v.y + A.xz * v.z, A.xy * v.x + A.yy * v.y + A.yz * v.z,
+             A.xz * v.x + A.yz * v.y + A.zz * v.z);
+}
+ODG_DEV S3 zero_s3() { S3 s; s.xx = s.xy = s.xz = s.yy = s.yz = s.zz = 0.f; return s; }
+ODG_DEV void add_outer(S3& A, V3 a, V3 b) {   // A += sym part of a b^T + b a^T scaled 0.5 ... used only with a==b scaled
+  A.xx += a.x * b.x; A.xy += a.x * b.y; A.xz += a.x * b.z; A.yy += a.y * b.y; A.yz += a.y * b.z; A.zz += a.z * b.z;
+}
+// R * A * R^T for symmetric A
+ODG_DEV S3 rotate_sym(const M3& R, const S3& A) {
+  V3 c0 = mul(A, mk3(R.m[0], R.m[1], R.m[2]));   // A * row0(R)^T
+  V3 c1 = mul(A, mk3(R.m[3], R.m[4], R.m[5]));
+  V3 c2 = mul(A, mk3(R.m[6], R.m[7], R.m[8]));
+  V3 r0 = mk3(R.m[0], R.m[1], R.m[2]), r1 = mk3(R.m[3], R.m[4], R.m[5]), r2 = mk3(R.m[6], R.m[7], R.m[8]);
+  S3 o;
+  o.xx = dot(r0, c0); o.xy = dot(r0, c1); o.xz = dot(r0, c2);
+  o.yy = dot(r1, c1); o.yz = dot(r1, c2); o.zz = dot(r2, c2);
+  return o;
+}
+
+// spatial inertia about O, world aligned
+struct SpI { float m; V3 h; S3 I; };
+ODG_DEV SpI spi_make(float mass, V3 c, const S3& Iw) {
+  SpI s; s.m = mass; s.h = mass * c;
+  float cc = dot(c, c);
+  s.I.xx = Iw.xx + mass * (cc - c.x * c.x); s.I.yy = Iw.yy + mass * (cc - c.y * c.y); s.I.zz = Iw.zz + mass * (cc - c.z * c.z);
+  s.I.xy = Iw.xy - mass * c.x * c.y; s.I.xz = Iw.xz - mass * c.x * c.z; s.I.yz = Iw.yz - mass * c.y * c.z;
+  return s;
+}
+ODG_DEV SpI spi_add(const SpI& a, const SpI& b) {
+  SpI s; s.m = a.m + b.m; s.h = a.h + b.h;
+  s.I.xx = a.I.xx + b.I.xx; s.I.xy = a.I.xy + b.I.xy; s.I.xz = a.I.xz + b.I.xz;
+  s.I.yy = a.I.yy + b.I.yy; s.I.yz = a.I.yz + b.I.yz; s.I.zz = a.I.zz + b.I.zz;
+  return s;
+}
+
+// ---- 4-lane group collectives
+#ifdef ODG_HOST_EMU
+ODG_DEV float grp_xor(float v, int m, unsigned) { return odg_emu_shfl_xor(v, m); }
+#else
+ODG_DEV float grp_xor(float v, int m, unsigned gmask) { return __shfl_xor_sync(gmask, v, m); }
+#endif
+#ifdef ODG_HOST_EMU
+ODG_DEV double grp_xor_d(double v, int m, unsigned) { return odg_emu_shfl_xor_d(v, m); }
+#else
+ODG_DEV double grp_xor_d(double v, int m, unsigned gmask) { return __shfl_xor_sync(gmask, v, m); }
+#endif
+#ifdef ODG_HOST_EMU
+ODG_DEV void grp_sync(unsigned) { (void)odg_emu_shfl_xor(0.f, 1); }
+#else
+ODG_DEV void grp_sync(unsigned gmask) { __syncwarp(gmask); }
+#endif
+ODG_DEV float grp_sum(float v, unsigned gm) { v += grp_xor(v, 1, gm); v += grp_xor(v, 2, gm); return v; }
+ODG_DEV float grp_sum21(float v, unsigned gm) { v += grp_xor(v, 2, gm); v += grp_xor(v, 1, gm); return v; }
+ODG_DEV float grp_max(float v, unsigned gm) { v = fmaxf(v, grp_xor(v, 1, gm)); v = fmaxf(v, grp_xor(v, 2, gm)); return v; }
+ODG_DEV V3 grp_sum(V3 v, unsigned gm) { return mk3(grp_sum(v.x, gm), grp_sum(v.y, gm), grp_sum(v.z, gm)); }
+ODG_DEV float grp_bcast(float v, int src_leg, int leg, unsigned gm) {   // value of lane `src_leg` to all 4
+  float a = grp_xor(v, 1, gm); float m1 = ((leg ^ src_leg) & 1) ? a : v;      // now correct within pair parity
+  float b = grp_xor(m1, 2, gm); return ((leg ^ src_leg) & 2) ? b : m1;
+}
+
+// ---- Philox4x32-10 (same stream definition as oracle/odg_oracle.c)
+ODG_DEV void philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
+  ODG_UNROLL for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+ODG_DEV float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
+constexpr uint32_t kStreamReset = 0x52534554u, kStreamDesvel = 0x44564c00u;
+
+// ---- solimp impedance (mj_makeImpedance::getimpedance); imp5 = d0,dmax,width,mid,power (pre-clamped on host)
+ODG_DEV float impedance(const float* imp5, float pos_minus_margin) {
+  float d0 = imp5[0], d1 = imp5[1], width = imp5[2], mid = imp5[3], power = imp5[4];
+  if (d0 == d1 || width <= 1e-15f) return 0.5f * (d0 + d1);
+  float x = fabsf(pos_minus_margin / width);
+  if (x >= 1.f) return d1;
+  if (x <= 0.f) return d0;
+  float y;
+  if (power == 1.f) y = x;
+  else if (power == 2.f) y = x <= mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
+  else y = x <= mid ? powf(x, power) / powf(mid, power - 1.f) : 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+  return d0 + y * (d1 - d0);
+}
+
+// friction-loss (Huber) row: z -> ds/dz, d2s/dz2
+ODG_DEV void fl_eval(float z, float f, float R, float D, float& g, float& hh) {
+  float rf = R * f;
+  if (z <= -rf) { g = -f; hh = 0.f; }
+  else if (z >= rf) { g = f; hh = 0.f; }
+  else { g = D * z; hh = D; }
+}
+
+// elliptic-cone contact block. z = (zx, zy, zn) in world axes (normal = +z). Returns zone (0 top,1 bottom,2 middle).
+ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, int condim, V3& g, S3& H) {
+  g = mk3(0.f, 0.f, 0.f); H = zero_s3();
+  if (condim == 1) {
+    if (z.z >= 0.f) return 0;
+    g.z = Dn * z.z; H.zz = Dn; return 1;
+  }
+  float U1 = z.x * fri, U2 = z.y * fri, N = z.z * mu;
+  float T2 = U1 * U1 + U2 * U2;
+  float T = sqrtf(T2);
+  if ((T <= 0.f && N >= 0.f) || (T > 0.f && N >= mu * T)) return 0;
+  if ((T <= 0.f && N < 0.f) || (T > 0.f && mu * N + T <= 0.f)) {
+    g = mk3(Dt * z.x, Dt * z.y, Dn * z.z);
+    H.xx = Dt; H.yy = Dt; H.zz = Dn;
+    return 1;
+  }
+  float Dm = Dn / (mu * mu * (1.f + mu * mu));
+  float NmT = N - mu * T;
+  float iT = 1.f / T;
+  float gU = -Dm * NmT * mu * iT;
+  g = mk3(gU * U1 * fri, gU * U2 * fri, Dm * NmT * mu);
+  float a = mu * N * iT * iT * iT, b = mu * mu - mu * N * iT;
+  float ff = Dm * fri * fri, fm = Dm * fri * mu;
+  H.xx = ff * (a * U1 * U1 + b); H.yy = ff * (a * U2 * U2 + b); H.xy = ff * a * U1 * U2;
+  H.xz = -fm * mu * U1 * iT; H.yz = -fm * mu * U2 * iT; H.zz = Dm * mu * mu;
+  return 2;
+}
+
+// unrolled dense Cholesky solve of a 6x6 SPD system held in registers. S is overwritten by its factor.
+ODG_DEV void chol6_solve(float (&S)[6][6], float (&x)[6]) {
+  ODG_UNROLL for (int j = 0; j < 6; j++) {
+    float s = S[j][j];
+    ODG_UNROLL for (int k = 0; k < j; k++) s -= S[j][k] * S[j][k];
+    s = fmaxf(s, 1e-20f);
+    float inv = rsqrtf(s);
+    S[j][j] = inv;                                // store 1/L_jj
+    ODG_UNROLL for (int i = j + 1; i < 6; i++) {
+      float t = S[i][j];
+      ODG_UNROLL for (int k = 0; k < j; k++) t -= S[i][k] * S[j][k];
+      S[i][j] = t * inv;
+    }
+  }
+  ODG_UNROLL for (int i = 0; i < 6; i++) {
+    float t = x[i];
+    ODG_UNROLL for (int k = 0; k < i; k++) t -= S[i][k] * x[k];
+    x[i] = t * S[i][i];
+  }
+  ODG_UNROLL for (int i = 5; i >= 0; i--) {
+    float t = x[i];
+    ODG_UNROLL for (int k = i + 1; k < 6; k++) t -= S[k][i] * x[k];
+    x[i] = t * S[i][i];
+  }
+}
+
+// in-place inverse of a small SPD matrix (NJL x NJL), NJL in {1,2,3}
+template <int N>
+ODG_DEV void spd_inverse(float (&A)[N][N]) {
+  if (N == 1) { A[0][0] = 1.f / A[0][0]; return; }
+  if (N == 2) {
+    float det = A[0][0] * A[1][1] - A[0][1] * A[0][1];
+    float id = 1.f / det;
+    float a = A[1][1] * id, b = -A[0][1] * id, c = A[0][0] * id;
+    A[0][0] = a; A[0][1] = b; A[1][0] = b; A[1][1] = c; return;
+  }
+  // N == 3: adjugate
+  float a = A[0][0], b = A[0][1], c = A[0][2], d = A[1][1], e = A[1][2], f = A[2][2];
+  float c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+  float det = a * c00 + b * c01 + c * c02;
+  float id = 1.f / det;
+  A[0][0] = c00 * id; A[0][1] = A[1][0] = c01 * id; A[0][2] = A[2][0] = c02 * id;
+  A[1][1] = (a * f - c * c) * id; A[1][2] = A[2][1] = (b * c - a * e) * id; A[2][2] = (a * d - b * b) * id;
+}
+
+struct Vec6 { V3 t, w; };   // linear / angular(world) parts
+ODG_DEV float dot6(const Vec6& a, const Vec6& b) { return dot(a.t, b.t) + dot(a.w, b.w); }
+
+// data the post-step code needs from the last forward pass
+template <int NJL>
+struct LastPass {
+  int foot_contact;            // this leg's foot geom has a contact (paws_in_ground)
+  V3 foot_force;               // (f_normal, f_t1, f_t2) of the LAST foot contact in MuJoCo's contact frame
+  M3 R_last;                   // rotation of the last link (xquat[paw_body-1])
+  float act[NJL];              // actuator forces
+  Vec6 a_b; float a_l[NJL];    // qacc (trunk: linear, angular WORLD)
+  int ncon, iters; float fn;
+};
+
+#define LCF(f, j) s_lc[((j) * LC_COUNT + (f)) * 4 + leg]
+#define GCF(f, s) s_gc[((s) * GC_COUNT + (f)) * 4 + leg]
+
+// One mj_step (or one mj_forward when integrate == false) for the 4-lane group of one environment.
+template <int NJL>
+ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const float* ODG_RESTRICT s_gc,
+                     const float4* ODG_RESTRICT s_vert, int leg, unsigned gm,
+                     V3& bp, float (&bq)[4], V3& bv, V3& bwl, float (&q)[NJL], float (&qd)[NJL],
+                     const float (&ctrl)[NJL], V3& warm_v, V3& warm_wl, float (&warm_l)[NJL],
+                     bool integrate, bool last, LastPass<NJL>& out) {
+  const bool lane0 = (leg == 0);
+  // ------------------------------------------------------------------ kinematics (mj_kinematics)
+  {
+    float n2 = bq[0] * bq[0] + bq[1] * bq[1] + bq[2] * bq[2] + bq[3] * bq[3];
+    if (n2 < 1e-30f) { bq[0] = 1.f; bq[1] = bq[2] = bq[3] = 0.f; }
+    else { float in = rsqrtf(n2); bq[0] *= in; bq[1] *= in; bq[2] *= in; bq[3] *= in; }
+  }
+  M3 R0;
+  {
+    float w = bq[0], x = bq[1], y = bq[2], z = bq[3];
+    R0.m[0] = w * w + x * x - y * y - z * z; R0.m[1] = 2.f * (x * y - w * z); R0.m[2] = 2.f * (x * z + w * y);
+    R0.m[3] = 2.f * (x * y + w * z); R0.m[4] = w * w - x * x + y * y - z * z; R0.m[5] = 2.f * (y * z - w * x);
+    R0.m[6] = 2.f * (x * z - w * y); R0.m[7] = 2.f * (y * z + w * x); R0.m[8] = w * w - x * x - y * y + z * z;
+  }
+  const V3 w0 = mul(R0, bwl);
+  M3 R[NJL]; V3 pos[NJL], anc[NJL], ax[NJL], com[NJL];
+  {
+    M3 Rp = R0; V3 pp = mk3(0.f, 0.f, 0.f);
+    ODG_UNROLL for (int j = 0; j < NJL; j++) {
+      V3 pre = pp + mul(Rp, mk3(LCF(LC_BP0, j), LCF(LC_BP1, j), LCF(LC_BP2, j)));
+      M3 Rpre = Rp;
+      if (!C.body_rot_identity) {
+        M3 Bq; ODG_UNROLL for (int k = 0; k < 9; k++) Bq.m[k] = LCF(LC_BR0 + k, j);
+        Rpre = mul(Rp, Bq);
+      }
+      V3 jp = mk3(LCF(LC_JP0, j), LCF(LC_JP1, j), LCF(LC_JP2, j));
+      V3 u = mk3(LCF(LC_JA0, j), LCF(LC_JA1, j), LCF(LC_JA2, j));
+      anc[j] = pre + mul(Rpre, jp);
+      ax[j] = mul(Rpre, u);
+      float s, c; sincosf(q[j], &s, &c);
+      float t = 1.f - c;
+      M3 Rl;
+      Rl.m[0] = c + t * u.x * u.x; Rl.m[1] = t * u.x * u.y - s * u.z; Rl.m[2] = t * u.x * u.z + s * u.y;
+      Rl.m[3] = t * u.x * u.y + s * u.z; Rl.m[4] = c + t * u.y * u.y; Rl.m[5] = t * u.y * u.z - s * u.x;
+      Rl.m[6] = t * u.x * u.z - s * u.y; Rl.m[7] = t * u.y * u.z + s * u.x; Rl.m[8] = c + t * u.z * u.z;
+      R[j] = mul(Rpre, Rl);
+      pos[j] = anc[j] - mul(R[j], jp);
+      com[j] = pos[j] + mul(R[j], mk3(LCF(LC_IP0, j), LCF(LC_IP1, j), LCF(LC_IP2, j)));
+      Rp = R[j]; pp = pos[j];
+    }
+  }
+  // ------------------------------------------------------------------ inertias, CRBA (mj_crb)
+  S3 Iw[NJL]; SpI cmp[NJL];
+  ODG_UNROLL for (int j = 0; j < NJL; j++) {
+    S3 Il; Il.xx = LCF(LC_IXX, j); Il.xy = LCF(LC_IXY, j); Il.xz = LCF(LC_IXZ, j);
+    Il.yy = LCF(LC_IYY, j); Il.yz = LCF(LC_IYZ, j); Il.zz = LCF(LC_IZZ, j);
+    Iw[j] = rotate_sym(R[j], Il);
+    cmp[j] = spi_make(LCF(LC_MASS, j), com[j], Iw[j]);
+  }
+  ODG_UNROLL for (int j = NJL - 2; j >= 0; j--) cmp[j] = spi_add(cmp[j], cmp[j + 1]);
+  // trunk body
+  const V3 com0 = mul(R0, mk3(C.base_ip[0], C.base_ip[1], C.base_ip[2]));
+  S3 Ib; Ib.xx = C.base_I[0]; Ib.xy = C.base_I[1]; Ib.xz = C.base_I[2]; Ib.yy = C.base_I[3]; Ib.yz = C.base_I[4]; Ib.zz = C.base_I[5];
+  const S3 Iw0 = rotate_sym(R0, Ib);
+  SpI T;                                           // trunk composite = trunk body + all legs
+  {
+    SpI b = spi_make(C.base_mass, com0, Iw0);
+    T.m = b.m + grp_sum(cmp[0].m, gm);
+    T.h = b.h + grp_sum(cmp[0].h, gm);
+    T.I.xx = b.I.xx + grp_sum(cmp[0].I.xx, gm); T.I.xy = b.I.xy + grp_sum(cmp[0].I.xy, gm);
+    T.I.xz = b.I.xz + grp_sum(cmp[0].I.xz, gm); T.I.yy = b.I.yy + grp_sum(cmp[0].I.yy, gm);
+    T.I.yz = b.I.yz + grp_sum(cmp[0].I.yz, gm); T.I.zz = b.I.zz + grp_sum(cmp[0].I.zz, gm);
+  }
+  // leg blocks of M:  Mlb[j] = momentum (p, L about O) of composite j under unit joint velocity
+  Vec6 Mlb[NJL]; float Mll[NJL][NJL]; V3 vax[NJL];
+  ODG_UNROLL for (int j = 0; j < NJL; j++) {
+    vax[j] = cross(anc[j], ax[j]);                 // velocity at O of unit rotation about the hinge
+    Mlb[j].t = cmp[j].m * vax[j] + cross(ax[j], cmp[j].h);
+    Mlb[j].w = mul(cmp[j].I, ax[j]) + cross(cmp[j].h, vax[j]);
+  }
+  ODG_UNROLL for (int j = 0; j < NJL; j++)
+    ODG_UNROLL for (int i = 0; i <= j; i++) {
+      float v = dot(ax[i], Mlb[j].w) + dot(vax[i], Mlb[j].t);
+      if (i == j) v += LCF(LC_ARM, j);
+      Mll[j][i] = v; Mll[i][j] = v;
+    }
+  // M_bb acts as: p = m*av + aw x h + arm_t.*av ; L = I*aw + h x av + arm_r*aw
+  auto Mbb_mul = [&](const Vec6& a) {
+    Vec6 r;
+    r.t = T.m * a.t + cross(a.w, T.h) + mk3(C.base_arm_t[0] * a.t.x, C.base_arm_t[1] * a.t.y, C.base_arm_t[2] * a.t.z);
+    r.w = mul(T.I, a.w) + cross(T.h, a.t) + C.base_arm_r * a.w;
+    return r;
+  };
+  // ------------------------------------------------------------------ bias forces (mj_rne, flg_acc = 0)
+  float cbias[NJL]; Vec6 cb;                       // cb = total inertial+gravity wrench about O (world)
+  {
+    const V3 g = mk3(C.gx, C.gy, C.gz);
+    V3 F[NJL], tauO[NJL];
+    V3 w = w0, al = mk3(0.f, 0.f, 0.f), r = mk3(0.f, 0.f, 0.f), aref = mk3(0.f, 0.f, 0.f);
+    ODG_UNROLL for (int j = 0; j < NJL; j++) {
+      V3 rho = anc[j] - r;
+      aref = aref + cross(al, rho) + cross(w, cross(w, rho));
+      r = anc[j];
+      al = al + qd[j] * cross(w, ax[j]);
+      w = w + qd[j] * ax[j];
+      V3 rc = com[j] - r;
+      V3 acom = aref + cross(al, rc) + cross(w, cross(w, rc));
+      F[j] = LCF(LC_MASS, j) * (acom - g);
+      V3 N = mul(Iw[j], al) + cross(w, mul(Iw[j], w));
+      tauO[j] = cross(com[j], F[j]) + N;
+    }
+    V3 Fs = mk3(0.f, 0.f, 0.f), Ts = mk3(0.f, 0.f, 0.f);
+    ODG_UNROLL for (int j = NJL - 1; j >= 0; j--) {
+      Fs = Fs + F[j]; Ts = Ts + tauO[j];
+      cbias[j] = dot(ax[j], Ts - cross(anc[j], Fs));
+    }
+    V3 a0 = cross(w0, cross(w0, com0));
+    V3 F0 = C.base_mass * (a0 - g);
+    V3 N0 = cross(w0, mul(Iw0, w0));
+    cb.t = F0 + grp_sum(Fs, gm);
+    cb.w = cross(com0, F0) + N0 + grp_sum(Ts, gm);
+  }
+  // ------------------------------------------------------------------ actuation + qfrc_smooth
+  float tau_l[NJL];
+  ODG_UNROLL for (int j = 0; j < NJL; j++) {
+    float f = 0.f;
+    if (LCF(LC_HASACT, j) != 0.f) {
+      float c = ctrl[j];
+      if (LCF(LC_CLIM, j) != 0.f) c = fmaxf(LCF(LC_CLO, j), fminf(LCF(LC_CHI, j), c));
+      f = LCF(LC_KP, j) * c - LCF(LC_KP, j) * q[j] - LCF(LC_KV, j) * qd[j];
+      if (LCF(LC_FLIM, j) != 0.f) f = fmaxf(LCF(LC_FLO, j), fminf(LCF(LC_FHI, j), f));
+    }
+    out.act[j] = f;
+    tau_l[j] = f - cbias[j] - LCF(LC_DAMP, j) * qd[j];
+  }
+  // ------------------------------------------------------------------ collision: floor plane vs hulls
+  V3 c_r[kMaxConLeg], c_aref[kMaxConLeg], c_z0[kMaxConLeg], c_dz[kMaxConLeg];
+  float c_Dn[kMaxConLeg]; int c_slot[kMaxConLeg];
+  int nc = 0;
+  int foot_last = -1;
+  for (int s = 0; s < C.nslot; s++) {
+    const int link = C.slot_link[s];
+    M3 Rl = R[0]; V3 pl = pos[0];
+    ODG_UNROLL for (int j = 1; j < NJL; j++) if (link == j) { Rl = R[j]; pl = pos[j]; }
+    const float margin = C.slot_margin[s];
+    const float zoff = bp.z + pl.z;
+    if (C.slot_type[s] == 1) {                     // sphere
+      V3 cc = pl + mul(Rl, mk3(GCF(GC_CX, s), GCF(GC_CY, s), GCF(GC_CZ, s)));
+      float dist = bp.z + cc.z - C.slot_radius[s];
+      if (dist <= margin && nc < kMaxConLeg) {
+        c_r[nc] = mk3(cc.x, cc.y, cc.z - C.slot_radius[s] - 0.5f * dist); c_Dn[nc] = dist; c_slot[nc] = s;
+        if (C.slot_isfoot[s]) foot_last = nc;
+        nc++;
+      }
+      continue;
+    }
+    const int nvt = C.slot_nvert[s], vs = C.slot_vstart[s];
+    const V3 rz = mk3(Rl.m[6], Rl.m[7], Rl.m[8]);
+    float zmin = 1e30f; int best = 0;
+    for (int k = 0; k < nvt; k++) {
+      float4 v = s_vert[(vs + k) * 4 + leg];
+      float z = zoff + rz.x * v.x + rz.y * v.y + rz.z * v.z;
+      if (z < zmin) { zmin = z; best = k; }
+    }
+    if (zmin > margin) continue;
+    int found[4]; int nf = 1; found[0] = best;
+    {
+      float4 v = s_vert[(vs + best) * 4 + leg];
+      V3 pw = pl + mul(Rl, mk3(v.x, v.y, v.z));
+      if (nc < kMaxConLeg) {
+        c_r[nc] = mk3(pw.x, pw.y, 0.5f * zmin - bp.z); c_Dn[nc] = zmin; c_slot[nc] = s;
+        if (C.slot_isfoot[s]) foot_last = nc;
+        nc++;
+      }
+    }
+    for (int i = 0; i < C.n_tilt; i++) {
+      V3 dl = tmul(Rl, mk3(C.tilt_dir[i][0], C.tilt_dir[i][1], C.tilt_dir[i][2]));
+      float smax = -1e30f; int bi = 0;
+      for (int k = 0; k < nvt; k++) {
+        float4 v = s_vert[(vs + k) * 4 + leg];
+        float sc = dl.x * v.x + dl.y * v.y + dl.z * v.z;
+        if (sc > smax) { smax = sc; bi = k; }
+      }
+      bool dup = false;
+      for (int k = 0; k < nf; k++) dup |= (found[k] == bi);
+      if (dup) continue;
+      float4 v = s_vert[(vs + bi) * 4 + leg];
+      V3 pw = pl + mul(Rl, mk3(v.x, v.y, v.z));
+      float z = bp.z + pw.z;
+      if (z > margin) continue;
+      found[nf++] = bi;
+      if (nc < kMaxConLeg) {
+        c_r[nc] = mk3(pw.x, pw.y, 0.5f * z - bp.z); c_Dn[nc] = z; c_slot[nc] = s;
+        if (C.slot_isfoot[s]) foot_last = nc;
+        nc++;
+      }
+    }
+  }
+  // ------------------------------------------------------------------ constraint rows (mj_makeConstraint/Impedance)
+  // contacts: c_Dn currently holds dist; turn into D_n and build aref
+  for (int c = 0; c < nc; c++) {
+    const int s = c_slot[c];
+    const int link = C.slot_link[s];
+    const float dist = c_Dn[c];
+    const V3 r = c_r[c];
+    V3 vc = bv + cross(w0, r);
+    ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) vc = vc + qd[j] * cross(ax[j], r - anc[j]);
+    const float margin = C.slot_margin[s];
+    float active = dist < margin ? 1.f : 0.f;       // excluded if in the gap (gap = 0: never for dist==margin only)
+    float imp = impedance(C.slot_imp[s], dist - margin);
+    float Rn = fmaxf(1e-15f, (1.f - imp) / imp * GCF(GC_INVW, s));
+    c_Dn[c] = active / Rn;
+    const float Bc = C.slot_B[s], Kc = C.slot_K[s];
+    c_aref[c] = mk3(-Bc * vc.x, -Bc * vc.y, -Bc * vc.z - Kc * imp * (dist - margin));
+  }
+  // own-joint friction-loss and limit rows
+  float aref_fl[NJL], lim_sgn[NJL], lim_aref[NJL], lim_D[NJL];
+  ODG_UNROLL for (int j = 0; j < NJL; j++) {
+    aref_fl[j] = -C.B_fl * qd[j];
+    lim_sgn[j] = 0.f; lim_aref[j] = 0.f; lim_D[j] = 0.f;
+    if (LCF(LC_LIMITED, j) != 0.f) {
+      float dlo = q[j] - LCF(LC_LO, j), dhi = LCF(LC_HI, j) - q[j];
+      float dist = 0.f, sg = 0.f;
+      if (dlo < 0.f) { dist = dlo; sg = 1.f; }
+      else if (dhi < 0.f) { dist = dhi; sg = -1.f; }
+      if (sg != 0.f) {
+        float imp = impedance(C.lim_imp, dist);
+        float Rr = fmaxf(1e-15f, (1.f - imp) / imp * LCF(LC_INVW, j));
+        lim_sgn[j] = sg; lim_D[j] = 1.f / Rr;
+        lim_aref[j] = -C.B_lim * (sg * qd[j]) - C.K_lim * imp * dist;
+      }
+    }
+  }
+  // trunk friction-loss rows (DoFs in MuJoCo's frames: world linear, trunk-frame angular)
+  const V3 aref_bt = mk3(-C.B_fl * bv.x, -C.B_fl * bv.y, -C.B_fl * bv.z);
+  const V3 aref_br = mk3(-C.B_fl * bwl.x, -C.B_fl * bwl.y, -C.B_fl * bwl.z);
+  const Vec6 tau_b = { -cb.t, -cb.w };
+  // ------------------------------------------------------------------ Newton solve of the primal problem
+  Vec6 a_b; float a_l[NJL];
+  a_b.t = warm_v; a_b.w = mul(R0, warm_wl);
+  ODG_UNROLL for (int j = 0; j < NJL; j++) a_l[j] = warm_l[j];
+  const float l0f = lane0 ? 1.f : 0.f;
+  int iters = 0;
+  bool conv = false;
+  for (int it = 0; it < C.solver_iters && !conv; it++) {
+    iters = it + 1;
+    // ---- gradient and Hessian at a
+    float g_l[NJL], Hll[NJL][NJL]; Vec6 Hlb[NJL]; Vec6 gb;
+    S3 Htt = zero_s3(), Hww = zero_s3(); float Htw[3][3];
+    ODG_UNROLL for (int i = 0; i < 3; i++) ODG_UNROLL for (int k = 0; k < 3; k++) Htw[i][k] = 0.f;
+    Vec6 Mab = Mbb_mul(a_b);
+    gb.t = l0f * (Mab.t - tau_b.t); gb.w = l0f * (Mab.w - tau_b.w);
+    float gauss_l[NJL];
+    ODG_UNROLL for (int j = 0; j < NJL; j++) {
+      float s = dot6(Mlb[j], a_b);
+      ODG_UNROLL for (int i = 0; i < NJL; i++) { s += Mll[j][i] * a_l[i]; Hll[j][i] = Mll[j][i]; }
+      gauss_l[j] = s - tau_l[j];
+      g_l[j] = gauss_l[j];
+      Hlb[j] = Mlb[j];
+      gb.t = gb.t + a_l[j] * Mlb[j].t; gb.w = gb.w + a_l[j] * Mlb[j].w;
+    }
+    const Vec6 gauss_b = gb;                        // lane-partial of (M a - tau)_trunk
+    // joint friction-loss + limits
+    ODG_UNROLL for (int j = 0; j < NJL; j++) {
+      float fl = LCF(LC_FL, j);
+      if (fl > 0.f) {
+        float g, hh; fl_eval(a_l[j] - aref_fl[j], fl, LCF(LC_RFL, j), LCF(LC_DFL, j), g, hh);
+        g_l[j] += g; Hll[j][j] += hh;
+      }
+      if (lim_sgn[j] != 0.f) {
+        float z = lim_sgn[j] * a_l[j] - lim_aref[j];
+        if (z < 0.f) { g_l[j] += lim_sgn[j] * lim_D[j] * z; Hll[j][j] += lim_D[j]; }
+      }
+    }
+    // trunk friction-loss rows (counted once: lane 0)
+    {
+      V3 al_loc = tmul(R0, a_b.w);
+      ODG_UNROLL for (int i = 0; i < 3; i++) {
+        if (C.base_fl[i] > 0.f) {
+          float g, hh; fl_eval(comp(a_b.t, i) - comp(aref_bt, i), C.base_fl[i], C.base_Rfl[i], C.base_Dfl[i], g, hh);
+          g *= l0f; hh *= l0f;
+          if (i == 0) { gb.t.x += g; Htt.xx += hh; } else if (i == 1) { gb.t.y += g; Htt.yy += hh; } else { gb.t.z += g; Htt.zz += hh; }
+        }
+        if (C.base_fl[3 + i] > 0.f) {
+          float g, hh; fl_eval(comp(al_loc, i) - comp(aref_br, i), C.base_fl[3 + i], C.base_Rfl[3 + i], C.base_Dfl[3 + i], g, hh);
+          g *= l0f; hh *= l0f;
+          V3 ci = col(R0, i);
+          gb.w = gb.w + g * ci;
+          Hww.xx += hh * ci.x * ci.x; Hww.xy += hh * ci.x * ci.y; Hww.xz += hh * ci.x * ci.z;
+          Hww.yy += hh * ci.y * ci.y; Hww.yz += hh * ci.y * ci.z; Hww.zz += hh * ci.z * ci.z;
+        }
+      }
+    }
+    // contacts
+    for (int c = 0; c < nc; c++) {
+      const int s = c_slot[c];
+      const int link = C.slot_link[s];
+      const V3 r = c_r[c];
+      V3 cj[NJL];
+      V3 ap = a_b.t + cross(a_b.w, r);
+      ODG_UNROLL for (int j = 0; j < NJL; j++) {
+        cj[j] = (j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f);
+        ap = ap + a_l[j] * cj[j];
+      }
+      V3 z = ap - c_aref[c];
+      c_z0[c] = z;
+      V3 g; S3 H;
+      const float Dn = c_Dn[c];
+      int zone = cone_eval(z, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_condim[s], g, H);
+      if (zone == 0 || Dn == 0.f) continue;
+      gb.t = gb.t + g; gb.w = gb.w + cross(r, g);
+      // H * X, X = -[r]x : column i of X is e_i x r
+      V3 X0 = mk3(0.f, -r.z, r.y), X1 = mk3(r.z, 0.f, -r.x), X2 = mk3(-r.y, r.x, 0.f);
+      V3 HX0 = mul(H, X0), HX1 = mul(H, X1), HX2 = mul(H, X2);
+      Htt.xx += H.xx; Htt.xy += H.xy; Htt.xz += H.xz; Htt.yy += H.yy; Htt.yz += H.yz; Htt.zz += H.zz;
+      Htw[0][0] += HX0.x; Htw[1][0] += HX0.y; Htw[2][0] += HX0.z;
+      Htw[0][1] += HX1.x; Htw[1][1] += HX1.y; Htw[2][1] += HX1.z;
+      Htw[0][2] += HX2.x; Htw[1][2] += HX2.y; Htw[2][2] += HX2.z;
+      Hww.xx += dot(X0, HX0); Hww.xy += dot(X0, HX1); Hww.xz += dot(X0, HX2);
+      Hww.yy += dot(X1, HX1); Hww.yz += dot(X1, HX2); Hww.zz += dot(X2, HX2);
+      ODG_UNROLL for (int j = 0; j < NJL; j++) {
+        if (j <= link) {
+          V3 hc = mul(H, cj[j]);
+          g_l[j] += dot(cj[j], g);
+          Hlb[j].t = Hlb[j].t + hc; Hlb[j].w = Hlb[j].w + cross(r, hc);
+          ODG_UNROLL for (int i = 0; i <= j; i++) {
+            float v = dot(cj[i], hc);
+            Hll[j][i] += v; if (i != j) Hll[i][j] += v;
+          }
+        }
+      }
+    }
+    // ---- eliminate the leg block: Schur complement on the trunk
+    spd_inverse<NJL>(Hll);                          // Hll now holds its inverse
+    Vec6 W[NJL]; float y[NJL];
+    ODG_UNROLL for (int j = 0; j < NJL; j++) {
+      W[j].t = mk3(0.f, 0.f, 0.f); W[j].w = mk3(0.f, 0.f, 0.f); y[j] = 0.f;
+      ODG_UNROLL for (int i = 0; i < NJL; i++) {
+        W[j].t = W[j].t + Hll[j][i] * Hlb[i].t; W[j].w = W[j].w + Hll[j][i] * Hlb[i].w;
+        y[j] += Hll[j][i] * g_l[i];
+      }
+    }
+    float S[6][6]; float rhs[6];
+    {
+      // lane-partial trunk block: (lane0 ? M_bb : 0) + friction/contact terms - sum_j Hlb[j]^T W[j]
+      float P[6][6];
+      ODG_UNROLL for (int i = 0; i < 6; i++) ODG_UNROLL for (int k = 0; k < 6; k++) P[i][k] = 0.f;
+      P[0][0] = Htt.xx; P[1][0] = Htt.xy; P[2][0] = Htt.xz; P[1][1] = Htt.yy; P[2][1] = Htt.yz; P[2][2] = Htt.zz;
+      P[3][3] = Hww.xx; P[4][3] = Hww.xy; P[5][3] = Hww.xz; P[4][4] = Hww.yy; P[5][4] = Hww.yz; P[5][5] = Hww.zz;
+      ODG_UNROLL for (int i = 0; i < 3; i++) ODG_UNROLL for (int k = 0; k < 3; k++) P[3 + k][i] = Htw[i][k];
+      // M_bb (lane 0): [[m I + arm_t, -[h]x], [[h]x, I + arm_r]]  (lower triangle rows w, cols t = [h]x)
+      P[0][0] += l0f * (T.m + C.base_arm_t[0]); P[1][1] += l0f * (T.m + C.base_arm_t[1]); P[2][2] += l0f * (T.m + C.base_arm_t[2]);
+      P[3][3] += l0f * (T.I.xx + C.base_arm_r); P[4][3] += l0f * T.I.xy; P[5][3] += l0f * T.I.xz;
+      P[4][4] += l0f * (T.I.yy + C.base_arm_r); P[5][4] += l0f * T.I.yz; P[5][5] += l0f * (T.I.zz + C.base_arm_r);
+      // [h]x = [[0,-hz,hy],[hz,0,-hx],[-hy,hx,0]] -> P[3+row][col]
+      P[3][1] += l0f * (-T.h.z); P[3][2] += l0f * (T.h.y);
+      P[4][0] += l0f * (T.h.z);  P[4][2] += l0f * (-T.h.x);
+      P[5][0] += l0f * (-T.h.y); P[5][1] += l0f * (T.h.x);
+      float gbv[6] = { gb.t.x, gb.t.y, gb.t.z, gb.w.x, gb.w.y, gb.w.z };
+      ODG_UNROLL for (int j = 0; j < NJL; j++) {
+        float hl[6] = { Hlb[j].t.x, Hlb[j].t.y, Hlb[j].t.z, Hlb[j].w.x, Hlb[j].w.y, Hlb[j].w.z };
+        float wl[6] = { W[j].t.x, W[j].t.y, W[j].t.z, W[j].w.x, W[j].w.y, W[j].w.z };
+        ODG_UNROLL for (int i = 0; i < 6; i++) {
+          ODG_UNROLL for (int k = 0; k <= i; k++) P[i][k] -= hl[i] * wl[k];
+          gbv[i] -= hl[i] * y[j];
+        }
+      }
+      ODG_UNROLL for (int i = 0; i < 6; i++) {
+        ODG_UNROLL for (int k = 0; k <= i; k++) S[i][k] = grp_sum(P[i][k], gm);
+        rhs[i] = -grp_sum(gbv[i], gm);
+      }
+    }
+    chol6_solve(S, rhs);
+    Vec6 p_b; p_b.t = mk3(rhs[0], rhs[1], rhs[2]); p_b.w = mk3(rhs[3], rhs[4], rhs[5]);
+    float p_l[NJL];
+    ODG_UNROLL for (int j = 0; j < NJL; j++) p_l[j] = -y[j] - dot6(W[j], p_b);
+    // ---- exact line search on phi(alpha) = cost(a + alpha p)  (convex, C1, piecewise quadratic)
+    // lane-partials of the Gauss part: phi'_gauss(alpha) = G + alpha*Hq
+    float G = dot6(gauss_b, p_b), Hq = 0.f;
+    {
+      Vec6 Mpb = Mbb_mul(p_b);
+      Hq = l0f * dot6(Mpb, p_b);
+      ODG_UNROLL for (int j = 0; j < NJL; j++) {
+        float mlp = dot6(Mlb[j], p_b);
+        G += p_l[j] * gauss_l[j];
+        float s = 2.f * mlp;
+        ODG_UNROLL for (int i = 0; i < NJL; i++) s += Mll[j][i] * p_l[i];
+        Hq += p_l[j] * s;
+      }
+    }
+    for (int c = 0; c < nc; c++) {
+      const int link = C.slot_link[c_slot[c]];
+      const V3 r = c_r[c];
+      V3 dz = p_b.t + cross(p_b.w, r);
+      ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) dz = dz + p_l[j] * cross(ax[j], r - anc[j]);
+      c_dz[c] = dz;
+    }
+    const V3 al_loc = tmul(R0, a_b.w), pl_loc = tmul(R0, p_b.w);
+    float alpha = 1.f, lo = 0.f, hi = -1.f;
+    for (int ls = 0; ls < C.ls_iters; ls++) {
+      float d1 = G + alpha * Hq, d2 = Hq;
+      ODG_UNROLL for (int j = 0; j < NJL; j++) {
+        float fl = LCF(LC_FL, j);
+        if (fl > 0.f) {
+          float g, hh; fl_eval(a_l[j] + alpha * p_l[j] - aref_fl[j], fl, LCF(LC_RFL, j), LCF(LC_DFL, j), g, hh);
+          d1 += g * p_l[j]; d2 += hh * p_l[j] * p_l[j];
+        }
+        if (lim_sgn[j] != 0.f) {
+          float dzl = lim_sgn[j] * p_l[j];
+          float z = lim_sgn[j] * a_l[j] - lim_aref[j] + alpha * dzl;
+          if (z < 0.f) { d1 += lim_D[j] * z * dzl; d2 += lim_D[j] * dzl * dzl; }
+        }
+      }
+      ODG_UNROLL for (int i = 0; i < 3; i++) {
+        if (C.base_fl[i] > 0.f) {
+          float g, hh, dzl = comp(p_b.t, i);
+          fl_eval(comp(a_b.t, i) + alpha * dzl - comp(aref_bt, i), C.base_fl[i], C.base_Rfl[i], C.base_Dfl[i], g, hh);
+          d1 += l0f * g * dzl; d2 += l0f * hh * dzl * dzl;
+        }
+        if (C.base_fl[3 + i] > 0.f) {
+          float g, hh, dzl = comp(pl_loc, i);
+          fl_eval(comp(al_loc, i) + alpha * dzl - comp(aref_br, i), C.base_fl[3 + i], C.base_Rfl[3 + i], C.base_Dfl[3 + i], g, hh);
+          d1 += l0f * g * dzl; d2 += l0f * hh * dzl * dzl;
+        }
+      }
+      for (int c = 0; c < nc; c++) {
+        const int s = c_slot[c];
+        const float Dn = c_Dn[c];
+        if (Dn == 0.f) continue;
+        V3 dz = c_dz[c];
+        V3 z = c_z0[c] + alpha * dz;
+        V3 g; S3 H;
+        int zone = cone_eval(z, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_condim[s], g, H);
+        if (zone == 0) continue;
+        d1 += dot(g, dz); d2 += dot(dz, mul(H, dz));
+      }
+      d1 = grp_sum(d1, gm); d2 = grp_sum(d2, gm);
+      if (!(d2 > 0.f)) { alpha = 0.f; break; }
+      float step = -d1 / d2;
+      if (fabsf(step) <= 1e-4f * alpha) { alpha += step; break; }
+      if (d1 < 0.f) lo = alpha; else hi = alpha;
+      float next = alpha + step;
+      if (hi < 0.f) { if (!(next > lo)) next = 2.f * alpha; }
+      else if (!(next > lo && next < hi)) next = 0.5f * (lo + hi);
+      alpha = next;
+    }
+    // ---- take the step, test convergence on the step size
+    float amax = 0.f, smax = 0.f;
+    a_b.t = a_b.t + alpha * p_b.t; a_b.w = a_b.w + alpha * p_b.w;
+    smax = fmaxf(fmaxf(fabsf(p_b.t.x), fabsf(p_b.t.y)), fmaxf(fabsf(p_b.t.z), fmaxf(fabsf(p_b.w.x), fmaxf(fabsf(p_b.w.y), fabsf(p_b.w.z)))));
+    amax = fmaxf(fmaxf(fabsf(a_b.t.x), fabsf(a_b.t.y)), fmaxf(fabsf(a_b.t.z), fmaxf(fabsf(a_b.w.x), fmaxf(fabsf(a_b.w.y), fabsf(a_b.w.z)))));
+    ODG_UNROLL for (int j = 0; j < NJL; j++) {
+      a_l[j] += alpha * p_l[j];
+      smax = fmaxf(smax, fabsf(p_l[j])); amax = fmaxf(amax, fabsf(a_l[j]));
+    }
+    smax = grp_max(smax, gm) * fabsf(alpha); amax = grp_max(amax, gm);
+    conv = smax <= C.tol * (1.f + amax);
+  }
+  // ------------------------------------------------------------------ outputs of the forward pass
+  if (last) {
+    out.a_b = a_b; ODG_UNROLL for (int j = 0; j < NJL; j++) out.a_l[j] = a_l[j];
+    out.ncon = nc; out.iters = iters; out.R_last = R[NJL - 1];
+    out.foot_contact = foot_last >= 0 ? 1 : 0;
+    out.foot_force = mk3(0.f, 0.f, 0.f);
+    float fn = 0.f;
+    for (int c = 0; c < nc; c++) {
+      const int s = c_slot[c];
+      const int link = C.slot_link[s];
+      const float Dn = c_Dn[c];
+      if (Dn == 0.f) continue;
+      const V3 r = c_r[c];
+      V3 ap = a_b.t + cross(a_b.w, r);
+      ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) ap = ap + a_l[j] * cross(ax[j], r - anc[j]);
+      V3 g; S3 H;
+      cone_eval(ap - c_aref[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_condim[s], g, H);
+      fn += -g.z;
+      if (c == foot_last) out.foot_force = mk3(-g.z, -g.y, g.x);   // MuJoCo frame: n=+z, t1=+y, t2=-x
+    }
+    out.fn = fn;
+  }
+  // ------------------------------------------------------------------ semi-implicit Euler (mj_Euler)
+  const V3 acc_wl = tmul(R0, a_b.w);
+  if (integrate) {
+    const float h = C.h;
+    bv = bv + h * a_b.t;
+    bwl = bwl + h * acc_wl;
+    ODG_UNROLL for (int j = 0; j < NJL; j++) { qd[j] += h * a_l[j]; q[j] += h * qd[j]; }
+    bp = bp + h * bv;
+    float wn = sqrtf(dot(bwl, bwl));
+    if (wn > 1e-15f) {
+      float s, c; sincosf(0.5f * h * wn, &s, &c);
+      float k = s / wn;
+      float dw = c, dx = k * bwl.x, dy = k * bwl.y, dz = k * bwl.z;
+      float w = bq[0], x = bq[1], y = bq[2], z = bq[3];
+      float nw = w * dw - x * dx - y * dy - z * dz;
+      float nx = w * dx + x * dw + y * dz - z * dy;
+      float ny = w * dy - x * dz + y * dw + z * dx;
+      float nz = w * dz + x * dy - y * dx + z * dw;
+      float in = rsqrtf(nw * nw + nx * nx + ny * ny + nz * nz);
+      bq[0] = nw * in; bq[1] = nx * in; bq[2] = ny * in; bq[3] = nz * in;
+    }
+  }
+  warm_v = a_b.t; warm_wl = acc_wl;
+  ODG_UNROLL for (int j = 0; j < NJL; j++) warm_l[j] = a_l[j];
+}
+
+// reward_calc:372-390 in double
+ODG_DEV void euler_from_quat(double w, double x, double y, double z, double& roll, double& pitch, double& yaw) {
+  double t0 = 2.0 * (w * x + y * z), t1 = 1.0 - 2.0 * (x * x + y * y);
+  roll = atan2(t0, t1);
+  double t2 = 2.0 * (w * y - z * x);
+  t2 = t2 > 1.0 ? 1.0 : t2; t2 = t2 < -1.0 ? -1.0 : t2;
+  pitch = asin(t2);
+  double t3 = 2.0 * (w * z + x * y), t4 = 1.0 - 2.0 * (y * y + z * z);
+  yaw = atan2(t3, t4);
+}
+
+// diagonal_gait_reward (reward_calc:203-234); pattern table :54-63, order FL FR BL BR = legs 0..3
+ODG_DEV int gait_call(int& idx, int& cnt, int paws_mask, float vx) {
+  const unsigned char pat[8] = { 0xF, 0xB, 0x9, 0xD, 0xF, 0x7, 0x6, 0xF };   // bit l = leg l on the ground
+  bool match = (paws_mask == (int)pat[idx]) && (vx >= 0.5f);
+  if (match) { cnt += 8; idx = (idx + 1) & 7; return cnt; }
+  cnt = 0; idx = 0; return 0;
+}
+
+// Full environment step for one 4-lane group: load state, frame_skip substeps, obs/reward/termination,
+// optional auto-reset, store state.
+template <int NJL>
+ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const float* ODG_RESTRICT s_gc,
+                      const float4* ODG_RESTRICT s_vert, const SimPtrs& P, const StepArgs& A,
+                      int env, int leg, unsigned gm) {
+  const int N = P.N;
+  const int obs_dim = 9 + 3 * C.nu;
+  // ---- load
+  V3 bp = mk3(P.qpos[0 * N + env], P.qpos[1 * N + env], P.qpos[2 * N + env]);
+  float bq[4] = { P.qpos[3 * N + env], P.qpos[4 * N + env], P.qpos[5 * N + env], P.qpos[6 * N + env] };
+  V3 bv = mk3(P.qvel[0 * N + env], P.qvel[1 * N + env], P.qvel[2 * N + env]);
+  V3 bwl = mk3(P.qvel[3 * N + env], P.qvel[4 * N + env], P.qvel[5 * N + env]);
+  V3 warm_v = mk3(P.warm[0 * N + env], P.warm[1 * N + env], P.warm[2 * N + env]);
+  V3 warm_wl = mk3(P.warm[3 * N + env], P.warm[4 * N + env], P.warm[5 * N + env]);
+  float q[NJL], qd[NJL], warm_l[NJL], ctrl[NJL], prev_act[NJL];
+  ODG_UNROLL for (int j = 0; j < NJL; j++) {
+    q[j] = P.qpos[(7 + leg * NJL + j) * N + env];
+    qd[j] = P.qvel[(6 + leg * NJL + j) * N + env];
+    warm_l[j] = P.warm[(6 + leg * NJL + j) * N + env];
+    const int u = (int)LCF(LC_UIDX, j);
+    float a = LCF(LC_HASACT, j) != 0.f ? A.action[env * C.nu + u] : 0.f;
+    if (C.scale_actions && A.mode == 0) {
+      // ScaleActionEnvironment.py:21-23 in float32, numpy evaluation order
+      float lo = LCF(LC_SLO, j), hi = LCF(LC_SHI, j);
+      a = odg_fadd_rn(lo, odg_fdiv_rn(odg_fmul_rn(odg_fadd_rn(a, 1.0f), odg_fsub_rn(hi, lo)), 2.0f));
+    }
+    ctrl[j] = a;
+    prev_act[j] = LCF(LC_HASACT, j) != 0.f ? P.last_action[u * N + env] : 0.f;
+  }
+  int step = P.step[env], gidx = P.gait_idx[env], gcnt = P.gait_cnt[env];
+  const bool fresh = P.fresh[env] != 0;
+  const V3 desvel = mk3(P.desvel[0 * N + env], P.desvel[1 * N + env], P.desvel[2 * N + env]);
+
+  // ---- physics
+  LastPass<NJL> lp;
+  if (A.mode == 0) {
+    step += 1;
+    for (int s = 0; s < C.frame_skip; s++)
+      substep<NJL>(C, s_lc, s_gc, s_vert, leg, gm, bp, bq, bv, bwl, q, qd, ctrl, warm_v, warm_wl, warm_l,
+                   true, s == C.frame_skip - 1, lp);
+  } else {
+    substep<NJL>(C, s_lc, s_gc, s_vert, leg, gm, bp, bq, bv, bwl, q, qd, ctrl, warm_v, warm_wl, warm_l,
+                 false, true, lp);
+  }
+
+  // ---- observation (WalkEnvironment.py:115-136), float32
+  float* obs = A.obs ? A.obs + (size_t)env * obs_dim : nullptr;
+  float* tobs = (A.terminal_obs && A.mode == 0) ? A.terminal_obs + (size_t)env * obs_dim : nullptr;
+  auto clip = [](float v) { return fminf(100.f, fmaxf(-100.f, v)); };
+  auto write_obs = [&](float* o, V3 v, V3 wl, const float (&qq)[NJL], const float (&qqd)[NJL], const float (&la)[NJL]) {
+    if (!o) return;
+    if (leg == 0) {
+      o[0] = clip(v.x * 2.0f); o[1] = clip(v.y * 2.0f); o[2] = clip(v.z * 2.0f);
+      o[3] = clip(wl.x * 0.25f); o[4] = clip(wl.y * 0.25f); o[5] = clip(wl.z * 0.25f);
+      o[6] = clip(desvel.x * 2.0f); o[7] = clip(desvel.y * 2.0f); o[8] = clip(desvel.z * 2.0f);
+    }
+    ODG_UNROLL for (int j = 0; j < NJL; j++) {
+      o[9 + leg * NJL + j] = clip(qq[j] - C.obs_joint_offset);
+      o[9 + C.nu + leg * NJL + j] = clip(qqd[j] * 0.05f);
+      if (LCF(LC_HASACT, j) != 0.f) o[9 + 2 * C.nu + (int)LCF(LC_UIDX, j)] = clip(la[j]);
+    }
+  };
+  write_obs(obs, bv, bwl, q, qd, prev_act);
+  if (tobs) write_obs(tobs, bv, bwl, q, qd, prev_act);
+
+  // ---- reward / termination (WalkEnvironment.py:81-109, reward_calc.py), double where the reference is
+  const double lim = 15.0 * 3.14159265358979323846 / 180.0;
+  bool finite = isfinite(bp.x) && isfinite(bp.y) && isfinite(bp.z) && isfinite(bq[0]) && isfinite(bq[1]) &&
+                isfinite(bq[2]) && isfinite(bq[3]) && isfinite(bv.x) && isfinite(bv.y) && isfinite(bv.z) &&
+                isfinite(bwl.x) && isfinite(bwl.y) && isfinite(bwl.z);
+  float fin_l = 1.f;
+  ODG_UNROLL for (int j = 0; j < NJL; j++) fin_l = (isfinite(q[j]) && isfinite(qd[j])) ? fin_l : 0.f;
+  finite = finite && (grp_sum(fin_l, gm) == 4.f);
+  double lin = 0.0;
+  if (bp.x > 0.f) {
+    double ex = (double)desvel.x - (double)bv.x, ey = (double)desvel.y - (double)bv.y;
+    lin = exp(-(ex * ex + ey * ey) / 0.25);
+  }
+  double roll = 0, pitch = 0, yaw = 0, safe = 0;
+  if (finite) {
+    euler_from_quat((double)bq[0], (double)bq[1], (double)bq[2], (double)bq[3], roll, pitch, yaw);
+    double dr = !(fabs(roll) > lim) ? lim - fabs(roll) : 0.0;
+    double dp = !(fabs(pitch) > lim) ? lim - fabs(pitch) : 0.0;
+    double dy = !(fabs(yaw) > lim) ? lim - fabs(yaw) : 0.0;
+    safe = (dr + dp + dy) / (0.110 + lim + lim + lim);
+  }
+  // paws_in_ground bitmask, bit l = leg l (FL FR BL BR)
+  int paws;
+  {
+    float bit = lp.foot_contact ? (float)(1 << leg) : 0.f;
+    paws = (int)grp_sum(bit, gm);
+  }
+  const int gait = gait_call(gidx, gcnt, paws, bv.x);
+  const double rewards = lin * 1.5 + safe * .015 + (double)gait * 3;
+  // costs: joint deviation (double, numpy pairwise order), action rate (float32 unless fresh), |y|
+  double jc = 0.0; float rate_f = 0.f; double rate_d = 0.0;
+  {
+    double s = 0.0; float sf = 0.f; double sd = 0.0;
+    ODG_UNROLL for (int j = 0; j < NJL; j++) {
+      double t = (double)q[j] - (double)C.key_ctrl[leg * NJL + j];
+      s += t * t;
+      if (LCF(LC_HASACT, j) != 0.f) {
+        float d = odg_fsub_rn(prev_act[j], ctrl[j]);
+        sf = odg_fadd_rn(sf, odg_fmul_rn(d, d));
+        double dd = 0.0 - (double)ctrl[j];
+        sd += dd * dd;
+      }
+    }
+    // numpy pairwise order over joints (body order): ((l0)+(l1)) + ((l2)+(l3)); IEEE + is commutative
+    double s2 = s + grp_xor_d(s, 1, gm);
+    jc = s2 + grp_xor_d(s2, 2, gm);
+    // actuator order FR BR FL BL: ((l1)+(l3)) + ((l0)+(l2)): xor 2 first, then xor 1
+    float t2 = odg_fadd_rn(sf, grp_xor(sf, 2, gm));
+    rate_f = odg_fadd_rn(t2, grp_xor(t2, 1, gm));
+    double sd2 = sd + grp_xor_d(sd, 2, gm);
+    rate_d = sd2 + grp_xor_d(sd2, 1, gm);
+  }
+  const double rate = fresh ? rate_d : (double)rate_f;
+  const double ycost = fabs((double)bp.y);
+  const double costs = jc * 0.1 + rate * 0.01 + ycost;
+  const double rr = rewards - costs;
+  const float reward = (float)(rr > 0.0 ? rr : 0.0);
+  const bool healthy = finite && (-lim < roll && roll < lim) && (-lim < pitch && pitch < lim) && (-lim < yaw && yaw < lim);
+  const bool terminated = !healthy;
+  const bool truncated = step >= C.max_steps;
+  // ---- info
+  if (A.want_info) {
+    if (A.paw_forces) {
+      // reward_calc:339-349,361-365: (R_c @ f) then R_calf^T
+      V3 f = lp.foot_force;                        // (fn, ft1, ft2)
+      V3 fg = mk3(f.z, f.y, -f.x);
+      V3 fb = lp.foot_contact ? tmul(lp.R_last, fg) : mk3(0.f, 0.f, 0.f);
+      float* o = A.paw_forces + ((size_t)env * 4 + leg) * 6;
+      o[0] = fb.x; o[1] = fb.y; o[2] = fb.z; o[3] = 0.f; o[4] = 0.f; o[5] = 0.f;
+    }
+    if (A.paws_in_ground) A.paws_in_ground[(size_t)env * 4 + leg] = (unsigned char)lp.foot_contact;
+    float tq = 0.f;
+    ODG_UNROLL for (int j = 0; j < NJL; j++) tq += lp.act[j] * lp.act[j];
+    tq = grp_sum(tq, gm);
+    float fn = grp_sum(lp.fn, gm);
+    float ncs = grp_sum((float)lp.ncon, gm);
+    if (A.qacc) {
+      ODG_UNROLL for (int j = 0; j < NJL; j++) A.qacc[(size_t)env * C.nv + 6 + leg * NJL + j] = lp.a_l[j];
+    }
+    if (leg == 0) {
+      if (A.x_position) A.x_position[env] = bp.x;
+      if (A.y_position) A.y_position[env] = bp.y;
+      if (A.distance) A.distance[env] = sqrtf(bp.x * bp.x + bp.y * bp.y);
+      if (A.lin_vel_reward) A.lin_vel_reward[env] = (float)lin;
+      if (A.reward_ctrl) A.reward_ctrl[env] = tq;
+      if (A.gait_reward) A.gait_reward[env] = gait;
+      if (A.ncon) A.ncon[env] = (int)ncs;
+      if (A.fn_sum) A.fn_sum[env] = fn;
+      if (A.solver_iters) A.solver_iters[env] = lp.iters;
+      if (A.qacc) {
+        float* o = A.qacc + (size_t)env * C.nv;
+        o[0] = lp.a_b.t.x; o[1] = lp.a_b.t.y; o[2] = lp.a_b.t.z;
+        o[3] = warm_wl.x; o[4] = warm_wl.y; o[5] = warm_wl.z;     // trunk-frame angular acceleration
+      }
+    }
+  }
+  // second diagonal_gait_reward call (info["patterns_matches"], WalkEnvironment.py:70; quirk C2)
+  const int gait2 = gait_call(gidx, gcnt, paws, bv.x);
+  if (leg == 0) {
+    if (A.want_info && A.patterns_matches) A.patterns_matches[env] = (float)gait2;
+    if (A.reward) A.reward[env] = reward;
+    if (A.terminated) A.terminated[env] = terminated ? 1 : 0;
+    if (A.truncated) A.truncated[env] = truncated ? 1 : 0;
+  }
+  // ---- auto-reset (SB3 worker) or plain state write-back
+  bool is_fresh = false;
+  float last_act[NJL];
+  ODG_UNROLL for (int j = 0; j < NJL; j++) last_act[j] = ctrl[j];          // set_last_action(action)
+  unsigned episode = 0;
+  const bool do_reset = (A.mode == 0) && C.auto_reset && (terminated || truncated);
+  if (do_reset) {
+    episode = P.episode[env];
+    grp_sync(gm);                                  // all lanes read the counter before lane 0 bumps it
+    const uint32_t gid = (uint32_t)(C.first_env_id + env);
+    float key_noise[kMaxNQ];
+    for (int blk = 0; blk * 4 < C.nq; blk++) {
+      uint32_t r[4];
+      philox4x32(C.seed_lo, C.seed_hi, gid, episode, (uint32_t)blk, kStreamReset, r);
+      for (int k = 0; k < 4; k++) if (blk * 4 + k < kMaxNQ) {
+        float u = u01(r[k]);
+        float nz = odg_fadd_rn(-C.noise, odg_fmul_rn(2.0f * C.noise, u));
+        key_noise[blk * 4 + k] = (blk * 4 + k < C.nq) ? odg_fadd_rn(C.key_qpos[blk * 4 + k], nz) : 0.f;
+      }
+    }
+    bp = mk3(key_noise[0], key_noise[1], key_noise[2]);
+    bq[0] = key_noise[3]; bq[1] = key_noise[4]; bq[2] = key_noise[5]; bq[3] = key_noise[6];
+    bv = mk3(0.f, 0.f, 0.f); bwl = mk3(0.f, 0.f, 0.f);
+    warm_v = mk3(0.f, 0.f, 0.f); warm_wl = mk3(0.f, 0.f, 0.f);
+    ODG_UNROLL for (int j = 0; j < NJL; j++) {
+      float v = 0.f;
+      for (int k = 0; k < kMaxNQ; k++) if (k == 7 + leg * NJL + j) v = key_noise[k];
+      q[j] = v; qd[j] = 0.f; warm_l[j] = 0.f; last_act[j] = 0.f;
+    }
+    step = 0; is_fresh = true; episode += 1;
+    write_obs(obs, bv, bwl, q, qd, last_act);
+  }
+  // ---- store
+  ODG_UNROLL for (int j = 0; j < NJL; j++) {
+    P.qpos[(7 + leg * NJL + j) * N + env] = q[j];
+    P.qvel[(6 + leg * NJL + j) * N + env] = qd[j];
+    P.warm[(6 + leg * NJL + j) * N + env] = warm_l[j];
+    if (LCF(LC_HASACT, j) != 0.f && A.mode == 0) P.last_action[(int)LCF(LC_UIDX, j) * N + env] = last_act[j];
+  }
+  if (leg == 0) {
+    P.qpos[0 * N + env] = bp.x; P.qpos[1 * N + env] = bp.y; P.qpos[2 * N + env] = bp.z;
+    P.qpos[3 * N + env] = bq[0]; P.qpos[4 * N + env] = bq[1]; P.qpos[5 * N + env] = bq[2]; P.qpos[6 * N + env] = bq[3];
+    P.qvel[0 * N + env] = bv.x; P.qvel[1 * N + env] = bv.y; P.qvel[2 * N + env] = bv.z;
+    P.qvel[3 * N + env] = bwl.x; P.qvel[4 * N + env] = bwl.y; P.qvel[5 * N + env] = bwl.z;
+    P.warm[0 * N + env] = warm_v.x; P.warm[1 * N + env] = warm_v.y; P.warm[2 * N + env] = warm_v.z;
+    P.warm[3 * N + env] = warm_wl.x; P.warm[4 * N + env] = warm_wl.y; P.warm[5 * N + env] = warm_wl.z;
+    P.gait_idx[env] = gidx; P.gait_cnt[env] = gcnt;
+    if (A.mode == 0) { P.step[env] = step; P.fresh[env] = is_fresh ? 1 : 0; }
+    if (do_reset) P.episode[env] = episode;
+  }
+}
+
+// reset_model (WalkEnvironment.py:138-151) for one 4-lane group
+template <int NJL>
+ODG_DEV void env_reset(const DevConst& C, const float* ODG_RESTRICT s_lc, const SimPtrs& P, float* obs_out,
+                       int env, int leg, unsigned gm) {
+  const int N = P.N;
+  const int obs_dim = 9 + 3 * C.nu;
+  const unsigned episode = P.episode[env];
+  grp_sync(gm);                                    // all lanes read the counter before lane 0 bumps it
+  const uint32_t gid = (uint32_t)(C.first_env_id + env);
+  float kq[kMaxNQ];
+  for (int blk = 0; blk * 4 < C.nq; blk++) {
+    uint32_t r[4];
+    philox4x32(C.seed_lo, C.seed_hi, gid, episode, (uint32_t)blk, kStreamReset, r);
+    for (int k = 0; k < 4; k++) if (blk * 4 + k < kMaxNQ) {
+      float u = u01(r[k]);
+      float nz = odg_fadd_rn(-C.noise, odg_fmul_rn(2.0f * C.noise, u));
+      kq[blk * 4 + k] = (blk * 4 + k < C.nq) ? odg_fadd_rn(C.key_qpos[blk * 4 + k], nz) : 0.f;
+    }
+  }
+  float* obs = obs_out ? obs_out + (size_t)env * obs_dim : nullptr;
+  auto clip = [](float v) { return fminf(100.f, fmaxf(-100.f, v)); };
+  for (int j = 0; j < NJL; j++) {
+    const int qi = 7 + leg * NJL + j;
+    P.qpos[qi * N + env] = kq[qi];
+    P.qvel[(6 + leg * NJL + j) * N + env] = 0.f;
+    P.warm[(6 + leg * NJL + j) * N + env] = 0.f;
+    if (LCF(LC_HASACT, j) != 0.f) P.last_action[(int)LCF(LC_UIDX, j) * N + env] = 0.f;
+    if (obs) {
+      obs[9 + leg * NJL + j] = clip(kq[qi] - C.obs_joint_offset);
+      obs[9 + C.nu + leg * NJL + j] = 0.f;
+      if (LCF(LC_HASACT, j) != 0.f) obs[9 + 2 * C.nu + (int)LCF(LC_UIDX, j)] = 0.f;
+    }
+  }
+  if (leg == 0) {
+    for (int i = 0; i < 7; i++) P.qpos[i * N + env] = kq[i];
+    for (int i = 0; i < 6; i++) { P.qvel[i * N + env] = 0.f; P.warm[i * N + env] = 0.f; }
+    P.step[env] = 0; P.fresh[env] = 1; P.episode[env] = episode + 1;
+    if (obs) {
+      for (int i = 0; i < 6; i++) obs[i] = 0.f;
+      for (int i = 0; i < 3; i++) obs[6 + i] = clip(P.desvel[i * N + env] * 2.0f);
+    }
+  }
+}
+
+// Construction-time state of one environment (single lane): noise-free home keyframe, zero
+// velocities, and the desired velocity sampled once (reward_calc:75,301-305: x ~ U[0.5, 1.0], y = z = 0).
+ODG_DEV void env_init(const DevConst& C, const SimPtrs& P, int env) {
+  const int N = P.N;
+  for (int i = 0; i < C.nq; i++) P.qpos[i * N + env] = C.key_qpos[i];
+  for (int i = 0; i < C.nv; i++) { P.qvel[i * N + env] = 0.f; P.warm[i * N + env] = 0.f; }
+  for (int u = 0; u < C.nu; u++) P.last_action[u * N + env] = 0.f;
+  uint32_t r[4];
+  philox4x32(C.seed_lo, C.seed_hi, (uint32_t)(C.first_env_id + env), 0u, 0u, kStreamDesvel, r);
+  P.desvel[0 * N + env] = odg_fadd_rn(0.5f, odg_fmul_rn(0.5f, u01(r[0])));
+  P.desvel[1 * N + env] = 0.f; P.desvel[2 * N + env] = 0.f;
+  P.step[env] = 0; P.gait_idx[env] = 0; P.gait_cnt[env] = 0; P.episode[env] = 0u; P.fresh[env] = 1;
+}
+
+#undef LCF
+#undef GCF
+
+}  // namespace odg

@@ -1,0 +1,194 @@
+// odg_prep.h — host-side preparation of the constants the step kernel reads: OdgModel (doubles,
+// MuJoCo layout) + OdgEnvConfig -> DevConst (__constant__), per-leg constant table and hull-vertex
+// table (staged into shared memory by every block). Pure host C++, no CUDA calls; shared by
+// odg_sim.cu and the test-only lane emulator.
+#pragma once
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/odg.h"
+#include "odg_core.cuh"
+
+namespace odg {
+
+struct Prepared {
+  DevConst C;
+  std::vector<float> lc;        // [njl][LC_COUNT][4]
+  std::vector<float> gc;        // [nslot][GC_COUNT][4]
+  std::vector<float> vert;      // [rows][4 legs][4 floats]
+};
+
+inline float clampf(double v, double lo, double hi) { return (float)std::fmin(hi, std::fmax(lo, v)); }
+
+inline void solref_kb(const OdgModel& m, const double* solref, const double* solimp, double* K, double* B) {
+  double dmax = std::fmin(0.9999, std::fmax(0.0001, solimp[1]));
+  if (solref[0] > 0) {
+    double tc = std::fmax(solref[0], 2 * m.timestep), dr = solref[1];
+    *K = 1 / std::fmax(1e-15, dmax * dmax * tc * tc * dr * dr);
+    *B = 2 / std::fmax(1e-15, dmax * tc);
+  } else {
+    *K = -solref[0] / std::fmax(1e-15, dmax * dmax);
+    *B = -solref[1] / std::fmax(1e-15, dmax);
+  }
+}
+inline void pack_imp(const double* solimp, float* out) {
+  out[0] = clampf(solimp[0], 0.0001, 0.9999); out[1] = clampf(solimp[1], 0.0001, 0.9999);
+  out[2] = (float)std::fmax(1e-15, solimp[2]); out[3] = clampf(solimp[3], 0.0001, 0.9999);
+  out[4] = (float)std::fmax(1.0, solimp[4]);
+}
+inline void quat2mat(const double* q, double* M) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  M[0] = w * w + x * x - y * y - z * z; M[1] = 2 * (x * y - w * z); M[2] = 2 * (x * z + w * y);
+  M[3] = 2 * (x * y + w * z); M[4] = w * w - x * x + y * y - z * z; M[5] = 2 * (y * z - w * x);
+  M[6] = 2 * (x * z - w * y); M[7] = 2 * (y * z + w * x); M[8] = w * w - x * x - y * y + z * z;
+}
+
+// Returns "" on success, otherwise why the model/config is not supported by the kernel.
+inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t seed, Prepared* out) {
+  DevConst& C = out->C;
+  std::memset(&C, 0, sizeof(C));
+  if (m.nleg != 4) return "kernel maps one leg per lane: nleg must be 4";
+  if (m.njl < 1 || m.njl > kMaxJL) return "njl out of range";
+  if (m.cone != 1) return "only cone=elliptic is supported";
+  if (cfg.task == ODG_TASK_WALK && (m.nu != 8 || m.njl != 2)) return "walk task needs the 8-actuator OpenDOG model";
+  for (int i = 0; i < 6; i++) if (m.base_damping[i] != 0) return "trunk damping is not supported";
+  for (int l = 0; l < m.nleg; l++) for (int j = 0; j < m.njl; j++)
+    if (m.damping[l][j] != 0) return "joint damping needs the implicit Euler path (not built yet)";
+  if (m.base_armature[3] != m.base_armature[4] || m.base_armature[3] != m.base_armature[5])
+    return "trunk rotational armature must be isotropic";
+  C.nleg = m.nleg; C.njl = m.njl; C.nq = m.nq; C.nv = m.nv; C.nu = m.nu;
+  C.h = (float)m.timestep; C.gx = (float)m.gravity[0]; C.gy = (float)m.gravity[1]; C.gz = (float)m.gravity[2];
+  C.impratio = (float)m.impratio;
+  C.base_mass = (float)m.base_mass;
+  for (int i = 0; i < 3; i++) { C.base_ip[i] = (float)m.base_ipos[i]; C.base_arm_t[i] = (float)m.base_armature[i]; }
+  C.base_arm_r = (float)m.base_armature[3];
+  const int sidx[6] = { 0, 1, 2, 4, 5, 8 };
+  for (int i = 0; i < 6; i++) C.base_I[i] = (float)m.base_inertia[sidx[i]];
+  double Kf, Bf, Kl, Bl;
+  solref_kb(m, m.dof_solref, m.dof_solimp, &Kf, &Bf);
+  solref_kb(m, m.lim_solref, m.lim_solimp, &Kl, &Bl);
+  C.B_fl = (float)Bf; C.K_lim = (float)Kl; C.B_lim = (float)Bl;
+  pack_imp(m.lim_solimp, C.lim_imp);
+  const double d0 = std::fmin(0.9999, std::fmax(0.0001, m.dof_solimp[0]));
+  for (int i = 0; i < 6; i++) {
+    C.base_fl[i] = (float)m.base_frictionloss[i];
+    double R = std::fmax(1e-15, (1 - d0) / d0 * m.base_invweight0[i]);
+    C.base_Rfl[i] = (float)R; C.base_Dfl[i] = (float)(1 / R);
+  }
+  // per-leg joint constants
+  const int njl = m.njl;
+  out->lc.assign((size_t)njl * LC_COUNT * 4, 0.f);
+  auto LC = [&](int f, int j, int l) -> float& { return out->lc[((size_t)j * LC_COUNT + f) * 4 + l]; };
+  bool ident = true;
+  for (int l = 0; l < 4; l++) for (int j = 0; j < njl; j++) {
+    double R[9]; quat2mat(m.body_quat[l][j], R);
+    for (int k = 0; k < 9; k++) { LC(LC_BR0 + k, j, l) = (float)R[k]; ident &= (R[k] == ((k % 4 == 0) ? 1.0 : 0.0)); }
+    for (int k = 0; k < 3; k++) {
+      LC(LC_BP0 + k, j, l) = (float)m.body_pos[l][j][k]; LC(LC_JP0 + k, j, l) = (float)m.jnt_pos[l][j][k];
+      LC(LC_JA0 + k, j, l) = (float)m.jnt_axis[l][j][k]; LC(LC_IP0 + k, j, l) = (float)m.ipos[l][j][k];
+    }
+    LC(LC_MASS, j, l) = (float)m.mass[l][j];
+    for (int k = 0; k < 6; k++) LC(LC_IXX + k, j, l) = (float)m.inertia[l][j][sidx[k]];
+    LC(LC_LO, j, l) = (float)m.jnt_range[l][j][0]; LC(LC_HI, j, l) = (float)m.jnt_range[l][j][1];
+    LC(LC_LIMITED, j, l) = m.jnt_limited[l][j] ? 1.f : 0.f;
+    LC(LC_ARM, j, l) = (float)m.armature[l][j]; LC(LC_FL, j, l) = (float)m.frictionloss[l][j];
+    double R_ = std::fmax(1e-15, (1 - d0) / d0 * m.dof_invweight0[l][j]);
+    LC(LC_RFL, j, l) = (float)R_; LC(LC_DFL, j, l) = (float)(1 / R_);
+    LC(LC_DAMP, j, l) = (float)m.damping[l][j]; LC(LC_INVW, j, l) = (float)m.dof_invweight0[l][j];
+    LC(LC_HOMEQ, j, l) = (float)m.key_qpos[7 + l * njl + j];
+    LC(LC_UIDX, j, l) = 0.f;
+  }
+  C.body_rot_identity = ident ? 1 : 0;
+  // ScaleActionEnvironment.py:8-17: float32 table, thigh [2.36, 2.8], knee [-1.8, -1.20] per actuator
+  const float slo[2] = { 2.36f, -1.8f }, shi[2] = { 2.8f, -1.20f };
+  for (int u = 0; u < m.nu; u++) {
+    int l = m.act_leg[u], j = m.act_joint[u];
+    if (LC(LC_HASACT, j, l) != 0.f) return "more than one actuator per joint";
+    LC(LC_HASACT, j, l) = 1.f; LC(LC_UIDX, j, l) = (float)u;
+    LC(LC_KP, j, l) = (float)m.act_kp[u]; LC(LC_KV, j, l) = (float)m.act_kv[u];
+    LC(LC_CLIM, j, l) = m.act_ctrllimited[u] ? 1.f : 0.f; LC(LC_FLIM, j, l) = m.act_forcelimited[u] ? 1.f : 0.f;
+    LC(LC_CLO, j, l) = (float)m.act_ctrlrange[u][0]; LC(LC_CHI, j, l) = (float)m.act_ctrlrange[u][1];
+    LC(LC_FLO, j, l) = (float)m.act_forcerange[u][0]; LC(LC_FHI, j, l) = (float)m.act_forcerange[u][1];
+    LC(LC_SLO, j, l) = slo[u & 1]; LC(LC_SHI, j, l) = shi[u & 1];
+    C.key_ctrl[u] = (float)m.key_ctrl[u];
+  }
+  if (cfg.task == ODG_TASK_WALK)
+    for (int u = 0; u < m.nu; u += 2)
+      if (m.act_leg[u] != m.act_leg[u + 1] || m.act_joint[u] != 0 || m.act_joint[u + 1] != 1)
+        return "walk task expects (thigh, knee) actuator pairs per leg";
+  for (int i = 0; i < m.nq; i++) C.key_qpos[i] = (float)m.key_qpos[i];
+  C.obs_joint_offset = (float)m.key_ctrl[m.nu - 1];       // key_ctrl[0, 7:] (WalkEnvironment.py:116)
+  // collision slots: every leg must carry the same sequence of (link, type)
+  std::vector<int> per_leg[4];
+  for (int g = 0; g < m.ngeom; g++) {
+    if (m.geom[g].leg < 0) return "trunk collision geoms are not supported by the kernel yet";
+    per_leg[m.geom[g].leg].push_back(g);
+  }
+  const int nslot = (int)per_leg[0].size();
+  if (nslot > kMaxSlot) return "too many collision geoms per leg";
+  for (int l = 1; l < 4; l++) if ((int)per_leg[l].size() != nslot) return "legs differ in collision geoms";
+  C.nslot = nslot;
+  out->gc.assign((size_t)(nslot > 0 ? nslot : 1) * GC_COUNT * 4, 0.f);
+  int rows = 0;
+  for (int s = 0; s < nslot; s++) {
+    const OdgGeom& g0 = m.geom[per_leg[0][s]];
+    int nv = 0;
+    for (int l = 0; l < 4; l++) {
+      const OdgGeom& g = m.geom[per_leg[l][s]];
+      if (g.link != g0.link || g.type != g0.type || g.condim != g0.condim || g.friction != g0.friction ||
+          g.margin != g0.margin) return "legs differ in collision geom parameters";
+      if (g.condim != 1 && g.condim != 3) return "contact condim must be 1 or 3";
+      nv = g.vert_count > nv ? g.vert_count : nv;
+      out->gc[((size_t)s * GC_COUNT + GC_INVW) * 4 + l] = (float)g.invweight0;
+      out->gc[((size_t)s * GC_COUNT + GC_CX) * 4 + l] = (float)g.center[0];
+      out->gc[((size_t)s * GC_COUNT + GC_CY) * 4 + l] = (float)g.center[1];
+      out->gc[((size_t)s * GC_COUNT + GC_CZ) * 4 + l] = (float)g.center[2];
+    }
+    C.slot_link[s] = g0.link; C.slot_type[s] = g0.type; C.slot_nvert[s] = nv; C.slot_vstart[s] = rows;
+    C.slot_condim[s] = g0.condim;
+    // reward_calc:93 body_feet_indices = [4, 7, 10, 13]: the last body of each leg chain
+    C.slot_isfoot[s] = (g0.mj_body_id == 1 + (njl + 1)) ? 1 : 0;
+    C.slot_margin[s] = (float)g0.margin; C.slot_radius[s] = (float)g0.radius;
+    double K, B; solref_kb(m, g0.solref, g0.solimp, &K, &B);
+    C.slot_K[s] = (float)K; C.slot_B[s] = (float)B; pack_imp(g0.solimp, C.slot_imp[s]);
+    C.slot_fri[s] = (float)g0.friction;
+    C.slot_mu[s] = (float)(g0.friction / std::sqrt(std::fmax(1e-15, m.impratio)));
+    rows += nv;
+  }
+  C.nvert_rows = rows;
+  out->vert.assign((size_t)(rows > 0 ? rows : 1) * 16, 0.f);
+  for (int s = 0; s < nslot; s++)
+    for (int l = 0; l < 4; l++) {
+      const OdgGeom& g = m.geom[per_leg[l][s]];
+      for (int k = 0; k < C.slot_nvert[s]; k++) {
+        int src = g.vert_count > 0 ? g.vert_start + (k < g.vert_count ? k : g.vert_count - 1) : -1;
+        float* dst = &out->vert[((size_t)(C.slot_vstart[s] + k) * 4 + l) * 4];
+        for (int c = 0; c < 3; c++) dst[c] = src >= 0 ? (float)m.vert[src][c] : 0.f;
+      }
+    }
+  // three extra support directions tilted off -normal, 120 degrees apart (frame t1=+y, t2=-x)
+  C.n_tilt = m.multicontact_tilt > 0 ? 3 : 0;
+  for (int i = 0; i < 3; i++) {
+    double ang = 2.0 * 3.14159265358979323846 * i / 3.0, t = m.multicontact_tilt;
+    C.tilt_dir[i][0] = (float)(-std::sin(t) * std::sin(ang));
+    C.tilt_dir[i][1] = (float)(std::sin(t) * std::cos(ang));
+    C.tilt_dir[i][2] = (float)(-std::cos(t));
+  }
+  C.frame_skip = cfg.frame_skip; C.max_steps = cfg.max_episode_steps; C.auto_reset = cfg.auto_reset;
+  C.solver_iters = cfg.solver_iterations; C.ls_iters = cfg.ls_iterations; C.scale_actions = cfg.scale_actions;
+  C.first_env_id = cfg.first_env_id; C.tol = cfg.solver_tolerance; C.noise = cfg.reset_noise_scale;
+  C.seed_lo = (uint32_t)seed; C.seed_hi = (uint32_t)(seed >> 32);
+  if (cfg.frame_skip < 1 || cfg.solver_iterations < 1 || cfg.ls_iterations < 1) return "bad config";
+  return "";
+}
+
+inline void default_config(OdgEnvConfig* c) {
+  c->task = ODG_TASK_WALK; c->frame_skip = 10; c->max_episode_steps = 750; c->auto_reset = 1;
+  c->solver_iterations = 8; c->ls_iterations = 6; c->solver_tolerance = 1e-5f; c->reset_noise_scale = 0.02f;
+  c->scale_actions = 1; c->first_env_id = 0;
+}
+
+}  // namespace odg
