@@ -46,9 +46,9 @@ typedef struct OdgEnvConfig {
   int auto_reset;            /* 1 = SB3 VecEnv worker semantics (train/train.py:81-86): done envs are
                                 reset inside odg_step and the returned obs is the reset obs */
   int solver_iterations;     /* max Newton iterations per substep (MuJoCo default 100, tol 1e-8);
-                                the kernel exits early on convergence. default 8 */
-  int ls_iterations;         /* max line-search evaluations per Newton iteration. default 6 */
-  float solver_tolerance;    /* relative step tolerance for early exit. default 1e-6 */
+                                the kernel exits early on convergence (mean ~5). default 30 */
+  int ls_iterations;         /* max line-search evaluations per Newton iteration. default 8 */
+  float solver_tolerance;    /* relative Newton-step tolerance for early exit. default 1e-5 */
   float reset_noise_scale;   /* reward_calc:106 -> 0.02 */
   int scale_actions;         /* 1 = apply ScaleActionWrapper.action (ScaleActionEnvironment.py:21-23)
                                 to actions in [-1,1]; 0 = actions are ctrl targets in rad */

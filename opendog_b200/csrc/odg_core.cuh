@@ -694,7 +694,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       P[3][1] += l0f * (-T.h.z); P[3][2] += l0f * (T.h.y);
       P[4][0] += l0f * (T.h.z);  P[4][2] += l0f * (-T.h.x);
       P[5][0] += l0f * (-T.h.y); P[5][1] += l0f * (T.h.x);
-      float gbv[6] = { gb.t.x, gb.t.y, gb.t.z, gb.w.x, gb.w.y, gb.w.z };
+      float gbv[6] = { gb.t.x, gb.t.y, gb.t.z, gb.w.x, gb.w.y, gb.w.z };   // gb itself stays the lane-partial gradient
       ODG_UNROLL for (int j = 0; j < NJL; j++) {
         float hl[6] = { Hlb[j].t.x, Hlb[j].t.y, Hlb[j].t.z, Hlb[j].w.x, Hlb[j].w.y, Hlb[j].w.z };
         float wl[6] = { W[j].t.x, W[j].t.y, W[j].t.z, W[j].w.x, W[j].w.y, W[j].w.z };
@@ -734,8 +734,14 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       c_dz[c] = dz;
     }
     const V3 al_loc = tmul(R0, a_b.w), pl_loc = tmul(R0, p_b.w);
-    float alpha = 1.f, lo = 0.f, hi = -1.f;
-    for (int ls = 0; ls < C.ls_iters; ls++) {
+    // phi'(0) = p . grad  (lane-partials of the trunk gradient were kept in gb)
+    float d10 = dot6(gb, p_b);
+    ODG_UNROLL for (int j = 0; j < NJL; j++) d10 += p_l[j] * g_l[j];
+    d10 = grp_sum(d10, gm);
+    float alpha = 1.f, lo = 0.f, hi = -1.f, d1_lo = d10, d1_hi = 0.f;
+    int side = 0;
+    if (!(d10 < 0.f)) alpha = 0.f;                  // not a descent direction (converged to rounding)
+    for (int ls = 0; ls < C.ls_iters && d10 < 0.f; ls++) {
       float d1 = G + alpha * Hq, d2 = Hq;
       ODG_UNROLL for (int j = 0; j < NJL; j++) {
         float fl = LCF(LC_FL, j);
@@ -774,12 +780,18 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       }
       d1 = grp_sum(d1, gm); d2 = grp_sum(d2, gm);
       if (!(d2 > 0.f)) { alpha = 0.f; break; }
+      if (fabsf(d1) <= 1e-4f * fabsf(d10)) break;
       float step = -d1 / d2;
-      if (fabsf(step) <= 1e-4f * alpha) { alpha += step; break; }
-      if (d1 < 0.f) lo = alpha; else hi = alpha;
+      // bracket bookkeeping (Illinois variant of regula falsi as the fallback)
+      if (d1 < 0.f) { lo = alpha; d1_lo = d1; if (side == -1) d1_hi *= 0.5f; side = -1; }
+      else { hi = alpha; d1_hi = d1; if (side == 1) d1_lo *= 0.5f; side = 1; }
       float next = alpha + step;
       if (hi < 0.f) { if (!(next > lo)) next = 2.f * alpha; }
-      else if (!(next > lo && next < hi)) next = 0.5f * (lo + hi);
+      else if (!(next > lo && next < hi)) {
+        next = lo - d1_lo * (hi - lo) / (d1_hi - d1_lo);
+        if (!(next > lo && next < hi)) next = 0.5f * (lo + hi);
+      }
+      if (fabsf(next - alpha) <= 1e-6f * alpha) { alpha = next; break; }
       alpha = next;
     }
     // ---- take the step, test convergence on the step size
@@ -791,8 +803,8 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       a_l[j] += alpha * p_l[j];
       smax = fmaxf(smax, fabsf(p_l[j])); amax = fmaxf(amax, fabsf(a_l[j]));
     }
-    smax = grp_max(smax, gm) * fabsf(alpha); amax = grp_max(amax, gm);
-    conv = smax <= C.tol * (1.f + amax);
+    smax = grp_max(smax, gm); amax = grp_max(amax, gm);
+    conv = smax <= C.tol * (1.f + amax);            // full Newton step is negligible
   }
   // ------------------------------------------------------------------ outputs of the forward pass
   if (last) {

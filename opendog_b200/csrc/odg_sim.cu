@@ -1,0 +1,355 @@
+// odg_sim.cu — libodgsim: kernels + the C ABI declared in include/odg.h.  sm_100a only.
+//
+// Kernel map
+//   k_step<NJL>   the fused environment step (odg_core.cuh: env_step). 4 lanes per environment,
+//                 8 environments per warp. Model constants arrive as a __grid_constant__ kernel
+//                 parameter (constant bank), per-leg constants and hull vertices are staged ONCE per
+//                 persistent block into shared memory; per-env state is SoA in HBM and is read and
+//                 written exactly once per env-step (all frame_skip substeps stay in registers).
+//   k_reset<NJL>  reset_model for masked environments.
+//   k_init        construction-time state.
+//   k_*_state     layout transposes between the caller's [N][dim] tensors and the SoA state.
+//
+// There is no CPU path in this library: without a CUDA device odg_create fails with ODG_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <new>
+#include <string>
+
+#include "odg_prep.h"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                         \
+  do { cudaError_t e_ = (expr);                                                                \
+       if (e_ != cudaSuccess) return fail(ODG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
+
+using odg::DevConst; using odg::SimPtrs; using odg::StepArgs;
+
+struct SmemLayout { int lc_floats, gc_floats, vert_floats; };
+
+__device__ __forceinline__ void stage_constants(float* smem, const float* __restrict__ g_lc, const float* __restrict__ g_gc,
+                                                const float* __restrict__ g_vert, SmemLayout L,
+                                                const float4** s_vert, const float** s_lc, const float** s_gc) {
+  // layout: [vert (16B aligned)][lc][gc]
+  float4* sv = reinterpret_cast<float4*>(smem);
+  const float4* gv = reinterpret_cast<const float4*>(g_vert);
+  for (int i = threadIdx.x; i < L.vert_floats / 4; i += blockDim.x) sv[i] = gv[i];
+  float* slc = smem + L.vert_floats;
+  for (int i = threadIdx.x; i < L.lc_floats; i += blockDim.x) slc[i] = g_lc[i];
+  float* sgc = slc + L.lc_floats;
+  for (int i = threadIdx.x; i < L.gc_floats; i += blockDim.x) sgc[i] = g_gc[i];
+  __syncthreads();
+  *s_vert = sv; *s_lc = slc; *s_gc = sgc;
+}
+
+#ifndef ODG_MIN_BLOCKS
+#define ODG_MIN_BLOCKS 1
+#endif
+template <int NJL>
+__global__ void __launch_bounds__(128, ODG_MIN_BLOCKS) k_step(const __grid_constant__ DevConst C, const SimPtrs P, const StepArgs A,
+                                              const float* __restrict__ g_lc, const float* __restrict__ g_gc,
+                                              const float* __restrict__ g_vert, SmemLayout L) {
+  extern __shared__ __align__(16) float smem[];
+  const float4* s_vert; const float* s_lc; const float* s_gc;
+  stage_constants(smem, g_lc, g_gc, g_vert, L, &s_vert, &s_lc, &s_gc);
+  const int leg = threadIdx.x & 3;
+  const unsigned gm = 0xFu << (threadIdx.x & 28);
+  const int envs_per_block = blockDim.x >> 2;
+  for (int base = blockIdx.x * envs_per_block; base < P.N; base += gridDim.x * envs_per_block) {
+    const int env = base + (threadIdx.x >> 2);
+    if (env < P.N) odg::env_step<NJL>(C, s_lc, s_gc, s_vert, P, A, env, leg, gm);
+  }
+}
+
+template <int NJL>
+__global__ void __launch_bounds__(128) k_reset(const __grid_constant__ DevConst C, const SimPtrs P,
+                                               const unsigned char* __restrict__ mask, float* obs,
+                                               const float* __restrict__ g_lc) {
+  extern __shared__ __align__(16) float smem[];
+  for (int i = threadIdx.x; i < NJL * odg::LC_COUNT * 4; i += blockDim.x) smem[i] = g_lc[i];
+  __syncthreads();
+  const int leg = threadIdx.x & 3;
+  const unsigned gm = 0xFu << (threadIdx.x & 28);
+  const int env = blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2);
+  if (env >= P.N) return;
+  if (mask && !mask[env]) return;
+  odg::env_reset<NJL>(C, smem, P, obs, env, leg, gm);
+}
+
+__global__ void k_init(const __grid_constant__ DevConst C, const SimPtrs P) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env < P.N) odg::env_init(C, P, env);
+}
+
+// dst[env][k] = src[k][env] (to_soa = false) or the reverse
+__global__ void k_transpose(float* aos, float* soa, int N, int dim, bool to_soa) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * dim) return;
+  const int env = (int)(i / dim), k = (int)(i % dim);
+  if (to_soa) soa[(size_t)k * N + env] = aos[i]; else aos[i] = soa[(size_t)k * N + env];
+}
+__global__ void k_fill(float* p, long long n, float v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+template <typename T>
+__global__ void k_copy(T* dst, const T* src, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+}  // namespace
+
+struct OdgSim {
+  int device = 0, N = 0, num_sms = 0;
+  odg::Prepared prep;
+  SimPtrs P{};
+  float* d_lc = nullptr; float* d_gc = nullptr; float* d_vert = nullptr;
+  void* d_state = nullptr;           // one allocation behind all SoA arrays
+  SmemLayout L{};
+  size_t smem_step = 0;
+  int step_block = 128, step_grid = 1;
+  long long launches = 0;
+};
+
+namespace {
+
+int choose_launch(OdgSim* s) {
+  // 4 lanes per env. Small batches are latency bound: one warp per block spreads them over all SMs and
+  // SM sub-partitions. Large batches run persistent 128-thread blocks (constants staged once per block).
+  const long long warps = ((long long)s->N * 4 + 31) / 32;
+  int dev_occ = 0;
+  auto kern = s->prep.C.njl == 2 ? (const void*)k_step<2> : (const void*)k_step<3>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_step));
+  if (warps <= (long long)s->num_sms * 8) {
+    s->step_block = 32;
+    s->step_grid = (int)warps;
+  } else {
+    s->step_block = 128;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev_occ, kern, s->step_block, s->smem_step));
+    if (dev_occ < 1) dev_occ = 1;
+    long long need = ((long long)s->N * 4 + s->step_block - 1) / s->step_block;
+    long long cap = (long long)s->num_sms * dev_occ;
+    s->step_grid = (int)(need < cap ? need : cap);
+  }
+  if (const char* env = std::getenv("ODG_STEP_BLOCK")) {           // tuning override (bench/profiling)
+    int b = std::atoi(env);
+    if (b == 32 || b == 64 || b == 128) {
+      s->step_block = b;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev_occ, kern, b, s->smem_step));
+      if (dev_occ < 1) dev_occ = 1;
+      long long need = ((long long)s->N * 4 + b - 1) / b, cap = (long long)s->num_sms * dev_occ;
+      s->step_grid = (int)(need < cap ? need : cap);
+    }
+  }
+  return ODG_OK;
+}
+
+int launch_step(OdgSim* s, const StepArgs& A, cudaStream_t st) {
+  if (s->prep.C.njl == 2)
+    k_step<2><<<s->step_grid, s->step_block, s->smem_step, st>>>(s->prep.C, s->P, A, s->d_lc, s->d_gc, s->d_vert, s->L);
+  else
+    k_step<3><<<s->step_grid, s->step_block, s->smem_step, st>>>(s->prep.C, s->P, A, s->d_lc, s->d_gc, s->d_vert, s->L);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ODG_OK;
+}
+
+void fill_args(StepArgs* A, const float* action, float* obs, float* reward, uint8_t* term, uint8_t* trunc,
+               const OdgInfoPtrs* info, int mode) {
+  std::memset(A, 0, sizeof(*A));
+  A->action = action; A->obs = obs; A->reward = reward; A->terminated = term; A->truncated = trunc; A->mode = mode;
+  if (info) {
+    A->want_info = 1;
+    A->x_position = info->x_position; A->y_position = info->y_position; A->distance = info->distance_from_origin;
+    A->paw_forces = info->paw_contact_forces; A->patterns_matches = info->patterns_matches;
+    A->lin_vel_reward = info->linear_vel_tracking_reward; A->reward_ctrl = info->reward_ctrl;
+    A->terminal_obs = info->terminal_obs; A->paws_in_ground = info->paws_in_ground; A->gait_reward = info->gait_reward;
+    A->qacc = info->qacc; A->ncon = info->ncon; A->fn_sum = info->contact_normal_force; A->solver_iters = info->solver_iters;
+  }
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" {
+
+void odg_default_config(OdgEnvConfig* cfg) { if (cfg) odg::default_config(cfg); }
+const char* odg_last_error(void) { return g_err.c_str(); }
+const char* odg_version(void) { return "odgsim 0.1 sm_100a"; }
+
+int odg_create(const OdgModel* model, const OdgEnvConfig* cfg_in, int num_envs, int device, uint64_t seed, OdgSim** out) {
+  if (!model || !out || num_envs < 1) return fail(ODG_ERR_INVALID, "odg_create: bad arguments");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(ODG_ERR_NO_DEVICE, "no CUDA device: libodgsim has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(ODG_ERR_INVALID, "odg_create: device out of range");
+  OdgEnvConfig cfg;
+  if (cfg_in) cfg = *cfg_in; else odg::default_config(&cfg);
+  OdgSim* s = new (std::nothrow) OdgSim();
+  if (!s) return fail(ODG_ERR_ALLOC, "out of host memory");
+  std::string why = odg::prepare(*model, cfg, seed, &s->prep);
+  if (!why.empty()) { delete s; return fail(ODG_ERR_INVALID, "odg_create: " + why); }
+  DeviceGuard guard(device);
+  s->device = device; s->N = num_envs;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  s->num_sms = prop.multiProcessorCount;
+  const DevConst& C = s->prep.C;
+  const size_t N = (size_t)num_envs;
+  // one slab: qpos, qvel, warm, last_action, desvel (float) | step, gait_idx, gait_cnt, episode (i32) | fresh (u8)
+  const size_t nfloat = (size_t)(C.nq + 2 * C.nv + C.nu + 3) * N, nint = 4 * N;
+  const size_t bytes = nfloat * 4 + nint * 4 + N;
+  if (cudaMalloc(&s->d_state, bytes) != cudaSuccess) { delete s; return fail(ODG_ERR_ALLOC, "cudaMalloc(state) failed"); }
+  float* f = static_cast<float*>(s->d_state);
+  s->P.N = num_envs;
+  s->P.qpos = f; f += (size_t)C.nq * N;
+  s->P.qvel = f; f += (size_t)C.nv * N;
+  s->P.warm = f; f += (size_t)C.nv * N;
+  s->P.last_action = f; f += (size_t)C.nu * N;
+  s->P.desvel = f; f += 3 * N;
+  int* ip = reinterpret_cast<int*>(f);
+  s->P.step = ip; s->P.gait_idx = ip + N; s->P.gait_cnt = ip + 2 * N; s->P.episode = reinterpret_cast<unsigned*>(ip + 3 * N);
+  s->P.fresh = reinterpret_cast<unsigned char*>(ip + 4 * N);
+  auto upload = [&](float** dst, const std::vector<float>& v) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, v.size() * sizeof(float));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice);
+  };
+  if (upload(&s->d_lc, s->prep.lc) != cudaSuccess || upload(&s->d_gc, s->prep.gc) != cudaSuccess ||
+      upload(&s->d_vert, s->prep.vert) != cudaSuccess) { odg_destroy(s); return fail(ODG_ERR_ALLOC, "constant upload failed"); }
+  s->L.lc_floats = (int)s->prep.lc.size(); s->L.gc_floats = (int)s->prep.gc.size(); s->L.vert_floats = (int)s->prep.vert.size();
+  s->smem_step = (size_t)(s->L.lc_floats + s->L.gc_floats + s->L.vert_floats) * sizeof(float);
+  int rc = choose_launch(s);
+  if (rc != ODG_OK) { odg_destroy(s); return rc; }
+  k_init<<<(num_envs + 127) / 128, 128>>>(C, s->P);
+  s->launches++;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { odg_destroy(s); return fail(ODG_ERR_CUDA, std::string("k_init: ") + cudaGetErrorString(e)); }
+  *out = s;
+  return ODG_OK;
+}
+
+void odg_destroy(OdgSim* s) {
+  if (!s) return;
+  DeviceGuard guard(s->device);
+  cudaFree(s->d_state); cudaFree(s->d_lc); cudaFree(s->d_gc); cudaFree(s->d_vert);
+  delete s;
+}
+
+int odg_num_envs(const OdgSim* s) { return s ? s->N : 0; }
+int odg_obs_dim(const OdgSim* s) { return s ? 9 + 3 * s->prep.C.nu : 0; }
+int odg_act_dim(const OdgSim* s) { return s ? s->prep.C.nu : 0; }
+int odg_nq(const OdgSim* s) { return s ? s->prep.C.nq : 0; }
+int odg_nv(const OdgSim* s) { return s ? s->prep.C.nv : 0; }
+long long odg_launch_count(const OdgSim* s) { return s ? s->launches : 0; }
+
+int odg_reset(OdgSim* s, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+  if (!s) return fail(ODG_ERR_INVALID, "odg_reset: null handle");
+  DeviceGuard guard(s->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int block = 128, grid = (s->N * 4 + block - 1) / block;
+  const size_t smem = (size_t)s->prep.C.njl * odg::LC_COUNT * 4 * sizeof(float);
+  if (s->prep.C.njl == 2) k_reset<2><<<grid, block, smem, st>>>(s->prep.C, s->P, mask_dev, obs_dev, s->d_lc);
+  else k_reset<3><<<grid, block, smem, st>>>(s->prep.C, s->P, mask_dev, obs_dev, s->d_lc);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ODG_OK;
+}
+
+int odg_step(OdgSim* s, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* terminated_dev,
+             uint8_t* truncated_dev, const OdgInfoPtrs* info, void* stream) {
+  if (!s || !action_dev) return fail(ODG_ERR_INVALID, "odg_step: null handle or action");
+  DeviceGuard guard(s->device);
+  StepArgs A;
+  fill_args(&A, action_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, info, 0);
+  return launch_step(s, A, static_cast<cudaStream_t>(stream));
+}
+
+int odg_evaluate(OdgSim* s, const float* ctrl_dev, float* obs_dev, float* reward_dev, uint8_t* terminated_dev,
+                 uint8_t* truncated_dev, const OdgInfoPtrs* info, void* stream) {
+  if (!s || !ctrl_dev) return fail(ODG_ERR_INVALID, "odg_evaluate: null handle or ctrl");
+  DeviceGuard guard(s->device);
+  StepArgs A;
+  fill_args(&A, ctrl_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, info, 1);
+  return launch_step(s, A, static_cast<cudaStream_t>(stream));
+}
+
+static int transpose(OdgSim* s, float* aos, float* soa, int dim, bool to_soa, cudaStream_t st) {
+  const long long n = (long long)s->N * dim;
+  k_transpose<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(aos, soa, s->N, dim, to_soa);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ODG_OK;
+}
+
+int odg_get_state(OdgSim* s, float* qpos_dev, float* qvel_dev, void* stream) {
+  if (!s) return fail(ODG_ERR_INVALID, "odg_get_state: null handle");
+  DeviceGuard guard(s->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ODG_OK;
+  if (qpos_dev) rc = transpose(s, qpos_dev, s->P.qpos, s->prep.C.nq, false, st);
+  if (rc == ODG_OK && qvel_dev) rc = transpose(s, qvel_dev, s->P.qvel, s->prep.C.nv, false, st);
+  return rc;
+}
+
+int odg_set_state(OdgSim* s, const float* qpos_dev, const float* qvel_dev, const float* warm_dev, void* stream) {
+  if (!s) return fail(ODG_ERR_INVALID, "odg_set_state: null handle");
+  DeviceGuard guard(s->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ODG_OK;
+  if (qpos_dev) rc = transpose(s, const_cast<float*>(qpos_dev), s->P.qpos, s->prep.C.nq, true, st);
+  if (rc == ODG_OK && qvel_dev) rc = transpose(s, const_cast<float*>(qvel_dev), s->P.qvel, s->prep.C.nv, true, st);
+  if (rc != ODG_OK) return rc;
+  if (warm_dev) return transpose(s, const_cast<float*>(warm_dev), s->P.warm, s->prep.C.nv, true, st);
+  const long long n = (long long)s->N * s->prep.C.nv;
+  k_fill<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->P.warm, n, 0.f);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ODG_OK;
+}
+
+int odg_get_env_state(OdgSim* s, int32_t* step, int32_t* gidx, int32_t* gcnt, float* last_action, float* desvel,
+                      uint8_t* fresh, void* stream) {
+  if (!s) return fail(ODG_ERR_INVALID, "odg_get_env_state: null handle");
+  DeviceGuard guard(s->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t N = (size_t)s->N;
+  if (step) CUDA_TRY(cudaMemcpyAsync(step, s->P.step, N * 4, cudaMemcpyDeviceToDevice, st));
+  if (gidx) CUDA_TRY(cudaMemcpyAsync(gidx, s->P.gait_idx, N * 4, cudaMemcpyDeviceToDevice, st));
+  if (gcnt) CUDA_TRY(cudaMemcpyAsync(gcnt, s->P.gait_cnt, N * 4, cudaMemcpyDeviceToDevice, st));
+  if (fresh) CUDA_TRY(cudaMemcpyAsync(fresh, s->P.fresh, N, cudaMemcpyDeviceToDevice, st));
+  int rc = ODG_OK;
+  if (last_action) rc = transpose(s, last_action, s->P.last_action, s->prep.C.nu, false, st);
+  if (rc == ODG_OK && desvel) rc = transpose(s, desvel, s->P.desvel, 3, false, st);
+  return rc;
+}
+
+int odg_set_env_state(OdgSim* s, const int32_t* step, const int32_t* gidx, const int32_t* gcnt, const float* last_action,
+                      const float* desvel, const uint8_t* fresh, void* stream) {
+  if (!s) return fail(ODG_ERR_INVALID, "odg_set_env_state: null handle");
+  DeviceGuard guard(s->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t N = (size_t)s->N;
+  if (step) CUDA_TRY(cudaMemcpyAsync(s->P.step, step, N * 4, cudaMemcpyDeviceToDevice, st));
+  if (gidx) CUDA_TRY(cudaMemcpyAsync(s->P.gait_idx, gidx, N * 4, cudaMemcpyDeviceToDevice, st));
+  if (gcnt) CUDA_TRY(cudaMemcpyAsync(s->P.gait_cnt, gcnt, N * 4, cudaMemcpyDeviceToDevice, st));
+  if (fresh) CUDA_TRY(cudaMemcpyAsync(s->P.fresh, fresh, N, cudaMemcpyDeviceToDevice, st));
+  int rc = ODG_OK;
+  if (last_action) rc = transpose(s, const_cast<float*>(last_action), s->P.last_action, s->prep.C.nu, true, st);
+  if (rc == ODG_OK && desvel) rc = transpose(s, const_cast<float*>(desvel), s->P.desvel, 3, true, st);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+"""Batched, GPU-resident environments behind the reference's Gym-style surface.
+
+`BatchedWalkEnv` is `ScaleActionWrapper(WalkEnvironmentV0)` (reference:
+Code/mujoco/environments/WalkEnvironment.py:26-158, ScaleActionEnvironment.py:5-23) for `num_envs`
+environments at once: `reset()` / `step(action) -> (obs, reward, done, info)` on CUDA tensors, state
+never leaves HBM. PyTorch only provides the device buffers and the stream; the work happens in
+libodgsim's hand-written kernels through the C ABI (include/odg.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import lib as _lib
+from .model.compile import load_compiled, to_struct
+
+_INFO_SPECS = {
+    # name in OdgInfoPtrs -> (dtype, trailing shape factory)
+    "x_position": (torch.float32, lambda e: ()),
+    "y_position": (torch.float32, lambda e: ()),
+    "distance_from_origin": (torch.float32, lambda e: ()),
+    "paw_contact_forces": (torch.float32, lambda e: (4, 6)),
+    "patterns_matches": (torch.float32, lambda e: ()),
+    "linear_vel_tracking_reward": (torch.float32, lambda e: ()),
+    "reward_ctrl": (torch.float32, lambda e: ()),
+    "terminal_obs": (torch.float32, lambda e: (e.obs_dim,)),
+    "paws_in_ground": (torch.uint8, lambda e: (4,)),
+    "gait_reward": (torch.int32, lambda e: ()),
+    "qacc": (torch.float32, lambda e: (e.nv,)),
+    "ncon": (torch.int32, lambda e: ()),
+    "contact_normal_force": (torch.float32, lambda e: ()),
+    "solver_iters": (torch.int32, lambda e: ()),
+}
+DEFAULT_INFO = ("x_position", "y_position", "distance_from_origin", "paw_contact_forces", "patterns_matches",
+                "linear_vel_tracking_reward", "reward_ctrl", "terminal_obs")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchedWalkEnv:
+    """`num_envs` copies of the reference walk environment stepped by one fused CUDA kernel.
+
+    Parameters mirror the reference's constants; see `OdgEnvConfig` in include/odg.h.
+    `info_keys`: which `info` tensors `step` fills (None = none: fastest).
+    """
+
+    def __init__(self, num_envs: int, model: str = "our_robot", device=None, seed: int = 0,
+                 info_keys=DEFAULT_INFO, **config):
+        if not torch.cuda.is_available():
+            raise _lib.OdgError("BatchedWalkEnv needs a CUDA device: opendog_b200 has no CPU fallback")
+        self.L = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.desc = load_compiled(model)
+        self._model = to_struct(self.desc)
+        self.cfg = _lib.OdgEnvConfig()
+        self.L.odg_default_config(C.byref(self.cfg))
+        for k, v in config.items():
+            if not hasattr(self.cfg, k):
+                raise TypeError(f"unknown config field {k!r}")
+            setattr(self.cfg, k, v)
+        self.num_envs = int(num_envs)
+        h = C.c_void_p()
+        _lib.check(self.L.odg_create(C.byref(self._model), C.byref(self.cfg), self.num_envs, self.device.index,
+                                     C.c_uint64(seed), C.byref(h)), "odg_create")
+        self._h = h
+        self.obs_dim = self.L.odg_obs_dim(h)
+        self.act_dim = self.L.odg_act_dim(h)
+        self.nq, self.nv = self.L.odg_nq(h), self.L.odg_nv(h)
+        N, dev = self.num_envs, self.device
+        self.obs = torch.empty(N, self.obs_dim, device=dev)
+        self.reward = torch.empty(N, device=dev)
+        self.terminated = torch.empty(N, dtype=torch.uint8, device=dev)
+        self.truncated = torch.empty(N, dtype=torch.uint8, device=dev)
+        self.info = {}
+        self._info_struct = None
+        self.set_info_keys(info_keys)
+
+    # ------------------------------------------------------------------ plumbing
+    def set_info_keys(self, keys):
+        self.info = {}
+        if not keys:
+            self._info_struct = None
+            return
+        s = _lib.OdgInfoPtrs()
+        for k in keys:
+            dt, shp = _INFO_SPECS[k]
+            t = torch.zeros((self.num_envs,) + tuple(shp(self)), dtype=dt, device=self.device)
+            self.info[k] = t
+            setattr(s, k, t.data_ptr())
+        self._info_struct = s
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.odg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.odg_launch_count(self._h))
+
+    # ------------------------------------------------------------------ Gym surface
+    def reset(self, mask: torch.Tensor | None = None) -> torch.Tensor:
+        """env.reset() for all (or masked) envs; returns obs [N, obs_dim] (a view of an internal buffer)."""
+        m = None
+        if mask is not None:
+            m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        _lib.check(self.L.odg_reset(self._h, _ptr(m), _ptr(self.obs), self._stream()), "odg_reset")
+        return self.obs
+
+    def step(self, action: torch.Tensor):
+        """(obs, reward, done, info): `done = terminated | truncated`; with auto_reset the returned obs of
+        a done env is its reset obs and info["terminal_obs"] holds the last obs of the episode."""
+        a = action
+        if a.device != self.device or a.dtype != torch.float32 or not a.is_contiguous():
+            a = a.to(device=self.device, dtype=torch.float32).contiguous()
+        if a.shape != (self.num_envs, self.act_dim):
+            raise ValueError(f"action must be [{self.num_envs}, {self.act_dim}]")
+        info = C.byref(self._info_struct) if self._info_struct is not None else None
+        _lib.check(self.L.odg_step(self._h, _ptr(a), _ptr(self.obs), _ptr(self.reward), _ptr(self.terminated),
+                                   _ptr(self.truncated), info, self._stream()), "odg_step")
+        done = (self.terminated | self.truncated).bool()
+        return self.obs, self.reward, done, self.info
+
+    def evaluate(self, ctrl: torch.Tensor):
+        """Test hook (odg_evaluate): one mj_forward on the current state + the post-step logic."""
+        a = ctrl.to(device=self.device, dtype=torch.float32).contiguous()
+        info = C.byref(self._info_struct) if self._info_struct is not None else None
+        _lib.check(self.L.odg_evaluate(self._h, _ptr(a), _ptr(self.obs), _ptr(self.reward), _ptr(self.terminated),
+                                       _ptr(self.truncated), info, self._stream()), "odg_evaluate")
+        return self.obs, self.reward, self.terminated.bool(), self.truncated.bool(), self.info
+
+    # ------------------------------------------------------------------ state access (parity tests)
+    def get_state(self):
+        qpos = torch.empty(self.num_envs, self.nq, device=self.device)
+        qvel = torch.empty(self.num_envs, self.nv, device=self.device)
+        _lib.check(self.L.odg_get_state(self._h, _ptr(qpos), _ptr(qvel), self._stream()), "odg_get_state")
+        return qpos, qvel
+
+    def set_state(self, qpos, qvel, qacc_warmstart=None):
+        f = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.float32).to(self.device).contiguous()
+        qpos, qvel, w = f(qpos), f(qvel), f(qacc_warmstart)
+        _lib.check(self.L.odg_set_state(self._h, _ptr(qpos), _ptr(qvel), _ptr(w), self._stream()), "odg_set_state")
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def get_env_state(self):
+        N, dev = self.num_envs, self.device
+        o = dict(step=torch.empty(N, dtype=torch.int32, device=dev), gait_index=torch.empty(N, dtype=torch.int32, device=dev),
+                 gait_matches=torch.empty(N, dtype=torch.int32, device=dev),
+                 last_action=torch.empty(N, self.act_dim, device=dev), desired_velocity=torch.empty(N, 3, device=dev),
+                 fresh=torch.empty(N, dtype=torch.uint8, device=dev))
+        _lib.check(self.L.odg_get_env_state(self._h, *[_ptr(o[k]) for k in (
+            "step", "gait_index", "gait_matches", "last_action", "desired_velocity", "fresh")], self._stream()),
+            "odg_get_env_state")
+        return o
+
+    def set_env_state(self, step=None, gait_index=None, gait_matches=None, last_action=None, desired_velocity=None,
+                      fresh=None):
+        def f(t, dt):
+            return None if t is None else torch.as_tensor(t).to(device=self.device, dtype=dt).contiguous()
+        args = [f(step, torch.int32), f(gait_index, torch.int32), f(gait_matches, torch.int32),
+                f(last_action, torch.float32), f(desired_velocity, torch.float32), f(fresh, torch.uint8)]
+        _lib.check(self.L.odg_set_env_state(self._h, *[_ptr(a) for a in args], self._stream()), "odg_set_env_state")
+        torch.cuda.current_stream(self.device).synchronize()

@@ -1,0 +1,83 @@
+"""ctypes binding of libodgsim.so — exactly the entry points include/odg.h declares.
+
+The library is CUDA-only. If it is missing or no CUDA device is present this module raises; there is
+no CPU or PyTorch fallback anywhere in the package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .model.compile import OdgModel
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("ODG_LIB_PATH") or os.path.join(PKG, "libodgsim.so")   # override: tuning variants
+
+# every symbol include/odg.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "odg_default_config", "odg_create", "odg_destroy", "odg_num_envs", "odg_obs_dim", "odg_act_dim",
+    "odg_nq", "odg_nv", "odg_reset", "odg_step", "odg_evaluate", "odg_get_state", "odg_set_state",
+    "odg_get_env_state", "odg_set_env_state", "odg_launch_count", "odg_last_error", "odg_version",
+    # rollout / policy entry points (include/odg_policy.h)
+]
+
+
+class OdgEnvConfig(C.Structure):
+    _fields_ = [("task", C.c_int), ("frame_skip", C.c_int), ("max_episode_steps", C.c_int),
+                ("auto_reset", C.c_int), ("solver_iterations", C.c_int), ("ls_iterations", C.c_int),
+                ("solver_tolerance", C.c_float), ("reset_noise_scale", C.c_float),
+                ("scale_actions", C.c_int), ("first_env_id", C.c_int)]
+
+
+_vp = C.c_void_p
+
+
+class OdgInfoPtrs(C.Structure):
+    _fields_ = [(n, _vp) for n in (
+        "x_position", "y_position", "distance_from_origin", "paw_contact_forces", "patterns_matches",
+        "linear_vel_tracking_reward", "reward_ctrl", "terminal_obs", "paws_in_ground", "gait_reward",
+        "qacc", "ncon", "contact_normal_force", "solver_iters")]
+
+
+class OdgError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libodgsim.so (building it with nvcc if the sources are newer). Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    L = C.CDLL(LIB_PATH)
+    L.odg_default_config.argtypes = [C.POINTER(OdgEnvConfig)]
+    L.odg_default_config.restype = None
+    L.odg_create.argtypes = [C.POINTER(OdgModel), C.POINTER(OdgEnvConfig), C.c_int, C.c_int, C.c_uint64,
+                             C.POINTER(_vp)]
+    L.odg_destroy.argtypes = [_vp]
+    L.odg_destroy.restype = None
+    for n in ("odg_num_envs", "odg_obs_dim", "odg_act_dim", "odg_nq", "odg_nv"):
+        getattr(L, n).argtypes = [_vp]
+    L.odg_launch_count.argtypes = [_vp]
+    L.odg_launch_count.restype = C.c_longlong
+    L.odg_reset.argtypes = [_vp, _vp, _vp, _vp]
+    L.odg_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(OdgInfoPtrs), _vp]
+    L.odg_evaluate.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(OdgInfoPtrs), _vp]
+    L.odg_get_state.argtypes = [_vp, _vp, _vp, _vp]
+    L.odg_set_state.argtypes = [_vp, _vp, _vp, _vp, _vp]
+    L.odg_get_env_state.argtypes = [_vp] * 8
+    L.odg_set_env_state.argtypes = [_vp] * 8
+    L.odg_last_error.restype = C.c_char_p
+    L.odg_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise OdgError(f"{what} failed ({rc}): {load().odg_last_error().decode()}")

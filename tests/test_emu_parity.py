@@ -1,0 +1,79 @@
+"""The CUDA step kernel's SOURCE (opendog_b200/csrc/odg_core.cuh) executed by the test-only lane emulator
+against the oracle — the same checks tests/test_gpu_parity.py makes on the B200, sized for the CPU suite.
+Tolerances are the stated fp32 ones (see test_gpu_parity.py)."""
+import numpy as np
+
+from emu import EmuEnv
+from oracle.oracle import Sim, WalkEnv
+
+
+def test_single_step_parity_through_flight_impact_and_stance():
+    env = EmuEnv(1, frame_skip=1, scale_actions=0, auto_reset=0, solver_iterations=30, ls_iterations=8)
+    sim = Sim()
+    sim.reset_keyframe()
+    rng = np.random.default_rng(1)
+    worst_q = worst_v = 0.0
+    for k in range(260):
+        if k % 10 == 0:
+            ctrl = (np.array([2.36, -1.8] * 4) + rng.uniform(0, 1, 8) * np.array([.44, .6] * 4)).astype(np.float32)[None]
+            sim.ctrl[:] = ctrl[0]
+        env.set_state(sim.qpos[None], sim.qvel[None], sim.qacc_warmstart[None])
+        _, _, _, _, info = env.step(ctrl)
+        sim.step()
+        qp, qv, _ = env.get_state()
+        eq = np.abs(qp[0] - sim.qpos) - (1e-6 + 1e-5 * np.abs(sim.qpos))
+        ev = np.abs(qv[0] - sim.qvel) - (1e-4 + 1e-3 * np.abs(sim.qvel))
+        worst_q, worst_v = max(worst_q, eq.max()), max(worst_v, ev.max())
+        assert info["ncon"][0] == sim.ncon
+        fn = sum(c["force"][0] for c in sim.contacts())
+        assert abs(info["fn_sum"][0] - fn) <= 1e-2 * max(1.0, fn)
+    assert worst_q <= 0 and worst_v <= 0
+
+
+def test_walk_env_and_reset_indexing():
+    N = 3
+    env = EmuEnv(N, seed=7, solver_iterations=30, ls_iterations=8, max_episode_steps=9)
+    ws = [WalkEnv(seed=7, env_id=i) for i in range(N)]
+    for w in ws:
+        w.e.max_steps = 9
+    obs = env.reset()
+    oobs = np.stack([w.reset() for w in ws])
+    qp, qv, _ = env.get_state()
+    assert np.array_equal(qp, np.stack([w.qpos for w in ws]).astype(np.float32))     # Philox reset bit-exact
+    assert np.abs(obs - oobs).max() < 1e-6
+    rng = np.random.default_rng(3)
+    ndone = 0
+    for t in range(20):
+        a = rng.uniform(-1, 1, (N, 8)).astype(np.float32)
+        obs, r, term, trunc, info = env.step(a)
+        res = [w.step_autoreset(a[i]) for i, w in enumerate(ws)]
+        done = term | trunc
+        assert np.array_equal(done, np.array([x[2] for x in res]))
+        ndone += done.sum()
+        assert np.abs(obs - np.stack([x[0] for x in res])).max() < 1e-4
+        assert np.abs(r - np.array([x[1] for x in res])).max() < 1e-4
+        assert np.array_equal(info["gait_reward"], [x[5]["gait_first_call"] for x in res])
+        assert np.array_equal(info["paws_in_ground"], np.stack([x[5]["paws_in_ground"] for x in res]))
+        for i in range(N):
+            if done[i]:
+                assert np.abs(info["terminal_obs"][i] - res[i][4]).max() < 1e-4
+        qp, qv, _ = env.get_state()
+        for i, w in enumerate(ws):                      # re-sync: per-step agreement, not chaos
+            w.qpos[:] = qp[i]; w.qvel[:] = qv[i]
+    assert ndone == 2 * N
+
+
+def test_results_do_not_depend_on_sharding():
+    """Envs are keyed by GLOBAL id: one handle of 4 envs == two handles of 2 (rank 0 / rank 1 shards)."""
+    whole = EmuEnv(4, seed=9)
+    parts = [EmuEnv(2, seed=9, first_env_id=0), EmuEnv(2, seed=9, first_env_id=2)]
+    o = whole.reset()
+    po = np.concatenate([p.reset() for p in parts])
+    assert np.array_equal(o, po)
+    rng = np.random.default_rng(0)
+    for t in range(3):
+        a = rng.uniform(-1, 1, (4, 8)).astype(np.float32)
+        o, r, te, tr, _ = whole.step(a, info=False)
+        outs = [p.step(a[2 * k:2 * k + 2], info=False) for k, p in enumerate(parts)]
+        assert np.array_equal(o, np.concatenate([x[0] for x in outs]))
+        assert np.array_equal(r, np.concatenate([x[1] for x in outs]))

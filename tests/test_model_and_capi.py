@@ -1,0 +1,70 @@
+"""Host logic: model compiler vs the committed asset, C struct layouts, and the C-ABI library surface."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_XML = "/root/reference/Code/mujoco/our_robot/walking_scene.xml"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_XML), reason="reference MJCF not mounted")
+def test_committed_asset_matches_a_fresh_compile():
+    from opendog_b200.model.compile import compile_model, load_compiled
+    from opendog_b200.model.mjcf import load_mjcf
+    fresh = compile_model(load_mjcf(REF_XML))
+    asset = load_compiled("our_robot")
+    assert fresh["nq"] == 15 and fresh["nv"] == 14 and fresh["nu"] == 8 and fresh["ngeom"] == 12
+    for k in ("mass", "ipos", "inertia", "body_pos", "jnt_pos", "jnt_range", "key_qpos", "key_ctrl", "verts",
+              "base_inertia", "base_invweight0", "dof_invweight0"):
+        assert np.allclose(np.asarray(fresh[k], dtype=float), np.asarray(asset[k], dtype=float), rtol=1e-12, atol=1e-15), k
+    assert abs(fresh["base_mass"] + np.sum(fresh["mass"]) - 1.95852) < 1e-12       # SURVEY A.1 total mass
+    assert fresh["act_leg"] == [1, 1, 3, 3, 0, 0, 2, 2]                            # our_robot.xml:99-111
+    assert [g["mj_body_id"] for g in fresh["geoms"] if g["link"] == 1][1::2] == [4, 7, 10, 13]
+    # floor (condim 3, friction 1) wins the max-mixing against the robot geoms (condim 1, friction .6)
+    assert all(g["condim"] == 3 and g["friction"] == 1.0 and g["margin"] == 0.001 for g in fresh["geoms"])
+    assert fresh["base_armature"] == [0.02] * 6 and fresh["base_frictionloss"] == [0.1] * 6
+
+
+def test_struct_layouts_match_the_c_headers():
+    from oracle import oracle
+    oracle.lib()          # asserts sizeof(OdgModel / OdgoData / OdgoWalkEnv) against the compiled C
+
+
+def test_libodgsim_exports_every_declared_symbol():
+    from opendog_b200 import build, lib
+    build.build()
+    L = C.CDLL(lib.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "odg.h")).read()
+    declared = set(re.findall(r"\b(odg_[a-z_]+)\s*\(", header))
+    assert declared == set(lib.SYMBOLS), declared ^ set(lib.SYMBOLS)
+    for s in declared:
+        assert hasattr(L, s), s
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly (ODG_ERR_NO_DEVICE), not compute."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from opendog_b200 import lib
+    from opendog_b200.model.compile import load_compiled, to_struct
+    L = lib.load()
+    m = to_struct(load_compiled("our_robot"))
+    h = C.c_void_p()
+    rc = L.odg_create(C.byref(m), None, 4, 0, 0, C.byref(h))
+    assert rc == -3 and b"no CPU fallback" in L.odg_last_error()
+    from opendog_b200.env import BatchedWalkEnv
+    with pytest.raises(lib.OdgError):
+        BatchedWalkEnv(4)
+
+
+def test_default_config_is_the_references_constants():
+    from opendog_b200 import lib
+    cfg = lib.OdgEnvConfig()
+    lib.load().odg_default_config(C.byref(cfg))
+    assert (cfg.frame_skip, cfg.max_episode_steps, cfg.auto_reset, cfg.scale_actions) == (10, 750, 1, 1)
+    assert abs(cfg.reset_noise_scale - 0.02) < 1e-9
