@@ -201,7 +201,7 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     N = args.envs_per_gpu
     K, W = args.steps, max(args.warmup, 3)
-    env = BatchedWalkEnv(N, device=dev, seed=0, first_env_id=rank * N, info_keys=None)
+    env = BatchedWalkEnv(N, device=dev, seed=0, first_env_id=rank * N, info_keys=None, regroup=args.regroup)
     env.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -280,6 +280,7 @@ def run_gpu(args):
                    "envs_per_gpu": N, "frame_skip": FRAME_SKIP, "physics_steps_per_s": value * FRAME_SKIP,
                    "l2": "flushed (256 MiB memset) between timed steps; per-step CUDA events summed",
                    "actions": "U(-1,1), fresh batch per step, pre-generated on device",
+                   "regroup": int(env.cfg.regroup),
                    "solver": {"max_newton_iters": env.cfg.solver_iterations, "ls_iters": env.cfg.ls_iterations,
                               "tol": env.cfg.solver_tolerance}},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -303,7 +304,7 @@ def run_gpu(args):
                                           f"warm-up steps (robots landed; {dt:.1f} s); fp64 restatement of mj_step + "
                                           "reward code, not MuJoCo itself"}
     if rank == 0 and args.large_batch and world == 1:
-        line["large_batch"] = large_batch_probe(dev, args.large_batch)
+        line["large_batch"] = large_batch_probe(dev, args.large_batch, args.regroup)
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
@@ -311,11 +312,11 @@ def run_gpu(args):
     return 0
 
 
-def large_batch_probe(dev, n_envs):
+def large_batch_probe(dev, n_envs, regroup=1):
     """Throughput at the batch size of BASELINE.json configs[3] (65536 envs/GPU), same timing hygiene."""
     import torch
     from opendog_b200.env import BatchedWalkEnv
-    env = BatchedWalkEnv(n_envs, device=dev, seed=0, info_keys=None)
+    env = BatchedWalkEnv(n_envs, device=dev, seed=0, info_keys=None, regroup=regroup)
     env.reset()
     acts = torch.rand(16, n_envs, 8, device=dev) * 2 - 1
     for i in range(6):
@@ -341,6 +342,7 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--large-batch", type=int, default=65536, help="also probe this batch size at N=1 (0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--regroup", type=int, default=1, help="workload regrouping of envs into warps (OdgEnvConfig.regroup)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -49,9 +49,14 @@ typedef struct OdgEnvConfig {
                                 the kernel exits early on convergence (mean ~5). default 30 */
   int ls_iterations;         /* max line-search evaluations per Newton iteration. default 8 */
   float solver_tolerance;    /* relative Newton-step tolerance for early exit. default 1e-5 */
+  float ls_tolerance;        /* line search stops when |phi'(alpha)| <= ls_tolerance * |phi'(0)|
+                                (MuJoCo opt.ls_tolerance, default 0.01) */
   float reset_noise_scale;   /* reward_calc:106 -> 0.02 */
   int scale_actions;         /* 1 = apply ScaleActionWrapper.action (ScaleActionEnvironment.py:21-23)
                                 to actions in [-1,1]; 0 = actions are ctrl targets in rad */
+  int regroup;               /* 1 = before each step, regroup environments into warps by the solver work of their
+                                previous step (counting sort on device). Changes only the schedule, never the
+                                per-environment results. default 1 */
   int first_env_id;          /* global id of env 0 of this handle (rank * num_envs): RNG streams are
                                 keyed by global env id so results do not depend on the sharding */
 } OdgEnvConfig;
@@ -73,6 +78,7 @@ typedef struct OdgInfoPtrs {
   int32_t* ncon;                 /* [N] number of contacts */
   float* contact_normal_force;   /* [N] sum of contact normal forces */
   int32_t* solver_iters;         /* [N] Newton iterations used in the last substep */
+  int32_t* ls_evals;             /* [N] line-search evaluations used in the last substep */
 } OdgInfoPtrs;
 
 void odg_default_config(OdgEnvConfig* cfg);

@@ -29,6 +29,7 @@
 
 #ifdef ODG_HOST_EMU
 #define ODG_DEV inline
+#define ODG_NOINLINE inline
 #define ODG_RESTRICT
 struct float4 { float x, y, z, w; };
 float odg_emu_shfl_xor(float v, int m);     // provided by the emulator
@@ -41,6 +42,7 @@ static inline float odg_fdiv_rn(float a, float b) { volatile float r = a / b; re
 #define ODG_UNROLL
 #else
 #define ODG_DEV __device__ __forceinline__
+#define ODG_NOINLINE __device__ __noinline__
 #define ODG_RESTRICT __restrict__
 #define odg_fmul_rn __fmul_rn
 #define odg_fadd_rn __fadd_rn
@@ -73,7 +75,7 @@ enum LegConstField {
   LC_COUNT
 };
 // per-slot, per-leg constants: s_gc[(slot*GC_COUNT + f)*4 + leg]
-enum GeomConstField { GC_INVW, GC_CX, GC_CY, GC_CZ, GC_COUNT };
+enum GeomConstField { GC_INVW, GC_CX, GC_CY, GC_CZ, GC_BX, GC_BY, GC_BZ, GC_BR, GC_COUNT };
 
 struct DevConst {
   int nleg, njl, nq, nv, nu, nslot, nvert_rows;
@@ -94,7 +96,7 @@ struct DevConst {
   int n_tilt;
   // env
   int frame_skip, max_steps, auto_reset, solver_iters, ls_iters, scale_actions, first_env_id;
-  float tol, noise;
+  float tol, ls_tol, noise;
   float key_qpos[kMaxNQ], key_ctrl[kMaxNU];
   float obs_joint_offset;                       // key_ctrl[0,7:] broadcast quirk (WalkEnvironment.py:116)
   uint32_t seed_lo, seed_hi;
@@ -107,6 +109,8 @@ struct SimPtrs {            // SoA state in HBM: x[i*N + env]
   float* desvel;                                 // [3][N]
   int* step; int* gait_idx; int* gait_cnt; unsigned* episode;   // [N]
   unsigned char* fresh;                          // [N] last_action is the float64 zeros of reset_model
+  int* work;                                     // [N] solver work of the last env-step (Newton iterations + line-search passes)
+  int* order;                                    // [N] env processed by each 4-lane slot (workload regrouping), or null
 };
 
 struct StepArgs {
@@ -119,7 +123,7 @@ struct StepArgs {
   // info (nullable)
   float* x_position; float* y_position; float* distance; float* paw_forces; float* patterns_matches;
   float* lin_vel_reward; float* reward_ctrl; float* terminal_obs; unsigned char* paws_in_ground;
-  int* gait_reward; float* qacc; int* ncon; float* fn_sum; int* solver_iters;
+  int* gait_reward; float* qacc; int* ncon; float* fn_sum; int* solver_iters; int* ls_evals;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -228,6 +232,9 @@ ODG_DEV float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f
 constexpr uint32_t kStreamReset = 0x52534554u, kStreamDesvel = 0x44564c00u;
 
 // ---- solimp impedance (mj_makeImpedance::getimpedance); imp5 = d0,dmax,width,mid,power (pre-clamped on host)
+ODG_NOINLINE float impedance_pow(float x, float mid, float power) {      // generic power (reference models use 2)
+  return x <= mid ? powf(x, power) / powf(mid, power - 1.f) : 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+}
 ODG_DEV float impedance(const float* imp5, float pos_minus_margin) {
   float d0 = imp5[0], d1 = imp5[1], width = imp5[2], mid = imp5[3], power = imp5[4];
   if (d0 == d1 || width <= 1e-15f) return 0.5f * (d0 + d1);
@@ -235,21 +242,27 @@ ODG_DEV float impedance(const float* imp5, float pos_minus_margin) {
   if (x >= 1.f) return d1;
   if (x <= 0.f) return d0;
   float y;
-  if (power == 1.f) y = x;
-  else if (power == 2.f) y = x <= mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
-  else y = x <= mid ? powf(x, power) / powf(mid, power - 1.f) : 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+  if (power == 2.f) y = x <= mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
+  else if (power == 1.f) y = x;
+  else y = impedance_pow(x, mid, power);
   return d0 + y * (d1 - d0);
 }
 
-// friction-loss (Huber) row: z -> ds/dz, d2s/dz2
+// friction-loss (Huber) row: z -> ds/dz, d2s/dz2   (D * R == 1, so clamping D*z at +-f is the linear zone)
 ODG_DEV void fl_eval(float z, float f, float R, float D, float& g, float& hh) {
-  float rf = R * f;
-  if (z <= -rf) { g = -f; hh = 0.f; }
-  else if (z >= rf) { g = f; hh = 0.f; }
-  else { g = D * z; hh = D; }
+  g = fminf(fmaxf(D * z, -f), f);
+  hh = fabsf(z) < R * f ? D : 0.f;
 }
 
-// elliptic-cone contact block. z = (zx, zy, zn) in world axes (normal = +z). Returns zone (0 top,1 bottom,2 middle).
+// zone of the elliptic cone for z (regular-cone coordinates N, T): 0 top (separating), 1 bottom (sticking),
+// 2 middle (on the cone surface, sliding)
+ODG_DEV int cone_zone(float N, float T2, float T, float mu) {
+  if (T2 <= 0.f) return N >= 0.f ? 0 : 1;
+  if (N >= mu * T) return 0;
+  return (mu * N + T <= 0.f) ? 1 : 2;
+}
+
+// elliptic-cone contact block. z = (zx, zy, zn) in world axes (normal = +z). Returns the zone.
 ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, int condim, V3& g, S3& H) {
   g = mk3(0.f, 0.f, 0.f); H = zero_s3();
   if (condim == 1) {
@@ -258,16 +271,17 @@ ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, int condim,
   }
   float U1 = z.x * fri, U2 = z.y * fri, N = z.z * mu;
   float T2 = U1 * U1 + U2 * U2;
-  float T = sqrtf(T2);
-  if ((T <= 0.f && N >= 0.f) || (T > 0.f && N >= mu * T)) return 0;
-  if ((T <= 0.f && N < 0.f) || (T > 0.f && mu * N + T <= 0.f)) {
+  float iT = rsqrtf(fmaxf(T2, 1e-30f));
+  float T = T2 * iT;
+  int zone = cone_zone(N, T2, T, mu);
+  if (zone == 0) return 0;
+  if (zone == 1) {
     g = mk3(Dt * z.x, Dt * z.y, Dn * z.z);
     H.xx = Dt; H.yy = Dt; H.zz = Dn;
     return 1;
   }
   float Dm = Dn / (mu * mu * (1.f + mu * mu));
   float NmT = N - mu * T;
-  float iT = 1.f / T;
   float gU = -Dm * NmT * mu * iT;
   g = mk3(gU * U1 * fri, gU * U2 * fri, Dm * NmT * mu);
   float a = mu * N * iT * iT * iT, b = mu * mu - mu * N * iT;
@@ -275,6 +289,33 @@ ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, int condim,
   H.xx = ff * (a * U1 * U1 + b); H.yy = ff * (a * U2 * U2 + b); H.xy = ff * a * U1 * U2;
   H.xz = -fm * mu * U1 * iT; H.yz = -fm * mu * U2 * iT; H.zz = Dm * mu * mu;
   return 2;
+}
+
+// the same block restricted to the line z + alpha*dz: adds d/dalpha and d2/dalpha2 of its cost
+ODG_DEV void cone_line(V3 z, V3 dz, float Dn, float Dt, float mu, float fri, int condim, float& d1, float& d2) {
+  if (condim == 1) {
+    if (z.z < 0.f) { d1 += Dn * z.z * dz.z; d2 += Dn * dz.z * dz.z; }
+    return;
+  }
+  float U1 = z.x * fri, U2 = z.y * fri, N = z.z * mu;
+  float T2 = U1 * U1 + U2 * U2;
+  float iT = rsqrtf(fmaxf(T2, 1e-30f));
+  float T = T2 * iT;
+  int zone = cone_zone(N, T2, T, mu);
+  if (zone == 0) return;
+  if (zone == 1) {
+    d1 += Dt * (z.x * dz.x + z.y * dz.y) + Dn * z.z * dz.z;
+    d2 += Dt * (dz.x * dz.x + dz.y * dz.y) + Dn * dz.z * dz.z;
+    return;
+  }
+  float V1 = dz.x * fri, V2 = dz.y * fri, Nd = dz.z * mu;
+  float Dm = Dn / (mu * mu * (1.f + mu * mu));
+  float NmT = N - mu * T;
+  float Td = (U1 * V1 + U2 * V2) * iT;                 // dT/dalpha
+  float Tdd = (V1 * V1 + V2 * V2 - Td * Td) * iT;      // d2T/dalpha2
+  float e = Nd - mu * Td;
+  d1 += Dm * NmT * e;
+  d2 += Dm * (e * e - NmT * mu * Tdd);
 }
 
 // unrolled dense Cholesky solve of a 6x6 SPD system held in registers. S is overwritten by its factor.
@@ -333,7 +374,7 @@ struct LastPass {
   M3 R_last;                   // rotation of the last link (xquat[paw_body-1])
   float act[NJL];              // actuator forces
   Vec6 a_b; float a_l[NJL];    // qacc (trunk: linear, angular WORLD)
-  int ncon, iters; float fn;
+  int ncon, iters, ls_evals; float fn;
 };
 
 #define LCF(f, j) s_lc[((j) * LC_COUNT + (f)) * 4 + leg]
@@ -345,7 +386,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
                      const float4* ODG_RESTRICT s_vert, int leg, unsigned gm,
                      V3& bp, float (&bq)[4], V3& bv, V3& bwl, float (&q)[NJL], float (&qd)[NJL],
                      const float (&ctrl)[NJL], V3& warm_v, V3& warm_wl, float (&warm_l)[NJL],
-                     bool integrate, bool last, LastPass<NJL>& out) {
+                     bool integrate, bool last, LastPass<NJL>& out, int& work) {
   const bool lane0 = (leg == 0);
   // ------------------------------------------------------------------ kinematics (mj_kinematics)
   {
@@ -492,6 +533,10 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       }
       continue;
     }
+    {                                               // conservative cull: hull's bounding sphere clear of the margin
+      V3 bc = pl + mul(Rl, mk3(GCF(GC_BX, s), GCF(GC_BY, s), GCF(GC_BZ, s)));
+      if (bp.z + bc.z - GCF(GC_BR, s) > margin) continue;
+    }
     const int nvt = C.slot_nvert[s], vs = C.slot_vstart[s];
     const V3 rz = mk3(Rl.m[6], Rl.m[7], Rl.m[8]);
     float zmin = 1e30f; int best = 0;
@@ -570,15 +615,20 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     }
   }
   // trunk friction-loss rows (DoFs in MuJoCo's frames: world linear, trunk-frame angular)
-  const V3 aref_bt = mk3(-C.B_fl * bv.x, -C.B_fl * bv.y, -C.B_fl * bv.z);
-  const V3 aref_br = mk3(-C.B_fl * bwl.x, -C.B_fl * bwl.y, -C.B_fl * bwl.z);
+  const int bfi = leg < 3 ? leg : 0;
+  const V3 bf_e = mk3(leg == 0 ? 1.f : 0.f, leg == 1 ? 1.f : 0.f, leg == 2 ? 1.f : 0.f);   // world axis of the row
+  const V3 bf_c = leg == 0 ? col(R0, 0) : (leg == 1 ? col(R0, 1) : col(R0, 2));             // trunk axis, world
+  const float bf_ft = leg < 3 ? C.base_fl[bfi] : 0.f, bf_Rt = C.base_Rfl[bfi], bf_Dt = C.base_Dfl[bfi];
+  const float bf_fr = leg < 3 ? C.base_fl[3 + bfi] : 0.f, bf_Rr = C.base_Rfl[3 + bfi], bf_Dr = C.base_Dfl[3 + bfi];
+  const float bf_aref_t = -C.B_fl * dot(bf_e, bv);
+  const float bf_aref_r = -C.B_fl * comp(bwl, bfi);
   const Vec6 tau_b = { -cb.t, -cb.w };
   // ------------------------------------------------------------------ Newton solve of the primal problem
   Vec6 a_b; float a_l[NJL];
   a_b.t = warm_v; a_b.w = mul(R0, warm_wl);
   ODG_UNROLL for (int j = 0; j < NJL; j++) a_l[j] = warm_l[j];
   const float l0f = lane0 ? 1.f : 0.f;
-  int iters = 0;
+  int iters = 0, ls_evals = 0;
   bool conv = false;
   for (int it = 0; it < C.solver_iters && !conv; it++) {
     iters = it + 1;
@@ -610,24 +660,17 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         if (z < 0.f) { g_l[j] += lim_sgn[j] * lim_D[j] * z; Hll[j][j] += lim_D[j]; }
       }
     }
-    // trunk friction-loss rows (counted once: lane 0)
-    {
-      V3 al_loc = tmul(R0, a_b.w);
-      ODG_UNROLL for (int i = 0; i < 3; i++) {
-        if (C.base_fl[i] > 0.f) {
-          float g, hh; fl_eval(comp(a_b.t, i) - comp(aref_bt, i), C.base_fl[i], C.base_Rfl[i], C.base_Dfl[i], g, hh);
-          g *= l0f; hh *= l0f;
-          if (i == 0) { gb.t.x += g; Htt.xx += hh; } else if (i == 1) { gb.t.y += g; Htt.yy += hh; } else { gb.t.z += g; Htt.zz += hh; }
-        }
-        if (C.base_fl[3 + i] > 0.f) {
-          float g, hh; fl_eval(comp(al_loc, i) - comp(aref_br, i), C.base_fl[3 + i], C.base_Rfl[3 + i], C.base_Dfl[3 + i], g, hh);
-          g *= l0f; hh *= l0f;
-          V3 ci = col(R0, i);
-          gb.w = gb.w + g * ci;
-          Hww.xx += hh * ci.x * ci.x; Hww.xy += hh * ci.x * ci.y; Hww.xz += hh * ci.x * ci.z;
-          Hww.yy += hh * ci.y * ci.y; Hww.yz += hh * ci.y * ci.z; Hww.zz += hh * ci.z * ci.z;
-        }
-      }
+    // trunk friction-loss rows: lane l < 3 owns translational row l and rotational row l
+    if (bf_ft > 0.f) {
+      float g, hh; fl_eval(dot(bf_e, a_b.t) - bf_aref_t, bf_ft, bf_Rt, bf_Dt, g, hh);
+      gb.t = gb.t + g * bf_e;
+      Htt.xx += hh * bf_e.x; Htt.yy += hh * bf_e.y; Htt.zz += hh * bf_e.z;
+    }
+    if (bf_fr > 0.f) {
+      float g, hh; fl_eval(dot(bf_c, a_b.w) - bf_aref_r, bf_fr, bf_Rr, bf_Dr, g, hh);
+      gb.w = gb.w + g * bf_c;
+      Hww.xx += hh * bf_c.x * bf_c.x; Hww.xy += hh * bf_c.x * bf_c.y; Hww.xz += hh * bf_c.x * bf_c.z;
+      Hww.yy += hh * bf_c.y * bf_c.y; Hww.yz += hh * bf_c.y * bf_c.z; Hww.zz += hh * bf_c.z * bf_c.z;
     }
     // contacts
     for (int c = 0; c < nc; c++) {
@@ -733,7 +776,8 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) dz = dz + p_l[j] * cross(ax[j], r - anc[j]);
       c_dz[c] = dz;
     }
-    const V3 al_loc = tmul(R0, a_b.w), pl_loc = tmul(R0, p_b.w);
+    const float bf_zt = dot(bf_e, a_b.t) - bf_aref_t, bf_dzt = dot(bf_e, p_b.t);
+    const float bf_zr = dot(bf_c, a_b.w) - bf_aref_r, bf_dzr = dot(bf_c, p_b.w);
     // phi'(0) = p . grad  (lane-partials of the trunk gradient were kept in gb)
     float d10 = dot6(gb, p_b);
     ODG_UNROLL for (int j = 0; j < NJL; j++) d10 += p_l[j] * g_l[j];
@@ -742,6 +786,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     int side = 0;
     if (!(d10 < 0.f)) alpha = 0.f;                  // not a descent direction (converged to rounding)
     for (int ls = 0; ls < C.ls_iters && d10 < 0.f; ls++) {
+      ls_evals++;
       float d1 = G + alpha * Hq, d2 = Hq;
       ODG_UNROLL for (int j = 0; j < NJL; j++) {
         float fl = LCF(LC_FL, j);
@@ -755,32 +800,25 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
           if (z < 0.f) { d1 += lim_D[j] * z * dzl; d2 += lim_D[j] * dzl * dzl; }
         }
       }
-      ODG_UNROLL for (int i = 0; i < 3; i++) {
-        if (C.base_fl[i] > 0.f) {
-          float g, hh, dzl = comp(p_b.t, i);
-          fl_eval(comp(a_b.t, i) + alpha * dzl - comp(aref_bt, i), C.base_fl[i], C.base_Rfl[i], C.base_Dfl[i], g, hh);
-          d1 += l0f * g * dzl; d2 += l0f * hh * dzl * dzl;
-        }
-        if (C.base_fl[3 + i] > 0.f) {
-          float g, hh, dzl = comp(pl_loc, i);
-          fl_eval(comp(al_loc, i) + alpha * dzl - comp(aref_br, i), C.base_fl[3 + i], C.base_Rfl[3 + i], C.base_Dfl[3 + i], g, hh);
-          d1 += l0f * g * dzl; d2 += l0f * hh * dzl * dzl;
-        }
+      if (bf_ft > 0.f) {
+        float g, hh;
+        fl_eval(bf_zt + alpha * bf_dzt, bf_ft, bf_Rt, bf_Dt, g, hh);
+        d1 += g * bf_dzt; d2 += hh * bf_dzt * bf_dzt;
+      }
+      if (bf_fr > 0.f) {
+        float g, hh;
+        fl_eval(bf_zr + alpha * bf_dzr, bf_fr, bf_Rr, bf_Dr, g, hh);
+        d1 += g * bf_dzr; d2 += hh * bf_dzr * bf_dzr;
       }
       for (int c = 0; c < nc; c++) {
         const int s = c_slot[c];
         const float Dn = c_Dn[c];
         if (Dn == 0.f) continue;
-        V3 dz = c_dz[c];
-        V3 z = c_z0[c] + alpha * dz;
-        V3 g; S3 H;
-        int zone = cone_eval(z, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_condim[s], g, H);
-        if (zone == 0) continue;
-        d1 += dot(g, dz); d2 += dot(dz, mul(H, dz));
+        cone_line(c_z0[c] + alpha * c_dz[c], c_dz[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_condim[s], d1, d2);
       }
       d1 = grp_sum(d1, gm); d2 = grp_sum(d2, gm);
       if (!(d2 > 0.f)) { alpha = 0.f; break; }
-      if (fabsf(d1) <= 1e-4f * fabsf(d10)) break;
+      if (fabsf(d1) <= C.ls_tol * fabsf(d10)) break;
       float step = -d1 / d2;
       // bracket bookkeeping (Illinois variant of regula falsi as the fallback)
       if (d1 < 0.f) { lo = alpha; d1_lo = d1; if (side == -1) d1_hi *= 0.5f; side = -1; }
@@ -792,6 +830,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         if (!(next > lo && next < hi)) next = 0.5f * (lo + hi);
       }
       if (fabsf(next - alpha) <= 1e-6f * alpha) { alpha = next; break; }
+      if (ls == C.ls_iters - 1 && lo > 0.f) { alpha = lo; break; }   // budget spent: best point known to descend
       alpha = next;
     }
     // ---- take the step, test convergence on the step size
@@ -806,10 +845,11 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     smax = grp_max(smax, gm); amax = grp_max(amax, gm);
     conv = smax <= C.tol * (1.f + amax);            // full Newton step is negligible
   }
+  work += iters + ls_evals;
   // ------------------------------------------------------------------ outputs of the forward pass
   if (last) {
     out.a_b = a_b; ODG_UNROLL for (int j = 0; j < NJL; j++) out.a_l[j] = a_l[j];
-    out.ncon = nc; out.iters = iters; out.R_last = R[NJL - 1];
+    out.ncon = nc; out.iters = iters; out.ls_evals = ls_evals; out.R_last = R[NJL - 1];
     out.foot_contact = foot_last >= 0 ? 1 : 0;
     out.foot_force = mk3(0.f, 0.f, 0.f);
     float fn = 0.f;
@@ -909,14 +949,15 @@ ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const f
 
   // ---- physics
   LastPass<NJL> lp;
+  int work = 0;
   if (A.mode == 0) {
     step += 1;
     for (int s = 0; s < C.frame_skip; s++)
       substep<NJL>(C, s_lc, s_gc, s_vert, leg, gm, bp, bq, bv, bwl, q, qd, ctrl, warm_v, warm_wl, warm_l,
-                   true, s == C.frame_skip - 1, lp);
+                   true, s == C.frame_skip - 1, lp, work);
   } else {
     substep<NJL>(C, s_lc, s_gc, s_vert, leg, gm, bp, bq, bv, bwl, q, qd, ctrl, warm_v, warm_wl, warm_l,
-                 false, true, lp);
+                 false, true, lp, work);
   }
 
   // ---- observation (WalkEnvironment.py:115-136), float32
@@ -1028,6 +1069,7 @@ ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const f
       if (A.ncon) A.ncon[env] = (int)ncs;
       if (A.fn_sum) A.fn_sum[env] = fn;
       if (A.solver_iters) A.solver_iters[env] = lp.iters;
+      if (A.ls_evals) A.ls_evals[env] = lp.ls_evals;
       if (A.qacc) {
         float* o = A.qacc + (size_t)env * C.nv;
         o[0] = lp.a_b.t.x; o[1] = lp.a_b.t.y; o[2] = lp.a_b.t.z;
@@ -1090,6 +1132,7 @@ ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const f
     P.warm[0 * N + env] = warm_v.x; P.warm[1 * N + env] = warm_v.y; P.warm[2 * N + env] = warm_v.z;
     P.warm[3 * N + env] = warm_wl.x; P.warm[4 * N + env] = warm_wl.y; P.warm[5 * N + env] = warm_wl.z;
     P.gait_idx[env] = gidx; P.gait_cnt[env] = gcnt;
+    if (P.work) P.work[env] = work;
     if (A.mode == 0) { P.step[env] = step; P.fresh[env] = is_fresh ? 1 : 0; }
     if (do_reset) P.episode[env] = episode;
   }

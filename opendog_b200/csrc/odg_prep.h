@@ -146,6 +146,19 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
       out->gc[((size_t)s * GC_COUNT + GC_CX) * 4 + l] = (float)g.center[0];
       out->gc[((size_t)s * GC_COUNT + GC_CY) * 4 + l] = (float)g.center[1];
       out->gc[((size_t)s * GC_COUNT + GC_CZ) * 4 + l] = (float)g.center[2];
+      if (g.vert_count > 0) {                        // bounding sphere of the hull (bbox centre, max distance)
+        double lo[3] = { 1e30, 1e30, 1e30 }, hi[3] = { -1e30, -1e30, -1e30 }, c[3], r2 = 0;
+        for (int k = 0; k < g.vert_count; k++) for (int a = 0; a < 3; a++) {
+          lo[a] = std::fmin(lo[a], m.vert[g.vert_start + k][a]); hi[a] = std::fmax(hi[a], m.vert[g.vert_start + k][a]);
+        }
+        for (int a = 0; a < 3; a++) c[a] = 0.5 * (lo[a] + hi[a]);
+        for (int k = 0; k < g.vert_count; k++) {
+          double d2 = 0; for (int a = 0; a < 3; a++) { double t = m.vert[g.vert_start + k][a] - c[a]; d2 += t * t; }
+          r2 = std::fmax(r2, d2);
+        }
+        for (int a = 0; a < 3; a++) out->gc[((size_t)s * GC_COUNT + GC_BX + a) * 4 + l] = (float)c[a];
+        out->gc[((size_t)s * GC_COUNT + GC_BR) * 4 + l] = (float)(std::sqrt(r2) * 1.0001 + 1e-6);
+      }
     }
     C.slot_link[s] = g0.link; C.slot_type[s] = g0.type; C.slot_nvert[s] = nv; C.slot_vstart[s] = rows;
     C.slot_condim[s] = g0.condim;
@@ -179,7 +192,7 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
   }
   C.frame_skip = cfg.frame_skip; C.max_steps = cfg.max_episode_steps; C.auto_reset = cfg.auto_reset;
   C.solver_iters = cfg.solver_iterations; C.ls_iters = cfg.ls_iterations; C.scale_actions = cfg.scale_actions;
-  C.first_env_id = cfg.first_env_id; C.tol = cfg.solver_tolerance; C.noise = cfg.reset_noise_scale;
+  C.first_env_id = cfg.first_env_id; C.tol = cfg.solver_tolerance; C.ls_tol = cfg.ls_tolerance; C.noise = cfg.reset_noise_scale;
   C.seed_lo = (uint32_t)seed; C.seed_hi = (uint32_t)(seed >> 32);
   if (cfg.frame_skip < 1 || cfg.solver_iterations < 1 || cfg.ls_iterations < 1) return "bad config";
   return "";
@@ -187,8 +200,8 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
 
 inline void default_config(OdgEnvConfig* c) {
   c->task = ODG_TASK_WALK; c->frame_skip = 10; c->max_episode_steps = 750; c->auto_reset = 1;
-  c->solver_iterations = 30; c->ls_iterations = 8; c->solver_tolerance = 1e-5f; c->reset_noise_scale = 0.02f;
-  c->scale_actions = 1; c->first_env_id = 0;
+  c->solver_iterations = 30; c->ls_iterations = 8; c->solver_tolerance = 1e-5f; c->ls_tolerance = 0.01f; c->reset_noise_scale = 0.02f;
+  c->scale_actions = 1; c->regroup = 1; c->first_env_id = 0;
 }
 
 }  // namespace odg

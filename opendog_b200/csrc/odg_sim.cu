@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(128, ODG_MIN_BLOCKS) k_step(const __grid_const
   const unsigned gm = 0xFu << (threadIdx.x & 28);
   const int envs_per_block = blockDim.x >> 2;
   for (int base = blockIdx.x * envs_per_block; base < P.N; base += gridDim.x * envs_per_block) {
-    const int env = base + (threadIdx.x >> 2);
-    if (env < P.N) odg::env_step<NJL>(C, s_lc, s_gc, s_vert, P, A, env, leg, gm);
+    const int slot = base + (threadIdx.x >> 2);
+    if (slot < P.N) odg::env_step<NJL>(C, s_lc, s_gc, s_vert, P, A, P.order ? P.order[slot] : slot, leg, gm);
   }
 }
 
@@ -97,6 +97,31 @@ __global__ void k_fill(float* p, long long n, float v) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
+// ---- workload regrouping: counting sort of env ids by the solver work of their last step, so that the 8
+// environments sharing a warp need similar numbers of Newton / line-search passes (less divergence).
+constexpr int kWorkBins = 256;
+__global__ void k_work_hist(const int* __restrict__ work, int N, int* hist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) atomicAdd(&hist[min(max(work[i], 0) >> 1, kWorkBins - 1)], 1);
+}
+__global__ void k_work_scan(int* hist) {          // one block of kWorkBins threads: exclusive scan in place
+  __shared__ int s[kWorkBins];
+  const int t = threadIdx.x;
+  s[t] = hist[t];
+  __syncthreads();
+  for (int d = 1; d < kWorkBins; d <<= 1) {
+    int v = t >= d ? s[t - d] : 0;
+    __syncthreads();
+    s[t] += v;
+    __syncthreads();
+  }
+  hist[t] = s[t] - hist[t];
+}
+__global__ void k_work_scatter(const int* __restrict__ work, int N, int* offs, int* order) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) order[atomicAdd(&offs[min(max(work[i], 0) >> 1, kWorkBins - 1)], 1)] = i;
+}
+
 template <typename T>
 __global__ void k_copy(T* dst, const T* src, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -114,6 +139,7 @@ struct OdgSim {
   SmemLayout L{};
   size_t smem_step = 0;
   int step_block = 128, step_grid = 1;
+  int* d_order = nullptr; int* d_hist = nullptr; int regroup = 0;
   long long launches = 0;
 };
 
@@ -151,6 +177,17 @@ int choose_launch(OdgSim* s) {
 }
 
 int launch_step(OdgSim* s, const StepArgs& A, cudaStream_t st) {
+  if (s->regroup && A.mode == 0) {
+    const int N = s->N, g = (N + 255) / 256;
+    CUDA_TRY(cudaMemsetAsync(s->d_hist, 0, kWorkBins * sizeof(int), st));
+    k_work_hist<<<g, 256, 0, st>>>(s->P.work, N, s->d_hist);
+    k_work_scan<<<1, kWorkBins, 0, st>>>(s->d_hist);
+    k_work_scatter<<<g, 256, 0, st>>>(s->P.work, N, s->d_hist, s->d_order);
+    s->launches += 3;
+    s->P.order = s->d_order;
+  } else {
+    s->P.order = nullptr;
+  }
   if (s->prep.C.njl == 2)
     k_step<2><<<s->step_grid, s->step_block, s->smem_step, st>>>(s->prep.C, s->P, A, s->d_lc, s->d_gc, s->d_vert, s->L);
   else
@@ -170,7 +207,7 @@ void fill_args(StepArgs* A, const float* action, float* obs, float* reward, uint
     A->paw_forces = info->paw_contact_forces; A->patterns_matches = info->patterns_matches;
     A->lin_vel_reward = info->linear_vel_tracking_reward; A->reward_ctrl = info->reward_ctrl;
     A->terminal_obs = info->terminal_obs; A->paws_in_ground = info->paws_in_ground; A->gait_reward = info->gait_reward;
-    A->qacc = info->qacc; A->ncon = info->ncon; A->fn_sum = info->contact_normal_force; A->solver_iters = info->solver_iters;
+    A->qacc = info->qacc; A->ncon = info->ncon; A->fn_sum = info->contact_normal_force; A->solver_iters = info->solver_iters; A->ls_evals = info->ls_evals;
   }
 }
 
@@ -209,7 +246,7 @@ int odg_create(const OdgModel* model, const OdgEnvConfig* cfg_in, int num_envs, 
   const DevConst& C = s->prep.C;
   const size_t N = (size_t)num_envs;
   // one slab: qpos, qvel, warm, last_action, desvel (float) | step, gait_idx, gait_cnt, episode (i32) | fresh (u8)
-  const size_t nfloat = (size_t)(C.nq + 2 * C.nv + C.nu + 3) * N, nint = 4 * N;
+  const size_t nfloat = (size_t)(C.nq + 2 * C.nv + C.nu + 3) * N, nint = 6 * N + kWorkBins;
   const size_t bytes = nfloat * 4 + nint * 4 + N;
   if (cudaMalloc(&s->d_state, bytes) != cudaSuccess) { delete s; return fail(ODG_ERR_ALLOC, "cudaMalloc(state) failed"); }
   float* f = static_cast<float*>(s->d_state);
@@ -221,7 +258,9 @@ int odg_create(const OdgModel* model, const OdgEnvConfig* cfg_in, int num_envs, 
   s->P.desvel = f; f += 3 * N;
   int* ip = reinterpret_cast<int*>(f);
   s->P.step = ip; s->P.gait_idx = ip + N; s->P.gait_cnt = ip + 2 * N; s->P.episode = reinterpret_cast<unsigned*>(ip + 3 * N);
-  s->P.fresh = reinterpret_cast<unsigned char*>(ip + 4 * N);
+  s->P.work = ip + 4 * N; s->d_order = ip + 5 * N; s->d_hist = ip + 6 * N;
+  s->P.order = nullptr;
+  s->P.fresh = reinterpret_cast<unsigned char*>(ip + 6 * N + kWorkBins);
   auto upload = [&](float** dst, const std::vector<float>& v) -> cudaError_t {
     cudaError_t e = cudaMalloc(dst, v.size() * sizeof(float));
     if (e != cudaSuccess) return e;
@@ -231,6 +270,8 @@ int odg_create(const OdgModel* model, const OdgEnvConfig* cfg_in, int num_envs, 
       upload(&s->d_vert, s->prep.vert) != cudaSuccess) { odg_destroy(s); return fail(ODG_ERR_ALLOC, "constant upload failed"); }
   s->L.lc_floats = (int)s->prep.lc.size(); s->L.gc_floats = (int)s->prep.gc.size(); s->L.vert_floats = (int)s->prep.vert.size();
   s->smem_step = (size_t)(s->L.lc_floats + s->L.gc_floats + s->L.vert_floats) * sizeof(float);
+  s->regroup = cfg.regroup;
+  CUDA_TRY(cudaMemset(s->P.work, 0, N * sizeof(int)));
   int rc = choose_launch(s);
   if (rc != ODG_OK) { odg_destroy(s); return rc; }
   k_init<<<(num_envs + 127) / 128, 128>>>(C, s->P);

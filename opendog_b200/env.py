@@ -31,6 +31,7 @@ _INFO_SPECS = {
     "ncon": (torch.int32, lambda e: ()),
     "contact_normal_force": (torch.float32, lambda e: ()),
     "solver_iters": (torch.int32, lambda e: ()),
+    "ls_evals": (torch.int32, lambda e: ()),
 }
 DEFAULT_INFO = ("x_position", "y_position", "distance_from_origin", "paw_contact_forces", "patterns_matches",
                 "linear_vel_tracking_reward", "reward_ctrl", "terminal_obs")

@@ -25,8 +25,8 @@ SYMBOLS = [
 class OdgEnvConfig(C.Structure):
     _fields_ = [("task", C.c_int), ("frame_skip", C.c_int), ("max_episode_steps", C.c_int),
                 ("auto_reset", C.c_int), ("solver_iterations", C.c_int), ("ls_iterations", C.c_int),
-                ("solver_tolerance", C.c_float), ("reset_noise_scale", C.c_float),
-                ("scale_actions", C.c_int), ("first_env_id", C.c_int)]
+                ("solver_tolerance", C.c_float), ("ls_tolerance", C.c_float), ("reset_noise_scale", C.c_float),
+                ("scale_actions", C.c_int), ("regroup", C.c_int), ("first_env_id", C.c_int)]
 
 
 _vp = C.c_void_p
@@ -36,7 +36,7 @@ class OdgInfoPtrs(C.Structure):
     _fields_ = [(n, _vp) for n in (
         "x_position", "y_position", "distance_from_origin", "paw_contact_forces", "patterns_matches",
         "linear_vel_tracking_reward", "reward_ctrl", "terminal_obs", "paws_in_ground", "gait_reward",
-        "qacc", "ncon", "contact_normal_force", "solver_iters")]
+        "qacc", "ncon", "contact_normal_force", "solver_iters", "ls_evals")]
 
 
 class OdgError(RuntimeError):

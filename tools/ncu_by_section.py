@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""Attribute ncu per-SASS-instruction counters to sections of odg_core.cuh.
+
+    python tools/ncu_by_section.py gpurun_out/prof.ncu-rep [kernel-substring]
+
+Joins `ncu --page source --csv` (SASS rows, in program order) with `nvdisasm -g` line info of the
+same cubin (extracted from opendog_b200/libodgsim.so), then buckets by the `// ----` section markers.
+"""
+import bisect
+import csv
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def num(x):
+    try:
+        return float(x.replace(",", ""))
+    except Exception:
+        return 0.0
+
+
+def main():
+    rep = sys.argv[1]
+    kern = sys.argv[2] if len(sys.argv) > 2 else "k_stepILi2"
+    so = os.environ.get("ODG_LIB_PATH", os.path.join(ROOT, "opendog_b200", "libodgsim.so"))
+    tmp = tempfile.mkdtemp()
+    subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+    # instructions of the kernel with their innermost odg_core.cuh line
+    in_k, lines_of_inst, cur = False, [], None
+    for l in dis:
+        if l.startswith("//---") and ".text." in l:
+            in_k = kern in l
+            continue
+        if not in_k:
+            continue
+        m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+        if m:
+            if m.group(1).endswith("odg_core.cuh"):
+                cur = int(m.group(2))
+            elif "inlined at" not in l:
+                cur = -int(m.group(2))
+            continue
+        if re.match(r"\s+/\*[0-9a-f]{4,6}\*/", l):
+            lines_of_inst.append(cur)
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()
+    rows = list(csv.reader(out))
+    hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    hdr = rows[hdr_i]
+    data = [dict(zip(hdr, r)) for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
+    n = min(len(data), len(lines_of_inst))
+    print(f"sass rows {len(data)}, disasm instructions {len(lines_of_inst)}")
+    src = open(os.path.join(ROOT, "opendog_b200", "csrc", "odg_core.cuh")).read().splitlines()
+    marks = [(i + 1, l.strip()) for i, l in enumerate(src) if l.strip().startswith("// ----") or l.startswith("template <int NJL>") or l.startswith("ODG_DEV")]
+    mlines = [m[0] for m in marks]
+    agg = {}
+    tot = sum(num(d["Instructions Executed"]) for d in data)
+    tots = sum(num(d["# Samples"]) for d in data)
+    for i in range(n):
+        ln = lines_of_inst[i]
+        if ln is None or ln < 0:
+            key = (0, "odg_sim.cu / other")
+        else:
+            k = bisect.bisect_right(mlines, ln) - 1
+            key = marks[k] if k >= 0 else (0, "pre")
+        a = agg.setdefault(key, [0.0, 0.0, 0.0, 0])
+        d = data[i]
+        a[0] += num(d["Instructions Executed"]); a[1] += num(d["Thread Instructions Executed"])
+        a[2] += num(d["# Samples"]); a[3] += 1
+    print(f"total warp-instructions {tot:.4g}, samples {tots:.0f}")
+    print("  line   %inst  thr/inst  %samples  static  section")
+    for (ln, name), a in sorted(agg.items()):
+        print(f"{ln:6d} {a[0] / tot * 100:6.2f}%  {a[1] / max(a[0], 1):6.1f}  {a[2] / max(tots, 1) * 100:7.2f}%  {a[3]:6d}  {name[:80]}")
+
+
+if __name__ == "__main__":
+    main()
