@@ -201,7 +201,11 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     N = args.envs_per_gpu
     K, W = args.steps, max(args.warmup, 3)
-    env = BatchedWalkEnv(N, device=dev, seed=0, first_env_id=rank * N, info_keys=None, regroup=args.regroup)
+    extra = {}
+    for kv in args.cfg:
+        k, v = kv.split("=")
+        extra[k] = float(v) if "." in v or "e" in v else int(v)
+    env = BatchedWalkEnv(N, device=dev, seed=0, first_env_id=rank * N, info_keys=None, regroup=args.regroup, **extra)
     env.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -304,7 +308,7 @@ def run_gpu(args):
                                           f"warm-up steps (robots landed; {dt:.1f} s); fp64 restatement of mj_step + "
                                           "reward code, not MuJoCo itself"}
     if rank == 0 and args.large_batch and world == 1:
-        line["large_batch"] = large_batch_probe(dev, args.large_batch, args.regroup)
+        line["large_batch"] = large_batch_probe(dev, args.large_batch, args.regroup, extra)
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
@@ -312,11 +316,11 @@ def run_gpu(args):
     return 0
 
 
-def large_batch_probe(dev, n_envs, regroup=1):
+def large_batch_probe(dev, n_envs, regroup=1, extra=None):
     """Throughput at the batch size of BASELINE.json configs[3] (65536 envs/GPU), same timing hygiene."""
     import torch
     from opendog_b200.env import BatchedWalkEnv
-    env = BatchedWalkEnv(n_envs, device=dev, seed=0, info_keys=None, regroup=regroup)
+    env = BatchedWalkEnv(n_envs, device=dev, seed=0, info_keys=None, regroup=regroup, **(extra or {}))
     env.reset()
     acts = torch.rand(16, n_envs, 8, device=dev) * 2 - 1
     for i in range(6):
@@ -342,6 +346,7 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--large-batch", type=int, default=65536, help="also probe this batch size at N=1 (0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cfg", action="append", default=[], help="OdgEnvConfig override key=value (experiments)")
     ap.add_argument("--regroup", type=int, default=1, help="workload regrouping of envs into warps (OdgEnvConfig.regroup)")
     args = ap.parse_args()
     if args.impl == "reference":

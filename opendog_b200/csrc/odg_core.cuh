@@ -80,6 +80,7 @@ enum GeomConstField { GC_INVW, GC_CX, GC_CY, GC_CZ, GC_BX, GC_BY, GC_BZ, GC_BR, 
 struct DevConst {
   int nleg, njl, nq, nv, nu, nslot, nvert_rows;
   int body_rot_identity;
+  int all_plane1;                               // every contact slot is condim 1 (scalar contact rows, substep<.., true>)
   float h, gx, gy, gz, impratio;
   // trunk
   float base_mass, base_ip[3], base_I[6];
@@ -292,21 +293,21 @@ ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, int condim,
 }
 
 // the same block restricted to the line z + alpha*dz: adds d/dalpha and d2/dalpha2 of its cost
-ODG_DEV void cone_line(V3 z, V3 dz, float Dn, float Dt, float mu, float fri, int condim, float& d1, float& d2) {
+ODG_DEV int cone_line(V3 z, V3 dz, float Dn, float Dt, float mu, float fri, int condim, float& d1, float& d2) {
   if (condim == 1) {
-    if (z.z < 0.f) { d1 += Dn * z.z * dz.z; d2 += Dn * dz.z * dz.z; }
-    return;
+    if (z.z < 0.f) { d1 += Dn * z.z * dz.z; d2 += Dn * dz.z * dz.z; return 1; }
+    return 0;
   }
   float U1 = z.x * fri, U2 = z.y * fri, N = z.z * mu;
   float T2 = U1 * U1 + U2 * U2;
   float iT = rsqrtf(fmaxf(T2, 1e-30f));
   float T = T2 * iT;
   int zone = cone_zone(N, T2, T, mu);
-  if (zone == 0) return;
+  if (zone == 0) return 0;
   if (zone == 1) {
     d1 += Dt * (z.x * dz.x + z.y * dz.y) + Dn * z.z * dz.z;
     d2 += Dt * (dz.x * dz.x + dz.y * dz.y) + Dn * dz.z * dz.z;
-    return;
+    return 1;
   }
   float V1 = dz.x * fri, V2 = dz.y * fri, Nd = dz.z * mu;
   float Dm = Dn / (mu * mu * (1.f + mu * mu));
@@ -316,6 +317,7 @@ ODG_DEV void cone_line(V3 z, V3 dz, float Dn, float Dt, float mu, float fri, int
   float e = Nd - mu * Td;
   d1 += Dm * NmT * e;
   d2 += Dm * (e * e - NmT * mu * Tdd);
+  return 2;
 }
 
 // unrolled dense Cholesky solve of a 6x6 SPD system held in registers. S is overwritten by its factor.
@@ -381,7 +383,10 @@ struct LastPass {
 #define GCF(f, s) s_gc[((s) * GC_COUNT + (f)) * 4 + leg]
 
 // One mj_step (or one mj_forward when integrate == false) for the 4-lane group of one environment.
-template <int NJL>
+// PL1 = every contact is a frictionless (condim 1) contact against the plane z = 0 — the OpenDOG model
+// (our_robot.xml:9 condim="1"). A contact row is then the scalar J = [e_z, r x e_z, (ax_j x (r - anc_j)).z]:
+// four numbers per contact (r.x, r.y and one per joint) instead of a 3x3 cone block.
+template <int NJL, bool PL1>
 ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const float* ODG_RESTRICT s_gc,
                      const float4* ODG_RESTRICT s_vert, int leg, unsigned gm,
                      V3& bp, float (&bq)[4], V3& bv, V3& bwl, float (&q)[NJL], float (&qd)[NJL],
@@ -513,10 +518,19 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     tau_l[j] = f - cbias[j] - LCF(LC_DAMP, j) * qd[j];
   }
   // ------------------------------------------------------------------ collision: floor plane vs hulls
-  V3 c_r[kMaxConLeg], c_aref[kMaxConLeg], c_z0[kMaxConLeg], c_dz[kMaxConLeg];
+  constexpr int kGen = PL1 ? 1 : kMaxConLeg, kPl = PL1 ? kMaxConLeg : 1;
+  V3 c_r[kGen], c_aref[kGen], c_z0[kGen], c_dz[kGen];                      // generic cone rows
+  float c_rx[kPl], c_ry[kPl], c_jz[NJL][kPl], c_ar[kPl], c_zz[kPl], c_dzz[kPl];   // PL1 scalar rows
   float c_Dn[kMaxConLeg]; int c_slot[kMaxConLeg];
   int nc = 0;
   int foot_last = -1;
+  auto add_contact = [&](float px, float py, float pz_mid, float dist, int s) {
+    if (nc >= kMaxConLeg) return;
+    if (PL1) { c_rx[nc] = px; c_ry[nc] = py; } else c_r[nc] = mk3(px, py, pz_mid);
+    c_Dn[nc] = dist; c_slot[nc] = s;
+    if (C.slot_isfoot[s]) foot_last = nc;
+    nc++;
+  };
   for (int s = 0; s < C.nslot; s++) {
     const int link = C.slot_link[s];
     M3 Rl = R[0]; V3 pl = pos[0];
@@ -526,11 +540,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     if (C.slot_type[s] == 1) {                     // sphere
       V3 cc = pl + mul(Rl, mk3(GCF(GC_CX, s), GCF(GC_CY, s), GCF(GC_CZ, s)));
       float dist = bp.z + cc.z - C.slot_radius[s];
-      if (dist <= margin && nc < kMaxConLeg) {
-        c_r[nc] = mk3(cc.x, cc.y, cc.z - C.slot_radius[s] - 0.5f * dist); c_Dn[nc] = dist; c_slot[nc] = s;
-        if (C.slot_isfoot[s]) foot_last = nc;
-        nc++;
-      }
+      if (dist <= margin) add_contact(cc.x, cc.y, cc.z - C.slot_radius[s] - 0.5f * dist, dist, s);
       continue;
     }
     {                                               // conservative cull: hull's bounding sphere clear of the margin
@@ -550,11 +560,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     {
       float4 v = s_vert[(vs + best) * 4 + leg];
       V3 pw = pl + mul(Rl, mk3(v.x, v.y, v.z));
-      if (nc < kMaxConLeg) {
-        c_r[nc] = mk3(pw.x, pw.y, 0.5f * zmin - bp.z); c_Dn[nc] = zmin; c_slot[nc] = s;
-        if (C.slot_isfoot[s]) foot_last = nc;
-        nc++;
-      }
+      add_contact(pw.x, pw.y, 0.5f * zmin - bp.z, zmin, s);
     }
     for (int i = 0; i < C.n_tilt; i++) {
       V3 dl = tmul(Rl, mk3(C.tilt_dir[i][0], C.tilt_dir[i][1], C.tilt_dir[i][2]));
@@ -572,11 +578,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       float z = bp.z + pw.z;
       if (z > margin) continue;
       found[nf++] = bi;
-      if (nc < kMaxConLeg) {
-        c_r[nc] = mk3(pw.x, pw.y, 0.5f * z - bp.z); c_Dn[nc] = z; c_slot[nc] = s;
-        if (C.slot_isfoot[s]) foot_last = nc;
-        nc++;
-      }
+      add_contact(pw.x, pw.y, 0.5f * z - bp.z, z, s);
     }
   }
   // ------------------------------------------------------------------ constraint rows (mj_makeConstraint/Impedance)
@@ -585,16 +587,27 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     const int s = c_slot[c];
     const int link = C.slot_link[s];
     const float dist = c_Dn[c];
-    const V3 r = c_r[c];
-    V3 vc = bv + cross(w0, r);
-    ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) vc = vc + qd[j] * cross(ax[j], r - anc[j]);
     const float margin = C.slot_margin[s];
     float active = dist < margin ? 1.f : 0.f;       // excluded if in the gap (gap = 0: never for dist==margin only)
     float imp = impedance(C.slot_imp[s], dist - margin);
     float Rn = fmaxf(1e-15f, (1.f - imp) / imp * GCF(GC_INVW, s));
     c_Dn[c] = active / Rn;
     const float Bc = C.slot_B[s], Kc = C.slot_K[s];
-    c_aref[c] = mk3(-Bc * vc.x, -Bc * vc.y, -Bc * vc.z - Kc * imp * (dist - margin));
+    if (PL1) {
+      const float rx = c_rx[c], ry = c_ry[c];
+      float vz = bv.z + w0.x * ry - w0.y * rx;
+      ODG_UNROLL for (int j = 0; j < NJL; j++) {
+        float jz = (j <= link) ? ax[j].x * (ry - anc[j].y) - ax[j].y * (rx - anc[j].x) : 0.f;
+        c_jz[j][c] = jz;
+        vz += qd[j] * jz;
+      }
+      c_ar[c] = -Bc * vz - Kc * imp * (dist - margin);
+    } else {
+      const V3 r = c_r[c];
+      V3 vc = bv + cross(w0, r);
+      ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) vc = vc + qd[j] * cross(ax[j], r - anc[j]);
+      c_aref[c] = mk3(-Bc * vc.x, -Bc * vc.y, -Bc * vc.z - Kc * imp * (dist - margin));
+    }
   }
   // own-joint friction-loss and limit rows
   float aref_fl[NJL], lim_sgn[NJL], lim_aref[NJL], lim_D[NJL];
@@ -673,40 +686,75 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       Hww.yy += hh * bf_c.y * bf_c.y; Hww.yz += hh * bf_c.y * bf_c.z; Hww.zz += hh * bf_c.z * bf_c.z;
     }
     // contacts
-    for (int c = 0; c < nc; c++) {
-      const int s = c_slot[c];
-      const int link = C.slot_link[s];
-      const V3 r = c_r[c];
-      V3 cj[NJL];
-      V3 ap = a_b.t + cross(a_b.w, r);
+    if (PL1) {
+      // active rows (z < 0) add D * J^T J with J = [0 0 1 | ry -rx 0 | jz_0 .. jz_NJL-1]
+      float sD = 0.f, sDx = 0.f, sDy = 0.f, sDxx = 0.f, sDxy = 0.f, sDyy = 0.f, sG = 0.f, sGx = 0.f, sGy = 0.f;
+      float sDj[NJL], sDjx[NJL], sDjy[NJL], sDjj[NJL][NJL];
       ODG_UNROLL for (int j = 0; j < NJL; j++) {
-        cj[j] = (j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f);
-        ap = ap + a_l[j] * cj[j];
+        sDj[j] = sDjx[j] = sDjy[j] = 0.f;
+        ODG_UNROLL for (int i = 0; i < NJL; i++) sDjj[j][i] = 0.f;
       }
-      V3 z = ap - c_aref[c];
-      c_z0[c] = z;
-      V3 g; S3 H;
-      const float Dn = c_Dn[c];
-      int zone = cone_eval(z, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_condim[s], g, H);
-      if (zone == 0 || Dn == 0.f) continue;
-      gb.t = gb.t + g; gb.w = gb.w + cross(r, g);
-      // H * X, X = -[r]x : column i of X is e_i x r
-      V3 X0 = mk3(0.f, -r.z, r.y), X1 = mk3(r.z, 0.f, -r.x), X2 = mk3(-r.y, r.x, 0.f);
-      V3 HX0 = mul(H, X0), HX1 = mul(H, X1), HX2 = mul(H, X2);
-      Htt.xx += H.xx; Htt.xy += H.xy; Htt.xz += H.xz; Htt.yy += H.yy; Htt.yz += H.yz; Htt.zz += H.zz;
-      Htw[0][0] += HX0.x; Htw[1][0] += HX0.y; Htw[2][0] += HX0.z;
-      Htw[0][1] += HX1.x; Htw[1][1] += HX1.y; Htw[2][1] += HX1.z;
-      Htw[0][2] += HX2.x; Htw[1][2] += HX2.y; Htw[2][2] += HX2.z;
-      Hww.xx += dot(X0, HX0); Hww.xy += dot(X0, HX1); Hww.xz += dot(X0, HX2);
-      Hww.yy += dot(X1, HX1); Hww.yz += dot(X1, HX2); Hww.zz += dot(X2, HX2);
+      const float azb = a_b.t.z, awx = a_b.w.x, awy = a_b.w.y;
+      for (int c = 0; c < nc; c++) {
+        const float rx = c_rx[c], ry = c_ry[c];
+        float z = azb + awx * ry - awy * rx - c_ar[c];
+        float jz[NJL];
+        ODG_UNROLL for (int j = 0; j < NJL; j++) { jz[j] = c_jz[j][c]; z += a_l[j] * jz[j]; }
+        c_zz[c] = z;
+        const float D = z < 0.f ? c_Dn[c] : 0.f;
+        const float g = D * z, Dx = D * rx, Dy = D * ry;
+        sD += D; sDx += Dx; sDy += Dy; sDxx += Dx * rx; sDxy += Dx * ry; sDyy += Dy * ry;
+        sG += g; sGx += g * rx; sGy += g * ry;
+        ODG_UNROLL for (int j = 0; j < NJL; j++) {
+          const float Dj = D * jz[j];
+          g_l[j] += g * jz[j];
+          sDj[j] += Dj; sDjx[j] += Dj * rx; sDjy[j] += Dj * ry;
+          ODG_UNROLL for (int i = 0; i <= j; i++) sDjj[j][i] += Dj * jz[i];
+        }
+      }
+      gb.t.z += sG; gb.w.x += sGy; gb.w.y -= sGx;
+      Htt.zz += sD; Htw[2][0] += sDy; Htw[2][1] -= sDx;
+      Hww.xx += sDyy; Hww.xy -= sDxy; Hww.yy += sDxx;
       ODG_UNROLL for (int j = 0; j < NJL; j++) {
-        if (j <= link) {
-          V3 hc = mul(H, cj[j]);
-          g_l[j] += dot(cj[j], g);
-          Hlb[j].t = Hlb[j].t + hc; Hlb[j].w = Hlb[j].w + cross(r, hc);
-          ODG_UNROLL for (int i = 0; i <= j; i++) {
-            float v = dot(cj[i], hc);
-            Hll[j][i] += v; if (i != j) Hll[i][j] += v;
+        Hlb[j].t.z += sDj[j]; Hlb[j].w.x += sDjy[j]; Hlb[j].w.y -= sDjx[j];
+        ODG_UNROLL for (int i = 0; i <= j; i++) { Hll[j][i] += sDjj[j][i]; if (i != j) Hll[i][j] += sDjj[j][i]; }
+      }
+    } else {
+      for (int c = 0; c < nc; c++) {
+        const int s = c_slot[c];
+        const int link = C.slot_link[s];
+        const V3 r = c_r[c];
+        V3 cj[NJL];
+        V3 ap = a_b.t + cross(a_b.w, r);
+        ODG_UNROLL for (int j = 0; j < NJL; j++) {
+          cj[j] = (j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f);
+          ap = ap + a_l[j] * cj[j];
+        }
+        V3 z = ap - c_aref[c];
+        c_z0[c] = z;
+        V3 g; S3 H;
+        const float Dn = c_Dn[c];
+        int zone = cone_eval(z, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_condim[s], g, H);
+        if (zone == 0 || Dn == 0.f) continue;
+        gb.t = gb.t + g; gb.w = gb.w + cross(r, g);
+        // H * X, X = -[r]x : column i of X is e_i x r
+        V3 X0 = mk3(0.f, -r.z, r.y), X1 = mk3(r.z, 0.f, -r.x), X2 = mk3(-r.y, r.x, 0.f);
+        V3 HX0 = mul(H, X0), HX1 = mul(H, X1), HX2 = mul(H, X2);
+        Htt.xx += H.xx; Htt.xy += H.xy; Htt.xz += H.xz; Htt.yy += H.yy; Htt.yz += H.yz; Htt.zz += H.zz;
+        Htw[0][0] += HX0.x; Htw[1][0] += HX0.y; Htw[2][0] += HX0.z;
+        Htw[0][1] += HX1.x; Htw[1][1] += HX1.y; Htw[2][1] += HX1.z;
+        Htw[0][2] += HX2.x; Htw[1][2] += HX2.y; Htw[2][2] += HX2.z;
+        Hww.xx += dot(X0, HX0); Hww.xy += dot(X0, HX1); Hww.xz += dot(X0, HX2);
+        Hww.yy += dot(X1, HX1); Hww.yz += dot(X1, HX2); Hww.zz += dot(X2, HX2);
+        ODG_UNROLL for (int j = 0; j < NJL; j++) {
+          if (j <= link) {
+            V3 hc = mul(H, cj[j]);
+            g_l[j] += dot(cj[j], g);
+            Hlb[j].t = Hlb[j].t + hc; Hlb[j].w = Hlb[j].w + cross(r, hc);
+            ODG_UNROLL for (int i = 0; i <= j; i++) {
+              float v = dot(cj[i], hc);
+              Hll[j][i] += v; if (i != j) Hll[i][j] += v;
+            }
           }
         }
       }
@@ -769,12 +817,20 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         Hq += p_l[j] * s;
       }
     }
-    for (int c = 0; c < nc; c++) {
-      const int link = C.slot_link[c_slot[c]];
-      const V3 r = c_r[c];
-      V3 dz = p_b.t + cross(p_b.w, r);
-      ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) dz = dz + p_l[j] * cross(ax[j], r - anc[j]);
-      c_dz[c] = dz;
+    if (PL1) {
+      for (int c = 0; c < nc; c++) {
+        float dz = p_b.t.z + p_b.w.x * c_ry[c] - p_b.w.y * c_rx[c];
+        ODG_UNROLL for (int j = 0; j < NJL; j++) dz += p_l[j] * c_jz[j][c];
+        c_dzz[c] = dz;
+      }
+    } else {
+      for (int c = 0; c < nc; c++) {
+        const int link = C.slot_link[c_slot[c]];
+        const V3 r = c_r[c];
+        V3 dz = p_b.t + cross(p_b.w, r);
+        ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) dz = dz + p_l[j] * cross(ax[j], r - anc[j]);
+        c_dz[c] = dz;
+      }
     }
     const float bf_zt = dot(bf_e, a_b.t) - bf_aref_t, bf_dzt = dot(bf_e, p_b.t);
     const float bf_zr = dot(bf_c, a_b.w) - bf_aref_r, bf_dzr = dot(bf_c, p_b.w);
@@ -810,11 +866,19 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         fl_eval(bf_zr + alpha * bf_dzr, bf_fr, bf_Rr, bf_Dr, g, hh);
         d1 += g * bf_dzr; d2 += hh * bf_dzr * bf_dzr;
       }
-      for (int c = 0; c < nc; c++) {
-        const int s = c_slot[c];
-        const float Dn = c_Dn[c];
-        if (Dn == 0.f) continue;
-        cone_line(c_z0[c] + alpha * c_dz[c], c_dz[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_condim[s], d1, d2);
+      if (PL1) {
+        for (int c = 0; c < nc; c++) {
+          const float dz = c_dzz[c], z = c_zz[c] + alpha * dz;
+          const float Ddz = z < 0.f ? c_Dn[c] * dz : 0.f;
+          d1 += Ddz * z; d2 += Ddz * dz;
+        }
+      } else {
+        for (int c = 0; c < nc; c++) {
+          const int s = c_slot[c];
+          const float Dn = c_Dn[c];
+          if (Dn == 0.f) continue;
+          cone_line(c_z0[c] + alpha * c_dz[c], c_dz[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_condim[s], d1, d2);
+        }
       }
       d1 = grp_sum(d1, gm); d2 = grp_sum(d2, gm);
       if (!(d2 > 0.f)) { alpha = 0.f; break; }
@@ -853,18 +917,28 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     out.foot_contact = foot_last >= 0 ? 1 : 0;
     out.foot_force = mk3(0.f, 0.f, 0.f);
     float fn = 0.f;
-    for (int c = 0; c < nc; c++) {
-      const int s = c_slot[c];
-      const int link = C.slot_link[s];
-      const float Dn = c_Dn[c];
-      if (Dn == 0.f) continue;
-      const V3 r = c_r[c];
-      V3 ap = a_b.t + cross(a_b.w, r);
-      ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) ap = ap + a_l[j] * cross(ax[j], r - anc[j]);
-      V3 g; S3 H;
-      cone_eval(ap - c_aref[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_condim[s], g, H);
-      fn += -g.z;
-      if (c == foot_last) out.foot_force = mk3(-g.z, -g.y, g.x);   // MuJoCo frame: n=+z, t1=+y, t2=-x
+    if (PL1) {
+      for (int c = 0; c < nc; c++) {
+        float z = a_b.t.z + a_b.w.x * c_ry[c] - a_b.w.y * c_rx[c] - c_ar[c];
+        ODG_UNROLL for (int j = 0; j < NJL; j++) z += a_l[j] * c_jz[j][c];
+        const float f = z < 0.f ? -c_Dn[c] * z : 0.f;
+        fn += f;
+        if (c == foot_last) out.foot_force = mk3(f, 0.f, 0.f);
+      }
+    } else {
+      for (int c = 0; c < nc; c++) {
+        const int s = c_slot[c];
+        const int link = C.slot_link[s];
+        const float Dn = c_Dn[c];
+        if (Dn == 0.f) continue;
+        const V3 r = c_r[c];
+        V3 ap = a_b.t + cross(a_b.w, r);
+        ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) ap = ap + a_l[j] * cross(ax[j], r - anc[j]);
+        V3 g; S3 H;
+        cone_eval(ap - c_aref[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_condim[s], g, H);
+        fn += -g.z;
+        if (c == foot_last) out.foot_force = mk3(-g.z, -g.y, g.x);   // MuJoCo frame: n=+z, t1=+y, t2=-x
+      }
     }
     out.fn = fn;
   }
@@ -915,7 +989,7 @@ ODG_DEV int gait_call(int& idx, int& cnt, int paws_mask, float vx) {
 
 // Full environment step for one 4-lane group: load state, frame_skip substeps, obs/reward/termination,
 // optional auto-reset, store state.
-template <int NJL>
+template <int NJL, bool PL1>
 ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const float* ODG_RESTRICT s_gc,
                       const float4* ODG_RESTRICT s_vert, const SimPtrs& P, const StepArgs& A,
                       int env, int leg, unsigned gm) {
@@ -953,10 +1027,10 @@ ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const f
   if (A.mode == 0) {
     step += 1;
     for (int s = 0; s < C.frame_skip; s++)
-      substep<NJL>(C, s_lc, s_gc, s_vert, leg, gm, bp, bq, bv, bwl, q, qd, ctrl, warm_v, warm_wl, warm_l,
+      substep<NJL, PL1>(C, s_lc, s_gc, s_vert, leg, gm, bp, bq, bv, bwl, q, qd, ctrl, warm_v, warm_wl, warm_l,
                    true, s == C.frame_skip - 1, lp, work);
   } else {
-    substep<NJL>(C, s_lc, s_gc, s_vert, leg, gm, bp, bq, bv, bwl, q, qd, ctrl, warm_v, warm_wl, warm_l,
+    substep<NJL, PL1>(C, s_lc, s_gc, s_vert, leg, gm, bp, bq, bv, bwl, q, qd, ctrl, warm_v, warm_wl, warm_l,
                  false, true, lp, work);
   }
 

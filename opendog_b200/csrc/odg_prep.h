@@ -172,6 +172,8 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
     rows += nv;
   }
   C.nvert_rows = rows;
+  C.all_plane1 = 1;
+  for (int s = 0; s < nslot; s++) if (C.slot_condim[s] != 1) C.all_plane1 = 0;
   out->vert.assign((size_t)(rows > 0 ? rows : 1) * 16, 0.f);
   for (int s = 0; s < nslot; s++)
     for (int l = 0; l < 4; l++) {
@@ -200,7 +202,7 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
 
 inline void default_config(OdgEnvConfig* c) {
   c->task = ODG_TASK_WALK; c->frame_skip = 10; c->max_episode_steps = 750; c->auto_reset = 1;
-  c->solver_iterations = 30; c->ls_iterations = 8; c->solver_tolerance = 1e-5f; c->ls_tolerance = 0.01f; c->reset_noise_scale = 0.02f;
+  c->solver_iterations = 30; c->ls_iterations = 8; c->solver_tolerance = 1e-5f; c->ls_tolerance = 0.3f; c->reset_noise_scale = 0.02f;
   c->scale_actions = 1; c->regroup = 1; c->first_env_id = 0;
 }
 

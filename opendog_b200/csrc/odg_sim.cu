@@ -50,19 +50,25 @@ __device__ __forceinline__ void stage_constants(float* smem, const float* __rest
 #ifndef ODG_MIN_BLOCKS
 #define ODG_MIN_BLOCKS 1
 #endif
-template <int NJL>
+template <int NJL, bool PL1>
 __global__ void __launch_bounds__(128, ODG_MIN_BLOCKS) k_step(const __grid_constant__ DevConst C, const SimPtrs P, const StepArgs A,
                                               const float* __restrict__ g_lc, const float* __restrict__ g_gc,
-                                              const float* __restrict__ g_vert, SmemLayout L) {
+                                              const float* __restrict__ g_vert, SmemLayout L, int lanes) {
   extern __shared__ __align__(16) float smem[];
   const float4* s_vert; const float* s_lc; const float* s_gc;
   stage_constants(smem, g_lc, g_gc, g_vert, L, &s_vert, &s_lc, &s_gc);
+  // `lanes` = active lanes per warp (32, 16 or 8 -> 8, 4 or 2 environments per warp). Small batches leave most of
+  // the GPU empty, so they run with fewer environments per warp: less divergence between the environments that
+  // share a warp, and more warps to interleave per scheduler.
   const int leg = threadIdx.x & 3;
-  const unsigned gm = 0xFu << (threadIdx.x & 28);
-  const int envs_per_block = blockDim.x >> 2;
+  const int lane = threadIdx.x & 31;
+  if (lane >= lanes) return;
+  const unsigned gm = 0xFu << (lane & 28);
+  const int envs_per_warp = lanes >> 2;
+  const int envs_per_block = (blockDim.x >> 5) * envs_per_warp;
   for (int base = blockIdx.x * envs_per_block; base < P.N; base += gridDim.x * envs_per_block) {
-    const int slot = base + (threadIdx.x >> 2);
-    if (slot < P.N) odg::env_step<NJL>(C, s_lc, s_gc, s_vert, P, A, P.order ? P.order[slot] : slot, leg, gm);
+    const int slot = base + (threadIdx.x >> 5) * envs_per_warp + (lane >> 2);
+    if (slot < P.N) odg::env_step<NJL, PL1>(C, s_lc, s_gc, s_vert, P, A, P.order ? P.order[slot] : slot, leg, gm);
   }
 }
 
@@ -138,41 +144,42 @@ struct OdgSim {
   void* d_state = nullptr;           // one allocation behind all SoA arrays
   SmemLayout L{};
   size_t smem_step = 0;
-  int step_block = 128, step_grid = 1;
+  int step_block = 128, step_grid = 1, step_lanes = 32;
   int* d_order = nullptr; int* d_hist = nullptr; int regroup = 0;
   long long launches = 0;
 };
 
 namespace {
 
+typedef void (*StepKernel)(const DevConst, const SimPtrs, const StepArgs, const float*, const float*, const float*, SmemLayout, int);
+StepKernel step_kernel_fn(const DevConst& C) {
+  if (C.njl == 2) return C.all_plane1 ? k_step<2, true> : k_step<2, false>;
+  return C.all_plane1 ? k_step<3, true> : k_step<3, false>;
+}
+const void* step_kernel(const DevConst& C) { return (const void*)step_kernel_fn(C); }
+
 int choose_launch(OdgSim* s) {
   // 4 lanes per env. Small batches are latency bound: one warp per block spreads them over all SMs and
   // SM sub-partitions. Large batches run persistent 128-thread blocks (constants staged once per block).
-  const long long warps = ((long long)s->N * 4 + 31) / 32;
   int dev_occ = 0;
-  auto kern = s->prep.C.njl == 2 ? (const void*)k_step<2> : (const void*)k_step<3>;
+  const void* kern = step_kernel(s->prep.C);
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_step));
-  if (warps <= (long long)s->num_sms * 8) {
-    s->step_block = 32;
-    s->step_grid = (int)warps;
-  } else {
-    s->step_block = 128;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev_occ, kern, s->step_block, s->smem_step));
-    if (dev_occ < 1) dev_occ = 1;
-    long long need = ((long long)s->N * 4 + s->step_block - 1) / s->step_block;
-    long long cap = (long long)s->num_sms * dev_occ;
-    s->step_grid = (int)(need < cap ? need : cap);
-  }
-  if (const char* env = std::getenv("ODG_STEP_BLOCK")) {           // tuning override (bench/profiling)
-    int b = std::atoi(env);
-    if (b == 32 || b == 64 || b == 128) {
-      s->step_block = b;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev_occ, kern, b, s->smem_step));
-      if (dev_occ < 1) dev_occ = 1;
-      long long need = ((long long)s->N * 4 + b - 1) / b, cap = (long long)s->num_sms * dev_occ;
-      s->step_grid = (int)(need < cap ? need : cap);
-    }
-  }
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev_occ, kern, 128, s->smem_step));
+  if (dev_occ < 1) dev_occ = 1;
+  const long long resident_warps = (long long)s->num_sms * dev_occ * 4;      // warps the GPU holds at once
+  // fewest environments per warp that still fit in one resident wave
+  int lanes = 32;
+  while (lanes > 8 && ((long long)s->N * 4 + lanes / 2 - 1) / (lanes / 2) <= resident_warps) lanes >>= 1;
+  int block = 128;
+  if (const char* env = std::getenv("ODG_STEP_LANES")) { int v = std::atoi(env); if (v == 8 || v == 16 || v == 32) lanes = v; }
+  const long long warps = ((long long)s->N * 4 + lanes - 1) / lanes;
+  if (warps <= resident_warps) block = 32;                                  // spread over all SMs / sub-partitions
+  if (const char* env = std::getenv("ODG_STEP_BLOCK")) { int v = std::atoi(env); if (v == 32 || v == 64 || v == 128) block = v; }
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev_occ, kern, block, s->smem_step));
+  if (dev_occ < 1) dev_occ = 1;
+  const long long wpb = block / 32, need = (warps + wpb - 1) / wpb, cap = (long long)s->num_sms * dev_occ;
+  s->step_lanes = lanes; s->step_block = block;
+  s->step_grid = (int)(need < cap ? need : cap);
   return ODG_OK;
 }
 
@@ -188,10 +195,7 @@ int launch_step(OdgSim* s, const StepArgs& A, cudaStream_t st) {
   } else {
     s->P.order = nullptr;
   }
-  if (s->prep.C.njl == 2)
-    k_step<2><<<s->step_grid, s->step_block, s->smem_step, st>>>(s->prep.C, s->P, A, s->d_lc, s->d_gc, s->d_vert, s->L);
-  else
-    k_step<3><<<s->step_grid, s->step_block, s->smem_step, st>>>(s->prep.C, s->P, A, s->d_lc, s->d_gc, s->d_vert, s->L);
+  step_kernel_fn(s->prep.C)<<<s->step_grid, s->step_block, s->smem_step, st>>>(s->prep.C, s->P, A, s->d_lc, s->d_gc, s->d_vert, s->L, s->step_lanes);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return ODG_OK;

@@ -86,8 +86,14 @@ void emu_step(Emu* e, const odg::StepArgs* A) {
   run4([=](int l) {
     const float4* sv = reinterpret_cast<const float4*>(e->prep.vert.data());
     for (int i = 0; i < e->N; i++) {
-      if (e->prep.C.njl == 2) odg::env_step<2>(e->prep.C, e->prep.lc.data(), e->prep.gc.data(), sv, e->P, a, i, l, 0xFu);
-      else odg::env_step<3>(e->prep.C, e->prep.lc.data(), e->prep.gc.data(), sv, e->P, a, i, l, 0xFu);
+      const bool pl1 = e->prep.C.all_plane1 != 0;
+      if (e->prep.C.njl == 2) {
+        if (pl1) odg::env_step<2, true>(e->prep.C, e->prep.lc.data(), e->prep.gc.data(), sv, e->P, a, i, l, 0xFu);
+        else odg::env_step<2, false>(e->prep.C, e->prep.lc.data(), e->prep.gc.data(), sv, e->P, a, i, l, 0xFu);
+      } else {
+        if (pl1) odg::env_step<3, true>(e->prep.C, e->prep.lc.data(), e->prep.gc.data(), sv, e->P, a, i, l, 0xFu);
+        else odg::env_step<3, false>(e->prep.C, e->prep.lc.data(), e->prep.gc.data(), sv, e->P, a, i, l, 0xFu);
+      }
     }
   });
 }

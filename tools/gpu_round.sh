@@ -1,27 +1,22 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, smoke, bench, register-cap variants, ncu launch list + full profile.
+# One GPU-box visit: parity tests, smoke, bench, ncu launch list + full profile (each ncu pass only after
+# the same command exited 0 without ncu). Usage: tools/gpu_round.sh [tag]
 set -u
+TAG=${1:-r01}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/pytest_gpu.log
 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 python bench.py > gpurun_out/bench_default.log 2>&1
-B="python bench.py --steps 10 --warmup 12 --no-cpu-baseline --large-batch 65536"
-for mb in 2 3 4; do
-  ODG_LIB_PATH=$PWD/build/variants/libodgsim_mb$mb.so $B > gpurun_out/bench_mb$mb.log 2>&1
-done
-for blk in 64 128; do
-  ODG_STEP_BLOCK=$blk $B > gpurun_out/bench_blk$blk.log 2>&1
-done
 P="python bench.py --steps 3 --warmup 12 --no-cpu-baseline --large-batch 0"
 $P > gpurun_out/plain_4096.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_4096.csv $P > gpurun_out/ncu_l_4096.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_4096_$TAG.csv $P > gpurun_out/ncu_l_4096.log 2>&1
 $P > gpurun_out/plain_4096b.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_step -s 13 -c 2 -o gpurun_out/prof_4096 $P > gpurun_out/ncu_f_4096.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_step -s 13 -c 1 -o gpurun_out/prof_4096_$TAG $P > gpurun_out/ncu_f_4096.log 2>&1
 Q="python bench.py --steps 3 --warmup 12 --no-cpu-baseline --large-batch 0 --envs-per-gpu 65536"
 $Q > gpurun_out/plain_65536.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_step -s 13 -c 1 -o gpurun_out/prof_65536 $Q > gpurun_out/ncu_f_65536.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_step -s 13 -c 1 -o gpurun_out/prof_65536_$TAG $Q > gpurun_out/ncu_f_65536.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log
-for f in gpurun_out/bench_*.log; do echo $f; python - "$f" <<'PY'
+for f in gpurun_out/bench_*.log gpurun_out/plain_*.log; do echo $f; python - "$f" <<'PY'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
@@ -29,4 +24,3 @@ try:
 except Exception as e: print('  ERR',e, open(sys.argv[1]).read()[-400:])
 PY
 done
-ls -la gpurun_out | tail -20

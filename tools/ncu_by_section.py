@@ -31,9 +31,14 @@ def main():
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
-    # instructions of the kernel with their innermost odg_core.cuh line
-    in_k, lines_of_inst, cur = False, [], None
+    dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+    src_path = os.environ.get("ODG_CORE_SRC", os.path.join(ROOT, "opendog_b200", "csrc", "odg_core.cuh"))
+    src = open(src_path).read().splitlines()
+    sub_lo = next(i + 1 for i, l in enumerate(src) if l.startswith("ODG_DEV void substep("))
+    sub_hi = next(i + 1 for i, l in enumerate(src) if i + 1 > sub_lo and l.startswith("}"))
+    # instructions of the kernel, each attributed to the OUTERMOST odg_core.cuh frame inside substep()
+    # (so inlined helpers like dot()/cross() count for the section that calls them), else the outermost frame
+    in_k, lines_of_inst, cur, chain, fresh = False, [], None, [], True
     for l in dis:
         if l.startswith("//---") and ".text." in l:
             in_k = kern in l
@@ -42,12 +47,16 @@ def main():
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', l)
         if m:
-            if m.group(1).endswith("odg_core.cuh"):
-                cur = int(m.group(2))
-            elif "inlined at" not in l:
-                cur = -int(m.group(2))
+            if fresh:
+                chain, fresh = [], False
+            chain.append((m.group(1), int(m.group(2))))
             continue
         if re.match(r"\s+/\*[0-9a-f]{4,6}\*/", l):
+            if not fresh:
+                core = [ln for f, ln in chain if f.endswith("odg_core.cuh")]
+                inside = [ln for ln in core if sub_lo <= ln <= sub_hi]
+                cur = inside[-1] if inside else (core[-1] if core else -1)
+                fresh = True
             lines_of_inst.append(cur)
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()
     rows = list(csv.reader(out))
@@ -56,7 +65,6 @@ def main():
     data = [dict(zip(hdr, r)) for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
     n = min(len(data), len(lines_of_inst))
     print(f"sass rows {len(data)}, disasm instructions {len(lines_of_inst)}")
-    src = open(os.path.join(ROOT, "opendog_b200", "csrc", "odg_core.cuh")).read().splitlines()
     marks = [(i + 1, l.strip()) for i, l in enumerate(src) if l.strip().startswith("// ----") or l.startswith("template <int NJL>") or l.startswith("ODG_DEV")]
     mlines = [m[0] for m in marks]
     agg = {}
