@@ -347,7 +347,7 @@ def main():
     ap.add_argument("--large-batch", type=int, default=65536, help="also probe this batch size at N=1 (0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cfg", action="append", default=[], help="OdgEnvConfig override key=value (experiments)")
-    ap.add_argument("--regroup", type=int, default=1, help="workload regrouping of envs into warps (OdgEnvConfig.regroup)")
+    ap.add_argument("--regroup", type=int, default=0, help="workload regrouping of envs into warps (OdgEnvConfig.regroup)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

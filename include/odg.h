@@ -47,18 +47,18 @@ typedef struct OdgEnvConfig {
                                 reset inside odg_step and the returned obs is the reset obs */
   int solver_iterations;     /* max Newton iterations per substep (MuJoCo default 100, tol 1e-8);
                                 the kernel exits early on convergence (mean ~5). default 30 */
-  int ls_iterations;         /* max line-search evaluations per Newton iteration. default 8 */
+  int ls_iterations;         /* line-search passes per Newton iteration; each pass evaluates phi' at 4 step
+                                lengths at once (first {0.5,1,2,4}, then 4 interior points of the bracket). default 4 */
   float solver_tolerance;    /* relative Newton-step tolerance for early exit. default 1e-5 */
-  float ls_tolerance;        /* line search stops when |phi'(alpha)| <= ls_tolerance * |phi'(0)|. Only the path of the
-                                Newton iteration depends on it, not the solution it converges to (MuJoCo's
-                                opt.ls_tolerance is 0.01; 0.3 needs ~25% fewer line-search passes for the same
-                                number of Newton iterations). default 0.3 */
+  float ls_tolerance;        /* the full Newton step (alpha = 1) is accepted without refinement when
+                                |phi'(1)| <= ls_tolerance * |phi'(0)|. Only the path of the iteration depends on the
+                                line search, not the solution it converges to. default 0.1 */
   float reset_noise_scale;   /* reward_calc:106 -> 0.02 */
   int scale_actions;         /* 1 = apply ScaleActionWrapper.action (ScaleActionEnvironment.py:21-23)
                                 to actions in [-1,1]; 0 = actions are ctrl targets in rad */
   int regroup;               /* 1 = before each step, regroup environments into warps by the solver work of their
                                 previous step (counting sort on device). Changes only the schedule, never the
-                                per-environment results. default 1 */
+                                per-environment results. default 0 (measured: no gain on B200) */
   int first_env_id;          /* global id of env 0 of this handle (rank * num_envs): RNG streams are
                                 keyed by global env id so results do not depend on the sharding */
 } OdgEnvConfig;

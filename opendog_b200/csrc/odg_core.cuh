@@ -320,6 +320,33 @@ ODG_DEV int cone_line(V3 z, V3 dz, float Dn, float Dt, float mu, float fri, int 
   return 2;
 }
 
+// phi' contribution of one contact block at four step lengths: f[k] += d/dalpha cost(z0 + al[k]*dz). Branch-free
+// zone selection so the four evaluations interleave.
+ODG_DEV void cone_line4(V3 z0, V3 dz, float Dn, float Dt, float mu, float fri, int condim, const float (&al)[4], float (&f)[4]) {
+  if (condim == 1) {
+    const float Ddz = Dn * dz.z;
+    ODG_UNROLL for (int k = 0; k < 4; k++) f[k] += fminf(z0.z + al[k] * dz.z, 0.f) * Ddz;
+    return;
+  }
+  const float U0x = z0.x * fri, U0y = z0.y * fri, Vx = dz.x * fri, Vy = dz.y * fri, N0 = z0.z * mu, Nd = dz.z * mu;
+  const float Dm = Dn / (mu * mu * (1.f + mu * mu));
+  const float qb1 = Dt * (z0.x * dz.x + z0.y * dz.y) + Dn * z0.z * dz.z;      // sticking zone: phi' = qb1 + alpha*qb2
+  const float qb2 = Dt * (dz.x * dz.x + dz.y * dz.y) + Dn * dz.z * dz.z;
+  ODG_UNROLL for (int k = 0; k < 4; k++) {
+    const float a = al[k];
+    const float Ux = U0x + a * Vx, Uy = U0y + a * Vy, N = N0 + a * Nd;
+    const float T2 = Ux * Ux + Uy * Uy;
+    const float iT = rsqrtf(fmaxf(T2, 1e-30f));
+    const float T = T2 * iT;
+    const float Td = (Ux * Vx + Uy * Vy) * iT;
+    const float fmid = Dm * (N - mu * T) * (Nd - mu * Td);
+    const float fbot = qb1 + a * qb2;
+    const bool top = N >= mu * T;                   // separating (T == 0: N >= 0)
+    const bool bot = mu * N + T <= 0.f;             // sticking
+    f[k] += top ? 0.f : (bot ? fbot : fmid);
+  }
+}
+
 // unrolled dense Cholesky solve of a 6x6 SPD system held in registers. S is overwritten by its factor.
 ODG_DEV void chol6_solve(float (&S)[6][6], float (&x)[6]) {
   ODG_UNROLL for (int j = 0; j < 6; j++) {
@@ -838,64 +865,72 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     float d10 = dot6(gb, p_b);
     ODG_UNROLL for (int j = 0; j < NJL; j++) d10 += p_l[j] * g_l[j];
     d10 = grp_sum(d10, gm);
-    float alpha = 1.f, lo = 0.f, hi = -1.f, d1_lo = d10, d1_hi = 0.f;
-    int side = 0;
-    if (!(d10 < 0.f)) alpha = 0.f;                  // not a descent direction (converged to rounding)
-    for (int ls = 0; ls < C.ls_iters && d10 < 0.f; ls++) {
-      ls_evals++;
-      float d1 = G + alpha * Hq, d2 = Hq;
+    // phi'(alpha) at four step lengths at once (lane-partial sums, then one group reduction per value). The four
+    // evaluations are independent, which gives the scheduler 4-way ILP in the kernel's hottest loop, and the
+    // number of passes is fixed (<= C.ls_iters), so environments sharing a warp do not diverge here.
+    auto eval4 = [&](const float (&al)[4], float (&f)[4]) {
+      ODG_UNROLL for (int k = 0; k < 4; k++) f[k] = G + al[k] * Hq;
       ODG_UNROLL for (int j = 0; j < NJL; j++) {
-        float fl = LCF(LC_FL, j);
+        const float fl = LCF(LC_FL, j);
         if (fl > 0.f) {
-          float g, hh; fl_eval(a_l[j] + alpha * p_l[j] - aref_fl[j], fl, LCF(LC_RFL, j), LCF(LC_DFL, j), g, hh);
-          d1 += g * p_l[j]; d2 += hh * p_l[j] * p_l[j];
+          const float D = LCF(LC_DFL, j), z0 = a_l[j] - aref_fl[j], dz = p_l[j];
+          ODG_UNROLL for (int k = 0; k < 4; k++) f[k] += fminf(fmaxf(D * (z0 + al[k] * dz), -fl), fl) * dz;
         }
         if (lim_sgn[j] != 0.f) {
-          float dzl = lim_sgn[j] * p_l[j];
-          float z = lim_sgn[j] * a_l[j] - lim_aref[j] + alpha * dzl;
-          if (z < 0.f) { d1 += lim_D[j] * z * dzl; d2 += lim_D[j] * dzl * dzl; }
+          const float dzl = lim_sgn[j] * p_l[j], z0 = lim_sgn[j] * a_l[j] - lim_aref[j], Dd = lim_D[j] * dzl;
+          ODG_UNROLL for (int k = 0; k < 4; k++) f[k] += fminf(z0 + al[k] * dzl, 0.f) * Dd;
         }
       }
       if (bf_ft > 0.f) {
-        float g, hh;
-        fl_eval(bf_zt + alpha * bf_dzt, bf_ft, bf_Rt, bf_Dt, g, hh);
-        d1 += g * bf_dzt; d2 += hh * bf_dzt * bf_dzt;
+        ODG_UNROLL for (int k = 0; k < 4; k++) f[k] += fminf(fmaxf(bf_Dt * (bf_zt + al[k] * bf_dzt), -bf_ft), bf_ft) * bf_dzt;
       }
       if (bf_fr > 0.f) {
-        float g, hh;
-        fl_eval(bf_zr + alpha * bf_dzr, bf_fr, bf_Rr, bf_Dr, g, hh);
-        d1 += g * bf_dzr; d2 += hh * bf_dzr * bf_dzr;
+        ODG_UNROLL for (int k = 0; k < 4; k++) f[k] += fminf(fmaxf(bf_Dr * (bf_zr + al[k] * bf_dzr), -bf_fr), bf_fr) * bf_dzr;
       }
       if (PL1) {
         for (int c = 0; c < nc; c++) {
-          const float dz = c_dzz[c], z = c_zz[c] + alpha * dz;
-          const float Ddz = z < 0.f ? c_Dn[c] * dz : 0.f;
-          d1 += Ddz * z; d2 += Ddz * dz;
+          const float dz = c_dzz[c], z0 = c_zz[c], Ddz = c_Dn[c] * dz;
+          ODG_UNROLL for (int k = 0; k < 4; k++) f[k] += fminf(z0 + al[k] * dz, 0.f) * Ddz;
         }
       } else {
         for (int c = 0; c < nc; c++) {
           const int s = c_slot[c];
           const float Dn = c_Dn[c];
           if (Dn == 0.f) continue;
-          cone_line(c_z0[c] + alpha * c_dz[c], c_dz[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_condim[s], d1, d2);
+          cone_line4(c_z0[c], c_dz[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_condim[s], al, f);
         }
       }
-      d1 = grp_sum(d1, gm); d2 = grp_sum(d2, gm);
-      if (!(d2 > 0.f)) { alpha = 0.f; break; }
-      if (fabsf(d1) <= C.ls_tol * fabsf(d10)) break;
-      float step = -d1 / d2;
-      // bracket bookkeeping (Illinois variant of regula falsi as the fallback)
-      if (d1 < 0.f) { lo = alpha; d1_lo = d1; if (side == -1) d1_hi *= 0.5f; side = -1; }
-      else { hi = alpha; d1_hi = d1; if (side == 1) d1_lo *= 0.5f; side = 1; }
-      float next = alpha + step;
-      if (hi < 0.f) { if (!(next > lo)) next = 2.f * alpha; }
-      else if (!(next > lo && next < hi)) {
-        next = lo - d1_lo * (hi - lo) / (d1_hi - d1_lo);
-        if (!(next > lo && next < hi)) next = 0.5f * (lo + hi);
+      ODG_UNROLL for (int k = 0; k < 4; k++) f[k] = grp_sum(f[k], gm);
+    };
+    float alpha = 0.f;
+    if (d10 < 0.f) {                                // else: not a descent direction (converged to rounding)
+      float al[4] = { 0.5f, 1.f, 2.f, 4.f }, f[4];
+      eval4(al, f);
+      ls_evals++;
+      if (fabsf(f[1]) <= C.ls_tol * fabsf(d10)) alpha = 1.f;       // the full Newton step is (nearly) the minimiser
+      else {
+        // phi' is increasing (phi convex): bracket its zero, refine the bracket with 4 interior points per pass,
+        // finish with the zero of the chord on the last bracket
+        float lo = 0.f, flo = d10, hi = -1.f, fhi = 0.f;
+        ODG_UNROLL for (int k = 0; k < 4; k++) {
+          if (hi < 0.f) { if (f[k] >= 0.f) { hi = al[k]; fhi = f[k]; } else { lo = al[k]; flo = f[k]; } }
+        }
+        if (hi < 0.f) alpha = al[3];
+        else {
+          for (int ls = 1; ls < C.ls_iters; ls++) {
+            const float w = (hi - lo) * 0.2f, lo0 = lo;
+            ODG_UNROLL for (int k = 0; k < 4; k++) al[k] = lo0 + w * (float)(k + 1);
+            eval4(al, f);
+            ls_evals++;
+            bool found = false;
+            ODG_UNROLL for (int k = 0; k < 4; k++) {
+              if (!found) { if (f[k] >= 0.f) { hi = al[k]; fhi = f[k]; found = true; } else { lo = al[k]; flo = f[k]; } }
+            }
+          }
+          alpha = lo - flo * (hi - lo) / (fhi - flo);
+          if (!(alpha >= lo && alpha <= hi)) alpha = 0.5f * (lo + hi);
+        }
       }
-      if (fabsf(next - alpha) <= 1e-6f * alpha) { alpha = next; break; }
-      if (ls == C.ls_iters - 1 && lo > 0.f) { alpha = lo; break; }   // budget spent: best point known to descend
-      alpha = next;
     }
     // ---- take the step, test convergence on the step size
     float amax = 0.f, smax = 0.f;

@@ -8,7 +8,7 @@ from oracle.oracle import Sim, WalkEnv
 
 
 def test_single_step_parity_through_flight_impact_and_stance():
-    env = EmuEnv(1, frame_skip=1, scale_actions=0, auto_reset=0, solver_iterations=30, ls_iterations=8)
+    env = EmuEnv(1, frame_skip=1, scale_actions=0, auto_reset=0)
     sim = Sim()
     sim.reset_keyframe()
     rng = np.random.default_rng(1)
@@ -32,7 +32,7 @@ def test_single_step_parity_through_flight_impact_and_stance():
 
 def test_walk_env_and_reset_indexing():
     N = 3
-    env = EmuEnv(N, seed=7, solver_iterations=30, ls_iterations=8, max_episode_steps=9)
+    env = EmuEnv(N, seed=7, max_episode_steps=9)
     ws = [WalkEnv(seed=7, env_id=i) for i in range(N)]
     for w in ws:
         w.e.max_steps = 9

@@ -1,16 +1,14 @@
 #!/bin/bash
-# quick perf visit: parity tests + bench at 4096 / 65536 envs for the default build, config overrides and variants
-# usage: tools/gpu_quick.sh [variant ...]   (variants: build/variants/libodgsim_<v>.so)
+# quick perf visit: parity tests + bench at 4096 / 65536 envs for config overrides given as arguments
+# usage: tools/gpu_quick.sh "tag:--cfg a=b --cfg c=d" ...
 set -u
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/pytest_gpu.log
-B="python bench.py --steps 20 --warmup 12 --no-cpu-baseline --large-batch 65536"
-$B --regroup 0 > gpurun_out/bench_default_rg0.log 2>&1
-$B --regroup 1 > gpurun_out/bench_default_rg1.log 2>&1
-$B --regroup 0 --cfg ls_tolerance=0.1 > gpurun_out/bench_lstol01.log 2>&1
-$B --regroup 0 --cfg ls_tolerance=0.3 > gpurun_out/bench_lstol03.log 2>&1
-for v in "$@"; do
-  ODG_LIB_PATH=$PWD/build/variants/libodgsim_$v.so $B --regroup 0 > gpurun_out/bench_$v.log 2>&1
+B="python bench.py --steps 20 --warmup 12 --no-cpu-baseline --large-batch 65536 --regroup 0"
+$B > gpurun_out/bench_default.log 2>&1
+for spec in "$@"; do
+  tag=${spec%%:*}; args=${spec#*:}
+  $B $args > gpurun_out/bench_$tag.log 2>&1
 done
 tail -3 gpurun_out/pytest_gpu.log
 for f in gpurun_out/bench_*.log; do echo $f; python - "$f" <<'PY'
