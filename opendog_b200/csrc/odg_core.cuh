@@ -904,32 +904,30 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     };
     float alpha = 0.f;
     if (d10 < 0.f) {                                // else: not a descent direction (converged to rounding)
+      // phi' is increasing (phi convex): bracket its zero with the first pass, shrink the bracket 5x per further
+      // pass, stop as soon as one evaluated point has |phi'| <= ls_tol*|phi'(0)|, else finish with the zero of the
+      // chord on the last bracket
+      const float ftol = C.ls_tol * fabsf(d10);
       float al[4] = { 0.5f, 1.f, 2.f, 4.f }, f[4];
-      eval4(al, f);
-      ls_evals++;
-      if (fabsf(f[1]) <= C.ls_tol * fabsf(d10)) alpha = 1.f;       // the full Newton step is (nearly) the minimiser
-      else {
-        // phi' is increasing (phi convex): bracket its zero, refine the bracket with 4 interior points per pass,
-        // finish with the zero of the chord on the last bracket
-        float lo = 0.f, flo = d10, hi = -1.f, fhi = 0.f;
+      float lo = 0.f, flo = d10, hi = -1.f, fhi = 0.f;
+      bool done = false;
+      for (int ls = 0; ls < C.ls_iters && !done; ls++) {
+        if (ls > 0) {
+          const float w = (hi - lo) * 0.2f, lo0 = lo;
+          ODG_UNROLL for (int k = 0; k < 4; k++) al[k] = lo0 + w * (float)(k + 1);
+        }
+        eval4(al, f);
+        ls_evals++;
+        bool found = hi >= 0.f && ls == 0;          // (false: a pass always starts without a new upper end)
         ODG_UNROLL for (int k = 0; k < 4; k++) {
-          if (hi < 0.f) { if (f[k] >= 0.f) { hi = al[k]; fhi = f[k]; } else { lo = al[k]; flo = f[k]; } }
+          if (!done && fabsf(f[k]) <= ftol) { alpha = al[k]; done = true; }
+          if (!found) { if (f[k] >= 0.f) { hi = al[k]; fhi = f[k]; found = true; } else { lo = al[k]; flo = f[k]; } }
         }
-        if (hi < 0.f) alpha = al[3];
-        else {
-          for (int ls = 1; ls < C.ls_iters; ls++) {
-            const float w = (hi - lo) * 0.2f, lo0 = lo;
-            ODG_UNROLL for (int k = 0; k < 4; k++) al[k] = lo0 + w * (float)(k + 1);
-            eval4(al, f);
-            ls_evals++;
-            bool found = false;
-            ODG_UNROLL for (int k = 0; k < 4; k++) {
-              if (!found) { if (f[k] >= 0.f) { hi = al[k]; fhi = f[k]; found = true; } else { lo = al[k]; flo = f[k]; } }
-            }
-          }
-          alpha = lo - flo * (hi - lo) / (fhi - flo);
-          if (!(alpha >= lo && alpha <= hi)) alpha = 0.5f * (lo + hi);
-        }
+        if (!done && hi < 0.f) { alpha = al[3]; done = true; }     // still descending at the largest step tried
+      }
+      if (!done) {
+        alpha = lo - flo * (hi - lo) / (fhi - flo);
+        if (!(alpha >= lo && alpha <= hi)) alpha = 0.5f * (lo + hi);
       }
     }
     // ---- take the step, test convergence on the step size

@@ -26,7 +26,7 @@ def num(x):
 
 def main():
     rep = sys.argv[1]
-    kern = sys.argv[2] if len(sys.argv) > 2 else "k_stepILi2"
+    kern = sys.argv[2] if len(sys.argv) > 2 else "k_stepILi2ELb0"
     so = os.environ.get("ODG_LIB_PATH", os.path.join(ROOT, "opendog_b200", "libodgsim.so"))
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
