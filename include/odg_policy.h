@@ -1,0 +1,77 @@
+/* odg_policy.h — C ABI of the rollout side of libodgsim: the policy MLP forward on tensor cores, GAE and
+ * advantage statistics. Companion of odg.h (same conventions: plain pointers and sizes, caller-owned device
+ * buffers, `stream` = cudaStream_t as void*, 0 / negative OdgStatus, never throws).
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/Code/mujoco):
+ *   ActorCritic.forward + dist.sample() + log_prob().sum(-1)      sim2real/train.py:132-149, 540-545
+ *   the GAE loop and advantage normalisation                      sim2real/train.py:557-564
+ * The reference runs the network with batch size 1 and a host<->device round trip per environment step; here one
+ * launch serves the whole batch of environments and nothing leaves HBM.
+ */
+#ifndef ODG_POLICY_H
+#define ODG_POLICY_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct OdgPolicy OdgPolicy;
+
+#define ODG_POLICY_H1 512      /* nn.Linear(state_dim, 512)   sim2real/train.py:136,141 */
+#define ODG_POLICY_H2 256      /* nn.Linear(512, 256)         sim2real/train.py:137,142 */
+#define ODG_POLICY_MAX_STATE 64
+#define ODG_POLICY_MAX_ACTION 16
+
+/* Weights of one ActorCritic in the layout of its torch state_dict (float32, device pointers):
+ * actor.{0,2,4}.weight [out][in] row-major, actor.{0,2,4}.bias [out], critic.{0,2,4}.*, action_log_std [A]. */
+typedef struct OdgPolicyWeights {
+  const float* actor_w[3];
+  const float* actor_b[3];
+  const float* critic_w[3];
+  const float* critic_b[3];
+  const float* action_log_std;
+} OdgPolicyWeights;
+
+/* Replaces `ActorCritic(state_dim, action_dim, std).to(device)` (sim2real/train.py:533). state_dim <= 64,
+ * action_dim <= 16; hidden sizes are the reference's 512 / 256. */
+int odg_policy_create(int state_dim, int action_dim, int device, OdgPolicy** out);
+void odg_policy_destroy(OdgPolicy* p);
+
+/* Replaces `agent.load_state_dict(...)` / the optimiser's in-place update: converts the fp32 weights to the
+ * bf16 tensor-core operand layout kept by the handle. Call after every optimiser step. */
+int odg_policy_load(OdgPolicy* p, const OdgPolicyWeights* w, void* stream);
+
+/* Replaces `dist, value = agent(state); action = dist.sample(); logp = dist.log_prob(action).sum(-1)`
+ * (sim2real/train.py:542-543) for n rows at once.
+ *   obs_dev    [n][state_dim] f32
+ *   mean_dev   [n][action_dim] f32   tanh output of the actor (dist.mean; the export path uses it, :613)
+ *   value_dev  [n] f32               critic output
+ *   action_dev [n][action_dim] f32   mean + exp(log_std) * eps, eps ~ N(0,1) from Philox4x32-10 keyed by
+ *                                    (seed, first_row_id + row, step); NULL = no sampling
+ *   logp_dev   [n] f32               sum over action dims of the Normal log-density of the sampled action; NULL ok
+ * bf16 operands, fp32 accumulation (tcgen05.mma, accumulators in TMEM). */
+int odg_policy_forward(OdgPolicy* p, const float* obs_dev, int n, float* mean_dev, float* value_dev,
+                       float* action_dev, float* logp_dev, uint64_t seed, uint32_t step, int first_row_id,
+                       void* stream);
+
+/* Replaces the GAE loop (sim2real/train.py:557-561), batched over n environments and T steps:
+ *   delta = r[t] + gamma * V[t+1] * (1 - done[t]) - V[t];  A[t] = delta + gamma*lambda*(1 - done[t]) * A[t+1]
+ *   reward_dev [T][n], value_dev [T+1][n] (value_dev[T] = bootstrap value), done_dev [T][n] u8
+ *   adv_dev, ret_dev [T][n] (returns = adv + value)
+ *   stats_dev [3] f64: sum(adv), sum(adv^2), count — summed in a fixed order (deterministic); all-reduce these
+ *   across ranks (NCCL) before odg_normalize_advantages when environments are sharded over GPUs. */
+int odg_gae(const float* reward_dev, const float* value_dev, const uint8_t* done_dev, int T, int n, float gamma,
+            float lambda, float* adv_dev, float* ret_dev, double* stats_dev, void* stream);
+
+/* Replaces `(adv - adv.mean()) / (adv.std() + 1e-8)` (sim2real/train.py:564; torch.std is the unbiased one)
+ * using the (possibly all-reduced) statistics. */
+int odg_normalize_advantages(float* adv_dev, long long count, const double* stats_dev, void* stream);
+
+long long odg_policy_launch_count(const OdgPolicy* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODG_POLICY_H */

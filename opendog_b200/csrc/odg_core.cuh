@@ -42,7 +42,7 @@ static inline float odg_fdiv_rn(float a, float b) { volatile float r = a / b; re
 #define ODG_UNROLL
 #else
 #define ODG_DEV __device__ __forceinline__
-#define ODG_NOINLINE __device__ __noinline__
+#define ODG_NOINLINE static __device__ __noinline__
 #define ODG_RESTRICT __restrict__
 #define odg_fmul_rn __fmul_rn
 #define odg_fadd_rn __fadd_rn

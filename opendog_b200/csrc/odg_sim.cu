@@ -29,6 +29,9 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
        if (e_ != cudaSuccess) return fail(ODG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
 
 using odg::DevConst; using odg::SimPtrs; using odg::StepArgs;
+}  // namespace
+namespace odg_internal { int set_error(int code, const std::string& msg) { return fail(code, msg); } }   // for odg_policy.cu
+namespace {
 
 struct SmemLayout { int lc_floats, gc_floats, vert_floats; };
 

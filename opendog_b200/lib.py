@@ -19,6 +19,8 @@ SYMBOLS = [
     "odg_nq", "odg_nv", "odg_reset", "odg_step", "odg_evaluate", "odg_get_state", "odg_set_state",
     "odg_get_env_state", "odg_set_env_state", "odg_launch_count", "odg_last_error", "odg_version",
     # rollout / policy entry points (include/odg_policy.h)
+    "odg_policy_create", "odg_policy_destroy", "odg_policy_load", "odg_policy_forward", "odg_gae",
+    "odg_normalize_advantages", "odg_policy_launch_count",
 ]
 
 
@@ -37,6 +39,11 @@ class OdgInfoPtrs(C.Structure):
         "x_position", "y_position", "distance_from_origin", "paw_contact_forces", "patterns_matches",
         "linear_vel_tracking_reward", "reward_ctrl", "terminal_obs", "paws_in_ground", "gait_reward",
         "qacc", "ncon", "contact_normal_force", "solver_iters", "ls_evals")]
+
+
+class OdgPolicyWeights(C.Structure):
+    _fields_ = [("actor_w", _vp * 3), ("actor_b", _vp * 3), ("critic_w", _vp * 3), ("critic_b", _vp * 3),
+                ("action_log_std", _vp)]
 
 
 class OdgError(RuntimeError):
@@ -72,6 +79,15 @@ def load():
     L.odg_set_state.argtypes = [_vp, _vp, _vp, _vp, _vp]
     L.odg_get_env_state.argtypes = [_vp] * 8
     L.odg_set_env_state.argtypes = [_vp] * 8
+    L.odg_policy_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]
+    L.odg_policy_destroy.argtypes = [_vp]
+    L.odg_policy_destroy.restype = None
+    L.odg_policy_load.argtypes = [_vp, C.POINTER(OdgPolicyWeights), _vp]
+    L.odg_policy_forward.argtypes = [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_int, _vp]
+    L.odg_gae.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_float, C.c_float, _vp, _vp, _vp, _vp]
+    L.odg_normalize_advantages.argtypes = [_vp, C.c_longlong, _vp, _vp]
+    L.odg_policy_launch_count.argtypes = [_vp]
+    L.odg_policy_launch_count.restype = C.c_longlong
     L.odg_last_error.restype = C.c_char_p
     L.odg_version.restype = C.c_char_p
     _lib = L

@@ -1,0 +1,131 @@
+"""The reference's ActorCritic (sim2real/train.py:132-149) with its rollout-time forward on B200 tensor cores.
+
+`ActorCriticB200` keeps the parameters in the reference's own `state_dict` layout (`actor.{0,2,4}.{weight,bias}`,
+`critic.*`, `action_log_std`), so a reference `.pth` loads unchanged and a torch optimiser can update them. The
+batched forward used while collecting rollouts (`act`) is libodgsim's fused tcgen05 kernel (include/odg_policy.h);
+`evaluate` — the differentiable forward the PPO/A2C update needs — stays plain torch autograd, as in the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import lib as _lib
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class ActorCriticB200(nn.Module):
+    def __init__(self, state_dim: int, action_dim: int, action_std_init: float = 0.4, device=None, seed: int = 0):
+        super().__init__()
+        if not torch.cuda.is_available():
+            raise _lib.OdgError("ActorCriticB200 needs a CUDA device: opendog_b200 has no CPU fallback")
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.state_dim, self.action_dim, self.seed = state_dim, action_dim, seed
+        self.actor = nn.Sequential(nn.Linear(state_dim, 512), nn.Tanh(), nn.Linear(512, 256), nn.Tanh(),
+                                   nn.Linear(256, action_dim), nn.Tanh())
+        self.critic = nn.Sequential(nn.Linear(state_dim, 512), nn.Tanh(), nn.Linear(512, 256), nn.Tanh(),
+                                    nn.Linear(256, 1))
+        self.action_log_std = nn.Parameter(torch.ones(1, action_dim) * math.log(action_std_init))
+        self.to(self.dev)
+        self.L = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.L.odg_policy_create(state_dim, action_dim, self.dev.index, C.byref(h)), "odg_policy_create")
+        self._h = h
+        self._step = 0
+        self.sync_weights()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.L.odg_policy_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.odg_policy_launch_count(self._h))
+
+    def sync_weights(self):
+        """Re-pack the fp32 parameters into the kernel's bf16 operand layout (call after every optimiser step
+        or load_state_dict)."""
+        w = _lib.OdgPolicyWeights()
+        keep = []
+        for name, net in (("actor", self.actor), ("critic", self.critic)):
+            for i, li in enumerate((0, 2, 4)):
+                wt = net[li].weight.detach().contiguous().float()
+                bs = net[li].bias.detach().contiguous().float()
+                keep += [wt, bs]
+                getattr(w, name + "_w")[i] = wt.data_ptr()
+                getattr(w, name + "_b")[i] = bs.data_ptr()
+        ls = self.action_log_std.detach().reshape(-1).contiguous().float()
+        keep.append(ls)
+        w.action_log_std = ls.data_ptr()
+        _lib.check(self.L.odg_policy_load(self._h, C.byref(w), self._stream()), "odg_policy_load")
+        torch.cuda.current_stream(self.dev).synchronize()      # `keep` must outlive the packing kernels
+
+    # ------------------------------------------------------------------ rollout-time forward (tensor cores)
+    def act(self, obs: torch.Tensor, sample: bool = True, out=None, first_row_id: int = 0, step: int | None = None):
+        """(action, logp, value, mean) for obs [N, state_dim]; `sample=False` returns the mean as the action
+        (the reference's export path, sim2real/train.py:613). `out` = dict of preallocated tensors (optional)."""
+        o = obs
+        if o.device != self.dev or o.dtype != torch.float32 or not o.is_contiguous():
+            o = o.to(device=self.dev, dtype=torch.float32).contiguous()
+        n = o.shape[0]
+        out = out or {}
+        mean = out.get("mean") if out.get("mean") is not None else torch.empty(n, self.action_dim, device=self.dev)
+        value = out.get("value") if out.get("value") is not None else torch.empty(n, device=self.dev)
+        action = logp = None
+        if sample:
+            action = out.get("action") if out.get("action") is not None else torch.empty(n, self.action_dim, device=self.dev)
+            logp = out.get("logp") if out.get("logp") is not None else torch.empty(n, device=self.dev)
+        if step is None:
+            step = self._step
+            self._step += 1
+        _lib.check(self.L.odg_policy_forward(self._h, _ptr(o), n, _ptr(mean), _ptr(value), _ptr(action), _ptr(logp),
+                                             C.c_uint64(self.seed), C.c_uint32(step & 0xFFFFFFFF), first_row_id,
+                                             self._stream()), "odg_policy_forward")
+        return (action if sample else mean), logp, value, mean
+
+    # ------------------------------------------------------------------ differentiable forward (update phase)
+    def forward(self, state):
+        """Same signature as the reference module: (Normal(mean, std), value)."""
+        mean = self.actor(state)
+        std = torch.exp(self.action_log_std.expand_as(mean))
+        return torch.distributions.Normal(mean, std), self.critic(state)
+
+
+def gae(reward, value, done, gamma=0.99, lam=0.95, normalize=True, group=None):
+    """GAE + advantage normalisation (sim2real/train.py:557-564) for [T, N] rollouts on the GPU.
+
+    reward [T,N] f32, value [T+1,N] f32 (last row = bootstrap), done [T,N] bool/uint8. With `group` (a
+    torch.distributed process group, NCCL) the advantage statistics [sum, sumsq, count] are all-reduced so
+    every rank normalises with the statistics of the whole job. Returns (adv, returns, stats)."""
+    L = _lib.load()
+    T, N = reward.shape
+    dev = reward.device
+    reward = reward.contiguous().float()
+    value = value.contiguous().float()
+    done = done.contiguous().to(torch.uint8)
+    adv = torch.empty(T, N, device=dev)
+    ret = torch.empty(T, N, device=dev)
+    stats = torch.empty(3, dtype=torch.float64, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(L.odg_gae(_ptr(reward), _ptr(value), _ptr(done), T, N, gamma, lam, _ptr(adv), _ptr(ret), _ptr(stats), st),
+               "odg_gae")
+    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized() and group is not False):
+        if torch.distributed.is_initialized():
+            torch.distributed.all_reduce(stats, group=group if group not in (None, True) else None)
+    if normalize:
+        count = int(T * N)
+        _lib.check(L.odg_normalize_advantages(_ptr(adv), count, _ptr(stats), st), "odg_normalize_advantages")
+    return adv, ret, stats

@@ -1,0 +1,101 @@
+"""GPU tests of the rollout kernels (through the C ABI): tcgen05 policy MLP vs a torch reference of the same
+ActorCritic (sim2real/train.py:132-149), sampling / log-prob vs a numpy restatement of the Philox stream, GAE vs
+the reference's Python loop (sim2real/train.py:557-564).
+
+Tolerances: the kernel computes with bf16 operands and fp32 accumulation. Against a torch model that rounds inputs,
+weights and hidden activations to bf16 the outputs agree to 4e-3 (tanh.approx + accumulation order); against the
+plain fp32 torch model to 3e-2 (bf16 quantisation of a 512-wide layer)."""
+import math
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _bf16(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def _ref_forward(m, obs, emulate_bf16):
+    def run(net, x, last_tanh):
+        for li in (0, 2, 4):
+            w, b = net[li].weight.detach(), net[li].bias.detach()
+            if emulate_bf16:
+                x = _bf16(x) @ _bf16(w).T + b
+            else:
+                x = x @ w.T + b
+            if li != 4 or last_tanh:
+                x = torch.tanh(x)
+        return x
+    return run(m.actor, obs, True), run(m.critic, obs, False)[:, 0]
+
+
+@pytest.mark.parametrize("S,A,N", [(33, 8, 300), (22, 4, 128), (48, 12, 1000), (64, 16, 129)])
+def test_policy_mlp_matches_torch(S, A, N):
+    from opendog_b200.policy import ActorCriticB200
+    torch.manual_seed(S * 100 + A)
+    m = ActorCriticB200(S, A, 0.4, seed=7)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 2 and p.shape[0] > 16:
+                p.mul_(2.0)                      # push hidden units into the non-linear range of tanh
+        m.action_log_std.copy_(torch.linspace(-1.5, -0.5, A)[None])
+    m.sync_weights()
+    obs = torch.randn(N, S, device="cuda") * 1.5
+    action, logp, value, mean = m.act(obs, step=3, first_row_id=1000)
+    torch.cuda.synchronize()
+    r_mean, r_val = _ref_forward(m, obs, True)
+    assert (mean - r_mean).abs().max().item() < 4e-3
+    assert (value - r_val).abs().max().item() < 4e-3 * max(1.0, r_val.abs().max().item())
+    f_mean, f_val = _ref_forward(m, obs, False)
+    assert (mean - f_mean).abs().max().item() < 3e-2
+    assert (value - f_val).abs().max().item() < 3e-2 * max(1.0, f_val.abs().max().item())
+    # sampling: action = mean + exp(log_std) * eps with eps from Philox (seed, first_row + row, step, block)
+    from oracle.oracle import philox
+    ls = m.action_log_std.detach().cpu().numpy().reshape(-1)
+    act = action.cpu().numpy(); mu = mean.cpu().numpy(); lp = logp.cpu().numpy()
+    for row in (0, 1, N // 2, N - 1):
+        eps = []
+        for blk in range((A + 3) // 4):
+            r = philox(7, 1000 + row, 3, blk, 0x53414d50)
+            for pr in range(2):
+                u1 = (np.float32(r[2 * pr] >> 8) + np.float32(1.0)) * np.float32(2.0 ** -24)
+                u2 = np.float32(r[2 * pr + 1] >> 8) * np.float32(2.0 ** -24)
+                rad = math.sqrt(-2.0 * math.log(u1))
+                eps += [rad * math.cos(2 * math.pi * u2), rad * math.sin(2 * math.pi * u2)]
+        eps = np.array(eps[:A])
+        assert np.abs(act[row] - (mu[row] + np.exp(ls) * eps)).max() < 1e-4
+        assert abs(lp[row] - np.sum(-0.5 * eps ** 2 - ls - 0.5 * math.log(2 * math.pi))) < 1e-3
+    # the eps of a whole batch look standard normal
+    z = ((action - mean) / torch.exp(m.action_log_std)).flatten()
+    assert abs(z.mean().item()) < 0.15 and abs(z.std().item() - 1.0) < 0.15
+    # deterministic path
+    a2, lp2, v2, mean2 = m.act(obs, sample=False)
+    assert lp2 is None and torch.equal(a2, mean2) and torch.equal(mean2, mean)
+
+
+def test_gae_matches_reference_loop():
+    from opendog_b200.policy import gae
+    T, N = 24, 777
+    g = torch.Generator().manual_seed(0)
+    rew = torch.randn(T, N, generator=g); val = torch.randn(T + 1, N, generator=g)
+    done = torch.rand(T, N, generator=g) < 0.1
+    adv, ret, stats = gae(rew.cuda(), val.cuda(), done.cuda(), 0.99, 0.95, normalize=False, group=False)
+    # sim2real/train.py:557-561 per environment
+    r64, v64, m64 = rew.double().numpy(), val.double().numpy(), (~done).double().numpy()
+    ref = np.zeros((T, N)); a = np.zeros(N)
+    for t in reversed(range(T)):
+        delta = r64[t] + 0.99 * v64[t + 1] * m64[t] - v64[t]
+        a = delta + 0.99 * 0.95 * m64[t] * a
+        ref[t] = a
+    assert np.abs(adv.cpu().numpy() - ref).max() < 1e-4
+    assert np.abs(ret.cpu().numpy() - (ref + v64[:T])).max() < 1e-4
+    s = stats.cpu().numpy()
+    a32 = adv.cpu().double().numpy()
+    assert abs(s[0] - a32.sum()) < 1e-6 * max(1, abs(a32.sum())) + 1e-6 and abs(s[1] - (a32 ** 2).sum()) < 1e-6 * (a32 ** 2).sum()
+    assert s[2] == T * N
+    adv_n, _, _ = gae(rew.cuda(), val.cuda(), done.cuda(), 0.99, 0.95, normalize=True, group=False)
+    ref_n = (torch.from_numpy(ref).float() - torch.from_numpy(ref).float().mean()) / (torch.from_numpy(ref).float().std() + 1e-8)
+    assert (adv_n.cpu() - ref_n).abs().max().item() < 1e-4
