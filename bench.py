@@ -302,13 +302,17 @@ def run_gpu(args):
         build()
         procs = os.cpu_count() or 1
         sample = procs * 16
-        v, dt = cpu_throughput(sample, 60, 12, procs)
+        v, dt = cpu_throughput(sample, 600, 12, procs)
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": procs, "kind": "port",
-                                "sample": f"{sample} oracle envs ({procs} processes x 16 envs) x 60 env-steps after 12 "
+                                "sample": f"{sample} oracle envs ({procs} processes x 16 envs) x 600 env-steps after 12 "
                                           f"warm-up steps (robots landed; {dt:.1f} s); fp64 restatement of mj_step + "
                                           "reward code, not MuJoCo itself"}
     if rank == 0 and args.large_batch and world == 1:
         line["large_batch"] = large_batch_probe(dev, args.large_batch, args.regroup, extra)
+    if args.rollout_envs and (world > 1 or rank == 0):
+        del env
+        line["rollout"] = rollout_probe(dev, args.rollout_envs if world == 1 else args.train_envs, args.horizon, rank, world,
+                                        dist, train=(world > 1 or args.train_probe))
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
@@ -337,6 +341,74 @@ def large_batch_probe(dev, n_envs, regroup=1, extra=None):
             "note": "state (>= 18 MB) cycles through 10 distinct batches; not L2-flushed"}
 
 
+def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False):
+    """BASELINE.json configs[2]/[3]: on-device PPO rollout (policy MLP on tensor cores + fused env step, one CUDA
+    graph per horizon), GAE, and — with `train` — the advantage-statistics all-reduce and one PPO epoch with a flat
+    gradient all-reduce per minibatch. Device-timed, max over ranks."""
+    import torch
+    from opendog_b200.env import BatchedWalkEnv
+    from opendog_b200.policy import ActorCriticB200
+    from opendog_b200.rollout import Rollout
+    from opendog_b200.train import ppo_update
+    torch.manual_seed(0)
+    env = BatchedWalkEnv(n_envs, device=dev, seed=0, first_env_id=rank * n_envs, info_keys=None)
+    pol = ActorCriticB200(env.obs_dim, env.act_dim, 0.4, device=dev, seed=0)
+    ro = Rollout(env, pol, horizon=horizon, use_graph=True, first_row_id=rank * n_envs)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    def sync():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+    for _ in range(3):
+        ro.collect()
+    sync()
+    iters = 3
+    e = [ev() for _ in range(4)]
+    t_roll = t_gae = t_upd = 0.0
+    opt = torch.optim.Adam(pol.parameters(), lr=1e-4)
+    for _ in range(iters):
+        e[0].record(); ro.collect(); e[1].record()
+        adv, ret, stats = ro.advantages(normalize=True)       # all-reduces [sum, sumsq, n] when world > 1
+        e[2].record()
+        if train:
+            T, N = ro.T, n_envs
+            ppo_update(pol, opt, ro.obs[:T].reshape(T * N, -1), ro.action.reshape(T * N, -1), ro.logp.reshape(-1),
+                       adv.reshape(-1), ret.reshape(-1), epochs=1, minibatches=4)
+        e[3].record()
+        torch.cuda.synchronize(dev)
+        t_roll += e[0].elapsed_time(e[1]); t_gae += e[1].elapsed_time(e[2]); t_upd += e[2].elapsed_time(e[3])
+    # the policy forward alone (same launches as inside the rollout)
+    l0 = pol.launch_count
+    e[0].record()
+    for t in range(horizon + 1):
+        pol.act(ro.obs[min(t, horizon)], sample=True, step=t, out=dict(mean=ro.mean, value=ro.value[t], action=ro.action[min(t, horizon - 1)], logp=ro.logp[min(t, horizon - 1)]))
+    e[1].record()
+    torch.cuda.synchronize(dev)
+    t_mlp = e[0].elapsed_time(e[1]) / (pol.launch_count - l0)
+    t = torch.tensor([t_roll, t_gae, t_upd, t_mlp], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_roll, t_gae, t_upd, t_mlp = [float(x) for x in t]
+    S, A = env.obs_dim, env.act_dim
+    flops = 2.0 * (S * 512 + 512 * 256 + 256 * A) + 2.0 * (S * 512 + 512 * 256 + 256)      # actor + critic, per env
+    pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = float(pk.get("bf16_tflops_sustained", 1400.0))
+    ach = flops * n_envs / (t_mlp * 1e-3) / 1e12
+    steps = n_envs * world * horizon * iters
+    out = {"workload": f"{n_envs} envs/GPU x horizon {horizon}, ActorCritic {S}-512-256-{A} (+critic) bf16 tcgen05, CUDA graph",
+           "env_steps_per_s_rollout": steps / (t_roll * 1e-3), "ms_per_rollout": t_roll / iters,
+           "ms_gae_and_stats_allreduce": t_gae / iters, "ms_policy_forward": t_mlp,
+           "policy_share_of_rollout": t_mlp * (horizon + 1) / (t_roll / iters),
+           "policy_roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                               "flops_per_env": flops, "note": "three skinny layers (K = 48/512/256) fused per 128-env CTA; weight streaming from L2 bound"},
+           "kernels_per_rollout": ro.kernels_per_collect}
+    if train:
+        out["ms_ppo_epoch_with_grad_allreduce"] = t_upd / iters
+        out["env_steps_per_s_train_iteration"] = steps / ((t_roll + t_gae + t_upd) * 1e-3)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -346,6 +418,10 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--large-batch", type=int, default=65536, help="also probe this batch size at N=1 (0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rollout-envs", type=int, default=16384, help="N=1: also time the on-device PPO rollout (0 = off)")
+    ap.add_argument("--train-envs", type=int, default=65536, help="N>1: envs per GPU of the train-iteration probe")
+    ap.add_argument("--horizon", type=int, default=24)
+    ap.add_argument("--train-probe", action="store_true", help="N=1: include the PPO epoch in the rollout probe")
     ap.add_argument("--cfg", action="append", default=[], help="OdgEnvConfig override key=value (experiments)")
     ap.add_argument("--regroup", type=int, default=0, help="workload regrouping of envs into warps (OdgEnvConfig.regroup)")
     args = ap.parse_args()

@@ -49,12 +49,14 @@ int odg_policy_load(OdgPolicy* p, const OdgPolicyWeights* w, void* stream);
  *   mean_dev   [n][action_dim] f32   tanh output of the actor (dist.mean; the export path uses it, :613)
  *   value_dev  [n] f32               critic output
  *   action_dev [n][action_dim] f32   mean + exp(log_std) * eps, eps ~ N(0,1) from Philox4x32-10 keyed by
- *                                    (seed, first_row_id + row, step); NULL = no sampling
+ *                                    (seed, first_row_id + row, step + *step_base_dev); NULL = no sampling.
+ *                                    step_base_dev (nullable, u32 in device memory) lets a captured CUDA graph
+ *                                    advance the noise stream between replays
  *   logp_dev   [n] f32               sum over action dims of the Normal log-density of the sampled action; NULL ok
  * bf16 operands, fp32 accumulation (tcgen05.mma, accumulators in TMEM). */
 int odg_policy_forward(OdgPolicy* p, const float* obs_dev, int n, float* mean_dev, float* value_dev,
-                       float* action_dev, float* logp_dev, uint64_t seed, uint32_t step, int first_row_id,
-                       void* stream);
+                       float* action_dev, float* logp_dev, uint64_t seed, uint32_t step,
+                       const uint32_t* step_base_dev, int first_row_id, void* stream);
 
 /* Replaces the GAE loop (sim2real/train.py:557-561), batched over n environments and T steps:
  *   delta = r[t] + gamma * V[t+1] * (1 - done[t]) - V[t];  A[t] = delta + gamma*lambda*(1 - done[t]) * A[t+1]

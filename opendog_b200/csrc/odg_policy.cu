@@ -139,7 +139,7 @@ struct MlpParams {
   const float* bias[2];        // b1[512] | b2[256] | b3[16]
   const float* log_std;
   float* mean; float* value; float* action; float* logp;
-  uint32_t seed_lo, seed_hi, step; int first_row;
+  uint32_t seed_lo, seed_hi, step; const uint32_t* step_base; int first_row;
 };
 
 // hidden-layer epilogue: D[row][0..ncols) (TMEM, fp32) + bias -> tanh -> bf16 -> A operand tile with `kc_out` columns,
@@ -267,12 +267,13 @@ __global__ void __launch_bounds__(kM, 1) k_mlp(const MlpParams P) {
   }
   // ---- Normal(mean, exp(log_std)): sample + log-prob  (sim2real/train.py:542-543)
   if (grow < P.n) {
+    const uint32_t step_ctr = P.step + (P.step_base ? __ldg(P.step_base) : 0u);
     float lp = 0.f;
 #pragma unroll
     for (int blk = 0; blk < kNOut / 4; blk++) {
       if (blk * 4 >= P.A) break;
       uint32_t r[4];
-      odg::philox4x32(P.seed_lo, P.seed_hi, (uint32_t)(P.first_row + grow), P.step, (uint32_t)blk, kStreamSample, r);
+      odg::philox4x32(P.seed_lo, P.seed_hi, (uint32_t)(P.first_row + grow), step_ctr, (uint32_t)blk, kStreamSample, r);
 #pragma unroll
       for (int pr = 0; pr < 2; pr++) {                                  // Box-Muller: 2 uniforms -> 2 normals
         const float u1 = ((float)(r[2 * pr] >> 8) + 1.0f) * 5.9604644775390625e-08f;     // (0, 1]
@@ -449,14 +450,15 @@ int odg_policy_load(OdgPolicy* p, const OdgPolicyWeights* w, void* stream) {
 }
 
 int odg_policy_forward(OdgPolicy* p, const float* obs_dev, int n, float* mean_dev, float* value_dev, float* action_dev,
-                       float* logp_dev, uint64_t seed, uint32_t step, int first_row_id, void* stream) {
+                       float* logp_dev, uint64_t seed, uint32_t step, const uint32_t* step_base_dev,
+                       int first_row_id, void* stream) {
   if (!p || !obs_dev || n < 1) return set_error(ODG_ERR_INVALID, "odg_policy_forward: bad arguments");
   DevGuard guard(p->device);
   MlpParams P;
   P.obs = obs_dev; P.n = n; P.S = p->S; P.A = p->A; P.K0p = p->K0p;
   P.wpack[0] = p->d_wpack[0]; P.wpack[1] = p->d_wpack[1]; P.bias[0] = p->d_bias[0]; P.bias[1] = p->d_bias[1];
   P.log_std = p->d_log_std; P.mean = mean_dev; P.value = value_dev; P.action = action_dev; P.logp = logp_dev;
-  P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32); P.step = step; P.first_row = first_row_id;
+  P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32); P.step = step; P.step_base = step_base_dev; P.first_row = first_row_id;
   k_mlp<<<(n + kM - 1) / kM, kM, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(P);
   p->launches++;
   CUDA_TRY(cudaGetLastError());

@@ -125,16 +125,20 @@ class BatchedWalkEnv:
     def step(self, action: torch.Tensor):
         """(obs, reward, done, info): `done = terminated | truncated`; with auto_reset the returned obs of
         a done env is its reset obs and info["terminal_obs"] holds the last obs of the episode."""
+        self.step_into(action, self.obs, self.reward, self.terminated, self.truncated)
+        done = (self.terminated | self.truncated).bool()
+        return self.obs, self.reward, done, self.info
+
+    def step_into(self, action: torch.Tensor, obs, reward, terminated, truncated):
+        """`step` writing straight into caller-owned CUDA tensors (rollout buffers): no copies, no extra kernels."""
         a = action
         if a.device != self.device or a.dtype != torch.float32 or not a.is_contiguous():
             a = a.to(device=self.device, dtype=torch.float32).contiguous()
         if a.shape != (self.num_envs, self.act_dim):
             raise ValueError(f"action must be [{self.num_envs}, {self.act_dim}]")
         info = C.byref(self._info_struct) if self._info_struct is not None else None
-        _lib.check(self.L.odg_step(self._h, _ptr(a), _ptr(self.obs), _ptr(self.reward), _ptr(self.terminated),
-                                   _ptr(self.truncated), info, self._stream()), "odg_step")
-        done = (self.terminated | self.truncated).bool()
-        return self.obs, self.reward, done, self.info
+        _lib.check(self.L.odg_step(self._h, _ptr(a), _ptr(obs), _ptr(reward), _ptr(terminated), _ptr(truncated), info,
+                                   self._stream()), "odg_step")
 
     def evaluate(self, ctrl: torch.Tensor):
         """Test hook (odg_evaluate): one mj_forward on the current state + the post-step logic."""

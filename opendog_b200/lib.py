@@ -83,7 +83,7 @@ def load():
     L.odg_policy_destroy.argtypes = [_vp]
     L.odg_policy_destroy.restype = None
     L.odg_policy_load.argtypes = [_vp, C.POINTER(OdgPolicyWeights), _vp]
-    L.odg_policy_forward.argtypes = [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_int, _vp]
+    L.odg_policy_forward.argtypes = [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint32, _vp, C.c_int, _vp]
     L.odg_gae.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_float, C.c_float, _vp, _vp, _vp, _vp]
     L.odg_normalize_advantages.argtypes = [_vp, C.c_longlong, _vp, _vp]
     L.odg_policy_launch_count.argtypes = [_vp]

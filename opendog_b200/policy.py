@@ -74,7 +74,8 @@ class ActorCriticB200(nn.Module):
         torch.cuda.current_stream(self.dev).synchronize()      # `keep` must outlive the packing kernels
 
     # ------------------------------------------------------------------ rollout-time forward (tensor cores)
-    def act(self, obs: torch.Tensor, sample: bool = True, out=None, first_row_id: int = 0, step: int | None = None):
+    def act(self, obs: torch.Tensor, sample: bool = True, out=None, first_row_id: int = 0, step: int | None = None,
+            step_base: torch.Tensor | None = None):
         """(action, logp, value, mean) for obs [N, state_dim]; `sample=False` returns the mean as the action
         (the reference's export path, sim2real/train.py:613). `out` = dict of preallocated tensors (optional)."""
         o = obs
@@ -92,7 +93,7 @@ class ActorCriticB200(nn.Module):
             step = self._step
             self._step += 1
         _lib.check(self.L.odg_policy_forward(self._h, _ptr(o), n, _ptr(mean), _ptr(value), _ptr(action), _ptr(logp),
-                                             C.c_uint64(self.seed), C.c_uint32(step & 0xFFFFFFFF), first_row_id,
+                                             C.c_uint64(self.seed), C.c_uint32(step & 0xFFFFFFFF), _ptr(step_base), first_row_id,
                                              self._stream()), "odg_policy_forward")
         return (action if sample else mean), logp, value, mean
 

@@ -1,0 +1,92 @@
+"""Multi-GPU training plumbing around the on-device rollout: how environments shard over ranks and the only two
+collectives of the whole job (BASELINE.json north_star: "NCCL over NVLink is used only to allreduce rollout and
+advantage statistics and policy gradients").
+
+Environments are independent (the reference runs one per OS process: train/train.py:81-86), so rank r owns the
+global env ids [r*N, (r+1)*N) and `step`/`reset` need no communication; RNG streams are keyed by GLOBAL env id, so
+results do not depend on the number of ranks. Collectives:
+  * advantage statistics [sum, sumsq, count] (3 x f64) — the reference normalises over the whole batch
+    (sim2real/train.py:564), so every rank must use the job-wide mean/std;
+  * the flat policy gradient (one buffer, ~0.3 M f32 for 33-512-256-8 actor+critic), averaged over ranks.
+The host logic here is device-agnostic torch (so the world_size-2 `gloo` tests in tests/ exercise it on CPU); the
+product path runs it on CUDA tensors over NCCL.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(rank: int, world: int, envs_per_rank: int):
+    """Global env ids owned by `rank`: [first, first + envs_per_rank)."""
+    first = rank * envs_per_rank
+    return first, first + envs_per_rank
+
+
+def _on(group):
+    return dist.is_available() and dist.is_initialized() and (group is not False)
+
+
+def allreduce_advantage_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place sum of [sum(adv), sum(adv^2), count] over ranks."""
+    if _on(group):
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group if group is not True else None)
+    return stats
+
+
+def stats_mean_std(stats: torch.Tensor):
+    """(mean, unbiased std) from [sum, sumsq, count] — the quantities of `(adv - adv.mean()) / (adv.std() + 1e-8)`."""
+    n = stats[2]
+    mean = stats[0] / n
+    var = torch.clamp((stats[1] - n * mean * mean) / torch.clamp(n - 1, min=1), min=0)
+    return mean, torch.sqrt(var)
+
+
+def allreduce_flat_grads(params, group=None, world: int | None = None):
+    """Average the gradients of `params` over ranks with ONE all-reduce of a flat buffer. Returns the buffer."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return None
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    if _on(group):
+        g = group if group is not True else None
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=g)
+        flat /= (world or dist.get_world_size(g))
+    off = 0
+    for gr in grads:
+        n = gr.numel()
+        gr.copy_(flat[off:off + n].view_as(gr))
+        off += n
+    return flat
+
+
+def ppo_update(policy, optimizer, obs, action, logp_old, adv, ret, clip: float = 0.2, vf_coef: float = 0.5,
+               ent_coef: float = 0.005, max_grad_norm: float = 0.5, epochs: int = 1, minibatches: int = 4, group=None):
+    """Clipped-surrogate update with the hyper-parameters of train/train.py:117-130 (clip .2, ent .005,
+    max_grad_norm .5). obs [B,S], action [B,A], logp_old/adv/ret [B]; minibatches are fixed contiguous slices.
+    Gradients are averaged over ranks (one flat all-reduce per minibatch); afterwards the tensor-core copy of the
+    weights is refreshed. Returns the last minibatch's loss terms."""
+    B = obs.shape[0]
+    mb = (B + minibatches - 1) // minibatches
+    params = [p for p in policy.parameters() if p.requires_grad]
+    out = {}
+    for _ in range(epochs):
+        for i in range(minibatches):
+            sl = slice(i * mb, min(B, (i + 1) * mb))
+            d, v = policy(obs[sl])
+            logp = d.log_prob(action[sl]).sum(-1)
+            ratio = torch.exp(logp - logp_old[sl])
+            a = adv[sl]
+            pg = -torch.min(ratio * a, torch.clamp(ratio, 1 - clip, 1 + clip) * a).mean()
+            vf = torch.nn.functional.mse_loss(v.squeeze(-1), ret[sl])
+            ent = d.entropy().sum(-1).mean()
+            loss = pg + vf_coef * vf - ent_coef * ent
+            optimizer.zero_grad(set_to_none=True)
+            loss.backward()
+            allreduce_flat_grads(params, group=group)
+            torch.nn.utils.clip_grad_norm_(params, max_grad_norm)
+            optimizer.step()
+            out = dict(loss=loss.detach(), pg=pg.detach(), vf=vf.detach(), entropy=ent.detach())
+    if hasattr(policy, "sync_weights"):
+        policy.sync_weights()
+    return out

@@ -38,8 +38,11 @@ def test_libodgsim_exports_every_declared_symbol():
     from opendog_b200 import build, lib
     build.build()
     L = C.CDLL(lib.LIB_PATH)
-    header = open(os.path.join(ROOT, "include", "odg.h")).read()
-    declared = set(re.findall(r"\b(odg_[a-z_]+)\s*\(", header))
+    declared = set()
+    for h in sorted(os.listdir(os.path.join(ROOT, "include"))):          # every include/*.h
+        header = open(os.path.join(ROOT, "include", h)).read()
+        declared |= set(re.findall(r"\b(odg_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
     assert declared == set(lib.SYMBOLS), declared ^ set(lib.SYMBOLS)
     for s in declared:
         assert hasattr(L, s), s
