@@ -1,0 +1,63 @@
+/* odg_sim2real.h — C ABI of the second environment surface of the reference: `QuadrupedEnv`
+ * (/root/reference/Code/mujoco/sim2real/train.py:151-411), the 4-tuple `reset()` / `step(action[4]) ->
+ * (obs[22], reward, done, info)` environment the hand-rolled actor-critic trains on. Batched: one handle steps
+ * `num_envs` environments; state never leaves HBM. It rides on an OdgSim created with frame_skip =
+ * int(0.10 / timestep) = 50, scale_actions = 0, auto_reset = 0 (this layer owns resets).
+ *
+ * Per policy step: k_s2r_pre (symmetric-trot mapping of 4 actions to 8 clipped ctrl targets, :235-285) ->
+ * the fused physics kernel (50 x mj_step) -> k_s2r_post (obs :184-207, the nine reward terms :313-392,
+ * termination :393-402, bookkeeping, optional auto-reset to the settled keyframe state :209-233).
+ * Same conventions as odg.h (caller-owned device pointers, stream as void*, 0 / negative status).
+ */
+#ifndef ODG_SIM2REAL_H
+#define ODG_SIM2REAL_H
+
+#include <stdint.h>
+#include "odg.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct OdgS2R OdgS2R;
+
+enum OdgS2RReason {                 /* info["termination_reason"], sim2real/train.py:393-402 */
+  ODG_S2R_RUNNING = 0,              /* "max_steps" is what the reference reports while not done */
+  ODG_S2R_MJ_ERROR = 1,
+  ODG_S2R_ORIENTATION_LIMIT = 2,
+  ODG_S2R_TOO_MUCH_BACKWARD = 3
+};
+
+typedef struct OdgS2RConfig {
+  double action_amplitude_rad;      /* ACTION_AMPLITUDE_RAD = radians(40)                 :75-76 */
+  int settle_steps;                 /* NUM_SETTLE_STEPS = 100 (multiple of the sim's frame_skip) :91 */
+  int auto_reset;                   /* 1: a done env is reset inside odg_s2r_step (obs = reset obs) */
+  double real_home_deg[8];          /* real_robot_home_deg_map in ACTUATOR_NAMES_ORDERED order  :95-102 */
+  double joint_scale[8];            /* joint_scale_factors (all 1)                               :103 */
+} OdgS2RConfig;
+
+void odg_s2r_default_config(OdgS2RConfig* cfg);
+
+/* Replaces `QuadrupedEnv(xml_path)` (:152-182). Computes the settled reset state once (keyframe + settle_steps
+ * x mj_step with ctrl = home; it is deterministic, so every reset restores the same state). */
+int odg_s2r_create(OdgSim* sim, const OdgModel* model, const OdgS2RConfig* cfg, OdgS2R** out);
+void odg_s2r_destroy(OdgS2R* e);
+
+/* Replaces `env.reset()` (:227-233). mask_dev [N] u8 or NULL = all; obs_dev [N][22] f32 or NULL. */
+int odg_s2r_reset(OdgS2R* e, const uint8_t* mask_dev, float* obs_dev, void* stream);
+
+/* Replaces `env.step(action)` (:287-411). action_dev [N][4] f32 in [-1,1]; obs_dev [N][22]; reward_dev [N];
+ * done_dev [N] u8; reason_dev [N] u8 (OdgS2RReason, nullable); sim_target_rad_dev [N][8] f32 in ctrl order
+ * (info["sim_target_rad"], nullable); terminal_obs_dev [N][22] (obs before auto-reset, nullable). */
+int odg_s2r_step(OdgS2R* e, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                 uint8_t* reason_dev, float* sim_target_rad_dev, float* terminal_obs_dev, void* stream);
+
+/* Test hook: overwrite the per-episode bookkeeping (step counter, previous x, cumulative +/- displacement,
+ * previous net displacement, last commanded targets [N][8]); NULL pointers are skipped. */
+int odg_s2r_set_bookkeeping(OdgS2R* e, const int32_t* counter, const double* prev_x, const double* cum_pos,
+                            const double* cum_neg, const double* prev_net, const float* last_cmd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODG_SIM2REAL_H */

@@ -18,7 +18,7 @@
 #include <new>
 #include <string>
 
-#include "odg_prep.h"
+#include "odg_sim_internal.h"
 
 namespace {
 
@@ -33,7 +33,6 @@ using odg::DevConst; using odg::SimPtrs; using odg::StepArgs;
 namespace odg_internal { int set_error(int code, const std::string& msg) { return fail(code, msg); } }   // for odg_policy.cu
 namespace {
 
-struct SmemLayout { int lc_floats, gc_floats, vert_floats; };
 
 __device__ __forceinline__ void stage_constants(float* smem, const float* __restrict__ g_lc, const float* __restrict__ g_gc,
                                                 const float* __restrict__ g_vert, SmemLayout L,
@@ -139,18 +138,6 @@ __global__ void k_copy(T* dst, const T* src, long long n) {
 
 }  // namespace
 
-struct OdgSim {
-  int device = 0, N = 0, num_sms = 0;
-  odg::Prepared prep;
-  SimPtrs P{};
-  float* d_lc = nullptr; float* d_gc = nullptr; float* d_vert = nullptr;
-  void* d_state = nullptr;           // one allocation behind all SoA arrays
-  SmemLayout L{};
-  size_t smem_step = 0;
-  int step_block = 128, step_grid = 1, step_lanes = 32;
-  int* d_order = nullptr; int* d_hist = nullptr; int regroup = 0;
-  long long launches = 0;
-};
 
 namespace {
 

@@ -21,6 +21,9 @@ SYMBOLS = [
     # rollout / policy entry points (include/odg_policy.h)
     "odg_policy_create", "odg_policy_destroy", "odg_policy_load", "odg_policy_forward", "odg_gae",
     "odg_normalize_advantages", "odg_policy_launch_count",
+    # QuadrupedEnv surface (include/odg_sim2real.h)
+    "odg_s2r_default_config", "odg_s2r_create", "odg_s2r_destroy", "odg_s2r_reset", "odg_s2r_step",
+    "odg_s2r_set_bookkeeping",
 ]
 
 
@@ -44,6 +47,11 @@ class OdgInfoPtrs(C.Structure):
 class OdgPolicyWeights(C.Structure):
     _fields_ = [("actor_w", _vp * 3), ("actor_b", _vp * 3), ("critic_w", _vp * 3), ("critic_b", _vp * 3),
                 ("action_log_std", _vp)]
+
+
+class OdgS2RConfig(C.Structure):
+    _fields_ = [("action_amplitude_rad", C.c_double), ("settle_steps", C.c_int), ("auto_reset", C.c_int),
+                ("real_home_deg", C.c_double * 8), ("joint_scale", C.c_double * 8)]
 
 
 class OdgError(RuntimeError):
@@ -88,6 +96,14 @@ def load():
     L.odg_normalize_advantages.argtypes = [_vp, C.c_longlong, _vp, _vp]
     L.odg_policy_launch_count.argtypes = [_vp]
     L.odg_policy_launch_count.restype = C.c_longlong
+    L.odg_s2r_default_config.argtypes = [C.POINTER(OdgS2RConfig)]
+    L.odg_s2r_default_config.restype = None
+    L.odg_s2r_create.argtypes = [_vp, C.POINTER(OdgModel), C.POINTER(OdgS2RConfig), C.POINTER(_vp)]
+    L.odg_s2r_destroy.argtypes = [_vp]
+    L.odg_s2r_destroy.restype = None
+    L.odg_s2r_reset.argtypes = [_vp, _vp, _vp, _vp]
+    L.odg_s2r_step.argtypes = [_vp] * 9
+    L.odg_s2r_set_bookkeeping.argtypes = [_vp] * 8
     L.odg_last_error.restype = C.c_char_p
     L.odg_version.restype = C.c_char_p
     _lib = L
