@@ -80,7 +80,8 @@ typedef struct OdgInfoPtrs {
   int32_t* ncon;                 /* [N] number of contacts */
   float* contact_normal_force;   /* [N] sum of contact normal forces */
   int32_t* solver_iters;         /* [N] Newton iterations used in the last substep */
-  int32_t* ls_evals;             /* [N] line-search evaluations used in the last substep */
+  int32_t* ls_evals;             /* [N] line-search passes used in the last substep */
+  float* reward_unclipped;       /* [N] rewards - costs BEFORE the max(0, .) clip of WalkEnvironment.py:84 (MPPI cost) */
 } OdgInfoPtrs;
 
 void odg_default_config(OdgEnvConfig* cfg);

@@ -125,6 +125,7 @@ struct StepArgs {
   float* x_position; float* y_position; float* distance; float* paw_forces; float* patterns_matches;
   float* lin_vel_reward; float* reward_ctrl; float* terminal_obs; unsigned char* paws_in_ground;
   int* gait_reward; float* qacc; int* ncon; float* fn_sum; int* solver_iters; int* ls_evals;
+  float* reward_raw;        // rewards - costs before the max(0, .) of WalkEnvironment.py:84
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1177,6 +1178,7 @@ ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const f
       if (A.fn_sum) A.fn_sum[env] = fn;
       if (A.solver_iters) A.solver_iters[env] = lp.iters;
       if (A.ls_evals) A.ls_evals[env] = lp.ls_evals;
+      if (A.reward_raw) A.reward_raw[env] = (float)rr;
       if (A.qacc) {
         float* o = A.qacc + (size_t)env * C.nv;
         o[0] = lp.a_b.t.x; o[1] = lp.a_b.t.y; o[2] = lp.a_b.t.z;

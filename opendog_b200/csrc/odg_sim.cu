@@ -202,6 +202,7 @@ void fill_args(StepArgs* A, const float* action, float* obs, float* reward, uint
     A->lin_vel_reward = info->linear_vel_tracking_reward; A->reward_ctrl = info->reward_ctrl;
     A->terminal_obs = info->terminal_obs; A->paws_in_ground = info->paws_in_ground; A->gait_reward = info->gait_reward;
     A->qacc = info->qacc; A->ncon = info->ncon; A->fn_sum = info->contact_normal_force; A->solver_iters = info->solver_iters; A->ls_evals = info->ls_evals;
+    A->reward_raw = info->reward_unclipped;
   }
 }
 

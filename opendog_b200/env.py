@@ -32,6 +32,7 @@ _INFO_SPECS = {
     "contact_normal_force": (torch.float32, lambda e: ()),
     "solver_iters": (torch.int32, lambda e: ()),
     "ls_evals": (torch.int32, lambda e: ()),
+    "reward_unclipped": (torch.float32, lambda e: ()),
 }
 DEFAULT_INFO = ("x_position", "y_position", "distance_from_origin", "paw_contact_forces", "patterns_matches",
                 "linear_vel_tracking_reward", "reward_ctrl", "terminal_obs")

@@ -24,6 +24,8 @@ SYMBOLS = [
     # QuadrupedEnv surface (include/odg_sim2real.h)
     "odg_s2r_default_config", "odg_s2r_create", "odg_s2r_destroy", "odg_s2r_reset", "odg_s2r_step",
     "odg_s2r_set_bookkeeping",
+    # MPPI (include/odg_mppi.h)
+    "odg_mppi_sample", "odg_mppi_accumulate", "odg_mppi_reduce",
 ]
 
 
@@ -41,7 +43,7 @@ class OdgInfoPtrs(C.Structure):
     _fields_ = [(n, _vp) for n in (
         "x_position", "y_position", "distance_from_origin", "paw_contact_forces", "patterns_matches",
         "linear_vel_tracking_reward", "reward_ctrl", "terminal_obs", "paws_in_ground", "gait_reward",
-        "qacc", "ncon", "contact_normal_force", "solver_iters", "ls_evals")]
+        "qacc", "ncon", "contact_normal_force", "solver_iters", "ls_evals", "reward_unclipped")]
 
 
 class OdgPolicyWeights(C.Structure):
@@ -104,6 +106,9 @@ def load():
     L.odg_s2r_reset.argtypes = [_vp, _vp, _vp, _vp]
     L.odg_s2r_step.argtypes = [_vp] * 9
     L.odg_s2r_set_bookkeeping.argtypes = [_vp] * 8
+    L.odg_mppi_sample.argtypes = [_vp, C.c_float, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, _vp, _vp]
+    L.odg_mppi_accumulate.argtypes = [_vp, _vp, C.c_int, C.c_float, _vp, _vp, _vp]
+    L.odg_mppi_reduce.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp, _vp]
     L.odg_last_error.restype = C.c_char_p
     L.odg_version.restype = C.c_char_p
     _lib = L

@@ -36,7 +36,7 @@ class StepArgs(C.Structure):
                 ("x_position", _p), ("y_position", _p), ("distance", _p), ("paw_forces", _p),
                 ("patterns_matches", _p), ("lin_vel_reward", _p), ("reward_ctrl", _p), ("terminal_obs", _p),
                 ("paws_in_ground", _p), ("gait_reward", _p), ("qacc", _p), ("ncon", _p), ("fn_sum", _p),
-                ("solver_iters", _p), ("ls_evals", _p)]
+                ("solver_iters", _p), ("ls_evals", _p), ("reward_raw", _p)]
 
 
 _lib = None
@@ -71,7 +71,7 @@ class EmuEnv:
     INFO = dict(x_position=("f", 1), y_position=("f", 1), distance=("f", 1), paw_forces=("f", 24),
                 patterns_matches=("f", 1), lin_vel_reward=("f", 1), reward_ctrl=("f", 1),
                 terminal_obs=("f", 33), paws_in_ground=("B", 4), gait_reward=("i", 1), qacc=("f", 14),
-                ncon=("i", 1), fn_sum=("f", 1), solver_iters=("i", 1), ls_evals=("i", 1))
+                ncon=("i", 1), fn_sum=("f", 1), solver_iters=("i", 1), ls_evals=("i", 1), reward_raw=("f", 1))
 
     def __init__(self, num_envs, model="our_robot", seed=0, **cfg):
         self.desc = load_compiled(model)
