@@ -219,12 +219,12 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     # settle: let the robots land (reset drops them 0.13 m) so the timed steps are stance/impact physics
     for i in range(W):
         env.step(actions[i])
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     launches0 = env.launch_count
@@ -309,6 +309,12 @@ def run_gpu(args):
                                           "reward code, not MuJoCo itself"}
     if rank == 0 and args.large_batch and world == 1:
         line["large_batch"] = large_batch_probe(dev, args.large_batch, args.regroup, extra)
+    tr = profile_traffic(N)
+    if tr:
+        line["roofline"]["traffic"] = tr[0]
+        line["roofline"]["traffic_source"] = f"profiles/{tr[1]} (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+    if rank == 0 and world == 1 and args.mppi:
+        line["mppi"] = mppi_probe(dev)
     if args.rollout_envs and (world > 1 or rank == 0):
         del env
         line["rollout"] = rollout_probe(dev, args.rollout_envs if world == 1 else args.train_envs, args.horizon, rank, world,
@@ -339,6 +345,44 @@ def large_batch_probe(dev, n_envs, regroup=1, extra=None):
     ms = s.elapsed_time(e) / 10
     return {"envs": n_envs, "ms_per_step": ms, "env_steps_per_s": n_envs / (ms * 1e-3),
             "note": "state (>= 18 MB) cycles through 10 distinct batches; not L2-flushed"}
+
+
+def profile_traffic(n_envs):
+    """DRAM bytes per k_step launch from the newest committed ncu summary for this batch size (profiles/*.json)."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_k_step_{n_envs}.json"))):
+        try:
+            d = json.load(open(f))
+            t = d["kernels"][0].get("dram_traffic_bytes")
+            if t:
+                best = (float(t), os.path.basename(f))
+        except Exception:
+            pass
+    return best
+
+
+def mppi_probe(dev, samples=1024, horizon=64):
+    """BASELINE.json configs[4]: MPPI, 1024 samples x horizon 64 from a shared state, cost reduction on device."""
+    import torch
+    from opendog_b200.mppi import MPPI
+    m = MPPI(samples, horizon, sigma=0.3, lam=1.0, seed=0, device=dev, use_graph=True)
+    q = torch.tensor(m.env.desc["key_qpos"], dtype=torch.float32); q[2] = 0.075
+    m.set_start(q, torch.zeros(m.env.nv))
+    for _ in range(3):
+        m.plan()
+    torch.cuda.synchronize(dev)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 5
+    s.record()
+    for _ in range(iters):
+        m.plan()
+    e.record()
+    torch.cuda.synchronize(dev)
+    ms = s.elapsed_time(e) / iters
+    return {"workload": f"{samples} samples x horizon {horizon}, shared start state, sigma 0.3, CUDA graph replay",
+            "ms_per_plan": ms, "env_steps_per_s": samples * horizon / (ms * 1e-3), "plans_per_s": 1e3 / ms,
+            "kernels_per_plan": m.kernels_per_plan, "min_cost": float(m.stats[0]), "mean_cost": float(m.stats[1])}
 
 
 def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False):
@@ -421,6 +465,7 @@ def main():
     ap.add_argument("--rollout-envs", type=int, default=16384, help="N=1: also time the on-device PPO rollout (0 = off)")
     ap.add_argument("--train-envs", type=int, default=65536, help="N>1: envs per GPU of the train-iteration probe")
     ap.add_argument("--horizon", type=int, default=24)
+    ap.add_argument("--mppi", type=int, default=1, help="N=1: also time one MPPI plan (1024 x 64); 0 = off")
     ap.add_argument("--train-probe", action="store_true", help="N=1: include the PPO epoch in the rollout probe")
     ap.add_argument("--cfg", action="append", default=[], help="OdgEnvConfig override key=value (experiments)")
     ap.add_argument("--regroup", type=int, default=0, help="workload regrouping of envs into warps (OdgEnvConfig.regroup)")

@@ -30,7 +30,8 @@ def main():
     so = os.environ.get("ODG_LIB_PATH", os.path.join(ROOT, "opendog_b200", "libodgsim.so"))
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+    cubins = [f for f in os.listdir(tmp) if f.endswith(".cubin")]
+    cubin = next((f for f in cubins if "odg_sim." in f), cubins[0])
     dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
     src_path = os.environ.get("ODG_CORE_SRC", os.path.join(ROOT, "opendog_b200", "csrc", "odg_core.cuh"))
     src = open(src_path).read().splitlines()
