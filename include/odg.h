@@ -131,6 +131,10 @@ int odg_set_env_state(OdgSim* sim, const int32_t* step, const int32_t* gait_inde
                       const int32_t* gait_matches, const float* last_action,
                       const float* desired_velocity, const uint8_t* fresh, void* stream);
 
+/* Change the number of mj_step calls per odg_step (open-loop playback holds each target for duration / timestep
+ * substeps: sim2real/run.py:286-330). */
+int odg_set_frame_skip(OdgSim* sim, int frame_skip);
+
 /* Number of kernels this library has launched on behalf of `sim` (bench.py's gpu_launches). */
 long long odg_launch_count(const OdgSim* sim);
 

@@ -290,6 +290,11 @@ int odg_act_dim(const OdgSim* s) { return s ? s->prep.C.nu : 0; }
 int odg_nq(const OdgSim* s) { return s ? s->prep.C.nq : 0; }
 int odg_nv(const OdgSim* s) { return s ? s->prep.C.nv : 0; }
 long long odg_launch_count(const OdgSim* s) { return s ? s->launches : 0; }
+int odg_set_frame_skip(OdgSim* s, int frame_skip) {
+  if (!s || frame_skip < 1) return fail(ODG_ERR_INVALID, "odg_set_frame_skip: bad arguments");
+  s->prep.C.frame_skip = frame_skip;
+  return ODG_OK;
+}
 
 int odg_reset(OdgSim* s, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   if (!s) return fail(ODG_ERR_INVALID, "odg_reset: null handle");

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("ODG_LIB_PATH") or os.path.join(PKG, "libodgsim.so")  
 SYMBOLS = [
     "odg_default_config", "odg_create", "odg_destroy", "odg_num_envs", "odg_obs_dim", "odg_act_dim",
     "odg_nq", "odg_nv", "odg_reset", "odg_step", "odg_evaluate", "odg_get_state", "odg_set_state",
-    "odg_get_env_state", "odg_set_env_state", "odg_launch_count", "odg_last_error", "odg_version",
+    "odg_get_env_state", "odg_set_env_state", "odg_launch_count", "odg_last_error", "odg_version", "odg_set_frame_skip",
     # rollout / policy entry points (include/odg_policy.h)
     "odg_policy_create", "odg_policy_destroy", "odg_policy_load", "odg_policy_forward", "odg_gae",
     "odg_normalize_advantages", "odg_policy_launch_count",
@@ -81,6 +81,7 @@ def load():
     for n in ("odg_num_envs", "odg_obs_dim", "odg_act_dim", "odg_nq", "odg_nv"):
         getattr(L, n).argtypes = [_vp]
     L.odg_launch_count.argtypes = [_vp]
+    L.odg_set_frame_skip.argtypes = [_vp, C.c_int]
     L.odg_launch_count.restype = C.c_longlong
     L.odg_reset.argtypes = [_vp, _vp, _vp, _vp]
     L.odg_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(OdgInfoPtrs), _vp]
