@@ -52,8 +52,11 @@ __device__ __forceinline__ void stage_constants(float* smem, const float* __rest
 #ifndef ODG_MIN_BLOCKS
 #define ODG_MIN_BLOCKS 1
 #endif
+#ifndef ODG_MAX_BLOCK
+#define ODG_MAX_BLOCK 128
+#endif
 template <int NJL, bool PL1>
-__global__ void __launch_bounds__(128, ODG_MIN_BLOCKS) k_step(const __grid_constant__ DevConst C, const SimPtrs P, const StepArgs A,
+__global__ void __launch_bounds__(ODG_MAX_BLOCK, ODG_MIN_BLOCKS) k_step(const __grid_constant__ DevConst C, const SimPtrs P, const StepArgs A,
                                               const float* __restrict__ g_lc, const float* __restrict__ g_gc,
                                               const float* __restrict__ g_vert, SmemLayout L, int lanes) {
   extern __shared__ __align__(16) float smem[];
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(128) k_reset(const __grid_constant__ DevConst 
   const unsigned gm = 0xFu << (threadIdx.x & 28);
   const int env = blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2);
   if (env >= P.N) return;
-  if (mask && !mask[env]) return;
+  if (mask && env < P.n && !mask[env]) return;
   odg::env_reset<NJL>(C, smem, P, obs, env, leg, gm);
 }
 
@@ -95,11 +98,11 @@ __global__ void k_init(const __grid_constant__ DevConst C, const SimPtrs P) {
 }
 
 // dst[env][k] = src[k][env] (to_soa = false) or the reverse
-__global__ void k_transpose(float* aos, float* soa, int N, int dim, bool to_soa) {
+__global__ void k_transpose(float* aos, float* soa, int n, int stride, int dim, bool to_soa) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)N * dim) return;
+  if (i >= (long long)n * dim) return;
   const int env = (int)(i / dim), k = (int)(i % dim);
-  if (to_soa) soa[(size_t)k * N + env] = aos[i]; else aos[i] = soa[(size_t)k * N + env];
+  if (to_soa) soa[(size_t)k * stride + env] = aos[i]; else aos[i] = soa[(size_t)k * stride + env];
 }
 __global__ void k_fill(float* p, long long n, float v) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -125,9 +128,10 @@ __global__ void k_work_scan(int* hist) {          // one block of kWorkBins thre
   }
   hist[t] = s[t] - hist[t];
 }
-__global__ void k_work_scatter(const int* __restrict__ work, int N, int* offs, int* order) {
+__global__ void k_work_scatter(const int* __restrict__ work, int N, int Npad, int* offs, int* order) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N) order[atomicAdd(&offs[min(max(work[i], 0) >> 1, kWorkBins - 1)], 1)] = i;
+  else if (i < Npad) order[i] = i;            // padding environments keep their own slots
 }
 
 template <typename T>
@@ -149,22 +153,20 @@ StepKernel step_kernel_fn(const DevConst& C) {
 const void* step_kernel(const DevConst& C) { return (const void*)step_kernel_fn(C); }
 
 int choose_launch(OdgSim* s) {
-  // 4 lanes per env. Small batches are latency bound: one warp per block spreads them over all SMs and
-  // SM sub-partitions. Large batches run persistent 128-thread blocks (constants staged once per block).
+  // 4 lanes per env, persistent blocks (constants staged once per block).
   int dev_occ = 0;
   const void* kern = step_kernel(s->prep.C);
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_step));
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev_occ, kern, 128, s->smem_step));
   if (dev_occ < 1) dev_occ = 1;
-  const long long resident_warps = (long long)s->num_sms * dev_occ * 4;      // warps the GPU holds at once
-  // fewest environments per warp that still fit in one resident wave
+  // Measured on B200 (tools/gpu_quick4.sh): 64-thread blocks (2 warps walking the Newton loop in lockstep, 4 blocks per
+  // SM) with 8 environments per warp are fastest at 4096 and at 65536 environments; fewer environments per warp or
+  // one-warp blocks lose more to instruction fetch than they gain in divergence.
   int lanes = 32;
-  while (lanes > 8 && ((long long)s->N * 4 + lanes / 2 - 1) / (lanes / 2) <= resident_warps) lanes >>= 1;
-  int block = 128;
+  int block = 64;
   if (const char* env = std::getenv("ODG_STEP_LANES")) { int v = std::atoi(env); if (v == 8 || v == 16 || v == 32) lanes = v; }
-  const long long warps = ((long long)s->N * 4 + lanes - 1) / lanes;
-  if (warps <= resident_warps) block = 32;                                  // spread over all SMs / sub-partitions
-  if (const char* env = std::getenv("ODG_STEP_BLOCK")) { int v = std::atoi(env); if (v == 32 || v == 64 || v == 128) block = v; }
+  const long long warps = ((long long)s->P.N * 4 + lanes - 1) / lanes;
+  if (const char* env = std::getenv("ODG_STEP_BLOCK")) { int v = std::atoi(env); if (v == 32 || v == 64 || v == 128 || (v == 256 && ODG_MAX_BLOCK >= 256)) block = v; }
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev_occ, kern, block, s->smem_step));
   if (dev_occ < 1) dev_occ = 1;
   const long long wpb = block / 32, need = (warps + wpb - 1) / wpb, cap = (long long)s->num_sms * dev_occ;
@@ -179,7 +181,7 @@ int launch_step(OdgSim* s, const StepArgs& A, cudaStream_t st) {
     CUDA_TRY(cudaMemsetAsync(s->d_hist, 0, kWorkBins * sizeof(int), st));
     k_work_hist<<<g, 256, 0, st>>>(s->P.work, N, s->d_hist);
     k_work_scan<<<1, kWorkBins, 0, st>>>(s->d_hist);
-    k_work_scatter<<<g, 256, 0, st>>>(s->P.work, N, s->d_hist, s->d_order);
+    k_work_scatter<<<(s->P.N + 255) / 256, 256, 0, st>>>(s->P.work, N, s->P.N, s->d_hist, s->d_order);
     s->launches += 3;
     s->P.order = s->d_order;
   } else {
@@ -239,13 +241,13 @@ int odg_create(const OdgModel* model, const OdgEnvConfig* cfg_in, int num_envs, 
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   s->num_sms = prop.multiProcessorCount;
   const DevConst& C = s->prep.C;
-  const size_t N = (size_t)num_envs;
+  const size_t N = ((size_t)num_envs + 63) / 64 * 64;      // stride: whole blocks of up to 64 environments
   // one slab: qpos, qvel, warm, last_action, desvel (float) | step, gait_idx, gait_cnt, episode (i32) | fresh (u8)
   const size_t nfloat = (size_t)(C.nq + 2 * C.nv + C.nu + 3) * N, nint = 6 * N + kWorkBins;
   const size_t bytes = nfloat * 4 + nint * 4 + N;
   if (cudaMalloc(&s->d_state, bytes) != cudaSuccess) { delete s; return fail(ODG_ERR_ALLOC, "cudaMalloc(state) failed"); }
   float* f = static_cast<float*>(s->d_state);
-  s->P.N = num_envs;
+  s->P.N = (int)N; s->P.n = num_envs;
   s->P.qpos = f; f += (size_t)C.nq * N;
   s->P.qvel = f; f += (size_t)C.nv * N;
   s->P.warm = f; f += (size_t)C.nv * N;
@@ -269,7 +271,7 @@ int odg_create(const OdgModel* model, const OdgEnvConfig* cfg_in, int num_envs, 
   CUDA_TRY(cudaMemset(s->P.work, 0, N * sizeof(int)));
   int rc = choose_launch(s);
   if (rc != ODG_OK) { odg_destroy(s); return rc; }
-  k_init<<<(num_envs + 127) / 128, 128>>>(C, s->P);
+  k_init<<<(unsigned)((N + 127) / 128), 128>>>(C, s->P);
   s->launches++;
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { odg_destroy(s); return fail(ODG_ERR_CUDA, std::string("k_init: ") + cudaGetErrorString(e)); }
@@ -300,7 +302,7 @@ int odg_reset(OdgSim* s, const uint8_t* mask_dev, float* obs_dev, void* stream) 
   if (!s) return fail(ODG_ERR_INVALID, "odg_reset: null handle");
   DeviceGuard guard(s->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int block = 128, grid = (s->N * 4 + block - 1) / block;
+  const int block = 128, grid = (s->P.N * 4 + block - 1) / block;
   const size_t smem = (size_t)s->prep.C.njl * odg::LC_COUNT * 4 * sizeof(float);
   if (s->prep.C.njl == 2) k_reset<2><<<grid, block, smem, st>>>(s->prep.C, s->P, mask_dev, obs_dev, s->d_lc);
   else k_reset<3><<<grid, block, smem, st>>>(s->prep.C, s->P, mask_dev, obs_dev, s->d_lc);
@@ -329,7 +331,7 @@ int odg_evaluate(OdgSim* s, const float* ctrl_dev, float* obs_dev, float* reward
 
 static int transpose(OdgSim* s, float* aos, float* soa, int dim, bool to_soa, cudaStream_t st) {
   const long long n = (long long)s->N * dim;
-  k_transpose<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(aos, soa, s->N, dim, to_soa);
+  k_transpose<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(aos, soa, s->N, s->P.N, dim, to_soa);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return ODG_OK;
@@ -354,7 +356,7 @@ int odg_set_state(OdgSim* s, const float* qpos_dev, const float* qvel_dev, const
   if (rc == ODG_OK && qvel_dev) rc = transpose(s, const_cast<float*>(qvel_dev), s->P.qvel, s->prep.C.nv, true, st);
   if (rc != ODG_OK) return rc;
   if (warm_dev) return transpose(s, const_cast<float*>(warm_dev), s->P.warm, s->prep.C.nv, true, st);
-  const long long n = (long long)s->N * s->prep.C.nv;
+  const long long n = (long long)s->P.N * s->prep.C.nv;
   k_fill<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->P.warm, n, 0.f);
   s->launches++;
   CUDA_TRY(cudaGetLastError());

@@ -19,7 +19,7 @@ using odg_internal::set_error;
 constexpr int kObs = 22;
 
 struct S2RConst {
-  int N, nq, nv, auto_reset;
+  int N, stride, nq, nv, auto_reset;   // N environments, SoA stride of the simulator's state arrays
   int act_id[8];            // ctrl index of ACTUATOR_NAMES_ORDERED[o]  (FR, FL, BR, BL) x (tigh, knee)
   int qidx[8], vidx[8];     // qpos / qvel index of that actuator's joint
   double home[8];           // sim_keyframe_home_qpos_map
@@ -48,7 +48,7 @@ __device__ void quat_to_ypr(double q0, double q1, double q2, double q3, double& 
 
 // _get_observation (:184-207)
 __device__ void write_obs(const S2RConst& C, const float* qpos, const float* qvel, int env, int counter, float* o) {
-  const int N = C.N;
+  const int N = C.stride;
   double yaw, pitch, roll;
   quat_to_ypr(qpos[3 * N + env], qpos[4 * N + env], qpos[5 * N + env], qpos[6 * N + env], yaw, pitch, roll);
   o[0] = (float)yaw; o[1] = (float)pitch; o[2] = (float)roll;
@@ -80,7 +80,7 @@ __global__ void k_s2r_pre(const S2RConst C, const S2RState S, const float* __res
 }
 
 __device__ void restore_settled(const S2RConst& C, const S2RState& S, const odg::SimPtrs& P, int env) {
-  const int N = C.N;
+  const int N = C.stride;
   for (int i = 0; i < C.nq; i++) P.qpos[i * N + env] = S.settled[i];
   for (int i = 0; i < C.nv; i++) { P.qvel[i * N + env] = S.settled[C.nq + i]; P.warm[i * N + env] = S.settled[C.nq + C.nv + i]; }
   S.counter[env] = 0; S.prev_x[env] = (double)S.settled[0];
@@ -92,8 +92,8 @@ __global__ void k_s2r_post(const S2RConst C, const S2RState S, const odg::SimPtr
                            float* __restrict__ reward, unsigned char* __restrict__ done_out, unsigned char* __restrict__ reason_out,
                            float* __restrict__ sim_target, float* __restrict__ terminal_obs, const float* __restrict__ home_ctrl) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
-  const int N = C.N;
-  if (env >= N) return;
+  const int N = C.stride;
+  if (env >= C.N) return;
   const int phase_action = S.counter[env] % 2;
   const int counter = S.counter[env] + 1;
   bool finite = true;
@@ -216,7 +216,7 @@ int odg_s2r_create(OdgSim* sim, const OdgModel* m, const OdgS2RConfig* cfg_in, O
   if (!e) return set_error(ODG_ERR_ALLOC, "out of host memory");
   e->sim = sim;
   S2RConst& C = e->C;
-  C.N = sim->N; C.nq = DC.nq; C.nv = DC.nv; C.auto_reset = cfg.auto_reset; C.amp = cfg.action_amplitude_rad;
+  C.N = sim->N; C.stride = sim->P.N; C.nq = DC.nq; C.nv = DC.nv; C.auto_reset = cfg.auto_reset; C.amp = cfg.action_amplitude_rad;
   // ACTUATOR_NAMES_ORDERED = FR FL BR BL; model legs are in body order FL FR BL BR
   const int leg_of[4] = { 1, 0, 3, 2 };
   for (int o = 0; o < 8; o++) {

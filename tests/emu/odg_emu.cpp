@@ -64,7 +64,7 @@ Emu* emu_create(const OdgModel* m, const OdgEnvConfig* cfg, int N, uint64_t seed
   e->qpos.assign((size_t)C.nq * N, 0.f); e->qvel.assign((size_t)C.nv * N, 0.f); e->warm.assign((size_t)C.nv * N, 0.f);
   e->last_action.assign((size_t)C.nu * N, 0.f); e->desvel.assign((size_t)3 * N, 0.f);
   e->step.assign(N, 0); e->gidx.assign(N, 0); e->gcnt.assign(N, 0); e->episode.assign(N, 0); e->fresh.assign(N, 1);
-  e->P = odg::SimPtrs{ N, e->qpos.data(), e->qvel.data(), e->warm.data(), e->last_action.data(), e->desvel.data(),
+  e->P = odg::SimPtrs{ N, N, e->qpos.data(), e->qvel.data(), e->warm.data(), e->last_action.data(), e->desvel.data(),
                        e->step.data(), e->gidx.data(), e->gcnt.data(), e->episode.data(), e->fresh.data(), nullptr, nullptr };
   for (int i = 0; i < N; i++) odg::env_init(C, e->P, i);
   return e;
