@@ -40,6 +40,7 @@ static inline float odg_fadd_rn(float a, float b) { volatile float r = a + b; re
 static inline float odg_fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float odg_fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 #define ODG_UNROLL
+#define ODG_NO_UNROLL
 #else
 #define ODG_DEV __device__ __forceinline__
 #define ODG_NOINLINE static __device__ __noinline__
@@ -49,6 +50,7 @@ static inline float odg_fdiv_rn(float a, float b) { volatile float r = a / b; re
 #define odg_fsub_rn __fsub_rn
 #define odg_fdiv_rn __fdiv_rn
 #define ODG_UNROLL _Pragma("unroll")
+#define ODG_NO_UNROLL _Pragma("unroll 1")
 #endif
 
 namespace odg {
@@ -924,7 +926,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       float al[4] = { 0.5f, 1.f, 2.f, 4.f }, f[4];
       float lo = 0.f, flo = d10, hi = -1.f, fhi = 0.f;
       bool done = false;
-      for (int ls = 0; ls < C.ls_iters && !done; ls++) {
+      ODG_NO_UNROLL for (int ls = 0; ls < C.ls_iters && !done; ls++) {
         if (ls > 0) {
           const float w = (hi - lo) * 0.2f, lo0 = lo;
           ODG_UNROLL for (int k = 0; k < 4; k++) al[k] = lo0 + w * (float)(k + 1);
@@ -1071,14 +1073,15 @@ ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const f
   // ---- physics
   LastPass<NJL> lp;
   int work = 0;
-  if (A.mode == 0) {
-    step += 1;
-    for (int s = 0; s < C.frame_skip; s++)
+  {
+    // mode 0: frame_skip x mj_step; mode 1 (odg_evaluate): one mj_forward, no integration. One call site, so the
+    // (large) substep body exists once in the kernel.
+    const bool stepping = A.mode == 0;
+    const int nsub = stepping ? C.frame_skip : 1;
+    if (stepping) step += 1;
+    for (int s = 0; s < nsub; s++)
       substep<NJL, PL1>(C, s_lc, s_gc, s_vert, leg, gm, bp, bq, bv, bwl, q, qd, ctrl, warm_v, warm_wl, warm_l,
-                   true, s == C.frame_skip - 1, lp, work);
-  } else {
-    substep<NJL, PL1>(C, s_lc, s_gc, s_vert, leg, gm, bp, bq, bv, bwl, q, qd, ctrl, warm_v, warm_wl, warm_l,
-                 false, true, lp, work);
+                        stepping, s == nsub - 1, lp, work);
   }
 
   // ---- observation (WalkEnvironment.py:115-136), float32
