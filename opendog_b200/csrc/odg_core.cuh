@@ -82,6 +82,7 @@ enum GeomConstField { GC_INVW, GC_CX, GC_CY, GC_CZ, GC_BX, GC_BY, GC_BZ, GC_BR, 
 struct DevConst {
   int nleg, njl, nq, nv, nu, nslot, nvert_rows;
   int body_rot_identity;
+  int any_damping;                              // some joint has damping > 0: mj_Euler integrates it implicitly
   int all_plane1;                               // every contact slot is condim 1 (scalar contact rows, substep<.., true>)
   float h, gx, gy, gz, impratio;
   // trunk
@@ -994,9 +995,59 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
   const V3 acc_wl = tmul(R0, a_b.w);
   if (integrate) {
     const float h = C.h;
-    bv = bv + h * a_b.t;
-    bwl = bwl + h * acc_wl;
-    ODG_UNROLL for (int j = 0; j < NJL; j++) { qd[j] += h * a_l[j]; q[j] += h * qd[j]; }
+    Vec6 v_b = a_b; float v_l[NJL];                 // acceleration used for the velocity update
+    ODG_UNROLL for (int j = 0; j < NJL; j++) v_l[j] = a_l[j];
+    if (C.any_damping) {
+      // mj_Euler with joint damping: solve (M + h*B) x = M*qacc (= qfrc_smooth + qfrc_constraint) and advance the
+      // velocity with x. Same block-arrow elimination as the Newton system: leg block per lane, 6x6 Schur complement
+      // on the trunk reduced over the group.
+      Vec6 rb = Mbb_mul(a_b);
+      rb.t = l0f * rb.t; rb.w = l0f * rb.w;
+      float rl[NJL], A[NJL][NJL];
+      ODG_UNROLL for (int j = 0; j < NJL; j++) {
+        float s = dot6(Mlb[j], a_b);
+        ODG_UNROLL for (int i = 0; i < NJL; i++) { s += Mll[j][i] * a_l[i]; A[j][i] = Mll[j][i]; }
+        A[j][j] += h * LCF(LC_DAMP, j);
+        rl[j] = s;
+        rb.t = rb.t + a_l[j] * Mlb[j].t; rb.w = rb.w + a_l[j] * Mlb[j].w;
+      }
+      spd_inverse<NJL>(A);
+      Vec6 W[NJL]; float y[NJL];
+      ODG_UNROLL for (int j = 0; j < NJL; j++) {
+        W[j].t = mk3(0.f, 0.f, 0.f); W[j].w = mk3(0.f, 0.f, 0.f); y[j] = 0.f;
+        ODG_UNROLL for (int i = 0; i < NJL; i++) {
+          W[j].t = W[j].t + A[j][i] * Mlb[i].t; W[j].w = W[j].w + A[j][i] * Mlb[i].w;
+          y[j] += A[j][i] * rl[i];
+        }
+      }
+      float P[6][6], S[6][6], rhs[6];
+      ODG_UNROLL for (int i = 0; i < 6; i++) ODG_UNROLL for (int k = 0; k < 6; k++) P[i][k] = 0.f;
+      P[0][0] = l0f * (T.m + C.base_arm_t[0]); P[1][1] = l0f * (T.m + C.base_arm_t[1]); P[2][2] = l0f * (T.m + C.base_arm_t[2]);
+      P[3][3] = l0f * (T.I.xx + C.base_arm_r); P[4][3] = l0f * T.I.xy; P[5][3] = l0f * T.I.xz;
+      P[4][4] = l0f * (T.I.yy + C.base_arm_r); P[5][4] = l0f * T.I.yz; P[5][5] = l0f * (T.I.zz + C.base_arm_r);
+      P[3][1] = l0f * (-T.h.z); P[3][2] = l0f * (T.h.y);
+      P[4][0] = l0f * (T.h.z);  P[4][2] = l0f * (-T.h.x);
+      P[5][0] = l0f * (-T.h.y); P[5][1] = l0f * (T.h.x);
+      float rbv[6] = { rb.t.x, rb.t.y, rb.t.z, rb.w.x, rb.w.y, rb.w.z };
+      ODG_UNROLL for (int j = 0; j < NJL; j++) {
+        float hl[6] = { Mlb[j].t.x, Mlb[j].t.y, Mlb[j].t.z, Mlb[j].w.x, Mlb[j].w.y, Mlb[j].w.z };
+        float wl[6] = { W[j].t.x, W[j].t.y, W[j].t.z, W[j].w.x, W[j].w.y, W[j].w.z };
+        ODG_UNROLL for (int i = 0; i < 6; i++) {
+          ODG_UNROLL for (int k = 0; k <= i; k++) P[i][k] -= hl[i] * wl[k];
+          rbv[i] -= hl[i] * y[j];
+        }
+      }
+      ODG_UNROLL for (int i = 0; i < 6; i++) {
+        ODG_UNROLL for (int k = 0; k <= i; k++) S[i][k] = grp_sum(P[i][k], gm);
+        rhs[i] = grp_sum(rbv[i], gm);
+      }
+      chol6_solve(S, rhs);
+      v_b.t = mk3(rhs[0], rhs[1], rhs[2]); v_b.w = mk3(rhs[3], rhs[4], rhs[5]);
+      ODG_UNROLL for (int j = 0; j < NJL; j++) v_l[j] = y[j] - dot6(W[j], v_b);
+    }
+    bv = bv + h * v_b.t;
+    bwl = bwl + h * tmul(R0, v_b.w);
+    ODG_UNROLL for (int j = 0; j < NJL; j++) { qd[j] += h * v_l[j]; q[j] += h * qd[j]; }
     bp = bp + h * bv;
     float wn = sqrtf(dot(bwl, bwl));
     if (wn > 1e-15f) {

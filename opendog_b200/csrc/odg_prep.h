@@ -53,10 +53,10 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
   if (m.nleg != 4) return "kernel maps one leg per lane: nleg must be 4";
   if (m.njl < 1 || m.njl > kMaxJL) return "njl out of range";
   if (m.cone != 1) return "only cone=elliptic is supported";
-  if (cfg.task == ODG_TASK_WALK && (m.nu != 8 || m.njl != 2)) return "walk task needs the 8-actuator OpenDOG model";
+  if (m.nu != m.nleg * m.njl) return "one position actuator per hinge joint is expected";
   for (int i = 0; i < 6; i++) if (m.base_damping[i] != 0) return "trunk damping is not supported";
   for (int l = 0; l < m.nleg; l++) for (int j = 0; j < m.njl; j++)
-    if (m.damping[l][j] != 0) return "joint damping needs the implicit Euler path (not built yet)";
+    if (m.damping[l][j] != 0) C.any_damping = 1;             // mj_Euler's implicit joint damping (Go1: go1.xml:9,12)
   if (m.base_armature[3] != m.base_armature[4] || m.base_armature[3] != m.base_armature[5])
     return "trunk rotational armature must be isotropic";
   C.nleg = m.nleg; C.njl = m.njl; C.nq = m.nq; C.nv = m.nv; C.nu = m.nu;
@@ -102,7 +102,9 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
     LC(LC_UIDX, j, l) = 0.f;
   }
   C.body_rot_identity = ident ? 1 : 0;
-  // ScaleActionEnvironment.py:8-17: float32 table, thigh [2.36, 2.8], knee [-1.8, -1.20] per actuator
+  // ScaleActionEnvironment.py:8-17: float32 table, thigh [2.36, 2.8], knee [-1.8, -1.20] per actuator (the OpenDOG
+  // model). Other models (Go1) scale [-1, 1] onto each actuator's ctrlrange, which is what that table is for OpenDOG.
+  const bool opendog = (m.nu == 8 && m.njl == 2);
   const float slo[2] = { 2.36f, -1.8f }, shi[2] = { 2.8f, -1.20f };
   for (int u = 0; u < m.nu; u++) {
     int l = m.act_leg[u], j = m.act_joint[u];
@@ -112,13 +114,14 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
     LC(LC_CLIM, j, l) = m.act_ctrllimited[u] ? 1.f : 0.f; LC(LC_FLIM, j, l) = m.act_forcelimited[u] ? 1.f : 0.f;
     LC(LC_CLO, j, l) = (float)m.act_ctrlrange[u][0]; LC(LC_CHI, j, l) = (float)m.act_ctrlrange[u][1];
     LC(LC_FLO, j, l) = (float)m.act_forcerange[u][0]; LC(LC_FHI, j, l) = (float)m.act_forcerange[u][1];
-    LC(LC_SLO, j, l) = slo[u & 1]; LC(LC_SHI, j, l) = shi[u & 1];
+    LC(LC_SLO, j, l) = opendog ? slo[u & 1] : (float)m.act_ctrlrange[u][0];
+    LC(LC_SHI, j, l) = opendog ? shi[u & 1] : (float)m.act_ctrlrange[u][1];
     C.key_ctrl[u] = (float)m.key_ctrl[u];
   }
   if (cfg.task == ODG_TASK_WALK)
-    for (int u = 0; u < m.nu; u += 2)
-      if (m.act_leg[u] != m.act_leg[u + 1] || m.act_joint[u] != 0 || m.act_joint[u + 1] != 1)
-        return "walk task expects (thigh, knee) actuator pairs per leg";
+    for (int u = 0; u < m.nu; u++)
+      if (m.act_leg[u] != m.act_leg[u - u % m.njl] || m.act_joint[u] != u % m.njl)
+        return "walk task expects the actuators of a leg to be consecutive, root to tip";
   for (int i = 0; i < m.nq; i++) C.key_qpos[i] = (float)m.key_qpos[i];
   C.obs_joint_offset = (float)m.key_ctrl[m.nu - 1];       // key_ctrl[0, 7:] (WalkEnvironment.py:116)
   // collision slots: every leg must carry the same sequence of (link, type)

@@ -148,6 +148,9 @@ def compile_model(m: MjcfModel, key: str = "home", multicontact_tilt: float = 0.
                 mix = g.solmix / (g.solmix + floor.solmix)
                 sref = mix * g.solref + (1 - mix) * floor.solref
                 simp = mix * g.solimp + (1 - mix) * floor.solimp
+            # condim 4/6 (torsional / rolling friction, Go1 feet: go1.xml:61-64) is reduced to the 3-row elliptic cone:
+            # the kernel and the oracle implement condim 1 and 3 (DESIGN.md "what comes next")
+            condim = min(int(condim), 3)
             e = dict(leg=leg, link=link, mj_geom_id=gid, mj_body_id=bid, condim=int(condim),
                      friction=float(fr[0]), margin=float(max(g.margin, floor.margin) - max(g.gap, floor.gap)),
                      solref=np.asarray(sref).tolist(), solimp=np.asarray(simp).tolist(),

@@ -333,7 +333,9 @@ def load_mjcf(path: str, inertia_mode: str = "legacy") -> MjcfModel:
         )
         fr = np.array([1.0, 0.005, 0.0001]); fr[:len(g.friction)] = g.friction; g.friction = fr
         si = _DEFAULT_OPTION["o_solimp"].copy(); si[:len(g.solimp)] = g.solimp; g.solimp = si
-        if gtype == "mesh":
+        # the hull is only needed for geoms that can collide (visual meshes, e.g. Go1's trunk.stl which is not even
+        # shipped in the reference, are never read unless a body's inertia must be inferred from them)
+        if gtype == "mesh" and (g.contype or g.conaffinity):
             md = mesh_data(g.mesh)
             R = quat_to_mat(quat)
             g.verts = md["hull"] @ R.T + pos

@@ -108,6 +108,7 @@ class EmuEnv:
         out = {}
         if info:
             for k, (t, n) in self.INFO.items():
+                n = {"terminal_obs": self.obs_dim, "qacc": self.nv}.get(k, n)
                 dt = {"f": np.float32, "i": np.int32, "B": np.uint8}[t]
                 out[k] = np.zeros((self.N, n) if n > 1 else self.N, dt)
                 setattr(A, k, _ptr(out[k]))

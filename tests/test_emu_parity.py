@@ -77,3 +77,30 @@ def test_results_do_not_depend_on_sharding():
         outs = [p.step(a[2 * k:2 * k + 2], info=False) for k, p in enumerate(parts)]
         assert np.array_equal(o, np.concatenate([x[0] for x in outs]))
         assert np.array_equal(r, np.concatenate([x[1] for x in outs]))
+
+
+def test_go1_single_step_parity():
+    """The second model descriptor (Unitree Go1: 3 joints per leg, joint damping -> implicit-damping Euler, sphere
+    feet; go1.xml) through the same kernel source, against the oracle: stand-up from the keyframe, then random targets."""
+    env = EmuEnv(1, model="go1", frame_skip=1, scale_actions=0, auto_reset=0, solver_iterations=100)   # MuJoCo's cap
+    sim = Sim("go1")
+    sim.reset_keyframe()
+    rng = np.random.default_rng(2)
+    lo = np.array([r[0] for r in sim.desc["act_ctrlrange"]]); hi = np.array([r[1] for r in sim.desc["act_ctrlrange"]])
+    ctrl = np.array(sim.desc["key_ctrl"], dtype=np.float32)[None]
+    worst_q = worst_v = 0.0
+    for k in range(220):
+        if k >= 60 and k % 40 == 0:
+            mid = np.array(sim.desc["key_ctrl"])
+            ctrl = np.clip(mid + rng.uniform(-0.15, 0.15, 12), lo, hi).astype(np.float32)[None]
+        sim.ctrl[:] = ctrl[0]
+        env.set_state(sim.qpos[None], sim.qvel[None], sim.qacc_warmstart[None])
+        _, _, _, _, info = env.step(ctrl)
+        sim.step()
+        qp, qv, _ = env.get_state()
+        eq = np.abs(qp[0] - sim.qpos) - (1e-6 + 1e-5 * np.abs(sim.qpos))
+        ev = np.abs(qv[0] - sim.qvel) - (1e-4 + 1e-3 * np.abs(sim.qvel))
+        worst_q, worst_v = max(worst_q, eq.max()), max(worst_v, ev.max())
+        assert info["ncon"][0] == sim.ncon, k
+    assert worst_q <= 0 and worst_v <= 0, (worst_q, worst_v)
+    assert sim.ncon >= 3                      # it is standing on its feet

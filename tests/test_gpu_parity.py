@@ -156,3 +156,50 @@ def test_evaluate_logic_bit_exact():
         assert abs(np.float32(orr) - rew[i]) <= 2 * np.spacing(np.float32(max(abs(orr), 1e-3)))
     assert mism <= 2, "paw contact flags disagree on identical states"
     assert term.any() and (~term).any() and trunc.any()
+
+
+def test_go1_physics_parity_and_env():
+    """Second model descriptor (Unitree Go1, go1.xml: 12 actuators, 3 joints per leg, joint damping -> implicit-damping
+    Euler, sphere feet) through the same kernel: single mj_step from identical states vs the oracle at the stated
+    tolerance, then the walk task on it (obs 9 + 3*12 = 45, the layout of landing_environment.py:116-136)."""
+    from opendog_b200.env import BatchedWalkEnv
+    from oracle.oracle import Sim
+    rng = np.random.default_rng(4)
+    s = Sim("go1"); s.reset_keyframe()
+    lo = np.array([r[0] for r in s.desc["act_ctrlrange"]]); hi = np.array([r[1] for r in s.desc["act_ctrlrange"]])
+    mid = np.array(s.desc["key_ctrl"])
+    states = []
+    for k in range(900):
+        if k % 40 == 0:
+            s.ctrl[:] = np.clip(mid + rng.uniform(-0.15, 0.15, 12), lo, hi)
+        s.step()
+        if k % 6 == 0:
+            states.append((s.qpos.copy(), s.qvel.copy(), s.qacc_warmstart.copy(), s.ctrl.copy()))
+    N = len(states)
+    env = BatchedWalkEnv(N, model="go1", frame_skip=1, scale_actions=0, auto_reset=0, solver_iterations=100,
+                         info_keys=("ncon", "contact_normal_force"))
+    f32 = lambda i: np.stack([st[i] for st in states]).astype(np.float32)
+    env.set_state(f32(0), f32(1), f32(2))
+    _, _, _, info = env.step(torch.from_numpy(f32(3)).cuda())
+    gq, gv = [t.cpu().numpy() for t in env.get_state()]
+    ncon = info["ncon"].cpu().numpy(); fn = info["contact_normal_force"].cpu().numpy()
+    bad = 0
+    for i in range(N):
+        s.reset_keyframe()
+        s.qpos[:] = f32(0)[i]; s.qvel[:] = f32(1)[i]; s.qacc_warmstart[:] = f32(2)[i]; s.ctrl[:] = f32(3)[i]
+        s.step()
+        ofn = sum(c["force"][0] for c in s.contacts())
+        ok = (np.all(np.abs(gq[i] - s.qpos) <= 1e-6 + 1e-5 * np.abs(s.qpos)) and
+              np.all(np.abs(gv[i] - s.qvel) <= 1e-4 + 1e-3 * np.abs(s.qvel)) and
+              abs(fn[i] - ofn) <= 1e-2 * max(1.0, abs(ofn)) and ncon[i] == s.ncon)
+        bad += (not ok)
+    # (sphere feet entering/leaving the 1 mm margin, and a much stiffer contact impedance than OpenDOG: 2 % allowed)
+    assert bad <= max(2, N // 50), f"{bad}/{N} Go1 states outside the single-step tolerance"
+    assert ncon.max() == 4 and ncon.min() >= 1
+    # the env surface on Go1
+    e = BatchedWalkEnv(256, model="go1", seed=3, info_keys=None)
+    obs = e.reset()
+    assert obs.shape == (256, 45) and e.act_dim == 12
+    for t in range(20):
+        obs, rew, done, _ = e.step((torch.rand(256, 12, device="cuda") * 2 - 1) * 0.3)
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and (rew >= 0).all()
