@@ -319,6 +319,9 @@ def run_gpu(args):
         del env
         line["rollout"] = rollout_probe(dev, args.rollout_envs if world == 1 else args.train_envs, args.horizon, rank, world,
                                         dist, train=(world > 1 or args.train_probe))
+        if world == 1 and args.go1:
+            # BASELINE.json configs[2] names the 12-actuator model: Unitree Go1 through the same kernels (45-512-256-12)
+            line["rollout_go1"] = rollout_probe(dev, args.rollout_envs, args.horizon, rank, world, dist, model="go1")
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
@@ -385,7 +388,7 @@ def mppi_probe(dev, samples=1024, horizon=64):
             "kernels_per_plan": m.kernels_per_plan, "min_cost": float(m.stats[0]), "mean_cost": float(m.stats[1])}
 
 
-def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False):
+def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="our_robot"):
     """BASELINE.json configs[2]/[3]: on-device PPO rollout (policy MLP on tensor cores + fused env step, one CUDA
     graph per horizon), GAE, and — with `train` — the advantage-statistics all-reduce and one PPO epoch with a flat
     gradient all-reduce per minibatch. Device-timed, max over ranks."""
@@ -395,7 +398,7 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False):
     from opendog_b200.rollout import Rollout
     from opendog_b200.train import ppo_update
     torch.manual_seed(0)
-    env = BatchedWalkEnv(n_envs, device=dev, seed=0, first_env_id=rank * n_envs, info_keys=None)
+    env = BatchedWalkEnv(n_envs, model=model, device=dev, seed=0, first_env_id=rank * n_envs, info_keys=None)
     pol = ActorCriticB200(env.obs_dim, env.act_dim, 0.4, device=dev, seed=0)
     ro = Rollout(env, pol, horizon=horizon, use_graph=True, first_row_id=rank * n_envs)
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -440,7 +443,7 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False):
     peak = float(pk.get("bf16_tflops_sustained", 1400.0))
     ach = flops * n_envs / (t_mlp * 1e-3) / 1e12
     steps = n_envs * world * horizon * iters
-    out = {"workload": f"{n_envs} envs/GPU x horizon {horizon}, ActorCritic {S}-512-256-{A} (+critic) bf16 tcgen05, CUDA graph",
+    out = {"workload": f"{n_envs} envs/GPU x horizon {horizon}, model {model}, ActorCritic {S}-512-256-{A} (+critic) bf16 tcgen05, CUDA graph",
            "env_steps_per_s_rollout": steps / (t_roll * 1e-3), "ms_per_rollout": t_roll / iters,
            "ms_gae_and_stats_allreduce": t_gae / iters, "ms_policy_forward": t_mlp,
            "policy_share_of_rollout": t_mlp * (horizon + 1) / (t_roll / iters),
@@ -465,6 +468,7 @@ def main():
     ap.add_argument("--rollout-envs", type=int, default=16384, help="N=1: also time the on-device PPO rollout (0 = off)")
     ap.add_argument("--train-envs", type=int, default=65536, help="N>1: envs per GPU of the train-iteration probe")
     ap.add_argument("--horizon", type=int, default=24)
+    ap.add_argument("--go1", type=int, default=1, help="N=1: also time the rollout on the 12-actuator Go1 model; 0 = off")
     ap.add_argument("--mppi", type=int, default=1, help="N=1: also time one MPPI plan (1024 x 64); 0 = off")
     ap.add_argument("--train-probe", action="store_true", help="N=1: include the PPO epoch in the rollout probe")
     ap.add_argument("--cfg", action="append", default=[], help="OdgEnvConfig override key=value (experiments)")

@@ -164,6 +164,7 @@ int choose_launch(OdgSim* s) {
   // one-warp blocks lose more to instruction fetch than they gain in divergence.
   int lanes = 32;
   int block = 64;
+  if (s->P.N / 16 < s->num_sms) block = 32;       // tiny batches (MPPI: 1024 samples): one warp per block, more SMs
   if (const char* env = std::getenv("ODG_STEP_LANES")) { int v = std::atoi(env); if (v == 8 || v == 16 || v == 32) lanes = v; }
   const long long warps = ((long long)s->P.N * 4 + lanes - 1) / lanes;
   if (const char* env = std::getenv("ODG_STEP_BLOCK")) { int v = std::atoi(env); if (v == 32 || v == 64 || v == 128 || (v == 256 && ODG_MAX_BLOCK >= 256)) block = v; }

@@ -2,7 +2,7 @@
 # variant comparison at 65536 envs: usage tools/gpu_quick3.sh "variant[:ENV=VAL]"...
 set -u
 mkdir -p gpurun_out
-B="python bench.py --steps 10 --warmup 12 --no-cpu-baseline --large-batch 65536 --rollout-envs 0 --mppi 0"
+B="python bench.py --steps 10 --warmup 12 --no-cpu-baseline --large-batch 65536 --rollout-envs 0 --mppi 0 --go1 0"
 $B > gpurun_out/bench_default.log 2>&1
 for spec in "$@"; do
   v=${spec%%:*}; e=""; [ "$spec" != "$v" ] && e=${spec#*:}

@@ -2,7 +2,7 @@
 set -u
 mkdir -p gpurun_out
 [ -n "${SKIP_TESTS:-}" ] || python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/pytest_gpu.log
-B="python bench.py --steps 10 --warmup 12 --no-cpu-baseline --large-batch 65536 --rollout-envs 0 --mppi 0"
+B="python bench.py --steps 10 --warmup 12 --no-cpu-baseline --large-batch 65536 --rollout-envs 0 --mppi 0 --go1 0"
 $B > gpurun_out/bench_default.log 2>&1
 for spec in "$@"; do
   tag=$(echo "$spec" | tr " =" "__"); env $spec $B > "gpurun_out/bench_$tag.log" 2>&1

@@ -8,7 +8,7 @@ python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/pytest_gpu.log
 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 python bench.py > gpurun_out/bench_default.log 2>&1
 python bench.py --impl reference --steps 30 --warmup 5 > gpurun_out/bench_reference.log 2>&1
-P="python bench.py --steps 3 --warmup 12 --no-cpu-baseline --large-batch 0 --rollout-envs 0 --mppi 0"
+P="python bench.py --steps 3 --warmup 12 --no-cpu-baseline --large-batch 0 --rollout-envs 0 --mppi 0 --go1 0"
 $P > gpurun_out/plain_4096.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_4096_$TAG.csv $P > gpurun_out/ncu_l_4096.log 2>&1
 $P > gpurun_out/plain_4096b.log 2>&1 && \
