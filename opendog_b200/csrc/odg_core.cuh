@@ -218,6 +218,25 @@ ODG_DEV void grp_sync(unsigned gmask) { __syncwarp(gmask); }
 #endif
 ODG_DEV float grp_sum(float v, unsigned gm) { v += grp_xor(v, 1, gm); v += grp_xor(v, 2, gm); return v; }
 ODG_DEV float grp_sum21(float v, unsigned gm) { v += grp_xor(v, 2, gm); v += grp_xor(v, 1, gm); return v; }
+// Sum of 28 values over the 4 lanes of a group through shared memory: one 112-byte row per lane (stride kRedStride
+// floats, so the float4 accesses of the 8 groups of a warp fall on different banks), summed in lane order 0,1,2,3 by
+// every lane (bit-identical results in all 4). 7 STS.128 + 28 LDS.128 + 84 FADD instead of 56 shuffles, each of which
+// costs a WARPSYNC/collective region under a partial mask: the Newton body is instruction-fetch bound.
+constexpr int kRedVals = 28, kRedStride = 36;
+ODG_DEV void grp_sum28(float (&v)[kRedVals], float* ODG_RESTRICT s_red, int leg, unsigned gm) {
+  grp_sync(gm);                                    // earlier readers of the rows are done
+  float4* mine = reinterpret_cast<float4*>(s_red + leg * kRedStride);
+  ODG_UNROLL for (int k = 0; k < kRedVals / 4; k++) { float4 t; t.x = v[4 * k]; t.y = v[4 * k + 1]; t.z = v[4 * k + 2]; t.w = v[4 * k + 3]; mine[k] = t; }
+  grp_sync(gm);
+  ODG_UNROLL for (int k = 0; k < kRedVals / 4; k++) {
+    const float4 a = reinterpret_cast<const float4*>(s_red)[k];
+    const float4 b = reinterpret_cast<const float4*>(s_red + kRedStride)[k];
+    const float4 c = reinterpret_cast<const float4*>(s_red + 2 * kRedStride)[k];
+    const float4 d = reinterpret_cast<const float4*>(s_red + 3 * kRedStride)[k];
+    v[4 * k] = ((a.x + b.x) + c.x) + d.x; v[4 * k + 1] = ((a.y + b.y) + c.y) + d.y;
+    v[4 * k + 2] = ((a.z + b.z) + c.z) + d.z; v[4 * k + 3] = ((a.w + b.w) + c.w) + d.w;
+  }
+}
 ODG_DEV float grp_max(float v, unsigned gm) { v = fmaxf(v, grp_xor(v, 1, gm)); v = fmaxf(v, grp_xor(v, 2, gm)); return v; }
 ODG_DEV V3 grp_sum(V3 v, unsigned gm) { return mk3(grp_sum(v.x, gm), grp_sum(v.y, gm), grp_sum(v.z, gm)); }
 ODG_DEV float grp_bcast(float v, int src_leg, int leg, unsigned gm) {   // value of lane `src_leg` to all 4
@@ -424,7 +443,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
                      const float4* ODG_RESTRICT s_vert, int leg, unsigned gm,
                      V3& bp, float (&bq)[4], V3& bv, V3& bwl, float (&q)[NJL], float (&qd)[NJL],
                      const float (&ctrl)[NJL], V3& warm_v, V3& warm_wl, float (&warm_l)[NJL],
-                     bool integrate, bool last, LastPass<NJL>& out, int& work) {
+                     bool integrate, bool last, LastPass<NJL>& out, int& work, float* ODG_RESTRICT s_red) {
   const bool lane0 = (leg == 0);
   // ------------------------------------------------------------------ kinematics (mj_kinematics)
   {
@@ -837,9 +856,18 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
           gbv[i] -= hl[i] * y[j];
         }
       }
-      ODG_UNROLL for (int i = 0; i < 6; i++) {
-        ODG_UNROLL for (int k = 0; k <= i; k++) S[i][k] = grp_sum(P[i][k], gm);
-        rhs[i] = -grp_sum(gbv[i], gm);
+      float red[kRedVals];
+      {
+        int n = 0;
+        ODG_UNROLL for (int i = 0; i < 6; i++) ODG_UNROLL for (int k = 0; k <= i; k++) red[n++] = P[i][k];
+        ODG_UNROLL for (int i = 0; i < 6; i++) red[21 + i] = gbv[i];
+        red[27] = 0.f;
+      }
+      grp_sum28(red, s_red, leg, gm);
+      {
+        int n = 0;
+        ODG_UNROLL for (int i = 0; i < 6; i++) ODG_UNROLL for (int k = 0; k <= i; k++) S[i][k] = red[n++];
+        ODG_UNROLL for (int i = 0; i < 6; i++) rhs[i] = -red[21 + i];
       }
     }
     chol6_solve(S, rhs);
@@ -1091,7 +1119,7 @@ ODG_DEV int gait_call(int& idx, int& cnt, int paws_mask, float vx) {
 template <int NJL, bool PL1>
 ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const float* ODG_RESTRICT s_gc,
                       const float4* ODG_RESTRICT s_vert, const SimPtrs& P, const StepArgs& A,
-                      int env, int leg, unsigned gm) {
+                      int env, int leg, unsigned gm, float* ODG_RESTRICT s_red) {
   const int N = P.N;
   const bool real = env < P.n;                     // padding environments never touch caller-owned buffers
   const int obs_dim = 9 + 3 * C.nu;
@@ -1132,7 +1160,7 @@ ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const f
     if (stepping) step += 1;
     for (int s = 0; s < nsub; s++)
       substep<NJL, PL1>(C, s_lc, s_gc, s_vert, leg, gm, bp, bq, bv, bwl, q, qd, ctrl, warm_v, warm_wl, warm_l,
-                        stepping, s == nsub - 1, lp, work);
+                        stepping, s == nsub - 1, lp, work, s_red);
   }
 
   // ---- observation (WalkEnvironment.py:115-136), float32

@@ -67,13 +67,15 @@ __global__ void __launch_bounds__(ODG_MAX_BLOCK, ODG_MIN_BLOCKS) k_step(const __
   // share a warp, and more warps to interleave per scheduler.
   const int leg = threadIdx.x & 3;
   const int lane = threadIdx.x & 31;
+  // per-group reduction rows (odg_core.cuh: grp_sum28) follow the staged constants
+  float* s_red = smem + L.vert_floats + L.lc_floats + L.gc_floats + (threadIdx.x >> 2) * (4 * odg::kRedStride);
   if (lane >= lanes) return;
   const unsigned gm = 0xFu << (lane & 28);
   const int envs_per_warp = lanes >> 2;
   const int envs_per_block = (blockDim.x >> 5) * envs_per_warp;
   for (int base = blockIdx.x * envs_per_block; base < P.N; base += gridDim.x * envs_per_block) {
     const int slot = base + (threadIdx.x >> 5) * envs_per_warp + (lane >> 2);
-    if (slot < P.N) odg::env_step<NJL, PL1>(C, s_lc, s_gc, s_vert, P, A, P.order ? P.order[slot] : slot, leg, gm);
+    if (slot < P.N) odg::env_step<NJL, PL1>(C, s_lc, s_gc, s_vert, P, A, P.order ? P.order[slot] : slot, leg, gm, s_red);
   }
 }
 
@@ -267,7 +269,8 @@ int odg_create(const OdgModel* model, const OdgEnvConfig* cfg_in, int num_envs, 
   if (upload(&s->d_lc, s->prep.lc) != cudaSuccess || upload(&s->d_gc, s->prep.gc) != cudaSuccess ||
       upload(&s->d_vert, s->prep.vert) != cudaSuccess) { odg_destroy(s); return fail(ODG_ERR_ALLOC, "constant upload failed"); }
   s->L.lc_floats = (int)s->prep.lc.size(); s->L.gc_floats = (int)s->prep.gc.size(); s->L.vert_floats = (int)s->prep.vert.size();
-  s->smem_step = (size_t)(s->L.lc_floats + s->L.gc_floats + s->L.vert_floats) * sizeof(float);
+  s->smem_const = (size_t)(s->L.lc_floats + s->L.gc_floats + s->L.vert_floats) * sizeof(float);
+  s->smem_step = s->smem_const + (size_t)ODG_MAX_BLOCK * odg::kRedStride * sizeof(float);
   s->regroup = cfg.regroup;
   CUDA_TRY(cudaMemset(s->P.work, 0, N * sizeof(int)));
   int rc = choose_launch(s);

@@ -13,7 +13,7 @@ struct OdgSim {
   float* d_lc = nullptr; float* d_gc = nullptr; float* d_vert = nullptr;
   void* d_state = nullptr;           // one allocation behind all SoA arrays
   SmemLayout L{};
-  size_t smem_step = 0;
+  size_t smem_step = 0, smem_const = 0;
   int step_block = 128, step_grid = 1, step_lanes = 32;
   int* d_order = nullptr; int* d_hist = nullptr; int regroup = 0;
   long long launches = 0;
