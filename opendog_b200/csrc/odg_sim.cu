@@ -174,6 +174,8 @@ int choose_launch(OdgSim* s) {
   if (dev_occ < 1) dev_occ = 1;
   const long long wpb = block / 32, need = (warps + wpb - 1) / wpb, cap = (long long)s->num_sms * dev_occ;
   s->step_lanes = lanes; s->step_block = block;
+  s->prep.C.lockstep = 2 * need > cap ? 1 : 0;    // measured: pays from ~8192 envs up (tools/gpu_quick6.sh)
+  if (const char* env = std::getenv("ODG_LOCKSTEP")) s->prep.C.lockstep = std::atoi(env) ? 1 : 0;
   s->step_grid = (int)(need < cap ? need : cap);
   return ODG_OK;
 }
