@@ -313,6 +313,13 @@ def run_gpu(args):
     if tr:
         line["roofline"]["traffic"] = tr[0]
         line["roofline"]["traffic_source"] = f"profiles/{tr[1]} (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+        if tr[2]:
+            # issue-slot view of the same launch: warp-instructions per launch (ncu) / live launch time vs 4 issue slots
+            # per SM per cycle. This, not HBM, is the resource the kernel is bound by.
+            peak_ips = 148 * 4 * (clocks.get("sm_mhz") or sm_max) * 1e6
+            ach = float(tr[2]) / launch_s
+            line["roofline"]["alu"] = {"bound": "issue", "warp_instructions_per_launch": float(tr[2]), "achieved": ach,
+                                       "peak": peak_ips, "unit": "warp-inst/s", "frac": ach / peak_ips}
     if rank == 0 and world == 1 and args.mppi:
         line["mppi"] = mppi_probe(dev)
     if args.rollout_envs and (world > 1 or rank == 0):
@@ -359,7 +366,7 @@ def profile_traffic(n_envs):
             d = json.load(open(f))
             t = d["kernels"][0].get("dram_traffic_bytes")
             if t:
-                best = (float(t), os.path.basename(f))
+                best = (float(t), os.path.basename(f), d["kernels"][0].get("smsp__inst_executed.sum"))
         except Exception:
             pass
     return best
