@@ -41,7 +41,7 @@ struct Emu {
   odg::Prepared prep;
   int N;
   std::vector<float> qpos, qvel, warm, last_action, desvel;
-  std::vector<int> step, gidx, gcnt; std::vector<unsigned> episode; std::vector<unsigned char> fresh;
+  std::vector<int> step, gidx, gcnt, work; std::vector<unsigned> episode; std::vector<unsigned char> fresh;
   odg::SimPtrs P;
 };
 
@@ -63,9 +63,9 @@ Emu* emu_create(const OdgModel* m, const OdgEnvConfig* cfg, int N, uint64_t seed
   e->N = N;
   e->qpos.assign((size_t)C.nq * N, 0.f); e->qvel.assign((size_t)C.nv * N, 0.f); e->warm.assign((size_t)C.nv * N, 0.f);
   e->last_action.assign((size_t)C.nu * N, 0.f); e->desvel.assign((size_t)3 * N, 0.f);
-  e->step.assign(N, 0); e->gidx.assign(N, 0); e->gcnt.assign(N, 0); e->episode.assign(N, 0); e->fresh.assign(N, 1);
+  e->work.assign(N, 0); e->step.assign(N, 0); e->gidx.assign(N, 0); e->gcnt.assign(N, 0); e->episode.assign(N, 0); e->fresh.assign(N, 1);
   e->P = odg::SimPtrs{ N, N, e->qpos.data(), e->qvel.data(), e->warm.data(), e->last_action.data(), e->desvel.data(),
-                       e->step.data(), e->gidx.data(), e->gcnt.data(), e->episode.data(), e->fresh.data(), nullptr, nullptr };
+                       e->step.data(), e->gidx.data(), e->gcnt.data(), e->episode.data(), e->fresh.data(), e->work.data(), nullptr };
   for (int i = 0; i < N; i++) odg::env_init(C, e->P, i);
   return e;
 }
@@ -139,6 +139,7 @@ void emu_set_env_state(Emu* e, const int* step, const int* gidx, const int* gcnt
     if (desvel) for (int k = 0; k < 3; k++) e->desvel[(size_t)k * N + i] = desvel[i * 3 + k];
   }
 }
+void emu_get_work(Emu* e, int* out) { for (int i = 0; i < e->N; i++) out[i] = e->work[i]; }   // Newton iterations + line-search passes of the last env-step
 int emu_sizeof_stepargs() { return (int)sizeof(odg::StepArgs); }
 void emu_default_config(OdgEnvConfig* c) { odg::default_config(c); }
 }
