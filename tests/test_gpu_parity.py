@@ -203,3 +203,33 @@ def test_go1_physics_parity_and_env():
     for t in range(20):
         obs, rew, done, _ = e.step((torch.rand(256, 12, device="cuda") * 2 - 1) * 0.3)
     assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and (rew >= 0).all()
+
+
+def test_physics_failure_is_contained_per_environment():
+    """Failure detection / recovery: a non-finite state in one environment becomes terminated = 1
+    for THAT environment (is_healthy, reward_calc:117-121; the `except mujoco.FatalError` path of
+    sim2real/train.py:282-283), the auto-reset brings it back, and its neighbours in the same warp are untouched."""
+    from opendog_b200.env import BatchedWalkEnv
+    N = 64
+    a = torch.rand(6, N, 8, device="cuda") * 2 - 1
+    ref = BatchedWalkEnv(N, seed=21, info_keys=None)
+    env = BatchedWalkEnv(N, seed=21, info_keys=("terminal_obs",))
+    ref.reset(); env.reset()
+    for t in range(2):
+        ref.step(a[t]); env.step(a[t])
+    q, v = env.get_state()
+    bad = [3, 17, 18, 40]
+    q[bad[0], 2] = float("nan"); v[bad[1], 7] = float("inf"); q[bad[2], 9] = float("nan"); v[bad[3], 0] = float("-inf")
+    qr, vr = ref.get_state()
+    env.set_state(q, v); ref.set_state(qr, vr)               # (both sides restart their solver warm start)
+    obs, rew, done, info = env.step(a[2]); robs, rrew, rdone, _ = ref.step(a[2])
+    term = env.terminated.bool().cpu()
+    assert term[bad].all() and done.cpu()[bad].all()
+    good = torch.ones(N, dtype=torch.bool); good[bad] = False
+    assert torch.equal(obs.cpu()[good], robs.cpu()[good]) and torch.equal(rew.cpu()[good], rrew.cpu()[good])
+    assert torch.isfinite(obs).all(), "the returned obs of a failed env is its reset obs"
+    q2, v2 = env.get_state()
+    assert torch.isfinite(q2).all() and torch.isfinite(v2).all()
+    for t in range(3, 6):
+        obs, rew, done, _ = env.step(a[t])
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
