@@ -252,12 +252,9 @@ def run_gpu(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(e2e_steps):
-        h_act.copy_(host_actions[i])                 # the caller's fresh host action batch
-        d_act.copy_(h_act, non_blocking=True)
-        env.step(d_act)
-        h_obs.copy_(env.obs, non_blocking=True); h_rew.copy_(env.reward, non_blocking=True)
-        h_term.copy_(env.terminated, non_blocking=True); h_trunc.copy_(env.truncated, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()  # the caller reads the results before acting again
+        # the reference-facing call with HOST buffers: fresh host action batch in (H2D), host obs / reward / terminated /
+        # truncated out (D2H), synchronised — the caller reads the results before acting again
+        h_obs, h_rew, h_term, h_trunc = env.step_host(host_actions[i])
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)

@@ -74,10 +74,16 @@ class BatchedWalkEnv:
         self.act_dim = self.L.odg_act_dim(h)
         self.nq, self.nv = self.L.odg_nq(h), self.L.odg_nv(h)
         N, dev = self.num_envs, self.device
-        self.obs = torch.empty(N, self.obs_dim, device=dev)
-        self.reward = torch.empty(N, device=dev)
-        self.terminated = torch.empty(N, dtype=torch.uint8, device=dev)
-        self.truncated = torch.empty(N, dtype=torch.uint8, device=dev)
+        # step outputs live in ONE device slab (obs | reward | terminated | truncated) so that a host-side caller
+        # fetches them with a single device->host copy (step_host)
+        nb = N * (self.obs_dim * 4 + 4 + 1 + 1)
+        self._out = torch.empty((nb + 3) // 4 * 4, dtype=torch.uint8, device=dev)
+        o = 0
+        self.obs = self._out[o:o + N * self.obs_dim * 4].view(torch.float32).view(N, self.obs_dim); o += N * self.obs_dim * 4
+        self.reward = self._out[o:o + N * 4].view(torch.float32); o += N * 4
+        self.terminated = self._out[o:o + N]; o += N
+        self.truncated = self._out[o:o + N]
+        self._host = None
         self.info = {}
         self._info_struct = None
         self.set_info_keys(info_keys)
@@ -129,6 +135,29 @@ class BatchedWalkEnv:
         self.step_into(action, self.obs, self.reward, self.terminated, self.truncated)
         done = (self.terminated | self.truncated).bool()
         return self.obs, self.reward, done, self.info
+
+    def step_host(self, action_host: torch.Tensor):
+        """`step` for a caller whose policy lives on the HOST (SB3, the reference's loops): pinned host action in,
+        pinned host (obs, reward, terminated, truncated) out — one H2D copy, one kernel, one D2H copy, one sync.
+        The returned arrays are views of an internal pinned buffer, valid until the next call."""
+        N = self.num_envs
+        if self._host is None:
+            self._host = dict(out=torch.empty_like(self._out, device="cpu").pin_memory(),
+                              act=torch.empty(N, self.act_dim).pin_memory(),
+                              dact=torch.empty(N, self.act_dim, device=self.device))
+            h, o = self._host["out"], 0
+            self._host["obs"] = h[o:o + N * self.obs_dim * 4].view(torch.float32).view(N, self.obs_dim); o += N * self.obs_dim * 4
+            self._host["reward"] = h[o:o + N * 4].view(torch.float32); o += N * 4
+            self._host["terminated"] = h[o:o + N]; o += N
+            self._host["truncated"] = h[o:o + N]
+        H = self._host
+        if action_host.data_ptr() != H["act"].data_ptr():
+            H["act"].copy_(action_host)
+        H["dact"].copy_(H["act"], non_blocking=True)
+        self.step_into(H["dact"], self.obs, self.reward, self.terminated, self.truncated)
+        H["out"].copy_(self._out, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return H["obs"], H["reward"], H["terminated"], H["truncated"]
 
     def step_into(self, action: torch.Tensor, obs, reward, terminated, truncated):
         """`step` writing straight into caller-owned CUDA tensors (rollout buffers): no copies, no extra kernels."""
