@@ -411,13 +411,19 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
-    for _ in range(3):
+    opt = torch.optim.Adam(pol.parameters(), lr=1e-4)
+    for w in range(3):
         ro.collect()
+        if w == 2:                       # untimed: first-use costs of the collectives and of autograd (NCCL lazy init)
+            adv, ret, stats = ro.advantages(normalize=True)
+            if train:
+                T, N = ro.T, n_envs
+                ppo_update(pol, opt, ro.obs[:T].reshape(T * N, -1), ro.action.reshape(T * N, -1), ro.logp.reshape(-1),
+                           adv.reshape(-1), ret.reshape(-1), epochs=1, minibatches=4)
     sync()
     iters = 3
     e = [ev() for _ in range(4)]
     t_roll = t_gae = t_upd = 0.0
-    opt = torch.optim.Adam(pol.parameters(), lr=1e-4)
     for _ in range(iters):
         e[0].record(); ro.collect(); e[1].record()
         adv, ret, stats = ro.advantages(normalize=True)       # all-reduces [sum, sumsq, n] when world > 1
