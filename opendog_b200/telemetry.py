@@ -1,0 +1,59 @@
+"""UDP + MessagePack telemetry of one environment of a batched simulator: the packet
+`wireless_comunication/server.py:95-118` sends and `client.py` plots, so the reference's live paw-force plotter keeps
+working against the GPU simulator. Same dict keys, same value layouts:
+    timestamp, num_qpos, num_qvel, num_act, qpos_data[3], qvel_data[3], ctr_data[nu],
+    contact_forces_data[4*6] (paw order 4, 7, 10, 13 = FL FR BL BR), active_contacts
+"""
+from __future__ import annotations
+
+import socket
+import time
+
+import msgpack
+
+
+def packet(env, index: int = 0, ctrl=None) -> dict:
+    """The reference's `_get_simulation_data` dict for environment `index` of a BatchedWalkEnv whose info_keys include
+    `paw_contact_forces` (and `ncon` for active_contacts)."""
+    qpos, qvel = env.get_state()
+    info = env.info
+    forces = info["paw_contact_forces"][index].reshape(-1).double().cpu().tolist() if "paw_contact_forces" in info else [0.0] * 24
+    ncon = int(info["ncon"][index]) if "ncon" in info else 0
+    if ctrl is None:
+        ctrl = env.get_env_state()["last_action"][index].double().cpu().tolist()     # last commanded targets (rad)
+    return {
+        "timestamp": time.time(), "num_qpos": env.nq, "num_qvel": env.nv,
+        "num_act": 0,                                   # `m.na` in the reference: activation states, none in this model
+        "qpos_data": qpos[index, :3].double().cpu().tolist(), "qvel_data": qvel[index, :3].double().cpu().tolist(),
+        "ctr_data": list(ctrl), "contact_forces_data": forces, "active_contacts": ncon,
+    }
+
+
+class TelemetryServer:
+    """Minimal stand-in for `MujocoCommunicationServer` (server.py:19-66): remembers the last client that sent a
+    datagram to (host, port) and answers `send(env)` with one msgpack datagram."""
+
+    def __init__(self, host: str = "127.0.0.1", port: int = 12345):
+        self.sock = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+        self.sock.bind((host, port))
+        self.sock.settimeout(0.0)
+        self.client = None
+        self.address = self.sock.getsockname()
+
+    def poll(self):
+        try:
+            _, addr = self.sock.recvfrom(1024)
+            self.client = addr
+        except (BlockingIOError, socket.timeout):
+            pass
+        return self.client
+
+    def send(self, env, index: int = 0):
+        self.poll()
+        if self.client is None:
+            return False
+        self.sock.sendto(msgpack.packb(packet(env, index)), self.client)
+        return True
+
+    def close(self):
+        self.sock.close()
