@@ -66,6 +66,10 @@ def ppo_update(policy, optimizer, obs, action, logp_old, adv, ret, clip: float =
     max_grad_norm .5). obs [B,S], action [B,A], logp_old/adv/ret [B]; minibatches are fixed contiguous slices.
     Gradients are averaged over ranks (one flat all-reduce per minibatch); afterwards the tensor-core copy of the
     weights is refreshed. Returns the last minibatch's loss terms."""
+    # the update's GEMMs ([B, 33..512] x [512, 256] ...) run on the tensor cores as TF32 (fp32 accumulate); the fp32
+    # CUDA-core path is ~5x slower on B200 and the reference's own update is plain fp32 torch on whatever device it finds
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
     B = obs.shape[0]
     mb = (B + minibatches - 1) // minibatches
     params = [p for p in policy.parameters() if p.requires_grad]
