@@ -298,7 +298,7 @@ ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, int condim,
   }
   float U1 = z.x * fri, U2 = z.y * fri, N = z.z * mu;
   float T2 = U1 * U1 + U2 * U2;
-  float iT = rsqrtf(fmaxf(T2, 1e-30f));
+  float iT = rsqrtf(fmaxf(T2, 1e-20f));
   float T = T2 * iT;
   int zone = cone_zone(N, T2, T, mu);
   if (zone == 0) return 0;
@@ -307,14 +307,19 @@ ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, int condim,
     H.xx = Dt; H.yy = Dt; H.zz = Dn;
     return 1;
   }
-  float Dm = Dn / (mu * mu * (1.f + mu * mu));
-  float NmT = N - mu * T;
-  float gU = -Dm * NmT * mu * iT;
-  g = mk3(gU * U1 * fri, gU * U2 * fri, Dm * NmT * mu);
-  float a = mu * N * iT * iT * iT, b = mu * mu - mu * N * iT;
-  float ff = Dm * fri * fri, fm = Dm * fri * mu;
-  H.xx = ff * (a * U1 * U1 + b); H.yy = ff * (a * U2 * U2 + b); H.xy = ff * a * U1 * U2;
-  H.xz = -fm * mu * U1 * iT; H.yz = -fm * mu * U2 * iT; H.zz = Dm * mu * mu;
+  // cost = Dm/2 * e^2 with e = N - mu*T < 0 on the cone surface. With u = U/T, w = de/dz = (-mu*u*fri, mu) and
+  // v = (u_perp*fri, 0):   g = Dm*e*w,   H = Dm * w w^T + kappa * v v^T,   kappa = Dm*mu*|e|/T >= 0.
+  // Written as this sum of two rank-1 PSD terms the block cannot turn indefinite in fp32; the algebraically equal
+  // closed form mu*N/T^3*U U^T + (mu^2 - mu*N/T) I cancels catastrophically when T is small.
+  const float Dm = Dn / (mu * mu * (1.f + mu * mu));
+  const float e = N - mu * T;
+  const float ux = U1 * iT, uy = U2 * iT;
+  const V3 w = mk3(-mu * ux * fri, -mu * uy * fri, mu);
+  g = (Dm * e) * w;
+  const float kap = -Dm * mu * e * iT;
+  const float vx = -uy * fri, vy = ux * fri;
+  H.xx = Dm * w.x * w.x + kap * vx * vx; H.xy = Dm * w.x * w.y + kap * vx * vy; H.yy = Dm * w.y * w.y + kap * vy * vy;
+  H.xz = Dm * w.x * w.z; H.yz = Dm * w.y * w.z; H.zz = Dm * w.z * w.z;
   return 2;
 }
 
@@ -326,7 +331,7 @@ ODG_DEV int cone_line(V3 z, V3 dz, float Dn, float Dt, float mu, float fri, int 
   }
   float U1 = z.x * fri, U2 = z.y * fri, N = z.z * mu;
   float T2 = U1 * U1 + U2 * U2;
-  float iT = rsqrtf(fmaxf(T2, 1e-30f));
+  float iT = rsqrtf(fmaxf(T2, 1e-20f));
   float T = T2 * iT;
   int zone = cone_zone(N, T2, T, mu);
   if (zone == 0) return 0;
@@ -362,7 +367,7 @@ ODG_DEV void cone_line4(V3 z0, V3 dz, float Dn, float Dt, float mu, float fri, i
     const float a = al[k];
     const float Ux = U0x + a * Vx, Uy = U0y + a * Vy, N = N0 + a * Nd;
     const float T2 = Ux * Ux + Uy * Uy;
-    const float iT = rsqrtf(fmaxf(T2, 1e-30f));
+    const float iT = rsqrtf(fmaxf(T2, 1e-20f));
     const float T = T2 * iT;
     const float Td = (Ux * Vx + Uy * Vy) * iT;
     const float fmid = Dm * (N - mu * T) * (Nd - mu * Td);
@@ -376,9 +381,13 @@ ODG_DEV void cone_line4(V3 z0, V3 dz, float Dn, float Dt, float mu, float fri, i
 // unrolled dense Cholesky solve of a 6x6 SPD system held in registers. S is overwritten by its factor.
 ODG_DEV void chol6_solve(float (&S)[6][6], float (&x)[6]) {
   ODG_UNROLL for (int j = 0; j < 6; j++) {
-    float s = S[j][j];
+    const float djj = S[j][j];
+    float s = djj;
     ODG_UNROLL for (int k = 0; k < j; k++) s -= S[j][k] * S[j][k];
-    s = fmaxf(s, 1e-20f);
+    // relative pivot floor: with contact stiffness D up to ~5e5 (deep penetration, impratio 100) against inertias of
+    // ~1e-2 the Schur complement can lose positive-definiteness in fp32; a floored pivot keeps the direction finite
+    // (the line search then decides whether it is still a descent direction) instead of producing NaN
+    s = fmaxf(s, 1e-6f * fabsf(djj) + 1e-20f);
     float inv = rsqrtf(s);
     S[j][j] = inv;                                // store 1/L_jj
     ODG_UNROLL for (int i = j + 1; i < 6; i++) {
@@ -416,6 +425,23 @@ ODG_DEV void spd_inverse(float (&A)[N][N]) {
   float id = 1.f / det;
   A[0][0] = c00 * id; A[0][1] = A[1][0] = c01 * id; A[0][2] = A[2][0] = c02 * id;
   A[1][1] = (a * f - c * c) * id; A[1][2] = A[2][1] = (b * c - a * e) * id; A[2][2] = (a * d - b * b) * id;
+}
+
+// Cholesky factor of a small SPD matrix in place: A[i][k] (k < i) = L_ik, iL[i] = 1 / L_ii (relative pivot floor)
+template <int N>
+ODG_DEV void chol_small(float (&A)[N][N], float (&iL)[N]) {
+  ODG_UNROLL for (int j = 0; j < N; j++) {
+    const float djj = A[j][j];
+    float s = djj;
+    ODG_UNROLL for (int k = 0; k < j; k++) s -= A[j][k] * A[j][k];
+    s = fmaxf(s, 1e-6f * fabsf(djj) + 1e-20f);
+    iL[j] = rsqrtf(s);
+    ODG_UNROLL for (int i = j + 1; i < N; i++) {
+      float t = A[i][j];
+      ODG_UNROLL for (int k = 0; k < j; k++) t -= A[i][k] * A[j][k];
+      A[i][j] = t * iL[j];
+    }
+  }
 }
 
 struct Vec6 { V3 t, w; };   // linear / angular(world) parts
@@ -827,14 +853,19 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       }
     }
     // ---- eliminate the leg block: Schur complement on the trunk
-    spd_inverse<NJL>(Hll);                          // Hll now holds its inverse
+    // block Cholesky: Hll = L L^T, W = L^-1 Hlb, y = L^-1 g_l (forward substitutions). The Schur complement is then
+    // P - W^T W — a symmetric subtraction that stays positive semi-definite in fp32, unlike P - Hlb^T (Hll^-1 Hlb) with
+    // an explicit adjugate inverse, which turned indefinite for stiff contacts (Go1 feet: D ~ 5e5 against 1e-2 inertias).
+    float iL[NJL];
+    chol_small<NJL>(Hll, iL);
     Vec6 W[NJL]; float y[NJL];
     ODG_UNROLL for (int j = 0; j < NJL; j++) {
-      W[j].t = mk3(0.f, 0.f, 0.f); W[j].w = mk3(0.f, 0.f, 0.f); y[j] = 0.f;
-      ODG_UNROLL for (int i = 0; i < NJL; i++) {
-        W[j].t = W[j].t + Hll[j][i] * Hlb[i].t; W[j].w = W[j].w + Hll[j][i] * Hlb[i].w;
-        y[j] += Hll[j][i] * g_l[i];
+      W[j] = Hlb[j]; y[j] = g_l[j];
+      ODG_UNROLL for (int i = 0; i < j; i++) {
+        W[j].t = W[j].t - Hll[j][i] * W[i].t; W[j].w = W[j].w - Hll[j][i] * W[i].w;
+        y[j] -= Hll[j][i] * y[i];
       }
+      W[j].t = iL[j] * W[j].t; W[j].w = iL[j] * W[j].w; y[j] *= iL[j];
     }
     float S[6][6]; float rhs[6];
     {
@@ -854,11 +885,10 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       P[5][0] += l0f * (-T.h.y); P[5][1] += l0f * (T.h.x);
       float gbv[6] = { gb.t.x, gb.t.y, gb.t.z, gb.w.x, gb.w.y, gb.w.z };   // gb itself stays the lane-partial gradient
       ODG_UNROLL for (int j = 0; j < NJL; j++) {
-        float hl[6] = { Hlb[j].t.x, Hlb[j].t.y, Hlb[j].t.z, Hlb[j].w.x, Hlb[j].w.y, Hlb[j].w.z };
         float wl[6] = { W[j].t.x, W[j].t.y, W[j].t.z, W[j].w.x, W[j].w.y, W[j].w.z };
         ODG_UNROLL for (int i = 0; i < 6; i++) {
-          ODG_UNROLL for (int k = 0; k <= i; k++) P[i][k] -= hl[i] * wl[k];
-          gbv[i] -= hl[i] * y[j];
+          ODG_UNROLL for (int k = 0; k <= i; k++) P[i][k] -= wl[i] * wl[k];
+          gbv[i] -= wl[i] * y[j];
         }
       }
       float red[kRedVals];
@@ -878,7 +908,12 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     chol6_solve(S, rhs);
     Vec6 p_b; p_b.t = mk3(rhs[0], rhs[1], rhs[2]); p_b.w = mk3(rhs[3], rhs[4], rhs[5]);
     float p_l[NJL];
-    ODG_UNROLL for (int j = 0; j < NJL; j++) p_l[j] = -y[j] - dot6(W[j], p_b);
+    // back substitution: p_l = -L^-T (y + W p_b)
+    ODG_UNROLL for (int j = NJL - 1; j >= 0; j--) {
+      float u = -y[j] - dot6(W[j], p_b);
+      ODG_UNROLL for (int i = j + 1; i < NJL; i++) u -= Hll[i][j] * p_l[i];
+      p_l[j] = u * iL[j];
+    }
     // ---- exact line search on phi(alpha) = cost(a + alpha p)  (convex, C1, piecewise quadratic)
     // lane-partials of the Gauss part: phi'_gauss(alpha) = G + alpha*Hq
     float G = dot6(gauss_b, p_b), Hq = 0.f;
@@ -989,7 +1024,9 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       smax = fmaxf(smax, fabsf(p_l[j])); amax = fmaxf(amax, fabsf(a_l[j]));
     }
     smax = grp_max(smax, gm); amax = grp_max(amax, gm);
-    conv = smax <= C.tol * (1.f + amax);            // full Newton step is negligible
+    // converged: the full Newton step is negligible, or p is no longer a descent direction in fp32 (nothing left to
+    // gain at this precision; without this exit such an environment idles until the iteration cap)
+    conv = smax <= C.tol * (1.f + amax) || !(d10 < 0.f);
   }
   work += iters + ls_evals;
   // ------------------------------------------------------------------ outputs of the forward pass

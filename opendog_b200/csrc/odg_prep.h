@@ -103,7 +103,7 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
   }
   C.body_rot_identity = ident ? 1 : 0;
   // ScaleActionEnvironment.py:8-17: float32 table, thigh [2.36, 2.8], knee [-1.8, -1.20] per actuator (the OpenDOG
-  // model). Other models (Go1) scale [-1, 1] onto each actuator's ctrlrange, which is what that table is for OpenDOG.
+  // model). Other models (Go1, which has no walk environment in the reference) map [-1, 1] around the home target.
   const bool opendog = (m.nu == 8 && m.njl == 2);
   const float slo[2] = { 2.36f, -1.8f }, shi[2] = { 2.8f, -1.20f };
   for (int u = 0; u < m.nu; u++) {
@@ -114,8 +114,13 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
     LC(LC_CLIM, j, l) = m.act_ctrllimited[u] ? 1.f : 0.f; LC(LC_FLIM, j, l) = m.act_forcelimited[u] ? 1.f : 0.f;
     LC(LC_CLO, j, l) = (float)m.act_ctrlrange[u][0]; LC(LC_CHI, j, l) = (float)m.act_ctrlrange[u][1];
     LC(LC_FLO, j, l) = (float)m.act_forcerange[u][0]; LC(LC_FHI, j, l) = (float)m.act_forcerange[u][1];
-    LC(LC_SLO, j, l) = opendog ? slo[u & 1] : (float)m.act_ctrlrange[u][0];
-    LC(LC_SHI, j, l) = opendog ? shi[u & 1] : (float)m.act_ctrlrange[u][1];
+    {
+      // other models: [-1, 1] -> home -+ d, d = min(0.5 rad, distance of the home target to either end of ctrlrange)
+      const double home = m.key_ctrl[u], lo_ = m.act_ctrlrange[u][0], hi_ = m.act_ctrlrange[u][1];
+      const double d = std::fmax(0.0, std::fmin(0.5, std::fmin(home - lo_, hi_ - home)));
+      LC(LC_SLO, j, l) = opendog ? slo[u & 1] : (float)(home - d);
+      LC(LC_SHI, j, l) = opendog ? shi[u & 1] : (float)(home + d);
+    }
     C.key_ctrl[u] = (float)m.key_ctrl[u];
   }
   if (cfg.task == ODG_TASK_WALK)
