@@ -986,8 +986,16 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       }
       ODG_UNROLL for (int k = 0; k < 4; k++) f[k] = grp_sum(f[k], gm);
     };
-    float alpha = 0.f;
-    if (d10 < 0.f) {                                // else: not a descent direction (converged to rounding)
+    // size of the full Newton step relative to the iterate: when it is already negligible this is the last iteration
+    // and the step is taken without a line search
+    float amax = 0.f, smax = 0.f;
+    smax = fmaxf(fmaxf(fabsf(p_b.t.x), fabsf(p_b.t.y)), fmaxf(fabsf(p_b.t.z), fmaxf(fabsf(p_b.w.x), fmaxf(fabsf(p_b.w.y), fabsf(p_b.w.z)))));
+    amax = fmaxf(fmaxf(fabsf(a_b.t.x), fabsf(a_b.t.y)), fmaxf(fabsf(a_b.t.z), fmaxf(fabsf(a_b.w.x), fmaxf(fabsf(a_b.w.y), fabsf(a_b.w.z)))));
+    ODG_UNROLL for (int j = 0; j < NJL; j++) { smax = fmaxf(smax, fabsf(p_l[j])); amax = fmaxf(amax, fabsf(a_l[j])); }
+    smax = grp_max(smax, gm); amax = grp_max(amax, gm);
+    const bool tiny = smax <= C.tol * (1.f + amax);
+    float alpha = (tiny && d10 < 0.f) ? 1.f : 0.f;
+    if (d10 < 0.f && !tiny) {                       // else: negligible step, or not a descent direction (converged to rounding)
       // phi' is increasing (phi convex): bracket its zero with the first pass, shrink the bracket 5x per further
       // pass, stop as soon as one evaluated point has |phi'| <= ls_tol*|phi'(0)|, else finish with the zero of the
       // chord on the last bracket
@@ -1015,18 +1023,11 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       }
     }
     // ---- take the step, test convergence on the step size
-    float amax = 0.f, smax = 0.f;
     a_b.t = a_b.t + alpha * p_b.t; a_b.w = a_b.w + alpha * p_b.w;
-    smax = fmaxf(fmaxf(fabsf(p_b.t.x), fabsf(p_b.t.y)), fmaxf(fabsf(p_b.t.z), fmaxf(fabsf(p_b.w.x), fmaxf(fabsf(p_b.w.y), fabsf(p_b.w.z)))));
-    amax = fmaxf(fmaxf(fabsf(a_b.t.x), fabsf(a_b.t.y)), fmaxf(fabsf(a_b.t.z), fmaxf(fabsf(a_b.w.x), fmaxf(fabsf(a_b.w.y), fabsf(a_b.w.z)))));
-    ODG_UNROLL for (int j = 0; j < NJL; j++) {
-      a_l[j] += alpha * p_l[j];
-      smax = fmaxf(smax, fabsf(p_l[j])); amax = fmaxf(amax, fabsf(a_l[j]));
-    }
-    smax = grp_max(smax, gm); amax = grp_max(amax, gm);
+    ODG_UNROLL for (int j = 0; j < NJL; j++) a_l[j] += alpha * p_l[j];
     // converged: the full Newton step is negligible, or p is no longer a descent direction in fp32 (nothing left to
     // gain at this precision; without this exit such an environment idles until the iteration cap)
-    conv = smax <= C.tol * (1.f + amax) || !(d10 < 0.f);
+    conv = tiny || !(d10 < 0.f);
   }
   work += iters + ls_evals;
   // ------------------------------------------------------------------ outputs of the forward pass
