@@ -44,7 +44,9 @@ constexpr int kA0Bytes = kM * ODG_POLICY_MAX_STATE * 2;       // 16 KB  obs tile
 constexpr int kA1Bytes = kM * kH1 * 2;                         // 128 KB hidden 1 (hidden 2 aliases its first half)
 constexpr int kWBufBytes = 256 * kK2Chunk * 2;                 // 32 KB  one weight chunk
 constexpr int kOffA0 = 0, kOffA1 = kOffA0 + kA0Bytes, kOffW = kOffA1 + kA1Bytes, kOffBar = kOffW + 2 * kWBufBytes;
-constexpr int kSmemBytes = kOffBar + 64;
+constexpr int kBiasFloats = kH1 + kH2 + kNOut;                  // per network: b1 | b2 | b3
+constexpr int kOffBias = kOffBar + 64;
+constexpr int kSmemBytes = kOffBias + 2 * kBiasFloats * 4;
 
 // byte offset of element (r, k) of an operand tile with kc columns in the canonical K-major no-swizzle layout:
 // 8x8 core matrices (8 rows x 16 bytes, contiguous 128 B); K-adjacent core matrices are 128 B apart (LBO),
@@ -133,6 +135,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+#ifdef ODG_MLP_TIMING
+__device__ long long g_mlp_t[64];
+#define MLP_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_mlp_t[i] = clock64(); } while (0)
+#else
+#define MLP_STAMP(i) do { } while (0)
+#endif
+
 struct MlpParams {
   const float* obs; int n, S, A, K0p;
   const uint8_t* wpack[2];     // actor / critic operand chunks (bf16, canonical layout, chunk after chunk)
@@ -155,8 +164,8 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t taddr_row, int ncols, c
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         const int col = cb + g * 8 + i * 2;
-        float x0 = tanh_fast(__uint_as_float(v[g * 8 + i * 2]) + __ldg(bias + col));
-        float x1 = tanh_fast(__uint_as_float(v[g * 8 + i * 2 + 1]) + __ldg(bias + col + 1));
+        float x0 = tanh_fast(__uint_as_float(v[g * 8 + i * 2]) + bias[col]);
+        float x1 = tanh_fast(__uint_as_float(v[g * 8 + i * 2 + 1]) + bias[col + 1]);
         w[i] = pack_bf16(x0, x1);
       }
       *reinterpret_cast<uint4*>(a_out + canon_off(row, kofs + cb + g * 8, kc_out)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -168,9 +177,11 @@ __global__ void __launch_bounds__(kM, 1) k_mlp(const MlpParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA0 = smem + kOffA0; uint8_t* sA1 = smem + kOffA1;
   uint8_t* sW[2] = { smem + kOffW, smem + kOffW + kWBufBytes };
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + kOffBar);       // [2] weight chunk landed
-  uint64_t* bar_mma = bar_w + 2;                                        // MMAs of the current chunk retired
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_w + 4);
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + kOffBar);       // [2] weight chunk landed in buffer b
+  uint64_t* bar_free = bar_w + 2;                                       // [2] the MMAs that read buffer b have retired
+  uint64_t* bar_acc = bar_w + 4;                                        // the accumulator of a layer is complete
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_w + 6);
+  float* s_bias = reinterpret_cast<float*>(smem + kOffBias);            // both networks' biases (epilogue broadcasts)
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row = tid;                                                  // TMEM lane = row of the tile
   const int grow = blockIdx.x * kM + row;                               // row in the batch
@@ -178,13 +189,14 @@ __global__ void __launch_bounds__(kM, 1) k_mlp(const MlpParams P) {
   const int total_chunks = 2 * kNumChunks;
 
   if (tid == 0) {
-    mbar_init(&bar_w[0], 1); mbar_init(&bar_w[1], 1); mbar_init(bar_mma, 1);
+    mbar_init(&bar_w[0], 1); mbar_init(&bar_w[1], 1); mbar_init(&bar_free[0], 1); mbar_init(&bar_free[1], 1); mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(s_tmem)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = tid; i < 2 * kBiasFloats; i += kM) s_bias[i] = P.bias[i / kBiasFloats][i % kBiasFloats];
   // obs tile -> bf16 A0 (rows past the batch and columns past S are zero)
   {
     const float* o = P.obs + (size_t)grow * P.S;
@@ -204,6 +216,7 @@ __global__ void __launch_bounds__(kM, 1) k_mlp(const MlpParams P) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  MLP_STAMP(0);
   const uint32_t tmem = *s_tmem;
   const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's lane quarter
   constexpr uint32_t kD1 = 0, kD2 = 256;                                // accumulator columns: layer 1 / 3 at 0, layer 2 at 256
@@ -218,9 +231,13 @@ __global__ void __launch_bounds__(kM, 1) k_mlp(const MlpParams P) {
   if (tid == 0) prefetch(0);
 
   int c = 0;                                                            // flat chunk counter (uniform across threads)
-  // one chunk: wait for its weights, issue `ksteps` MMAs (K = 16 each) D[.., ncols] (+)= A[128 x 16k] * W_chunk^T,
-  // prefetch the next chunk into the other buffer, wait for the MMAs to retire
-  auto run_chunk = [&](uint32_t a_saddr, uint32_t a_sbo, int ksteps, uint32_t dcol, int ncols, bool accumulate) {
+  int n_acc = 0;                                                        // accumulators completed so far (bar_acc phase)
+  // One chunk, issued by thread 0 only: wait for its weights, issue `ksteps` MMAs (K = 16 each)
+  // D[.., ncols] (+)= A[128 x 16k] * W_chunk^T, commit them to the buffer's "free" barrier (and, for the last chunk of
+  // a layer, to the accumulator barrier), then prefetch the next chunk into the other buffer as soon as the MMAs that
+  // read it (chunk c-1) have retired. MMAs of consecutive chunks queue back to back in the tensor pipe; nobody waits for
+  // an individual chunk. The other 127 threads only wait for the accumulator (`wait_acc`).
+  auto run_chunk = [&](uint32_t a_saddr, uint32_t a_sbo, int ksteps, uint32_t dcol, int ncols, bool accumulate, bool last) {
     if (tid == 0) {
       mbar_wait(&bar_w[c & 1], (uint32_t)((c >> 1) & 1));
       tc_fence_after();
@@ -230,41 +247,54 @@ __global__ void __launch_bounds__(kM, 1) k_mlp(const MlpParams P) {
       for (int k = 0; k < ksteps; k++)
         umma_bf16(tmem + dcol, make_desc(a_saddr + k * 256, 128, a_sbo), make_desc(b_saddr + k * 256, 128, b_sbo), idesc,
                   (accumulate || k > 0) ? 1u : 0u);
-      umma_commit(bar_mma);
-      if (c + 1 < total_chunks) prefetch(c + 1);    // buffer (c+1)&1 was read by chunk c-1, whose MMAs have retired
+      umma_commit(&bar_free[c & 1]);
+      if (last) umma_commit(bar_acc);
+      if (c + 1 < total_chunks) {
+        if (c >= 1) mbar_wait(&bar_free[(c + 1) & 1], (uint32_t)(((c - 1) >> 1) & 1));   // chunk c-1 read that buffer
+        prefetch(c + 1);
+      }
     }
-    mbar_wait(bar_mma, (uint32_t)(c & 1));
-    tc_fence_after();
     c++;
   };
+  auto wait_acc = [&]() { mbar_wait(bar_acc, (uint32_t)(n_acc & 1)); tc_fence_after(); n_acc++; };
   // all tcgen05.ld of an accumulator region done + A operand writes visible to the async proxy, before the next MMAs
   auto sync_after_epilogue = [&]() { fence_async_smem(); tc_fence_before(); __syncthreads(); tc_fence_after(); };
 
   float outv[kNOut];
   for (int net = 0; net < 2; net++) {
-    const float* b1 = P.bias[net]; const float* b2 = b1 + kH1; const float* b3 = b2 + kH2;
+    const float* b1 = s_bias + net * kBiasFloats; const float* b2 = b1 + kH1; const float* b3 = b2 + kH2;
     for (int h = 0; h < 2; h++) {                                        // layer 1, two 256-wide halves
-      run_chunk(smem_u32(sA0), (uint32_t)(K0p >> 3) * 128u, K0p / 16, kD1, 256, false);
+      run_chunk(smem_u32(sA0), (uint32_t)(K0p >> 3) * 128u, K0p / 16, kD1, 256, false, true);
+      wait_acc();
+      MLP_STAMP(1 + net * 12 + h * 2);
       epilogue_hidden(tmem_row + kD1, 256, b1 + h * 256, sA1, kH1, h * 256, row);
       sync_after_epilogue();
+      MLP_STAMP(2 + net * 12 + h * 2);
     }
     for (int kc = 0; kc < kH1 / kK2Chunk; kc++)                          // layer 2, K streamed in 64-column chunks
-      run_chunk(smem_u32(sA1) + kc * (kK2Chunk / 8) * 128, (uint32_t)(kH1 >> 3) * 128u, kK2Chunk / 16, kD2, 256, kc > 0);
+      run_chunk(smem_u32(sA1) + kc * (kK2Chunk / 8) * 128, (uint32_t)(kH1 >> 3) * 128u, kK2Chunk / 16, kD2, 256, kc > 0,
+                kc == kH1 / kK2Chunk - 1);
+    wait_acc();
+    MLP_STAMP(5 + net * 12);
     epilogue_hidden(tmem_row + kD2, 256, b2, sA1, kH2, 0, row);          // hidden 2 overwrites hidden 1 (all its MMAs retired)
     sync_after_epilogue();
-    run_chunk(smem_u32(sA1), (uint32_t)(kH2 >> 3) * 128u, kH2 / 16, kD1, kNOut, false);   // output layer
+    MLP_STAMP(6 + net * 12);
+    run_chunk(smem_u32(sA1), (uint32_t)(kH2 >> 3) * 128u, kH2 / 16, kD1, kNOut, false, true);   // output layer
+    wait_acc();
+    MLP_STAMP(7 + net * 12);
     {
       uint32_t v[16];
       tmem_ld16(tmem_row + kD1, v);
       if (net == 0) {
 #pragma unroll
-        for (int a = 0; a < kNOut; a++) outv[a] = tanhf(__uint_as_float(v[a]) + __ldg(b3 + a));   // actor: Tanh head
+        for (int a = 0; a < kNOut; a++) outv[a] = tanhf(__uint_as_float(v[a]) + b3[a]);   // actor: Tanh head
       } else if (grow < P.n && P.value) {
-        P.value[grow] = __uint_as_float(v[0]) + __ldg(b3);
+        P.value[grow] = __uint_as_float(v[0]) + b3[0];
       }
     }
     sync_after_epilogue();
   }
+  MLP_STAMP(30);
   // ---- Normal(mean, exp(log_std)): sample + log-prob  (sim2real/train.py:542-543)
   if (grow < P.n) {
     const uint32_t step_ctr = P.step + (P.step_base ? __ldg(P.step_base) : 0u);
@@ -492,5 +522,8 @@ int odg_normalize_advantages(float* adv_dev, long long count, const double* stat
 }
 
 long long odg_policy_launch_count(const OdgPolicy* p) { return p ? p->launches : 0; }
+#ifdef ODG_MLP_TIMING
+int odg_mlp_timing(long long* out) { return cudaMemcpyFromSymbol(out, g_mlp_t, sizeof(long long) * 64) == cudaSuccess ? 0 : -1; }
+#endif
 
 }  // extern "C"
