@@ -233,3 +233,36 @@ def test_physics_failure_is_contained_per_environment():
     for t in range(3, 6):
         obs, rew, done, _ = env.step(a[t])
     assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+
+
+def test_determinism_sharding_and_soak():
+    """(1) Same seed twice -> bit-identical trajectories. (2) A handle of 128 envs equals two handles of 64 with
+    first_env_id 0 / 64 (the layout of two ranks): RNG streams are keyed by global env id and an environment's result
+    does not depend on which environments share its warp or block. (3) Soak: 1024 envs x 600 random-action steps stay
+    finite, episodes end and restart, rewards stay in range."""
+    from opendog_b200.env import BatchedWalkEnv
+    g = torch.Generator(device="cuda").manual_seed(7)
+    acts = torch.rand(25, 128, 8, device="cuda", generator=g) * 2 - 1
+
+    def run(n, first, sl):
+        e = BatchedWalkEnv(n, seed=5, first_env_id=first, info_keys=None, max_episode_steps=12)
+        out = [e.reset().clone()]
+        for t in range(25):
+            o, r, d, _ = e.step(acts[t, sl].contiguous())
+            out += [o.clone(), r.clone(), d.clone()]
+        return out
+    a, b = run(128, 0, slice(0, 128)), run(128, 0, slice(0, 128))
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    lo, hi = run(64, 0, slice(0, 64)), run(64, 64, slice(64, 128))
+    for x, y, z in zip(a, lo, hi):
+        assert torch.equal(x, torch.cat([y, z]))
+    e = BatchedWalkEnv(1024, seed=9, info_keys=None, max_episode_steps=100)
+    e.reset()
+    ndone, rmax = 0, 0.0
+    for t in range(600):
+        o, r, d, _ = e.step(torch.rand(1024, 8, device="cuda") * 2 - 1)
+        ndone += int(d.sum()); rmax = max(rmax, float(r.max()))
+    q, v = e.get_state()
+    assert torch.isfinite(o).all() and torch.isfinite(q).all() and torch.isfinite(v).all()
+    assert ndone >= 5 * 1024 and 0.0 <= rmax < 200.0
+    assert float(q[:, 2].min()) > -0.01 and float(q[:, 2].max()) < 0.5          # nobody fell through the floor or flew away
