@@ -1008,8 +1008,14 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       bool done = false;
       ODG_NO_UNROLL for (int ls = 0; ls < C.ls_iters && !done; ls++) {
         if (ls > 0) {
-          const float w = (hi - lo) * 0.2f, lo0 = lo;
-          ODG_UNROLL for (int k = 0; k < 4; k++) al[k] = lo0 + w * (float)(k + 1);
+          if (lo == 0.f) {
+            // the zero lies below every step tried so far: a geometric ladder resolves zeros that are orders of
+            // magnitude smaller than the Newton step (a stiff row switching on right next to the iterate) in one pass
+            al[0] = 0.008f * hi; al[1] = 0.04f * hi; al[2] = 0.2f * hi; al[3] = 0.6f * hi;
+          } else {
+            const float w = (hi - lo) * 0.2f, lo0 = lo;
+            ODG_UNROLL for (int k = 0; k < 4; k++) al[k] = lo0 + w * (float)(k + 1);
+          }
         }
         eval4(al, f);
         ls_evals++;
@@ -1021,8 +1027,13 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         if (!done && hi < 0.f) { alpha = al[3]; done = true; }     // still descending at the largest step tried
       }
       if (!done) {
+        // zero of the chord — unless phi' is an order of magnitude smaller at the upper end: then a stiff row switches
+        // on between lo and hi (phi' flat, then very steep), the chord lands on or before that kink, the next Hessian is
+        // assembled without the row, and the iteration repeats the same tiny step until the cap (seen with Go1's feet,
+        // D ~ 5e5). The upper end is past the kink and within the bracket width of the zero.
         alpha = lo - flo * (hi - lo) / (fhi - flo);
         if (!(alpha >= lo && alpha <= hi)) alpha = 0.5f * (lo + hi);
+        if (fhi < -0.1f * flo) alpha = hi;
       }
     }
     // ---- take the step, test convergence on the step size
