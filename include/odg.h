@@ -63,6 +63,12 @@ typedef struct OdgEnvConfig {
                                 per-environment results. default 0 (measured: no gain on B200) */
   int first_env_id;          /* global id of env 0 of this handle (rank * num_envs): RNG streams are
                                 keyed by global env id so results do not depend on the sharding */
+  int obs_layout;            /* 0 = WalkEnvironmentV0._get_obs (WalkEnvironment.py:115-136): 9 + 3*nu values
+                                [2 v, 0.25 w, 2 v_des, q - key_ctrl[0,7:] (length-1 slice broadcast), 0.05 qd, last_action];
+                                1 = the 12-actuator layout of landing_environment.py:116-136 plus the desired velocity
+                                (the "48" of BASELINE configs[2]): 12 + 3*nu values
+                                [2 v, 0.25 w, projected_gravity (reward_calc get_projected_gravity, its Euler-angle
+                                formula), 2 v_des, q - key_qpos[0,7:], 0.05 qd, last_action] */
 } OdgEnvConfig;
 
 /* Optional per-step outputs (any pointer may be NULL). WalkEnvironment.py:65-72 `info`. */

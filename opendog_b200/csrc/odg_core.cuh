@@ -101,6 +101,7 @@ struct DevConst {
   int n_tilt;
   // env
   int frame_skip, max_steps, auto_reset, solver_iters, ls_iters, scale_actions, first_env_id;
+  int obs_layout;                               // OdgEnvConfig::obs_layout
   float tol, ls_tol, noise;
   float key_qpos[kMaxNQ], key_ctrl[kMaxNU];
   float obs_joint_offset;                       // key_ctrl[0,7:] broadcast quirk (WalkEnvironment.py:116)
@@ -1163,6 +1164,17 @@ ODG_DEV void euler_from_quat(double w, double x, double y, double z, double& rol
   yaw = atan2(t3, t4);
 }
 
+// get_projected_gravity (walk_environment_reward_calc.py / landing_environment_reward_calc.py:88-98): the reference's
+// formula, not a rotation of g: with e = (roll, pitch, yaw), v = (g . e) e, returned normalised unless |v| == 0.
+ODG_DEV void projected_gravity(const DevConst& C, const float (&quat)[4], float (&pg)[3]) {
+  double e[3];
+  euler_from_quat((double)quat[0], (double)quat[1], (double)quat[2], (double)quat[3], e[0], e[1], e[2]);
+  const double d = (double)C.gx * e[0] + (double)C.gy * e[1] + (double)C.gz * e[2];
+  const double v0 = d * e[0], v1 = d * e[1], v2 = d * e[2];
+  const double n = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+  pg[0] = (float)(n == 0.0 ? v0 : v0 / n); pg[1] = (float)(n == 0.0 ? v1 : v1 / n); pg[2] = (float)(n == 0.0 ? v2 : v2 / n);
+}
+
 // diagonal_gait_reward (reward_calc:203-234); pattern table :54-63, order FL FR BL BR = legs 0..3
 ODG_DEV int gait_call(int& idx, int& cnt, int paws_mask, float vx) {
   const unsigned char pat[8] = { 0xF, 0xB, 0x9, 0xD, 0xF, 0x7, 0x6, 0xF };   // bit l = leg l on the ground
@@ -1179,7 +1191,7 @@ ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const f
                       int env, int leg, unsigned gm, float* ODG_RESTRICT s_red) {
   const int N = P.N;
   const bool real = env < P.n;                     // padding environments never touch caller-owned buffers
-  const int obs_dim = 9 + 3 * C.nu;
+  const int obs_dim = (C.obs_layout ? 12 : 9) + 3 * C.nu;
   // ---- load
   V3 bp = mk3(P.qpos[0 * N + env], P.qpos[1 * N + env], P.qpos[2 * N + env]);
   float bq[4] = { P.qpos[3 * N + env], P.qpos[4 * N + env], P.qpos[5 * N + env], P.qpos[6 * N + env] };
@@ -1241,21 +1253,24 @@ ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const f
   float* obs = (A.obs && real) ? A.obs + (size_t)env * obs_dim : nullptr;
   float* tobs = (A.terminal_obs && A.mode == 0 && real) ? A.terminal_obs + (size_t)env * obs_dim : nullptr;
   auto clip = [](float v) { return fminf(100.f, fmaxf(-100.f, v)); };
-  auto write_obs = [&](float* o, V3 v, V3 wl, const float (&qq)[NJL], const float (&qqd)[NJL], const float (&la)[NJL]) {
+  const int ob = C.obs_layout ? 12 : 9;           // first joint entry (OdgEnvConfig::obs_layout)
+  auto write_obs = [&](float* o, V3 v, V3 wl, const float (&quat)[4], const float (&qq)[NJL], const float (&qqd)[NJL],
+                       const float (&la)[NJL]) {
     if (!o) return;
     if (leg == 0) {
       o[0] = clip(v.x * 2.0f); o[1] = clip(v.y * 2.0f); o[2] = clip(v.z * 2.0f);
       o[3] = clip(wl.x * 0.25f); o[4] = clip(wl.y * 0.25f); o[5] = clip(wl.z * 0.25f);
-      o[6] = clip(desvel.x * 2.0f); o[7] = clip(desvel.y * 2.0f); o[8] = clip(desvel.z * 2.0f);
+      if (C.obs_layout) { float pg[3]; projected_gravity(C, quat, pg); o[6] = pg[0]; o[7] = pg[1]; o[8] = pg[2]; }
+      o[ob - 3] = clip(desvel.x * 2.0f); o[ob - 2] = clip(desvel.y * 2.0f); o[ob - 1] = clip(desvel.z * 2.0f);
     }
     ODG_UNROLL for (int j = 0; j < NJL; j++) {
-      o[9 + leg * NJL + j] = clip(qq[j] - C.obs_joint_offset);
-      o[9 + C.nu + leg * NJL + j] = clip(qqd[j] * 0.05f);
-      if (LCF(LC_HASACT, j) != 0.f) o[9 + 2 * C.nu + (int)LCF(LC_UIDX, j)] = clip(la[j]);
+      o[ob + leg * NJL + j] = clip(qq[j] - (C.obs_layout ? LCF(LC_HOMEQ, j) : C.obs_joint_offset));
+      o[ob + C.nu + leg * NJL + j] = clip(qqd[j] * 0.05f);
+      if (LCF(LC_HASACT, j) != 0.f) o[ob + 2 * C.nu + (int)LCF(LC_UIDX, j)] = clip(la[j]);
     }
   };
-  write_obs(obs, bv, bwl, q, qd, prev_act);
-  if (tobs) write_obs(tobs, bv, bwl, q, qd, prev_act);
+  write_obs(obs, bv, bwl, bq, q, qd, prev_act);
+  if (tobs) write_obs(tobs, bv, bwl, bq, q, qd, prev_act);
 
   // ---- reward / termination (WalkEnvironment.py:81-109, reward_calc.py), double where the reference is
   const double lim = 15.0 * 3.14159265358979323846 / 180.0;
@@ -1393,7 +1408,7 @@ ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const f
       q[j] = v; qd[j] = 0.f; warm_l[j] = 0.f; last_act[j] = 0.f;
     }
     step = 0; is_fresh = true; episode += 1;
-    write_obs(obs, bv, bwl, q, qd, last_act);
+    write_obs(obs, bv, bwl, bq, q, qd, last_act);
   }
   // ---- store
   ODG_UNROLL for (int j = 0; j < NJL; j++) {
@@ -1421,7 +1436,7 @@ template <int NJL>
 ODG_DEV void env_reset(const DevConst& C, const float* ODG_RESTRICT s_lc, const SimPtrs& P, float* obs_out,
                        int env, int leg, unsigned gm) {
   const int N = P.N;
-  const int obs_dim = 9 + 3 * C.nu;
+  const int obs_dim = (C.obs_layout ? 12 : 9) + 3 * C.nu;
   const unsigned episode = P.episode[env];
   grp_sync(gm);                                    // all lanes read the counter before lane 0 bumps it
   const uint32_t gid = (uint32_t)(C.first_env_id + env);
@@ -1437,6 +1452,7 @@ ODG_DEV void env_reset(const DevConst& C, const float* ODG_RESTRICT s_lc, const 
   }
   float* obs = (obs_out && env < P.n) ? obs_out + (size_t)env * obs_dim : nullptr;
   auto clip = [](float v) { return fminf(100.f, fmaxf(-100.f, v)); };
+  const int ob = C.obs_layout ? 12 : 9;
   for (int j = 0; j < NJL; j++) {
     const int qi = 7 + leg * NJL + j;
     P.qpos[qi * N + env] = kq[qi];
@@ -1444,9 +1460,9 @@ ODG_DEV void env_reset(const DevConst& C, const float* ODG_RESTRICT s_lc, const 
     P.warm[(6 + leg * NJL + j) * N + env] = 0.f;
     if (LCF(LC_HASACT, j) != 0.f) P.last_action[(int)LCF(LC_UIDX, j) * N + env] = 0.f;
     if (obs) {
-      obs[9 + leg * NJL + j] = clip(kq[qi] - C.obs_joint_offset);
-      obs[9 + C.nu + leg * NJL + j] = 0.f;
-      if (LCF(LC_HASACT, j) != 0.f) obs[9 + 2 * C.nu + (int)LCF(LC_UIDX, j)] = 0.f;
+      obs[ob + leg * NJL + j] = clip(kq[qi] - (C.obs_layout ? LCF(LC_HOMEQ, j) : C.obs_joint_offset));
+      obs[ob + C.nu + leg * NJL + j] = 0.f;
+      if (LCF(LC_HASACT, j) != 0.f) obs[ob + 2 * C.nu + (int)LCF(LC_UIDX, j)] = 0.f;
     }
   }
   if (leg == 0) {
@@ -1455,7 +1471,12 @@ ODG_DEV void env_reset(const DevConst& C, const float* ODG_RESTRICT s_lc, const 
     P.step[env] = 0; P.fresh[env] = 1; P.episode[env] = episode + 1;
     if (obs) {
       for (int i = 0; i < 6; i++) obs[i] = 0.f;
-      for (int i = 0; i < 3; i++) obs[6 + i] = clip(P.desvel[i * N + env] * 2.0f);
+      if (C.obs_layout) {
+        const float quat[4] = { kq[3], kq[4], kq[5], kq[6] };
+        float pg[3]; projected_gravity(C, quat, pg);
+        for (int i = 0; i < 3; i++) obs[6 + i] = pg[i];
+      }
+      for (int i = 0; i < 3; i++) obs[ob - 3 + i] = clip(P.desvel[i * N + env] * 2.0f);
     }
   }
 }

@@ -204,6 +204,7 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
   }
   C.frame_skip = cfg.frame_skip; C.max_steps = cfg.max_episode_steps; C.auto_reset = cfg.auto_reset;
   C.solver_iters = cfg.solver_iterations; C.ls_iters = cfg.ls_iterations; C.scale_actions = cfg.scale_actions;
+  C.obs_layout = cfg.obs_layout ? 1 : 0;
   C.first_env_id = cfg.first_env_id; C.tol = cfg.solver_tolerance; C.ls_tol = cfg.ls_tolerance; C.noise = cfg.reset_noise_scale;
   C.seed_lo = (uint32_t)seed; C.seed_hi = (uint32_t)(seed >> 32);
   if (cfg.frame_skip < 1 || cfg.solver_iterations < 1 || cfg.ls_iterations < 1) return "bad config";
@@ -213,7 +214,7 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
 inline void default_config(OdgEnvConfig* c) {
   c->task = ODG_TASK_WALK; c->frame_skip = 10; c->max_episode_steps = 750; c->auto_reset = 1;
   c->solver_iterations = 30; c->ls_iterations = 4; c->solver_tolerance = 1e-4f; c->ls_tolerance = 0.1f; c->reset_noise_scale = 0.02f;
-  c->scale_actions = 1; c->regroup = 0; c->first_env_id = 0;
+  c->scale_actions = 1; c->regroup = 0; c->first_env_id = 0; c->obs_layout = 0;
 }
 
 }  // namespace odg

@@ -61,6 +61,8 @@ class BatchedWalkEnv:
         self._model = to_struct(self.desc)
         self.cfg = _lib.OdgEnvConfig()
         self.L.odg_default_config(C.byref(self.cfg))
+        if self.desc["nu"] == 12:
+            self.cfg.obs_layout = 1        # 12-actuator models: the 48-value layout (landing_environment.py:116-136 + v_des)
         for k, v in config.items():
             if not hasattr(self.cfg, k):
                 raise TypeError(f"unknown config field {k!r}")

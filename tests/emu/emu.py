@@ -24,7 +24,7 @@ class OdgEnvConfig(C.Structure):
     _fields_ = [("task", C.c_int), ("frame_skip", C.c_int), ("max_episode_steps", C.c_int),
                 ("auto_reset", C.c_int), ("solver_iterations", C.c_int), ("ls_iterations", C.c_int),
                 ("solver_tolerance", C.c_float), ("ls_tolerance", C.c_float), ("reset_noise_scale", C.c_float),
-                ("scale_actions", C.c_int), ("regroup", C.c_int), ("first_env_id", C.c_int)]
+                ("scale_actions", C.c_int), ("regroup", C.c_int), ("first_env_id", C.c_int), ("obs_layout", C.c_int)]
 
 
 _p = C.c_void_p
@@ -84,7 +84,7 @@ class EmuEnv:
         self.h = lib().emu_create(C.byref(self.m), C.byref(self.cfg), num_envs, seed)
         assert self.h
         self.nq, self.nv, self.nu = self.desc["nq"], self.desc["nv"], self.desc["nu"]
-        self.obs_dim = 9 + 3 * self.nu
+        self.obs_dim = (12 if self.cfg.obs_layout else 9) + 3 * self.nu
 
     def __del__(self):
         if getattr(self, "h", None):

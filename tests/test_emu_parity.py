@@ -104,3 +104,29 @@ def test_go1_single_step_parity():
         assert info["ncon"][0] == sim.ncon, k
     assert worst_q <= 0 and worst_v <= 0, (worst_q, worst_v)
     assert sim.ncon >= 3                      # it is standing on its feet
+
+
+def test_go1_observation_layout_48():
+    """OdgEnvConfig::obs_layout = 1, the 48-value observation of the 12-actuator model (BASELINE configs[2]):
+    landing_environment.py:116-136 plus the desired velocity, with the reference's get_projected_gravity formula
+    (landing_environment_reward_calc.py:88-98) restated in numpy here."""
+    e48 = EmuEnv(4, model="go1", seed=3, obs_layout=1)
+    e45 = EmuEnv(4, model="go1", seed=3)
+    rng = np.random.default_rng(0)
+    o48, o45 = e48.reset(), e45.reset()
+    for t in range(4):
+        assert o48.shape == (4, 48) and o45.shape == (4, 45)
+        assert np.array_equal(o48[:, :6], o45[:, :6]) and np.array_equal(o48[:, 9:12], o45[:, 6:9])
+        assert np.array_equal(o48[:, 24:], o45[:, 21:])                   # joint velocities, last action
+        q, _, _ = e48.get_state()
+        key = np.array(e48.desc["key_qpos"][7:19], np.float32)
+        assert np.allclose(o48[:, 12:24], q[:, 7:19] - key, atol=1e-6)
+        w, x, y, z = q[:, 3:7].astype(np.float64).T
+        eul = np.stack([np.arctan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y)),
+                        np.arcsin(np.clip(2 * (w * y - z * x), -1, 1)),
+                        np.arctan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))], 1)
+        v = (eul @ np.array(e48.desc["gravity"]))[:, None] * eul
+        n = np.linalg.norm(v, axis=1, keepdims=True)
+        assert np.allclose(o48[:, 6:9], np.where(n == 0, v, v / np.where(n == 0, 1, n)), atol=1e-6)
+        a = rng.uniform(-0.3, 0.3, (4, 12)).astype(np.float32)
+        o48, o45 = e48.step(a, info=False)[0], e45.step(a, info=False)[0]

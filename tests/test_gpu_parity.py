@@ -199,7 +199,24 @@ def test_go1_physics_parity_and_env():
     # the env surface on Go1
     e = BatchedWalkEnv(256, model="go1", seed=3, info_keys=None)
     obs = e.reset()
-    assert obs.shape == (256, 45) and e.act_dim == 12
+    assert obs.shape == (256, 48) and e.act_dim == 12          # BASELINE configs[2]: policy MLP 48-512-256-12
+    e45 = BatchedWalkEnv(256, model="go1", seed=3, info_keys=None, obs_layout=0)
+    o45 = e45.reset()
+    assert o45.shape == (256, 45)
+    # layout 1 = [v, w, projected_gravity, v_des, q - key_qpos, qd, last_action]; the shared entries agree with layout 0
+    assert torch.equal(obs[:, :6], o45[:, :6]) and torch.equal(obs[:, 9:12], o45[:, 6:9]) and torch.equal(obs[:, 24:], o45[:, 21:])
+    q0, _ = e.get_state()
+    from opendog_b200.model.compile import load_compiled
+    key = torch.tensor(load_compiled("go1")["key_qpos"][7:19], dtype=torch.float32, device="cuda")
+    assert torch.allclose(obs[:, 12:24], q0[:, 7:19] - key, atol=1e-6)
+    # projected_gravity is the reference's Euler-angle formula (landing_environment_reward_calc.py:88-98), in double
+    qq = q0[:, 3:7].double().cpu().numpy()
+    w, x, y, z = qq.T
+    eul = np.stack([np.arctan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y)), np.arcsin(np.clip(2 * (w * y - z * x), -1, 1)),
+                    np.arctan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))], 1)
+    v = (eul @ np.array([0.0, 0.0, -9.81]))[:, None] * eul
+    pg = v / np.linalg.norm(v, axis=1, keepdims=True)
+    assert np.allclose(obs[:, 6:9].cpu().numpy(), pg, atol=1e-6)
     for t in range(20):
         obs, rew, done, _ = e.step((torch.rand(256, 12, device="cuda") * 2 - 1) * 0.3)
     assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and (rew >= 0).all()
@@ -253,6 +270,23 @@ def test_determinism_sharding_and_soak():
         return out
     a, b = run(128, 0, slice(0, 128)), run(128, 0, slice(0, 128))
     assert all(torch.equal(x, y) for x, y in zip(a, b))
+    # the launch shape is a host-side choice (2 environments per warp for tiny batches, 8 otherwise; 1-4 warps per
+    # block): it must not change a single bit. Block-lockstep iterations (large batches) start each substep's Newton
+    # iteration from MuJoCo's plain warm start instead of the extrapolated one, so that mode is compared with itself.
+    import os
+
+    def shaped(**shape):
+        os.environ.update(shape)
+        try:
+            return run(128, 0, slice(0, 128))
+        finally:
+            for k in shape: os.environ.pop(k, None)
+    c = shaped(ODG_STEP_LANES="32", ODG_STEP_BLOCK="128", ODG_LOCKSTEP="0")
+    assert all(torch.equal(x, y) for x, y in zip(a, c))
+    d1 = shaped(ODG_STEP_LANES="32", ODG_STEP_BLOCK="64", ODG_LOCKSTEP="1")
+    d2 = shaped(ODG_STEP_LANES="16", ODG_STEP_BLOCK="128", ODG_LOCKSTEP="1")
+    assert all(torch.equal(x, y) for x, y in zip(d1, d2))
+    assert float((a[1] - d1[1]).abs().median()) < 1e-4       # first-step obs: same minimiser, different starting point
     lo, hi = run(64, 0, slice(0, 64)), run(64, 64, slice(64, 128))
     for x, y, z in zip(a, lo, hi):
         assert torch.equal(x, torch.cat([y, z]))
