@@ -97,6 +97,7 @@ struct DevConst {
   int slot_condim[kMaxSlot], slot_isfoot[kMaxSlot];
   float slot_margin[kMaxSlot], slot_K[kMaxSlot], slot_B[kMaxSlot], slot_imp[kMaxSlot][5];
   float slot_fri[kMaxSlot], slot_mu[kMaxSlot], slot_radius[kMaxSlot];
+  float slot_dmk[kMaxSlot];                     // 1 / (mu^2 (1 + mu^2)): Dm = Dn * slot_dmk (cone surface stiffness)
   float tilt_dir[3][3];                         // extra support directions (world)
   int n_tilt;
   // env
@@ -291,7 +292,7 @@ ODG_DEV int cone_zone(float N, float T2, float T, float mu) {
 }
 
 // elliptic-cone contact block. z = (zx, zy, zn) in world axes (normal = +z). Returns the zone.
-ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, int condim, V3& g, S3& H) {
+ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, float dmk, int condim, V3& g, S3& H) {
   g = mk3(0.f, 0.f, 0.f); H = zero_s3();
   if (condim == 1) {
     if (z.z >= 0.f) return 0;
@@ -312,7 +313,7 @@ ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, int condim,
   // v = (u_perp*fri, 0):   g = Dm*e*w,   H = Dm * w w^T + kappa * v v^T,   kappa = Dm*mu*|e|/T >= 0.
   // Written as this sum of two rank-1 PSD terms the block cannot turn indefinite in fp32; the algebraically equal
   // closed form mu*N/T^3*U U^T + (mu^2 - mu*N/T) I cancels catastrophically when T is small.
-  const float Dm = Dn / (mu * mu * (1.f + mu * mu));
+  const float Dm = Dn * dmk;
   const float e = N - mu * T;
   const float ux = U1 * iT, uy = U2 * iT;
   const V3 w = mk3(-mu * ux * fri, -mu * uy * fri, mu);
@@ -325,7 +326,7 @@ ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, int condim,
 }
 
 // the same block restricted to the line z + alpha*dz: adds d/dalpha and d2/dalpha2 of its cost
-ODG_DEV int cone_line(V3 z, V3 dz, float Dn, float Dt, float mu, float fri, int condim, float& d1, float& d2) {
+ODG_DEV int cone_line(V3 z, V3 dz, float Dn, float Dt, float mu, float fri, float dmk, int condim, float& d1, float& d2) {
   if (condim == 1) {
     if (z.z < 0.f) { d1 += Dn * z.z * dz.z; d2 += Dn * dz.z * dz.z; return 1; }
     return 0;
@@ -342,7 +343,7 @@ ODG_DEV int cone_line(V3 z, V3 dz, float Dn, float Dt, float mu, float fri, int 
     return 1;
   }
   float V1 = dz.x * fri, V2 = dz.y * fri, Nd = dz.z * mu;
-  float Dm = Dn / (mu * mu * (1.f + mu * mu));
+  float Dm = Dn * dmk;
   float NmT = N - mu * T;
   float Td = (U1 * V1 + U2 * V2) * iT;                 // dT/dalpha
   float Tdd = (V1 * V1 + V2 * V2 - Td * Td) * iT;      // d2T/dalpha2
@@ -354,14 +355,14 @@ ODG_DEV int cone_line(V3 z, V3 dz, float Dn, float Dt, float mu, float fri, int 
 
 // phi' contribution of one contact block at four step lengths: f[k] += d/dalpha cost(z0 + al[k]*dz). Branch-free
 // zone selection so the four evaluations interleave.
-ODG_DEV void cone_line4(V3 z0, V3 dz, float Dn, float Dt, float mu, float fri, int condim, const float (&al)[4], float (&f)[4]) {
+ODG_DEV void cone_line4(V3 z0, V3 dz, float Dn, float Dt, float mu, float fri, float dmk, int condim, const float (&al)[4], float (&f)[4]) {
   if (condim == 1) {
     const float Ddz = Dn * dz.z;
     ODG_UNROLL for (int k = 0; k < 4; k++) f[k] += fminf(z0.z + al[k] * dz.z, 0.f) * Ddz;
     return;
   }
   const float U0x = z0.x * fri, U0y = z0.y * fri, Vx = dz.x * fri, Vy = dz.y * fri, N0 = z0.z * mu, Nd = dz.z * mu;
-  const float Dm = Dn / (mu * mu * (1.f + mu * mu));
+  const float Dm = Dn * dmk;
   const float qb1 = Dt * (z0.x * dz.x + z0.y * dz.y) + Dn * z0.z * dz.z;      // sticking zone: phi' = qb1 + alpha*qb2
   const float qb2 = Dt * (dz.x * dz.x + dz.y * dz.y) + Dn * dz.z * dz.z;
   ODG_UNROLL for (int k = 0; k < 4; k++) {
@@ -831,7 +832,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         c_z0[c] = z;
         V3 g; S3 H;
         const float Dn = c_Dn[c];
-        int zone = cone_eval(z, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_condim[s], g, H);
+        int zone = cone_eval(z, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
         if (zone == 0 || Dn == 0.f) continue;
         gb.t = gb.t + g; gb.w = gb.w + cross(r, g);
         // H * X, X = -[r]x : column i of X is e_i x r
@@ -985,7 +986,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
           const int s = c_slot[c];
           const float Dn = c_Dn[c];
           if (Dn == 0.f) continue;
-          cone_line4(c_z0[c], c_dz[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_condim[s], al, f);
+          cone_line4(c_z0[c], c_dz[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], al, f);
         }
       }
       ODG_UNROLL for (int k = 0; k < 4; k++) f[k] = grp_sum(f[k], gm);
@@ -1070,7 +1071,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         V3 ap = a_b.t + cross(a_b.w, r);
         ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) ap = ap + a_l[j] * cross(ax[j], r - anc[j]);
         V3 g; S3 H;
-        cone_eval(ap - c_aref[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_condim[s], g, H);
+        cone_eval(ap - c_aref[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
         fn += -g.z;
         if (c == foot_last) out.foot_force = mk3(-g.z, -g.y, g.x);   // MuJoCo frame: n=+z, t1=+y, t2=-x
       }

@@ -179,6 +179,7 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
     C.slot_K[s] = (float)K; C.slot_B[s] = (float)B; pack_imp(g0.solimp, C.slot_imp[s]);
     C.slot_fri[s] = (float)g0.friction;
     C.slot_mu[s] = (float)(g0.friction / std::sqrt(std::fmax(1e-15, m.impratio)));
+    { const double mu = (double)C.slot_mu[s]; C.slot_dmk[s] = (float)(1.0 / std::fmax(1e-30, mu * mu * (1.0 + mu * mu))); }
     rows += nv;
   }
   C.nvert_rows = rows;

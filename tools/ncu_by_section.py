@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Attribute ncu per-SASS-instruction counters to sections of odg_core.cuh.
 
-    python tools/ncu_by_section.py gpurun_out/prof.ncu-rep [kernel-substring]
+    python tools/ncu_by_section.py gpurun_out/prof.ncu-rep [kernel-substring] [--lines=40]
 
 Joins `ncu --page source --csv` (SASS rows, in program order) with `nvdisasm -g` line info of the
 same cubin (extracted from opendog_b200/libodgsim.so), then buckets by the `// ----` section markers.
@@ -25,8 +25,10 @@ def num(x):
 
 
 def main():
-    rep = sys.argv[1]
-    kern = sys.argv[2] if len(sys.argv) > 2 else "k_stepILi2ELb0"
+    argv = [a for a in sys.argv[1:] if not a.startswith("--lines")]
+    top_lines = next((int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--lines=")), 0)
+    rep = argv[0]
+    kern = argv[1] if len(argv) > 1 else "k_stepILi2ELb0"
     so = os.environ.get("ODG_LIB_PATH", os.path.join(ROOT, "opendog_b200", "libodgsim.so"))
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
@@ -86,6 +88,18 @@ def main():
     print("  line   %inst  thr/inst  %samples  static  section")
     for (ln, name), a in sorted(agg.items()):
         print(f"{ln:6d} {a[0] / tot * 100:6.2f}%  {a[1] / max(a[0], 1):6.1f}  {a[2] / max(tots, 1) * 100:7.2f}%  {a[3]:6d}  {name[:80]}")
+    if top_lines:
+        per = {}
+        for i in range(n):
+            a = per.setdefault(lines_of_inst[i], [0.0, 0.0, 0.0, 0])
+            d = data[i]
+            a[0] += num(d["Instructions Executed"]); a[1] += num(d["Thread Instructions Executed"])
+            a[2] += num(d["# Samples"]); a[3] += 1
+        print(f"\ntop {top_lines} source lines of odg_core.cuh by executed warp-instructions")
+        print("  line   %inst  thr/inst  %samples  static  source")
+        for ln, a in sorted(per.items(), key=lambda kv: -kv[1][0])[:top_lines]:
+            text = src[ln - 1].strip() if ln and 0 < ln <= len(src) else "?"
+            print(f"{ln or 0:6d} {a[0] / tot * 100:6.2f}%  {a[1] / max(a[0], 1):6.1f}  {a[2] / max(tots, 1) * 100:7.2f}%  {a[3]:6d}  {text[:110]}")
 
 
 if __name__ == "__main__":
