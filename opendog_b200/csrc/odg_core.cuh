@@ -53,6 +53,10 @@ static inline float odg_fdiv_rn(float a, float b) { volatile float r = a / b; re
 #define ODG_NO_UNROLL _Pragma("unroll 1")
 #endif
 
+#ifndef ODG_LS_WIDTH
+#define ODG_LS_WIDTH 4
+#endif
+
 namespace odg {
 
 constexpr int kMaxJL = 3;
@@ -355,17 +359,18 @@ ODG_DEV int cone_line(V3 z, V3 dz, float Dn, float Dt, float mu, float fri, floa
 
 // phi' contribution of one contact block at four step lengths: f[k] += d/dalpha cost(z0 + al[k]*dz). Branch-free
 // zone selection so the four evaluations interleave.
-ODG_DEV void cone_line4(V3 z0, V3 dz, float Dn, float Dt, float mu, float fri, float dmk, int condim, const float (&al)[4], float (&f)[4]) {
+template <int W>
+ODG_DEV void cone_line4(V3 z0, V3 dz, float Dn, float Dt, float mu, float fri, float dmk, int condim, const float (&al)[W], float (&f)[W]) {
   if (condim == 1) {
     const float Ddz = Dn * dz.z;
-    ODG_UNROLL for (int k = 0; k < 4; k++) f[k] += fminf(z0.z + al[k] * dz.z, 0.f) * Ddz;
+    ODG_UNROLL for (int k = 0; k < W; k++) f[k] += fminf(z0.z + al[k] * dz.z, 0.f) * Ddz;
     return;
   }
   const float U0x = z0.x * fri, U0y = z0.y * fri, Vx = dz.x * fri, Vy = dz.y * fri, N0 = z0.z * mu, Nd = dz.z * mu;
   const float Dm = Dn * dmk;
   const float qb1 = Dt * (z0.x * dz.x + z0.y * dz.y) + Dn * z0.z * dz.z;      // sticking zone: phi' = qb1 + alpha*qb2
   const float qb2 = Dt * (dz.x * dz.x + dz.y * dz.y) + Dn * dz.z * dz.z;
-  ODG_UNROLL for (int k = 0; k < 4; k++) {
+  ODG_UNROLL for (int k = 0; k < W; k++) {
     const float a = al[k];
     const float Ux = U0x + a * Vx, Uy = U0y + a * Vy, N = N0 + a * Nd;
     const float T2 = Ux * Ux + Uy * Uy;
@@ -957,39 +962,61 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     // phi'(alpha) at four step lengths at once (lane-partial sums, then one group reduction per value). The four
     // evaluations are independent, which gives the scheduler 4-way ILP in the kernel's hottest loop, and the
     // number of passes is fixed (<= C.ls_iters), so environments sharing a warp do not diverge here.
-    auto eval4 = [&](const float (&al)[4], float (&f)[4]) {
-      ODG_UNROLL for (int k = 0; k < 4; k++) f[k] = G + al[k] * Hq;
+    constexpr int LW = ODG_LS_WIDTH;                // step lengths evaluated per trip through the row code
+    auto evalw = [&](const float (&al)[LW], float (&f)[LW]) {
+      ODG_UNROLL for (int k = 0; k < LW; k++) f[k] = G + al[k] * Hq;
       ODG_UNROLL for (int j = 0; j < NJL; j++) {
         const float fl = LCF(LC_FL, j);
         if (fl > 0.f) {
           const float D = LCF(LC_DFL, j), z0 = a_l[j] - aref_fl[j], dz = p_l[j];
-          ODG_UNROLL for (int k = 0; k < 4; k++) f[k] += fminf(fmaxf(D * (z0 + al[k] * dz), -fl), fl) * dz;
+          ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(fmaxf(D * (z0 + al[k] * dz), -fl), fl) * dz;
         }
         if (lim_sgn[j] != 0.f) {
           const float dzl = lim_sgn[j] * p_l[j], z0 = lim_sgn[j] * a_l[j] - lim_aref[j], Dd = lim_D[j] * dzl;
-          ODG_UNROLL for (int k = 0; k < 4; k++) f[k] += fminf(z0 + al[k] * dzl, 0.f) * Dd;
+          ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(z0 + al[k] * dzl, 0.f) * Dd;
         }
       }
       if (bf_ft > 0.f) {
-        ODG_UNROLL for (int k = 0; k < 4; k++) f[k] += fminf(fmaxf(bf_Dt * (bf_zt + al[k] * bf_dzt), -bf_ft), bf_ft) * bf_dzt;
+        ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(fmaxf(bf_Dt * (bf_zt + al[k] * bf_dzt), -bf_ft), bf_ft) * bf_dzt;
       }
       if (bf_fr > 0.f) {
-        ODG_UNROLL for (int k = 0; k < 4; k++) f[k] += fminf(fmaxf(bf_Dr * (bf_zr + al[k] * bf_dzr), -bf_fr), bf_fr) * bf_dzr;
+        ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(fmaxf(bf_Dr * (bf_zr + al[k] * bf_dzr), -bf_fr), bf_fr) * bf_dzr;
       }
       if (PL1) {
         for (int c = 0; c < nc; c++) {
           const float dz = c_dzz[c], z0 = c_zz[c], Ddz = c_Dn[c] * dz;
-          ODG_UNROLL for (int k = 0; k < 4; k++) f[k] += fminf(z0 + al[k] * dz, 0.f) * Ddz;
+          ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(z0 + al[k] * dz, 0.f) * Ddz;
         }
       } else {
         for (int c = 0; c < nc; c++) {
           const int s = c_slot[c];
           const float Dn = c_Dn[c];
           if (Dn == 0.f) continue;
-          cone_line4(c_z0[c], c_dz[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], al, f);
+          cone_line4<LW>(c_z0[c], c_dz[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], al, f);
         }
       }
-      ODG_UNROLL for (int k = 0; k < 4; k++) f[k] = grp_sum(f[k], gm);
+      ODG_UNROLL for (int k = 0; k < LW; k++) f[k] = grp_sum(f[k], gm);
+    };
+    auto eval4 = [&](const float (&al)[4], float (&f)[4]) {
+      if (LW == 4) {
+        float a4[LW], f4[LW];
+        ODG_UNROLL for (int k = 0; k < LW; k++) a4[k] = al[k % 4];
+        evalw(a4, f4);
+        ODG_UNROLL for (int k = 0; k < LW; k++) f[k % 4] = f4[k];
+      } else {
+        // narrower row code run 4/LW times in a rolled loop: a smaller Newton-iteration body (instruction fetch is what
+        // bounds this kernel) for less instruction-level parallelism
+        ODG_NO_UNROLL for (int h = 0; h < 4 / LW; h++) {
+          float aw[LW], fw[LW];
+          ODG_UNROLL for (int k = 0; k < LW; k++) {
+            aw[k] = al[k];
+            ODG_UNROLL for (int g = 1; g < 4 / LW; g++) aw[k] = (h == g) ? al[(g * LW + k) % 4] : aw[k];
+          }
+          evalw(aw, fw);
+          ODG_UNROLL for (int k = 0; k < LW; k++)
+            ODG_UNROLL for (int g = 0; g < 4 / LW; g++) if (h == g) f[(g * LW + k) % 4] = fw[k];
+        }
+      }
     };
     // size of the full Newton step relative to the iterate: when it is already negligible this is the last iteration
     // and the step is taken without a line search
