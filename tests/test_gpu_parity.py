@@ -300,3 +300,48 @@ def test_determinism_sharding_and_soak():
     assert torch.isfinite(o).all() and torch.isfinite(q).all() and torch.isfinite(v).all()
     assert ndone >= 5 * 1024 and 0.0 <= rmax < 200.0
     assert float(q[:, 2].min()) > -0.01 and float(q[:, 2].max()) < 0.5          # nobody fell through the floor or flew away
+
+
+def test_full_size_batches_equal_small_batches_and_hold_their_weight():
+    """BASELINE.json's full sizes through size-independent properties. (1) The first and last 64 environments of a
+    65536-environment handle (configs[3]) are bit-identical to 64-environment handles with the same global ids — the
+    small shapes are the ones checked against the oracle above (same iteration mode: ODG_LOCKSTEP pinned, see the
+    determinism test). (2) Same for 4096 environments (configs[1]). (3) 4096 robots holding the home pose come to
+    rest carrying their weight: sum of contact normal forces = total mass x 9.81 within 2 %, quaternions stay
+    normalised, nobody sinks below the floor."""
+    import os
+    from opendog_b200.env import BatchedWalkEnv
+    from opendog_b200.model.compile import load_compiled
+    os.environ["ODG_LOCKSTEP"] = "1"
+    try:
+        for n in (65536, 4096):
+            g = torch.Generator(device="cuda").manual_seed(n)
+            acts = torch.rand(6, n, 8, device="cuda", generator=g) * 2 - 1
+            big = BatchedWalkEnv(n, seed=13, info_keys=None)
+            lo = BatchedWalkEnv(64, seed=13, info_keys=None)
+            hi = BatchedWalkEnv(64, seed=13, first_env_id=n - 64, info_keys=None)
+            ob, ol, oh = big.reset(), lo.reset(), hi.reset()
+            assert torch.equal(ob[:64], ol) and torch.equal(ob[-64:], oh)
+            for t in range(6):
+                ob, rb, db, _ = big.step(acts[t])
+                ol, rl, dl, _ = lo.step(acts[t, :64].contiguous())
+                oh, rh, dh, _ = hi.step(acts[t, -64:].contiguous())
+                assert torch.equal(ob[:64], ol) and torch.equal(rb[:64], rl) and torch.equal(db[:64], dl), (n, t)
+                assert torch.equal(ob[-64:], oh) and torch.equal(rb[-64:], rh) and torch.equal(db[-64:], dh), (n, t)
+            assert torch.isfinite(ob).all() and torch.isfinite(rb).all()
+            del big, lo, hi
+    finally:
+        os.environ.pop("ODG_LOCKSTEP", None)
+    desc = load_compiled("our_robot")
+    weight = (desc["base_mass"] + float(np.sum(desc["mass"]))) * 9.81
+    env = BatchedWalkEnv(4096, seed=2, info_keys=("contact_normal_force",), scale_actions=0, max_episode_steps=10**6)
+    env.reset()
+    home = torch.tensor(desc["key_ctrl"], dtype=torch.float32, device="cuda").expand(4096, 8).contiguous()
+    for t in range(60):
+        obs, rew, done, info = env.step(home)
+    q, v = env.get_state()
+    rest = (v.abs().max(dim=1).values < 0.05) & ~done
+    assert int(rest.sum()) > 3500, int(rest.sum())
+    fn = info["contact_normal_force"][rest]
+    assert float((fn / weight - 1).abs().max()) < 0.02, (float(fn.min()), float(fn.max()), weight)
+    assert float((q[:, 3:7].norm(dim=1) - 1).abs().max()) < 1e-3 and float(q[:, 2].min()) > 0.0
