@@ -297,22 +297,18 @@ ODG_DEV int cone_zone(float N, float T2, float T, float mu) {
 
 // elliptic-cone contact block. z = (zx, zy, zn) in world axes (normal = +z). Returns the zone.
 ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, float dmk, int condim, V3& g, S3& H) {
-  g = mk3(0.f, 0.f, 0.f); H = zero_s3();
-  if (condim == 1) {
-    if (z.z >= 0.f) return 0;
-    g.z = Dn * z.z; H.zz = Dn; return 1;
-  }
-  float U1 = z.x * fri, U2 = z.y * fri, N = z.z * mu;
-  float T2 = U1 * U1 + U2 * U2;
-  float iT = rsqrtf(fmaxf(T2, 1e-20f));
-  float T = T2 * iT;
-  int zone = cone_zone(N, T2, T, mu);
-  if (zone == 0) return 0;
-  if (zone == 1) {
-    g = mk3(Dt * z.x, Dt * z.y, Dn * z.z);
-    H.xx = Dt; H.yy = Dt; H.zz = Dn;
-    return 1;
-  }
+  // Branch-free: both the sticking-zone and the cone-surface blocks are formed and one is selected (top zone and
+  // D = 0 rows select zeros). Branches here cost more than the arithmetic they skip: every lane of the warp walks the
+  // contact loop anyway, and a branch ends the basic block the scheduler can interleave over.
+  // A frictionless (condim 1) row is the same cone with fri = Dt = 0: T = 0, zone = (N >= 0 ? top : bottom).
+  if (condim == 1) { fri = 0.f; Dt = 0.f; }
+  const float U1 = z.x * fri, U2 = z.y * fri, N = z.z * mu;
+  const float T2 = U1 * U1 + U2 * U2;
+  const float iT = rsqrtf(fmaxf(T2, 1e-20f));
+  const float T = T2 * iT;
+  const bool top = N >= mu * T;                      // separating (T == 0: N >= 0)
+  const bool bot = !top && (mu * N + T <= 0.f);      // sticking
+  const bool mid = !top && !bot;                     // on the cone surface, sliding
   // cost = Dm/2 * e^2 with e = N - mu*T < 0 on the cone surface. With u = U/T, w = de/dz = (-mu*u*fri, mu) and
   // v = (u_perp*fri, 0):   g = Dm*e*w,   H = Dm * w w^T + kappa * v v^T,   kappa = Dm*mu*|e|/T >= 0.
   // Written as this sum of two rank-1 PSD terms the block cannot turn indefinite in fp32; the algebraically equal
@@ -321,12 +317,19 @@ ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, float dmk, 
   const float e = N - mu * T;
   const float ux = U1 * iT, uy = U2 * iT;
   const V3 w = mk3(-mu * ux * fri, -mu * uy * fri, mu);
-  g = (Dm * e) * w;
+  const float De = Dm * e;
   const float kap = -Dm * mu * e * iT;
   const float vx = -uy * fri, vy = ux * fri;
-  H.xx = Dm * w.x * w.x + kap * vx * vx; H.xy = Dm * w.x * w.y + kap * vx * vy; H.yy = Dm * w.y * w.y + kap * vy * vy;
-  H.xz = Dm * w.x * w.z; H.yz = Dm * w.y * w.z; H.zz = Dm * w.z * w.z;
-  return 2;
+  g.x = mid ? De * w.x : (bot ? Dt * z.x : 0.f);
+  g.y = mid ? De * w.y : (bot ? Dt * z.y : 0.f);
+  g.z = mid ? De * w.z : (bot ? Dn * z.z : 0.f);
+  H.xx = mid ? Dm * w.x * w.x + kap * vx * vx : (bot ? Dt : 0.f);
+  H.yy = mid ? Dm * w.y * w.y + kap * vy * vy : (bot ? Dt : 0.f);
+  H.zz = mid ? Dm * w.z * w.z : (bot ? Dn : 0.f);
+  H.xy = mid ? Dm * w.x * w.y + kap * vx * vy : 0.f;
+  H.xz = mid ? Dm * w.x * w.z : 0.f;
+  H.yz = mid ? Dm * w.y * w.z : 0.f;
+  return top ? 0 : (bot ? 1 : 2);
 }
 
 // the same block restricted to the line z + alpha*dz: adds d/dalpha and d2/dalpha2 of its cost
@@ -361,11 +364,9 @@ ODG_DEV int cone_line(V3 z, V3 dz, float Dn, float Dt, float mu, float fri, floa
 // zone selection so the four evaluations interleave.
 template <int W>
 ODG_DEV void cone_line4(V3 z0, V3 dz, float Dn, float Dt, float mu, float fri, float dmk, int condim, const float (&al)[W], float (&f)[W]) {
-  if (condim == 1) {
-    const float Ddz = Dn * dz.z;
-    ODG_UNROLL for (int k = 0; k < W; k++) f[k] += fminf(z0.z + al[k] * dz.z, 0.f) * Ddz;
-    return;
-  }
+  // a frictionless (condim 1) row is the same cone with no tangential part: fri = Dt = 0 gives T = 0, zone = (N >= 0 ?
+  // top : bottom) and phi' = Dn * dz.z * min(z.z, 0) without a branch
+  if (condim == 1) { fri = 0.f; Dt = 0.f; }
   const float U0x = z0.x * fri, U0y = z0.y * fri, Vx = dz.x * fri, Vy = dz.y * fri, N0 = z0.z * mu, Nd = dz.z * mu;
   const float Dm = Dn * dmk;
   const float qb1 = Dt * (z0.x * dz.x + z0.y * dz.y) + Dn * z0.z * dz.z;      // sticking zone: phi' = qb1 + alpha*qb2
@@ -765,24 +766,25 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     }
     const Vec6 gauss_b = gb;                        // lane-partial of (M a - tau)_trunk
     // joint friction-loss + limits
+    // (branch-free: a row that does not exist has fl = 0 / D = 0 and adds exactly 0)
     ODG_UNROLL for (int j = 0; j < NJL; j++) {
-      float fl = LCF(LC_FL, j);
-      if (fl > 0.f) {
-        float g, hh; fl_eval(a_l[j] - aref_fl[j], fl, LCF(LC_RFL, j), LCF(LC_DFL, j), g, hh);
+      {
+        float g, hh; fl_eval(a_l[j] - aref_fl[j], LCF(LC_FL, j), LCF(LC_RFL, j), LCF(LC_DFL, j), g, hh);
         g_l[j] += g; Hll[j][j] += hh;
       }
-      if (lim_sgn[j] != 0.f) {
-        float z = lim_sgn[j] * a_l[j] - lim_aref[j];
-        if (z < 0.f) { g_l[j] += lim_sgn[j] * lim_D[j] * z; Hll[j][j] += lim_D[j]; }
+      {
+        const float z = lim_sgn[j] * a_l[j] - lim_aref[j];
+        const float Dl = z < 0.f ? lim_D[j] : 0.f;
+        g_l[j] += lim_sgn[j] * Dl * z; Hll[j][j] += Dl;
       }
     }
     // trunk friction-loss rows: lane l < 3 owns translational row l and rotational row l
-    if (bf_ft > 0.f) {
+    {
       float g, hh; fl_eval(dot(bf_e, a_b.t) - bf_aref_t, bf_ft, bf_Rt, bf_Dt, g, hh);
       gb.t = gb.t + g * bf_e;
       Htt.xx += hh * bf_e.x; Htt.yy += hh * bf_e.y; Htt.zz += hh * bf_e.z;
     }
-    if (bf_fr > 0.f) {
+    {
       float g, hh; fl_eval(dot(bf_c, a_b.w) - bf_aref_r, bf_fr, bf_Rr, bf_Dr, g, hh);
       gb.w = gb.w + g * bf_c;
       Hww.xx += hh * bf_c.x * bf_c.x; Hww.xy += hh * bf_c.x * bf_c.y; Hww.xz += hh * bf_c.x * bf_c.z;
@@ -837,8 +839,8 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         c_z0[c] = z;
         V3 g; S3 H;
         const float Dn = c_Dn[c];
-        int zone = cone_eval(z, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
-        if (zone == 0 || Dn == 0.f) continue;
+        cone_eval(z, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
+        // (separated rows and rows with D = 0 come back as g = 0, H = 0 and add exactly 0 below)
         gb.t = gb.t + g; gb.w = gb.w + cross(r, g);
         // H * X, X = -[r]x : column i of X is e_i x r
         V3 X0 = mk3(0.f, -r.z, r.y), X1 = mk3(r.z, 0.f, -r.x), X2 = mk3(-r.y, r.x, 0.f);
@@ -849,15 +851,13 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         Htw[0][2] += HX2.x; Htw[1][2] += HX2.y; Htw[2][2] += HX2.z;
         Hww.xx += dot(X0, HX0); Hww.xy += dot(X0, HX1); Hww.xz += dot(X0, HX2);
         Hww.yy += dot(X1, HX1); Hww.yz += dot(X1, HX2); Hww.zz += dot(X2, HX2);
-        ODG_UNROLL for (int j = 0; j < NJL; j++) {
-          if (j <= link) {
-            V3 hc = mul(H, cj[j]);
-            g_l[j] += dot(cj[j], g);
-            Hlb[j].t = Hlb[j].t + hc; Hlb[j].w = Hlb[j].w + cross(r, hc);
-            ODG_UNROLL for (int i = 0; i <= j; i++) {
-              float v = dot(cj[i], hc);
-              Hll[j][i] += v; if (i != j) Hll[i][j] += v;
-            }
+        ODG_UNROLL for (int j = 0; j < NJL; j++) {    // (cj[j] = 0 for joints below the contact's link: adds exactly 0)
+          V3 hc = mul(H, cj[j]);
+          g_l[j] += dot(cj[j], g);
+          Hlb[j].t = Hlb[j].t + hc; Hlb[j].w = Hlb[j].w + cross(r, hc);
+          ODG_UNROLL for (int i = 0; i <= j; i++) {
+            float v = dot(cj[i], hc);
+            Hll[j][i] += v; if (i != j) Hll[i][j] += v;
           }
         }
       }
@@ -949,7 +949,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         const int link = C.slot_link[c_slot[c]];
         const V3 r = c_r[c];
         V3 dz = p_b.t + cross(p_b.w, r);
-        ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) dz = dz + p_l[j] * cross(ax[j], r - anc[j]);
+        ODG_UNROLL for (int j = 0; j < NJL; j++) dz = dz + (j <= link ? p_l[j] : 0.f) * cross(ax[j], r - anc[j]);
         c_dz[c] = dz;
       }
     }
@@ -965,33 +965,29 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     constexpr int LW = ODG_LS_WIDTH;                // step lengths evaluated per trip through the row code
     auto evalw = [&](const float (&al)[LW], float (&f)[LW]) {
       ODG_UNROLL for (int k = 0; k < LW; k++) f[k] = G + al[k] * Hq;
+      // friction-loss and limit rows, branch-free: a row that does not exist has fl = 0 / D = 0 and adds exactly 0
       ODG_UNROLL for (int j = 0; j < NJL; j++) {
         const float fl = LCF(LC_FL, j);
-        if (fl > 0.f) {
+        {
           const float D = LCF(LC_DFL, j), z0 = a_l[j] - aref_fl[j], dz = p_l[j];
           ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(fmaxf(D * (z0 + al[k] * dz), -fl), fl) * dz;
         }
-        if (lim_sgn[j] != 0.f) {
+        {
           const float dzl = lim_sgn[j] * p_l[j], z0 = lim_sgn[j] * a_l[j] - lim_aref[j], Dd = lim_D[j] * dzl;
           ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(z0 + al[k] * dzl, 0.f) * Dd;
         }
       }
-      if (bf_ft > 0.f) {
-        ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(fmaxf(bf_Dt * (bf_zt + al[k] * bf_dzt), -bf_ft), bf_ft) * bf_dzt;
-      }
-      if (bf_fr > 0.f) {
-        ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(fmaxf(bf_Dr * (bf_zr + al[k] * bf_dzr), -bf_fr), bf_fr) * bf_dzr;
-      }
+      ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(fmaxf(bf_Dt * (bf_zt + al[k] * bf_dzt), -bf_ft), bf_ft) * bf_dzt;
+      ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(fmaxf(bf_Dr * (bf_zr + al[k] * bf_dzr), -bf_fr), bf_fr) * bf_dzr;
       if (PL1) {
         for (int c = 0; c < nc; c++) {
           const float dz = c_dzz[c], z0 = c_zz[c], Ddz = c_Dn[c] * dz;
           ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(z0 + al[k] * dz, 0.f) * Ddz;
         }
       } else {
-        for (int c = 0; c < nc; c++) {
+        for (int c = 0; c < nc; c++) {               // (a row with D = 0 adds exactly 0: no skip, no branch)
           const int s = c_slot[c];
           const float Dn = c_Dn[c];
-          if (Dn == 0.f) continue;
           cone_line4<LW>(c_z0[c], c_dz[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], al, f);
         }
       }
