@@ -39,6 +39,7 @@ static inline float odg_fmul_rn(float a, float b) { volatile float r = a * b; re
 static inline float odg_fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float odg_fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float odg_fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline float odg_fdiv_fast(float a, float b) { return a / b; }
 #define ODG_UNROLL
 #define ODG_NO_UNROLL
 #else
@@ -49,6 +50,7 @@ static inline float odg_fdiv_rn(float a, float b) { volatile float r = a / b; re
 #define odg_fadd_rn __fadd_rn
 #define odg_fsub_rn __fsub_rn
 #define odg_fdiv_rn __fdiv_rn
+#define odg_fdiv_fast __fdividef               // 2-ulp quotient without the IEEE slow-path call (step lengths, stiffnesses)
 #define ODG_UNROLL _Pragma("unroll")
 #define ODG_NO_UNROLL _Pragma("unroll 1")
 #endif
@@ -949,7 +951,10 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         const int link = C.slot_link[c_slot[c]];
         const V3 r = c_r[c];
         V3 dz = p_b.t + cross(p_b.w, r);
-        ODG_UNROLL for (int j = 0; j < NJL; j++) dz = dz + (j <= link ? p_l[j] : 0.f) * cross(ax[j], r - anc[j]);
+        ODG_UNROLL for (int j = 0; j < NJL; j++) {    // joints below the contact's link do not move it: arithmetic mask
+          const float on = fminf(fmaxf((float)(link - j + 1), 0.f), 1.f);
+          dz = dz + (on * p_l[j]) * cross(ax[j], r - anc[j]);
+        }
         c_dz[c] = dz;
       }
     }
@@ -1032,33 +1037,42 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       float lo = 0.f, flo = d10, hi = -1.f, fhi = 0.f;
       bool done = false;
       ODG_NO_UNROLL for (int ls = 0; ls < C.ls_iters && !done; ls++) {
-        if (ls > 0) {
-          if (lo == 0.f) {
-            // the zero lies below every step tried so far: a geometric ladder resolves zeros that are orders of
-            // magnitude smaller than the Newton step (a stiff row switching on right next to the iterate) in one pass
-            al[0] = 0.008f * hi; al[1] = 0.04f * hi; al[2] = 0.2f * hi; al[3] = 0.6f * hi;
-          } else {
-            const float w = (hi - lo) * 0.2f, lo0 = lo;
-            ODG_UNROLL for (int k = 0; k < 4; k++) al[k] = lo0 + w * (float)(k + 1);
+        {
+          // further passes: 4 interior points of the bracket — or, while the zero lies below every step tried so far, a
+          // geometric ladder, which resolves zeros that are orders of magnitude smaller than the Newton step (a stiff
+          // row switching on right next to the iterate) in one pass. Selects, not branches.
+          const bool first = ls == 0, ladder = lo == 0.f;
+          const float w = (hi - lo) * 0.2f, lo0 = lo;
+          const float lad[4] = { 0.008f, 0.04f, 0.2f, 0.6f };
+          ODG_UNROLL for (int k = 0; k < 4; k++) {
+            const float nxt = ladder ? lad[k] * hi : lo0 + w * (float)(k + 1);
+            al[k] = first ? al[k] : nxt;
           }
         }
         eval4(al, f);
         ls_evals++;
-        bool found = hi >= 0.f && ls == 0;          // (false: a pass always starts without a new upper end)
+        bool found = false;                         // a pass always starts without a new upper end
         ODG_UNROLL for (int k = 0; k < 4; k++) {
-          if (!done && fabsf(f[k]) <= ftol) { alpha = al[k]; done = true; }
-          if (!found) { if (f[k] >= 0.f) { hi = al[k]; fhi = f[k]; found = true; } else { lo = al[k]; flo = f[k]; } }
+          const bool hit = !done && fabsf(f[k]) <= ftol;
+          alpha = hit ? al[k] : alpha; done = done || hit;
+          const bool up = !found && f[k] >= 0.f, dn = !found && !(f[k] >= 0.f);
+          hi = up ? al[k] : hi; fhi = up ? f[k] : fhi;
+          lo = dn ? al[k] : lo; flo = dn ? f[k] : flo;
+          found = found || up;
         }
-        if (!done && hi < 0.f) { alpha = al[3]; done = true; }     // still descending at the largest step tried
+        {
+          const bool run = !done && hi < 0.f;       // still descending at the largest step tried
+          alpha = run ? al[3] : alpha; done = done || run;
+        }
       }
       if (!done) {
         // zero of the chord — unless phi' is an order of magnitude smaller at the upper end: then a stiff row switches
         // on between lo and hi (phi' flat, then very steep), the chord lands on or before that kink, the next Hessian is
         // assembled without the row, and the iteration repeats the same tiny step until the cap (seen with Go1's feet,
         // D ~ 5e5). The upper end is past the kink and within the bracket width of the zero.
-        alpha = lo - flo * (hi - lo) / (fhi - flo);
-        if (!(alpha >= lo && alpha <= hi)) alpha = 0.5f * (lo + hi);
-        if (fhi < -0.1f * flo) alpha = hi;
+        alpha = lo - flo * odg_fdiv_fast(hi - lo, fhi - flo);
+        alpha = (alpha >= lo && alpha <= hi) ? alpha : 0.5f * (lo + hi);
+        alpha = (fhi < -0.1f * flo) ? hi : alpha;
       }
     }
     // ---- take the step, test convergence on the step size
