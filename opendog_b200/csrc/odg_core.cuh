@@ -827,7 +827,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         ODG_UNROLL for (int i = 0; i <= j; i++) { Hll[j][i] += sDjj[j][i]; if (i != j) Hll[i][j] += sDjj[j][i]; }
       }
     } else {
-      for (int c = 0; c < nc; c++) {
+      ODG_NO_UNROLL for (int c = 0; c < nc; c++) {
         const int s = c_slot[c];
         const int link = C.slot_link[s];
         const V3 r = c_r[c];
@@ -947,7 +947,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         c_dzz[c] = dz;
       }
     } else {
-      for (int c = 0; c < nc; c++) {
+      ODG_NO_UNROLL for (int c = 0; c < nc; c++) {
         const int link = C.slot_link[c_slot[c]];
         const V3 r = c_r[c];
         V3 dz = p_b.t + cross(p_b.w, r);
@@ -990,7 +990,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
           ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(z0 + al[k] * dz, 0.f) * Ddz;
         }
       } else {
-        for (int c = 0; c < nc; c++) {               // (a row with D = 0 adds exactly 0: no skip, no branch)
+        ODG_NO_UNROLL for (int c = 0; c < nc; c++) {               // (a row with D = 0 adds exactly 0: no skip, no branch)
           const int s = c_slot[c];
           const float Dn = c_Dn[c];
           cone_line4<LW>(c_z0[c], c_dz[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], al, f);
