@@ -641,35 +641,44 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     }
     const int nvt = C.slot_nvert[s], vs = C.slot_vstart[s];
     const V3 rz = mk3(Rl.m[6], Rl.m[7], Rl.m[8]);
+    // one pass over the hull's vertices finds the support vertex towards the floor (lowest world z) and towards the
+    // three tilted directions of the multi-contact search at once: each vertex is loaded once and the four running
+    // arg-extrema are independent chains. (Somewhere in the warp a paw touches the floor in nearly every substep, so
+    // the warp walks the tilted scans anyway; separate passes cost four loads per vertex and four short chains.)
+    V3 dl[3];
+    ODG_UNROLL for (int i = 0; i < 3; i++) dl[i] = tmul(Rl, mk3(C.tilt_dir[i][0], C.tilt_dir[i][1], C.tilt_dir[i][2]));
     float zmin = 1e30f; int best = 0;
+    float smax[3] = { -1e30f, -1e30f, -1e30f }; int bi3[3] = { 0, 0, 0 };
     for (int k = 0; k < nvt; k++) {
-      float4 v = s_vert[(vs + k) * 4 + leg];
-      float z = zoff + rz.x * v.x + rz.y * v.y + rz.z * v.z;
-      if (z < zmin) { zmin = z; best = k; }
+      const float4 v = s_vert[(vs + k) * 4 + leg];
+      const float z = zoff + rz.x * v.x + rz.y * v.y + rz.z * v.z;
+      const bool lower = z < zmin;
+      zmin = lower ? z : zmin; best = lower ? k : best;
+      ODG_UNROLL for (int i = 0; i < 3; i++) {
+        const float sc = dl[i].x * v.x + dl[i].y * v.y + dl[i].z * v.z;
+        const bool more = sc > smax[i];
+        smax[i] = more ? sc : smax[i]; bi3[i] = more ? k : bi3[i];
+      }
     }
     if (zmin > margin) continue;
-    int found[4]; int nf = 1; found[0] = best;
+    int found[4] = { best, -1, -1, -1 }; int nf = 1;
     {
       float4 v = s_vert[(vs + best) * 4 + leg];
       V3 pw = pl + mul(Rl, mk3(v.x, v.y, v.z));
       add_contact(pw.x, pw.y, 0.5f * zmin - bp.z, zmin, s);
     }
-    for (int i = 0; i < C.n_tilt; i++) {
-      V3 dl = tmul(Rl, mk3(C.tilt_dir[i][0], C.tilt_dir[i][1], C.tilt_dir[i][2]));
-      float smax = -1e30f; int bi = 0;
-      for (int k = 0; k < nvt; k++) {
-        float4 v = s_vert[(vs + k) * 4 + leg];
-        float sc = dl.x * v.x + dl.y * v.y + dl.z * v.z;
-        if (sc > smax) { smax = sc; bi = k; }
-      }
+    ODG_UNROLL for (int i = 0; i < 3; i++) {
+      if (i >= C.n_tilt) continue;
+      const int bi = bi3[i];
       bool dup = false;
-      for (int k = 0; k < nf; k++) dup |= (found[k] == bi);
+      ODG_UNROLL for (int k = 0; k < 4; k++) dup |= (found[k] == bi);
       if (dup) continue;
       float4 v = s_vert[(vs + bi) * 4 + leg];
       V3 pw = pl + mul(Rl, mk3(v.x, v.y, v.z));
       float z = bp.z + pw.z;
       if (z > margin) continue;
-      found[nf++] = bi;
+      ODG_UNROLL for (int k = 1; k < 4; k++) if (k == nf) found[k] = bi;
+      nf++;
       add_contact(pw.x, pw.y, 0.5f * z - bp.z, z, s);
     }
   }
