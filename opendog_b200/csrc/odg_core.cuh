@@ -271,16 +271,22 @@ ODG_NOINLINE float impedance_pow(float x, float mid, float power) {      // gene
   return x <= mid ? powf(x, power) / powf(mid, power - 1.f) : 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
 }
 ODG_DEV float impedance(const float* imp5, float pos_minus_margin) {
-  float d0 = imp5[0], d1 = imp5[1], width = imp5[2], mid = imp5[3], power = imp5[4];
-  if (d0 == d1 || width <= 1e-15f) return 0.5f * (d0 + d1);
-  float x = fabsf(pos_minus_margin / width);
-  if (x >= 1.f) return d1;
-  if (x <= 0.f) return d0;
+  const float d0 = imp5[0], d1 = imp5[1], width = imp5[2], mid = imp5[3], power = imp5[4];
+  const bool flat = d0 == d1 || width <= 1e-15f;
+  // x clamped to [0, 1]: the sigmoid is 0 at 0 and 1 at 1, so the d0 / d1 plateaus need no branches
+  const float x = fminf(fabsf(odg_fdiv_fast(pos_minus_margin, flat ? 1.f : width)), 1.f);
   float y;
-  if (power == 2.f) y = x <= mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
-  else if (power == 1.f) y = x;
-  else y = impedance_pow(x, mid, power);
-  return d0 + y * (d1 - d0);
+  if (power == 2.f) {                              // (uniform: the reference models use the default power 2)
+    const bool low = x <= mid;
+    const float t = low ? x : 1.f - x;
+    const float q = odg_fdiv_fast(t * t, low ? mid : 1.f - mid);
+    y = low ? q : 1.f - q;
+  } else if (power == 1.f) {
+    y = x;
+  } else {
+    y = (x <= 0.f) ? 0.f : ((x >= 1.f) ? 1.f : impedance_pow(x, mid, power));
+  }
+  return flat ? 0.5f * (d0 + d1) : d0 + y * (d1 - d0);
 }
 
 // friction-loss (Huber) row: z -> ds/dz, d2s/dz2   (D * R == 1, so clamping D*z at +-f is the linear zone)
@@ -485,8 +491,10 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
   // ------------------------------------------------------------------ kinematics (mj_kinematics)
   {
     float n2 = bq[0] * bq[0] + bq[1] * bq[1] + bq[2] * bq[2] + bq[3] * bq[3];
-    if (n2 < 1e-30f) { bq[0] = 1.f; bq[1] = bq[2] = bq[3] = 0.f; }
-    else { float in = rsqrtf(n2); bq[0] *= in; bq[1] *= in; bq[2] *= in; bq[3] *= in; }
+    const bool degenerate = n2 < 1e-30f;
+    const float in = rsqrtf(fmaxf(n2, 1e-30f));
+    bq[0] = degenerate ? 1.f : bq[0] * in; bq[1] = degenerate ? 0.f : bq[1] * in;
+    bq[2] = degenerate ? 0.f : bq[2] * in; bq[3] = degenerate ? 0.f : bq[3] * in;
   }
   M3 R0;
   {
@@ -691,8 +699,8 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     const float margin = C.slot_margin[s];
     float active = dist < margin ? 1.f : 0.f;       // excluded if in the gap (gap = 0: never for dist==margin only)
     float imp = impedance(C.slot_imp[s], dist - margin);
-    float Rn = fmaxf(1e-15f, (1.f - imp) / imp * GCF(GC_INVW, s));
-    c_Dn[c] = active / Rn;
+    float Rn = fmaxf(1e-15f, odg_fdiv_fast(1.f - imp, imp) * GCF(GC_INVW, s));
+    c_Dn[c] = odg_fdiv_fast(active, Rn);
     const float Bc = C.slot_B[s], Kc = C.slot_K[s];
     if (PL1) {
       const float rx = c_rx[c], ry = c_ry[c];
@@ -706,7 +714,10 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     } else {
       const V3 r = c_r[c];
       V3 vc = bv + cross(w0, r);
-      ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) vc = vc + qd[j] * cross(ax[j], r - anc[j]);
+      ODG_UNROLL for (int j = 0; j < NJL; j++) {
+        const float on = fminf(fmaxf((float)(link - j + 1), 0.f), 1.f);
+        vc = vc + (on * qd[j]) * cross(ax[j], r - anc[j]);
+      }
       c_aref[c] = mk3(-Bc * vc.x, -Bc * vc.y, -Bc * vc.z - Kc * imp * (dist - margin));
     }
   }
@@ -714,18 +725,15 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
   float aref_fl[NJL], lim_sgn[NJL], lim_aref[NJL], lim_D[NJL];
   ODG_UNROLL for (int j = 0; j < NJL; j++) {
     aref_fl[j] = -C.B_fl * qd[j];
-    lim_sgn[j] = 0.f; lim_aref[j] = 0.f; lim_D[j] = 0.f;
-    if (LCF(LC_LIMITED, j) != 0.f) {
-      float dlo = q[j] - LCF(LC_LO, j), dhi = LCF(LC_HI, j) - q[j];
-      float dist = 0.f, sg = 0.f;
-      if (dlo < 0.f) { dist = dlo; sg = 1.f; }
-      else if (dhi < 0.f) { dist = dhi; sg = -1.f; }
-      if (sg != 0.f) {
-        float imp = impedance(C.lim_imp, dist);
-        float Rr = fmaxf(1e-15f, (1.f - imp) / imp * LCF(LC_INVW, j));
-        lim_sgn[j] = sg; lim_D[j] = 1.f / Rr;
-        lim_aref[j] = -C.B_lim * (sg * qd[j]) - C.K_lim * imp * dist;
-      }
+    {
+      // (branch-free: an inactive or absent limit ends up with sgn = D = aref = 0)
+      const float dlo = q[j] - LCF(LC_LO, j), dhi = LCF(LC_HI, j) - q[j];
+      const bool lim = LCF(LC_LIMITED, j) != 0.f, lo_on = lim && dlo < 0.f, hi_on = lim && !lo_on && dhi < 0.f;
+      const float dist = lo_on ? dlo : (hi_on ? dhi : 0.f), sg = lo_on ? 1.f : (hi_on ? -1.f : 0.f);
+      const float imp = impedance(C.lim_imp, dist);
+      const float Rr = fmaxf(1e-15f, odg_fdiv_fast(1.f - imp, imp) * LCF(LC_INVW, j));
+      lim_sgn[j] = sg; lim_D[j] = sg != 0.f ? odg_fdiv_fast(1.f, Rr) : 0.f;
+      lim_aref[j] = sg != 0.f ? -C.B_lim * (sg * qd[j]) - C.K_lim * imp * dist : 0.f;
     }
   }
   // trunk friction-loss rows (DoFs in MuJoCo's frames: world linear, trunk-frame angular)
