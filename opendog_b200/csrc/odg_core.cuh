@@ -58,6 +58,9 @@ static inline float odg_fdiv_fast(float a, float b) { return a / b; }
 #ifndef ODG_LS_WIDTH
 #define ODG_LS_WIDTH 4
 #endif
+#ifndef ODG_CONE_QUADRATIC
+#define ODG_CONE_QUADRATIC 1
+#endif
 
 namespace odg {
 
@@ -379,18 +382,30 @@ ODG_DEV void cone_line4(V3 z0, V3 dz, float Dn, float Dt, float mu, float fri, f
   const float Dm = Dn * dmk;
   const float qb1 = Dt * (z0.x * dz.x + z0.y * dz.y) + Dn * z0.z * dz.z;      // sticking zone: phi' = qb1 + alpha*qb2
   const float qb2 = Dt * (dz.x * dz.x + dz.y * dz.y) + Dn * dz.z * dz.z;
+#if ODG_CONE_QUADRATIC
+  // |U(alpha)|^2 and U.V as polynomials in alpha (three coefficients per contact instead of two vector updates per
+  // step length). The line search only positions the step; the solution the iteration converges to does not depend on it.
+  const float cA = U0x * U0x + U0y * U0y, cB = U0x * Vx + U0y * Vy, cC = Vx * Vx + Vy * Vy;
+#endif
   ODG_UNROLL for (int k = 0; k < W; k++) {
     const float a = al[k];
-    const float Ux = U0x + a * Vx, Uy = U0y + a * Vy, N = N0 + a * Nd;
+    const float N = N0 + a * Nd;
+#if ODG_CONE_QUADRATIC
+    const float UV = cB + a * cC;
+    const float T2 = fmaxf(cA + a * (cB + UV), 0.f);
+#else
+    const float Ux = U0x + a * Vx, Uy = U0y + a * Vy;
     const float T2 = Ux * Ux + Uy * Uy;
+    const float UV = Ux * Vx + Uy * Vy;
+#endif
     const float iT = rsqrtf(fmaxf(T2, 1e-20f));
     const float T = T2 * iT;
-    const float Td = (Ux * Vx + Uy * Vy) * iT;
-    const float fmid = Dm * (N - mu * T) * (Nd - mu * Td);
+    const float Td = UV * iT;
+    const float e = N - mu * T;                     // >= 0: separating (T == 0: N >= 0)
+    const float fmid = Dm * e * (Nd - mu * Td);
     const float fbot = qb1 + a * qb2;
-    const bool top = N >= mu * T;                   // separating (T == 0: N >= 0)
     const bool bot = mu * N + T <= 0.f;             // sticking
-    f[k] += top ? 0.f : (bot ? fbot : fmid);
+    f[k] += e >= 0.f ? 0.f : (bot ? fbot : fmid);
   }
 }
 

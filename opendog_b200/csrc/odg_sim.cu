@@ -161,7 +161,7 @@ int choose_launch(OdgSim* s) {
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_step));
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev_occ, kern, 128, s->smem_step));
   if (dev_occ < 1) dev_occ = 1;
-  // Measured on B200 (tools/gpu_quick4.sh): 64-thread blocks (2 warps walking the Newton loop in lockstep, 4 blocks per
+  // Measured on B200 (tools/tune_launch_shape.sh): 64-thread blocks (2 warps walking the Newton loop in lockstep, 4 blocks per
   // SM) with 8 environments per warp are fastest at 4096 and at 65536 environments; fewer environments per warp or
   // one-warp blocks lose more to instruction fetch than they gain in divergence.
   int lanes = 32;
@@ -176,7 +176,7 @@ int choose_launch(OdgSim* s) {
   if (dev_occ < 1) dev_occ = 1;
   const long long wpb = block / 32, need = (warps + wpb - 1) / wpb, cap = (long long)s->num_sms * dev_occ;
   s->step_lanes = lanes; s->step_block = block;
-  s->prep.C.lockstep = 2 * need > cap ? 1 : 0;    // measured: pays from ~8192 envs up (tools/gpu_quick6.sh)
+  s->prep.C.lockstep = 2 * need > cap ? 1 : 0;    // measured: pays from ~8192 envs up (tools/tune_launch_shape.sh)
   if (const char* env = std::getenv("ODG_LOCKSTEP")) s->prep.C.lockstep = std::atoi(env) ? 1 : 0;
   s->step_grid = (int)(need < cap ? need : cap);
   return ODG_OK;

@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of library variants (build/variants/*.so) at 4096 and 65536 envs. Usage: tools/gpu_quick10.sh name1 name2 ...
+# A/B of library variants (build/variants/*.so) at 4096 and 65536 envs. Usage: tools/ab_variants.sh name1 name2 ...
 for v in "$@"; do
   if [ "$v" = default ]; then unset ODG_LIB_PATH; else export ODG_LIB_PATH=$PWD/build/variants/libodgsim_$v.so; fi
   for cfg in "4096 32 0" "65536 32 1"; do
