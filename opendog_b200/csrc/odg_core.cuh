@@ -298,14 +298,6 @@ ODG_DEV void fl_eval(float z, float f, float R, float D, float& g, float& hh) {
   hh = fabsf(z) < R * f ? D : 0.f;
 }
 
-// zone of the elliptic cone for z (regular-cone coordinates N, T): 0 top (separating), 1 bottom (sticking),
-// 2 middle (on the cone surface, sliding)
-ODG_DEV int cone_zone(float N, float T2, float T, float mu) {
-  if (T2 <= 0.f) return N >= 0.f ? 0 : 1;
-  if (N >= mu * T) return 0;
-  return (mu * N + T <= 0.f) ? 1 : 2;
-}
-
 // elliptic-cone contact block. z = (zx, zy, zn) in world axes (normal = +z). Returns the zone.
 ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, float dmk, int condim, V3& g, S3& H) {
   // Branch-free: both the sticking-zone and the cone-surface blocks are formed and one is selected (top zone and
@@ -341,34 +333,6 @@ ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, float dmk, 
   H.xz = mid ? Dm * w.x * w.z : 0.f;
   H.yz = mid ? Dm * w.y * w.z : 0.f;
   return top ? 0 : (bot ? 1 : 2);
-}
-
-// the same block restricted to the line z + alpha*dz: adds d/dalpha and d2/dalpha2 of its cost
-ODG_DEV int cone_line(V3 z, V3 dz, float Dn, float Dt, float mu, float fri, float dmk, int condim, float& d1, float& d2) {
-  if (condim == 1) {
-    if (z.z < 0.f) { d1 += Dn * z.z * dz.z; d2 += Dn * dz.z * dz.z; return 1; }
-    return 0;
-  }
-  float U1 = z.x * fri, U2 = z.y * fri, N = z.z * mu;
-  float T2 = U1 * U1 + U2 * U2;
-  float iT = rsqrtf(fmaxf(T2, 1e-20f));
-  float T = T2 * iT;
-  int zone = cone_zone(N, T2, T, mu);
-  if (zone == 0) return 0;
-  if (zone == 1) {
-    d1 += Dt * (z.x * dz.x + z.y * dz.y) + Dn * z.z * dz.z;
-    d2 += Dt * (dz.x * dz.x + dz.y * dz.y) + Dn * dz.z * dz.z;
-    return 1;
-  }
-  float V1 = dz.x * fri, V2 = dz.y * fri, Nd = dz.z * mu;
-  float Dm = Dn * dmk;
-  float NmT = N - mu * T;
-  float Td = (U1 * V1 + U2 * V2) * iT;                 // dT/dalpha
-  float Tdd = (V1 * V1 + V2 * V2 - Td * Td) * iT;      // d2T/dalpha2
-  float e = Nd - mu * Td;
-  d1 += Dm * NmT * e;
-  d2 += Dm * (e * e - NmT * mu * Tdd);
-  return 2;
 }
 
 // phi' contribution of one contact block at four step lengths: f[k] += d/dalpha cost(z0 + al[k]*dz). Branch-free
