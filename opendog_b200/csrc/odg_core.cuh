@@ -93,7 +93,6 @@ struct DevConst {
   int body_rot_identity;
   int lockstep;                                 // block-lockstep Newton iterations (batches of more than one wave)
   int any_damping;                              // some joint has damping > 0: mj_Euler integrates it implicitly
-  int all_plane1;                               // every contact slot is condim 1 (scalar contact rows, substep<.., true>)
   float h, gx, gy, gz, impratio;
   // trunk
   float base_mass, base_ip[3], base_I[6];
@@ -457,10 +456,9 @@ struct LastPass {
 #define GCF(f, s) s_gc[((s) * GC_COUNT + (f)) * 4 + leg]
 
 // One mj_step (or one mj_forward when integrate == false) for the 4-lane group of one environment.
-// PL1 = every contact is a frictionless (condim 1) contact against the plane z = 0 — the OpenDOG model
-// (our_robot.xml:9 condim="1"). A contact row is then the scalar J = [e_z, r x e_z, (ax_j x (r - anc_j)).z]:
-// four numbers per contact (r.x, r.y and one per joint) instead of a 3x3 cone block.
-template <int NJL, bool PL1>
+// Every contact is an elliptic-cone block against the plane z = 0; a frictionless (condim 1) row is the same block
+// with no tangential part (cone_eval / cone_line4).
+template <int NJL>
 ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const float* ODG_RESTRICT s_gc,
                      const float4* ODG_RESTRICT s_vert, int leg, unsigned gm,
                      V3& bp, float (&bq)[4], V3& bv, V3& bwl, float (&q)[NJL], float (&qd)[NJL],
@@ -594,15 +592,13 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     tau_l[j] = f - cbias[j] - LCF(LC_DAMP, j) * qd[j];
   }
   // ------------------------------------------------------------------ collision: floor plane vs hulls
-  constexpr int kGen = PL1 ? 1 : kMaxConLeg, kPl = PL1 ? kMaxConLeg : 1;
-  V3 c_r[kGen], c_aref[kGen], c_z0[kGen], c_dz[kGen];                      // generic cone rows
-  float c_rx[kPl], c_ry[kPl], c_jz[NJL][kPl], c_ar[kPl], c_zz[kPl], c_dzz[kPl];   // PL1 scalar rows
+  V3 c_r[kMaxConLeg], c_aref[kMaxConLeg], c_z0[kMaxConLeg], c_dz[kMaxConLeg];     // cone rows of this leg's contacts
   float c_Dn[kMaxConLeg]; int c_slot[kMaxConLeg];
   int nc = 0;
   int foot_last = -1;
   auto add_contact = [&](float px, float py, float pz_mid, float dist, int s) {
     if (nc >= kMaxConLeg) return;
-    if (PL1) { c_rx[nc] = px; c_ry[nc] = py; } else c_r[nc] = mk3(px, py, pz_mid);
+    c_r[nc] = mk3(px, py, pz_mid);
     c_Dn[nc] = dist; c_slot[nc] = s;
     if (C.slot_isfoot[s]) foot_last = nc;
     nc++;
@@ -681,24 +677,13 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     float Rn = fmaxf(1e-15f, odg_fdiv_fast(1.f - imp, imp) * GCF(GC_INVW, s));
     c_Dn[c] = odg_fdiv_fast(active, Rn);
     const float Bc = C.slot_B[s], Kc = C.slot_K[s];
-    if (PL1) {
-      const float rx = c_rx[c], ry = c_ry[c];
-      float vz = bv.z + w0.x * ry - w0.y * rx;
-      ODG_UNROLL for (int j = 0; j < NJL; j++) {
-        float jz = (j <= link) ? ax[j].x * (ry - anc[j].y) - ax[j].y * (rx - anc[j].x) : 0.f;
-        c_jz[j][c] = jz;
-        vz += qd[j] * jz;
-      }
-      c_ar[c] = -Bc * vz - Kc * imp * (dist - margin);
-    } else {
-      const V3 r = c_r[c];
-      V3 vc = bv + cross(w0, r);
-      ODG_UNROLL for (int j = 0; j < NJL; j++) {
-        const float on = fminf(fmaxf((float)(link - j + 1), 0.f), 1.f);
-        vc = vc + (on * qd[j]) * cross(ax[j], r - anc[j]);
-      }
-      c_aref[c] = mk3(-Bc * vc.x, -Bc * vc.y, -Bc * vc.z - Kc * imp * (dist - margin));
+    const V3 r = c_r[c];
+    V3 vc = bv + cross(w0, r);
+    ODG_UNROLL for (int j = 0; j < NJL; j++) {
+      const float on = fminf(fmaxf((float)(link - j + 1), 0.f), 1.f);
+      vc = vc + (on * qd[j]) * cross(ax[j], r - anc[j]);
     }
+    c_aref[c] = mk3(-Bc * vc.x, -Bc * vc.y, -Bc * vc.z - Kc * imp * (dist - margin));
   }
   // own-joint friction-loss and limit rows
   float aref_fl[NJL], lim_sgn[NJL], lim_aref[NJL], lim_D[NJL];
@@ -789,74 +774,39 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       Hww.yy += hh * bf_c.y * bf_c.y; Hww.yz += hh * bf_c.y * bf_c.z; Hww.zz += hh * bf_c.z * bf_c.z;
     }
     // contacts
-    if (PL1) {
-      // active rows (z < 0) add D * J^T J with J = [0 0 1 | ry -rx 0 | jz_0 .. jz_NJL-1]
-      float sD = 0.f, sDx = 0.f, sDy = 0.f, sDxx = 0.f, sDxy = 0.f, sDyy = 0.f, sG = 0.f, sGx = 0.f, sGy = 0.f;
-      float sDj[NJL], sDjx[NJL], sDjy[NJL], sDjj[NJL][NJL];
+    ODG_NO_UNROLL for (int c = 0; c < nc; c++) {
+      const int s = c_slot[c];
+      const int link = C.slot_link[s];
+      const V3 r = c_r[c];
+      V3 cj[NJL];
+      V3 ap = a_b.t + cross(a_b.w, r);
       ODG_UNROLL for (int j = 0; j < NJL; j++) {
-        sDj[j] = sDjx[j] = sDjy[j] = 0.f;
-        ODG_UNROLL for (int i = 0; i < NJL; i++) sDjj[j][i] = 0.f;
+        cj[j] = (j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f);
+        ap = ap + a_l[j] * cj[j];
       }
-      const float azb = a_b.t.z, awx = a_b.w.x, awy = a_b.w.y;
-      for (int c = 0; c < nc; c++) {
-        const float rx = c_rx[c], ry = c_ry[c];
-        float z = azb + awx * ry - awy * rx - c_ar[c];
-        float jz[NJL];
-        ODG_UNROLL for (int j = 0; j < NJL; j++) { jz[j] = c_jz[j][c]; z += a_l[j] * jz[j]; }
-        c_zz[c] = z;
-        const float D = z < 0.f ? c_Dn[c] : 0.f;
-        const float g = D * z, Dx = D * rx, Dy = D * ry;
-        sD += D; sDx += Dx; sDy += Dy; sDxx += Dx * rx; sDxy += Dx * ry; sDyy += Dy * ry;
-        sG += g; sGx += g * rx; sGy += g * ry;
-        ODG_UNROLL for (int j = 0; j < NJL; j++) {
-          const float Dj = D * jz[j];
-          g_l[j] += g * jz[j];
-          sDj[j] += Dj; sDjx[j] += Dj * rx; sDjy[j] += Dj * ry;
-          ODG_UNROLL for (int i = 0; i <= j; i++) sDjj[j][i] += Dj * jz[i];
-        }
-      }
-      gb.t.z += sG; gb.w.x += sGy; gb.w.y -= sGx;
-      Htt.zz += sD; Htw[2][0] += sDy; Htw[2][1] -= sDx;
-      Hww.xx += sDyy; Hww.xy -= sDxy; Hww.yy += sDxx;
-      ODG_UNROLL for (int j = 0; j < NJL; j++) {
-        Hlb[j].t.z += sDj[j]; Hlb[j].w.x += sDjy[j]; Hlb[j].w.y -= sDjx[j];
-        ODG_UNROLL for (int i = 0; i <= j; i++) { Hll[j][i] += sDjj[j][i]; if (i != j) Hll[i][j] += sDjj[j][i]; }
-      }
-    } else {
-      ODG_NO_UNROLL for (int c = 0; c < nc; c++) {
-        const int s = c_slot[c];
-        const int link = C.slot_link[s];
-        const V3 r = c_r[c];
-        V3 cj[NJL];
-        V3 ap = a_b.t + cross(a_b.w, r);
-        ODG_UNROLL for (int j = 0; j < NJL; j++) {
-          cj[j] = (j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f);
-          ap = ap + a_l[j] * cj[j];
-        }
-        V3 z = ap - c_aref[c];
-        c_z0[c] = z;
-        V3 g; S3 H;
-        const float Dn = c_Dn[c];
-        cone_eval(z, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
-        // (separated rows and rows with D = 0 come back as g = 0, H = 0 and add exactly 0 below)
-        gb.t = gb.t + g; gb.w = gb.w + cross(r, g);
-        // H * X, X = -[r]x : column i of X is e_i x r
-        V3 X0 = mk3(0.f, -r.z, r.y), X1 = mk3(r.z, 0.f, -r.x), X2 = mk3(-r.y, r.x, 0.f);
-        V3 HX0 = mul(H, X0), HX1 = mul(H, X1), HX2 = mul(H, X2);
-        Htt.xx += H.xx; Htt.xy += H.xy; Htt.xz += H.xz; Htt.yy += H.yy; Htt.yz += H.yz; Htt.zz += H.zz;
-        Htw[0][0] += HX0.x; Htw[1][0] += HX0.y; Htw[2][0] += HX0.z;
-        Htw[0][1] += HX1.x; Htw[1][1] += HX1.y; Htw[2][1] += HX1.z;
-        Htw[0][2] += HX2.x; Htw[1][2] += HX2.y; Htw[2][2] += HX2.z;
-        Hww.xx += dot(X0, HX0); Hww.xy += dot(X0, HX1); Hww.xz += dot(X0, HX2);
-        Hww.yy += dot(X1, HX1); Hww.yz += dot(X1, HX2); Hww.zz += dot(X2, HX2);
-        ODG_UNROLL for (int j = 0; j < NJL; j++) {    // (cj[j] = 0 for joints below the contact's link: adds exactly 0)
-          V3 hc = mul(H, cj[j]);
-          g_l[j] += dot(cj[j], g);
-          Hlb[j].t = Hlb[j].t + hc; Hlb[j].w = Hlb[j].w + cross(r, hc);
-          ODG_UNROLL for (int i = 0; i <= j; i++) {
-            float v = dot(cj[i], hc);
-            Hll[j][i] += v; if (i != j) Hll[i][j] += v;
-          }
+      V3 z = ap - c_aref[c];
+      c_z0[c] = z;
+      V3 g; S3 H;
+      const float Dn = c_Dn[c];
+      cone_eval(z, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
+      // (separated rows and rows with D = 0 come back as g = 0, H = 0 and add exactly 0 below)
+      gb.t = gb.t + g; gb.w = gb.w + cross(r, g);
+      // H * X, X = -[r]x : column i of X is e_i x r
+      V3 X0 = mk3(0.f, -r.z, r.y), X1 = mk3(r.z, 0.f, -r.x), X2 = mk3(-r.y, r.x, 0.f);
+      V3 HX0 = mul(H, X0), HX1 = mul(H, X1), HX2 = mul(H, X2);
+      Htt.xx += H.xx; Htt.xy += H.xy; Htt.xz += H.xz; Htt.yy += H.yy; Htt.yz += H.yz; Htt.zz += H.zz;
+      Htw[0][0] += HX0.x; Htw[1][0] += HX0.y; Htw[2][0] += HX0.z;
+      Htw[0][1] += HX1.x; Htw[1][1] += HX1.y; Htw[2][1] += HX1.z;
+      Htw[0][2] += HX2.x; Htw[1][2] += HX2.y; Htw[2][2] += HX2.z;
+      Hww.xx += dot(X0, HX0); Hww.xy += dot(X0, HX1); Hww.xz += dot(X0, HX2);
+      Hww.yy += dot(X1, HX1); Hww.yz += dot(X1, HX2); Hww.zz += dot(X2, HX2);
+      ODG_UNROLL for (int j = 0; j < NJL; j++) {    // (cj[j] = 0 for joints below the contact's link: adds exactly 0)
+        V3 hc = mul(H, cj[j]);
+        g_l[j] += dot(cj[j], g);
+        Hlb[j].t = Hlb[j].t + hc; Hlb[j].w = Hlb[j].w + cross(r, hc);
+        ODG_UNROLL for (int i = 0; i <= j; i++) {
+          float v = dot(cj[i], hc);
+          Hll[j][i] += v; if (i != j) Hll[i][j] += v;
         }
       }
     }
@@ -936,23 +886,15 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         Hq += p_l[j] * s;
       }
     }
-    if (PL1) {
-      for (int c = 0; c < nc; c++) {
-        float dz = p_b.t.z + p_b.w.x * c_ry[c] - p_b.w.y * c_rx[c];
-        ODG_UNROLL for (int j = 0; j < NJL; j++) dz += p_l[j] * c_jz[j][c];
-        c_dzz[c] = dz;
+    ODG_NO_UNROLL for (int c = 0; c < nc; c++) {
+      const int link = C.slot_link[c_slot[c]];
+      const V3 r = c_r[c];
+      V3 dz = p_b.t + cross(p_b.w, r);
+      ODG_UNROLL for (int j = 0; j < NJL; j++) {    // joints below the contact's link do not move it: arithmetic mask
+        const float on = fminf(fmaxf((float)(link - j + 1), 0.f), 1.f);
+        dz = dz + (on * p_l[j]) * cross(ax[j], r - anc[j]);
       }
-    } else {
-      ODG_NO_UNROLL for (int c = 0; c < nc; c++) {
-        const int link = C.slot_link[c_slot[c]];
-        const V3 r = c_r[c];
-        V3 dz = p_b.t + cross(p_b.w, r);
-        ODG_UNROLL for (int j = 0; j < NJL; j++) {    // joints below the contact's link do not move it: arithmetic mask
-          const float on = fminf(fmaxf((float)(link - j + 1), 0.f), 1.f);
-          dz = dz + (on * p_l[j]) * cross(ax[j], r - anc[j]);
-        }
-        c_dz[c] = dz;
-      }
+      c_dz[c] = dz;
     }
     const float bf_zt = dot(bf_e, a_b.t) - bf_aref_t, bf_dzt = dot(bf_e, p_b.t);
     const float bf_zr = dot(bf_c, a_b.w) - bf_aref_r, bf_dzr = dot(bf_c, p_b.w);
@@ -980,17 +922,10 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       }
       ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(fmaxf(bf_Dt * (bf_zt + al[k] * bf_dzt), -bf_ft), bf_ft) * bf_dzt;
       ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(fmaxf(bf_Dr * (bf_zr + al[k] * bf_dzr), -bf_fr), bf_fr) * bf_dzr;
-      if (PL1) {
-        for (int c = 0; c < nc; c++) {
-          const float dz = c_dzz[c], z0 = c_zz[c], Ddz = c_Dn[c] * dz;
-          ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(z0 + al[k] * dz, 0.f) * Ddz;
-        }
-      } else {
-        ODG_NO_UNROLL for (int c = 0; c < nc; c++) {               // (a row with D = 0 adds exactly 0: no skip, no branch)
-          const int s = c_slot[c];
-          const float Dn = c_Dn[c];
-          cone_line4<LW>(c_z0[c], c_dz[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], al, f);
-        }
+      ODG_NO_UNROLL for (int c = 0; c < nc; c++) {               // (a row with D = 0 adds exactly 0: no skip, no branch)
+        const int s = c_slot[c];
+        const float Dn = c_Dn[c];
+        cone_line4<LW>(c_z0[c], c_dz[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], al, f);
       }
       ODG_UNROLL for (int k = 0; k < LW; k++) f[k] = grp_sum(f[k], gm);
     };
@@ -1086,28 +1021,18 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     out.foot_contact = foot_last >= 0 ? 1 : 0;
     out.foot_force = mk3(0.f, 0.f, 0.f);
     float fn = 0.f;
-    if (PL1) {
-      for (int c = 0; c < nc; c++) {
-        float z = a_b.t.z + a_b.w.x * c_ry[c] - a_b.w.y * c_rx[c] - c_ar[c];
-        ODG_UNROLL for (int j = 0; j < NJL; j++) z += a_l[j] * c_jz[j][c];
-        const float f = z < 0.f ? -c_Dn[c] * z : 0.f;
-        fn += f;
-        if (c == foot_last) out.foot_force = mk3(f, 0.f, 0.f);
-      }
-    } else {
-      for (int c = 0; c < nc; c++) {
-        const int s = c_slot[c];
-        const int link = C.slot_link[s];
-        const float Dn = c_Dn[c];
-        if (Dn == 0.f) continue;
-        const V3 r = c_r[c];
-        V3 ap = a_b.t + cross(a_b.w, r);
-        ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) ap = ap + a_l[j] * cross(ax[j], r - anc[j]);
-        V3 g; S3 H;
-        cone_eval(ap - c_aref[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
-        fn += -g.z;
-        if (c == foot_last) out.foot_force = mk3(-g.z, -g.y, g.x);   // MuJoCo frame: n=+z, t1=+y, t2=-x
-      }
+    for (int c = 0; c < nc; c++) {
+      const int s = c_slot[c];
+      const int link = C.slot_link[s];
+      const float Dn = c_Dn[c];
+      if (Dn == 0.f) continue;
+      const V3 r = c_r[c];
+      V3 ap = a_b.t + cross(a_b.w, r);
+      ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) ap = ap + a_l[j] * cross(ax[j], r - anc[j]);
+      V3 g; S3 H;
+      cone_eval(ap - c_aref[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
+      fn += -g.z;
+      if (c == foot_last) out.foot_force = mk3(-g.z, -g.y, g.x);   // MuJoCo frame: n=+z, t1=+y, t2=-x
     }
     out.fn = fn;
   }
@@ -1219,7 +1144,7 @@ ODG_DEV int gait_call(int& idx, int& cnt, int paws_mask, float vx) {
 
 // Full environment step for one 4-lane group: load state, frame_skip substeps, obs/reward/termination,
 // optional auto-reset, store state.
-template <int NJL, bool PL1>
+template <int NJL>
 ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const float* ODG_RESTRICT s_gc,
                       const float4* ODG_RESTRICT s_vert, const SimPtrs& P, const StepArgs& A,
                       int env, int leg, unsigned gm, float* ODG_RESTRICT s_red) {
@@ -1278,7 +1203,7 @@ ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const f
       pv = ov; pw = ow;
       ODG_UNROLL for (int j = 0; j < NJL; j++) pl[j] = ol[j];
       }
-      substep<NJL, PL1>(C, s_lc, s_gc, s_vert, leg, gm, bp, bq, bv, bwl, q, qd, ctrl, warm_v, warm_wl, warm_l,
+      substep<NJL>(C, s_lc, s_gc, s_vert, leg, gm, bp, bq, bv, bwl, q, qd, ctrl, warm_v, warm_wl, warm_l,
                         stepping, s == nsub - 1, lp, work, s_red);
     }
   }

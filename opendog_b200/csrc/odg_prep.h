@@ -183,8 +183,6 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
     rows += nv;
   }
   C.nvert_rows = rows;
-  C.all_plane1 = 1;
-  for (int s = 0; s < nslot; s++) if (C.slot_condim[s] != 1) C.all_plane1 = 0;
   out->vert.assign((size_t)(rows > 0 ? rows : 1) * 16, 0.f);
   for (int s = 0; s < nslot; s++)
     for (int l = 0; l < 4; l++) {

@@ -55,7 +55,7 @@ __device__ __forceinline__ void stage_constants(float* smem, const float* __rest
 #ifndef ODG_MAX_BLOCK
 #define ODG_MAX_BLOCK 128
 #endif
-template <int NJL, bool PL1>
+template <int NJL>
 __global__ void __launch_bounds__(ODG_MAX_BLOCK, ODG_MIN_BLOCKS) k_step(const __grid_constant__ DevConst C, const SimPtrs P, const StepArgs A,
                                               const float* __restrict__ g_lc, const float* __restrict__ g_gc,
                                               const float* __restrict__ g_vert, SmemLayout L, int lanes) {
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(ODG_MAX_BLOCK, ODG_MIN_BLOCKS) k_step(const __
   const int envs_per_block = (blockDim.x >> 5) * envs_per_warp;
   for (int base = blockIdx.x * envs_per_block; base < P.N; base += gridDim.x * envs_per_block) {
     const int slot = base + (threadIdx.x >> 5) * envs_per_warp + (lane >> 2);
-    if (slot < P.N) odg::env_step<NJL, PL1>(C, s_lc, s_gc, s_vert, P, A, P.order ? P.order[slot] : slot, leg, gm, s_red);
+    if (slot < P.N) odg::env_step<NJL>(C, s_lc, s_gc, s_vert, P, A, P.order ? P.order[slot] : slot, leg, gm, s_red);
   }
 }
 
@@ -149,8 +149,7 @@ namespace {
 
 typedef void (*StepKernel)(const DevConst, const SimPtrs, const StepArgs, const float*, const float*, const float*, SmemLayout, int);
 StepKernel step_kernel_fn(const DevConst& C) {
-  if (C.njl == 2) return C.all_plane1 ? k_step<2, true> : k_step<2, false>;
-  return C.all_plane1 ? k_step<3, true> : k_step<3, false>;
+  return C.njl == 2 ? k_step<2> : k_step<3>;
 }
 const void* step_kernel(const DevConst& C) { return (const void*)step_kernel_fn(C); }
 

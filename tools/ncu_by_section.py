@@ -28,7 +28,7 @@ def main():
     argv = [a for a in sys.argv[1:] if not a.startswith("--lines")]
     top_lines = next((int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--lines=")), 0)
     rep = argv[0]
-    kern = argv[1] if len(argv) > 1 else "k_stepILi2ELb0"
+    kern = argv[1] if len(argv) > 1 else "k_stepILi2EE"
     so = os.environ.get("ODG_LIB_PATH", os.path.join(ROOT, "opendog_b200", "libodgsim.so"))
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
