@@ -74,7 +74,7 @@ class EmuEnv:
                 ncon=("i", 1), fn_sum=("f", 1), solver_iters=("i", 1), ls_evals=("i", 1), reward_raw=("f", 1))
 
     def __init__(self, num_envs, model="our_robot", seed=0, **cfg):
-        self.desc = load_compiled(model)
+        self.desc = load_compiled(model) if isinstance(model, str) else model      # (a descriptor dict: model variants)
         self.m = to_struct(self.desc)
         self.cfg = OdgEnvConfig()
         lib().emu_default_config(C.byref(self.cfg))

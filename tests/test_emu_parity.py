@@ -30,6 +30,34 @@ def test_single_step_parity_through_flight_impact_and_stance():
     assert worst_q <= 0 and worst_v <= 0
 
 
+def test_frictionless_rows_go_through_the_cone_block():
+    """A model variant whose contacts are all condim 1 (the robot geoms' own setting, our_robot.xml:9, without the
+    floor's condim 3): the kernel has no separate path for such rows — they are the cone block with fri = D_t = 0 —
+    and must still match the oracle's scalar rows."""
+    import copy
+    from opendog_b200.model.compile import load_compiled
+    desc = copy.deepcopy(load_compiled("our_robot"))
+    for g in desc["geoms"]:
+        g["condim"] = 1
+    env = EmuEnv(1, model=desc, frame_skip=1, scale_actions=0, auto_reset=0)
+    sim = Sim(desc)
+    sim.reset_keyframe()
+    rng = np.random.default_rng(4)
+    worst_q = worst_v = 0.0
+    for k in range(160):
+        if k % 10 == 0:
+            ctrl = (np.array([2.36, -1.8] * 4) + rng.uniform(0, 1, 8) * np.array([.44, .6] * 4)).astype(np.float32)[None]
+            sim.ctrl[:] = ctrl[0]
+        env.set_state(sim.qpos[None], sim.qvel[None], sim.qacc_warmstart[None])
+        _, _, _, _, info = env.step(ctrl)
+        sim.step()
+        qp, qv, _ = env.get_state()
+        worst_q = max(worst_q, (np.abs(qp[0] - sim.qpos) - (1e-6 + 1e-5 * np.abs(sim.qpos))).max())
+        worst_v = max(worst_v, (np.abs(qv[0] - sim.qvel) - (1e-4 + 1e-3 * np.abs(sim.qvel))).max())
+        assert info["ncon"][0] == sim.ncon
+    assert sim.ncon >= 2 and worst_q <= 0 and worst_v <= 0, (sim.ncon, worst_q, worst_v)
+
+
 def test_walk_env_and_reset_indexing():
     N = 3
     env = EmuEnv(N, seed=7, max_episode_steps=9)
