@@ -624,23 +624,43 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     }
     const int nvt = C.slot_nvert[s], vs = C.slot_vstart[s];
     const V3 rz = mk3(Rl.m[6], Rl.m[7], Rl.m[8]);
-    // one pass over the hull's vertices finds the support vertex towards the floor (lowest world z) and towards the
-    // three tilted directions of the multi-contact search at once: each vertex is loaded once and the four running
-    // arg-extrema are independent chains. (Somewhere in the warp a paw touches the floor in nearly every substep, so
-    // the warp walks the tilted scans anyway; separate passes cost four loads per vertex and four short chains.)
+    // Foot hulls: one pass over the vertices finds the support vertex towards the floor (lowest world z) and towards
+    // the three tilted directions of the multi-contact search at once — each vertex is loaded once and the four running
+    // arg-extrema are independent chains (somewhere in the warp a paw touches the floor in nearly every substep, so
+    // the warp walks the tilted scans anyway). Other hulls (thigh, calf) often pass the box cull without touching: they
+    // get the cheap z-only pass first and the three tilted directions only when they do touch. The choice depends on
+    // the slot index alone, so it is uniform across the warp.
     V3 dl[3];
     ODG_UNROLL for (int i = 0; i < 3; i++) dl[i] = tmul(Rl, mk3(C.tilt_dir[i][0], C.tilt_dir[i][1], C.tilt_dir[i][2]));
     float zmin = 1e30f; int best = 0;
     float smax[3] = { -1e30f, -1e30f, -1e30f }; int bi3[3] = { 0, 0, 0 };
-    for (int k = 0; k < nvt; k++) {
-      const float4 v = s_vert[(vs + k) * 4 + leg];
-      const float z = zoff + rz.x * v.x + rz.y * v.y + rz.z * v.z;
-      const bool lower = z < zmin;
-      zmin = lower ? z : zmin; best = lower ? k : best;
-      ODG_UNROLL for (int i = 0; i < 3; i++) {
-        const float sc = dl[i].x * v.x + dl[i].y * v.y + dl[i].z * v.z;
-        const bool more = sc > smax[i];
-        smax[i] = more ? sc : smax[i]; bi3[i] = more ? k : bi3[i];
+    if (C.slot_isfoot[s]) {
+      for (int k = 0; k < nvt; k++) {
+        const float4 v = s_vert[(vs + k) * 4 + leg];
+        const float z = zoff + rz.x * v.x + rz.y * v.y + rz.z * v.z;
+        const bool lower = z < zmin;
+        zmin = lower ? z : zmin; best = lower ? k : best;
+        ODG_UNROLL for (int i = 0; i < 3; i++) {
+          const float sc = dl[i].x * v.x + dl[i].y * v.y + dl[i].z * v.z;
+          const bool more = sc > smax[i];
+          smax[i] = more ? sc : smax[i]; bi3[i] = more ? k : bi3[i];
+        }
+      }
+    } else {
+      for (int k = 0; k < nvt; k++) {
+        const float4 v = s_vert[(vs + k) * 4 + leg];
+        const float z = zoff + rz.x * v.x + rz.y * v.y + rz.z * v.z;
+        const bool lower = z < zmin;
+        zmin = lower ? z : zmin; best = lower ? k : best;
+      }
+      if (zmin > margin) continue;
+      for (int k = 0; k < nvt; k++) {
+        const float4 v = s_vert[(vs + k) * 4 + leg];
+        ODG_UNROLL for (int i = 0; i < 3; i++) {
+          const float sc = dl[i].x * v.x + dl[i].y * v.y + dl[i].z * v.z;
+          const bool more = sc > smax[i];
+          smax[i] = more ? sc : smax[i]; bi3[i] = more ? k : bi3[i];
+        }
       }
     }
     if (zmin > margin) continue;
