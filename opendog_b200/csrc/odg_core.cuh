@@ -738,12 +738,13 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
   bool conv = false;
   for (int it = 0; it < C.solver_iters; it++) {
 #if !defined(ODG_NO_LOCKSTEP) && !defined(ODG_HOST_EMU)
-    // All warps of the block walk the (large: ~80 KB of SASS) Newton-iteration body together, so its instruction-cache
-    // lines are fetched once per block instead of once per warp: the step kernel is instruction-fetch bound on B200
-    // (32 KB L1.5 I-cache; stall reason no_instruction, profiles/). Every thread of the block reaches this barrier the
-    // same number of times: substeps are uniform and padding environments are stepped like real ones.
-    // It pays when the batch is several waves deep (+19 % at 65536 envs) and costs a little when every warp has a
-    // scheduler to itself (-4 % at 4096), so the host enables it per batch size (DevConst::lockstep).
+    // All warps of the block walk the Newton-iteration body (~26 KB of SASS) together, so its instruction-cache lines
+    // are fetched once per block instead of once per warp: with more than ~4 independent instruction streams per SM
+    // the step kernel is instruction-fetch bound on B200 (32 KB L1.5 I-cache; stall reason no_instruction, profiles/).
+    // Every thread of the block reaches this barrier the same number of times: substeps are uniform and padding
+    // environments are stepped like real ones. It pays when the batch is several waves deep (+27 % at 65536 envs,
+    // although 13 % of the samples then sit here) and costs a little when every warp has a scheduler to itself
+    // (-2 % at 4096), so the host enables it per batch size (DevConst::lockstep).
     if (C.lockstep) {
       if (!__syncthreads_or(conv ? 0 : 1)) break;
       if (conv) continue;

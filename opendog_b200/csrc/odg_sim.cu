@@ -168,7 +168,7 @@ int choose_launch(OdgSim* s) {
   // tiny batches (MPPI: 1024 samples) leave most schedulers empty: 2 environments per warp, so 4x the warps share the
   // work and fewer environments wait on the slowest one of their warp (40.5 vs 46.6 ms per 1024 x 64 plan)
   if (s->P.N / 8 < s->num_sms) lanes = 8;
-  if (const char* env = std::getenv("ODG_STEP_LANES")) { int v = std::atoi(env); if (v == 8 || v == 16 || v == 32) lanes = v; }
+  if (const char* env = std::getenv("ODG_STEP_LANES")) { int v = std::atoi(env); if (v >= 4 && v <= 32 && v % 4 == 0) lanes = v; }
   const long long warps = ((long long)s->P.N * 4 + lanes - 1) / lanes;
   if (const char* env = std::getenv("ODG_STEP_BLOCK")) { int v = std::atoi(env); if (v == 32 || v == 64 || v == 128 || (v == 256 && ODG_MAX_BLOCK >= 256)) block = v; }
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev_occ, kern, block, s->smem_step));
