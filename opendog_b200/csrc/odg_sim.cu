@@ -34,19 +34,28 @@ namespace odg_internal { int set_error(int code, const std::string& msg) { retur
 namespace {
 
 
+// Stage the model constants of a persistent block into shared memory with 16-byte asynchronous copies (LDGSTS): every
+// thread issues all of its copies back to back and waits once, instead of a load -> store round trip per element (at
+// 4096 environments a block lives for a single tile, so this prologue is on the critical path of the step).
 __device__ __forceinline__ void stage_constants(float* smem, const float* __restrict__ g_lc, const float* __restrict__ g_gc,
                                                 const float* __restrict__ g_vert, SmemLayout L,
                                                 const float4** s_vert, const float** s_lc, const float** s_gc) {
-  // layout: [vert (16B aligned)][lc][gc]
-  float4* sv = reinterpret_cast<float4*>(smem);
-  const float4* gv = reinterpret_cast<const float4*>(g_vert);
-  for (int i = threadIdx.x; i < L.vert_floats / 4; i += blockDim.x) sv[i] = gv[i];
+  // layout: [vert (16B aligned)][lc][gc]; all three sizes are multiples of 4 floats (host: SmemLayout)
   float* slc = smem + L.vert_floats;
-  for (int i = threadIdx.x; i < L.lc_floats; i += blockDim.x) slc[i] = g_lc[i];
   float* sgc = slc + L.lc_floats;
-  for (int i = threadIdx.x; i < L.gc_floats; i += blockDim.x) sgc[i] = g_gc[i];
+  auto copy16 = [](float* dst, const float* src, int n_floats) {
+    for (int i = threadIdx.x * 4; i < n_floats; i += blockDim.x * 4) {
+      const unsigned d = (unsigned)__cvta_generic_to_shared(dst + i);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i) : "memory");
+    }
+  };
+  copy16(smem, g_vert, L.vert_floats);
+  copy16(slc, g_lc, L.lc_floats);
+  copy16(sgc, g_gc, L.gc_floats);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  *s_vert = sv; *s_lc = slc; *s_gc = sgc;
+  *s_vert = reinterpret_cast<const float4*>(smem); *s_lc = slc; *s_gc = sgc;
 }
 
 #ifndef ODG_MIN_BLOCKS
