@@ -71,3 +71,31 @@ def test_default_config_is_the_references_constants():
     lib.load().odg_default_config(C.byref(cfg))
     assert (cfg.frame_skip, cfg.max_episode_steps, cfg.auto_reset, cfg.scale_actions) == (10, 750, 1, 1)
     assert abs(cfg.reset_noise_scale - 0.02) < 1e-9
+
+
+def test_c_abi_error_behaviour():
+    """The boundary never throws or exits: bad arguments come back as negative OdgStatus codes with a message from
+    odg_last_error(), and queries on a null handle return 0 (include/odg.h). No device work is issued here."""
+    from opendog_b200 import lib
+    from opendog_b200.model.compile import load_compiled, to_struct
+    L = lib.load()
+    m = to_struct(load_compiled("our_robot"))
+    h = C.c_void_p()
+    INVALID = -1
+    assert L.odg_create(None, None, 4, 0, 0, C.byref(h)) == INVALID and b"odg_create" in L.odg_last_error()
+    assert L.odg_create(C.byref(m), None, 0, 0, 0, C.byref(h)) == INVALID
+    assert L.odg_create(C.byref(m), None, 4, 0, 0, None) == INVALID
+    assert L.odg_step(None, None, None, None, None, None, None, None) == INVALID and b"odg_step" in L.odg_last_error()
+    assert L.odg_evaluate(None, None, None, None, None, None, None, None) == INVALID
+    assert L.odg_reset(None, None, None, None) == INVALID and b"odg_reset" in L.odg_last_error()
+    assert L.odg_get_state(None, None, None, None) == INVALID
+    assert L.odg_set_frame_skip(None, 10) == INVALID
+    assert (L.odg_num_envs(None), L.odg_obs_dim(None), L.odg_act_dim(None), L.odg_nq(None), L.odg_nv(None)) == (0,) * 5
+    assert L.odg_launch_count(None) == 0
+    L.odg_destroy(None)                                   # a no-op, like free(NULL)
+    assert L.odg_policy_create(1000, 8, 0, C.byref(h)) < 0      # state_dim above ODG_POLICY_MAX_STATE
+    assert L.odg_policy_forward(None, None, 16, None, None, None, None, 0, 0, None, 0, None) < 0
+    L.odg_policy_destroy(None)
+    assert L.odg_s2r_step(None, None, None, None, None, None, None, None, None) < 0
+    L.odg_s2r_destroy(None)
+    assert isinstance(L.odg_version(), bytes) and L.odg_version()
