@@ -90,6 +90,7 @@ enum GeomConstField { GC_INVW, GC_CX, GC_CY, GC_CZ, GC_BX, GC_BY, GC_BZ, GC_BR, 
 
 struct DevConst {
   int nleg, njl, nq, nv, nu, nslot, nvert_rows;
+  int oct_off, idx_off;                         // s_gc offsets (floats) of the support-vertex candidate table / byte lists
   int body_rot_identity;
   int lockstep;                                 // block-lockstep Newton iterations (batches of more than one wave)
   int any_damping;                              // some joint has damping > 0: mj_Euler integrates it implicitly
@@ -234,6 +235,7 @@ ODG_DEV float grp_sum21(float v, unsigned gm) { v += grp_xor(v, 2, gm); v += grp
 // every lane (bit-identical results in all 4). 7 STS.128 + 28 LDS.128 + 84 FADD instead of 56 shuffles, each of which
 // costs a WARPSYNC/collective region under a partial mask: the Newton body is instruction-fetch bound.
 constexpr int kRedVals = 28, kRedStride = 36;
+constexpr int kSupportCells = 24;     // direction cells of the support-vertex candidate lists: dominant axis (3) x signs (8)
 ODG_DEV void grp_sum28(float (&v)[kRedVals], float* ODG_RESTRICT s_red, int leg, unsigned gm) {
   grp_sync(gm);                                    // earlier readers of the rows are done
   float4* mine = reinterpret_cast<float4*>(s_red + leg * kRedStride);
@@ -622,7 +624,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       const float ext = fabsf(Rl.m[6]) * GCF(GC_HX, s) + fabsf(Rl.m[7]) * GCF(GC_HY, s) + fabsf(Rl.m[8]) * GCF(GC_HZ, s);
       if (bp.z + bc.z - ext > margin) continue;
     }
-    const int nvt = C.slot_nvert[s], vs = C.slot_vstart[s];
+    const int vs = C.slot_vstart[s];
     const V3 rz = mk3(Rl.m[6], Rl.m[7], Rl.m[8]);
     // Foot hulls: one pass over the vertices finds the support vertex towards the floor (lowest world z) and towards
     // the three tilted directions of the multi-contact search at once — each vertex is loaded once and the four running
@@ -632,10 +634,20 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     // the slot index alone, so it is uniform across the warp.
     V3 dl[3];
     ODG_UNROLL for (int i = 0; i < 3; i++) dl[i] = tmul(Rl, mk3(C.tilt_dir[i][0], C.tilt_dir[i][1], C.tilt_dir[i][2]));
+    // Only the hull vertices whose normal cone meets the (widened) cell of the floor direction -rz in the link frame
+    // can win any of the four searches: the host lists them per cell (dominant axis x component signs; odg_prep.h:
+    // hull_vertex_is_candidate), in index order, so the first-index tie rule of a full scan is preserved.
+    const float arx = fabsf(rz.x), ary = fabsf(rz.y), arz = fabsf(rz.z);
+    const int axis = (arx >= ary && arx >= arz) ? 0 : (ary >= arz ? 1 : 2);
+    const int oct = (rz.x > 0.f ? 1 : 0) | (rz.y > 0.f ? 2 : 0) | (rz.z > 0.f ? 4 : 0);     // signs of -rz
+    const int oct_ent = reinterpret_cast<const int*>(s_gc + C.oct_off)[(s * kSupportCells + axis * 8 + oct) * 4 + leg];
+    const unsigned char* ODG_RESTRICT cand = reinterpret_cast<const unsigned char*>(s_gc + C.idx_off) + (oct_ent & 0xFFFF);
+    const int ncand = oct_ent >> 16;
     float zmin = 1e30f; int best = 0;
     float smax[3] = { -1e30f, -1e30f, -1e30f }; int bi3[3] = { 0, 0, 0 };
     if (C.slot_isfoot[s]) {
-      for (int k = 0; k < nvt; k++) {
+      for (int kk = 0; kk < ncand; kk++) {
+        const int k = cand[kk];
         const float4 v = s_vert[(vs + k) * 4 + leg];
         const float z = zoff + rz.x * v.x + rz.y * v.y + rz.z * v.z;
         const bool lower = z < zmin;
@@ -647,14 +659,16 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         }
       }
     } else {
-      for (int k = 0; k < nvt; k++) {
+      for (int kk = 0; kk < ncand; kk++) {
+        const int k = cand[kk];
         const float4 v = s_vert[(vs + k) * 4 + leg];
         const float z = zoff + rz.x * v.x + rz.y * v.y + rz.z * v.z;
         const bool lower = z < zmin;
         zmin = lower ? z : zmin; best = lower ? k : best;
       }
       if (zmin > margin) continue;
-      for (int k = 0; k < nvt; k++) {
+      for (int kk = 0; kk < ncand; kk++) {
+        const int k = cand[kk];
         const float4 v = s_vert[(vs + k) * 4 + leg];
         ODG_UNROLL for (int i = 0; i < 3; i++) {
           const float sc = dl[i].x * v.x + dl[i].y * v.y + dl[i].z * v.z;

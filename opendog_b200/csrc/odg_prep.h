@@ -17,9 +17,52 @@ namespace odg {
 struct Prepared {
   DevConst C;
   std::vector<float> lc;        // [njl][LC_COUNT][4]
-  std::vector<float> gc;        // [nslot][GC_COUNT][4]
+  std::vector<float> gc;        // [nslot][GC_COUNT][4], then (DevConst::oct_off / idx_off, in floats) the support-vertex
+                                // candidate table [nslot][24 cells][4 legs] of (start | count << 16) and the byte lists
   std::vector<float> vert;      // [rows][4 legs][4 floats]
 };
+
+// Support-vertex candidates of a hull for one cell of query directions.
+// The collision pass looks for the hull vertex that is extreme towards the floor and towards three directions tilted
+// by `tilt` off it (odg_core.cuh: collision). A vertex v can win for a direction d only if d lies in v's normal cone
+// {d : d.(v - u) >= 0 for all hull vertices u}. Directions are binned into 24 cells: dominant axis of d (3) x the signs
+// of its components (8), i.e. a quarter of a cube face each. All four query directions of one pass lie in the cell of
+// the floor direction widened by the tilt, so per cell only the vertices whose normal cone meets the widened cell
+// need to be scanned. The test is exact up to a tolerance that only adds vertices: on the plane d_axis = +-1 the
+// widened cell is a square, and the normal cone clips it half-plane by half-plane (Sutherland-Hodgman); the vertex
+// is a candidate iff something is left.
+inline bool hull_vertex_is_candidate(const double (*verts)[3], int n, int v, int axis, const int sigma[3], double w_lo,
+                                     double w_hi, double tol) {
+  struct P3 { double x[3]; };
+  std::vector<P3> poly, next;
+  const int b = (axis + 1) % 3, c = (axis + 2) % 3;
+  const double lo = -w_lo, hi = 1.0 + w_hi;
+  const double cb[4] = { lo, hi, hi, lo }, cc[4] = { lo, lo, hi, hi };
+  for (int i = 0; i < 4; i++) {
+    P3 p; p.x[axis] = sigma[axis]; p.x[b] = sigma[b] * cb[i]; p.x[c] = sigma[c] * cc[i];
+    poly.push_back(p);
+  }
+  for (int u = 0; u < n && !poly.empty(); u++) {
+    if (u == v) continue;
+    const double nx = verts[v][0] - verts[u][0], ny = verts[v][1] - verts[u][1], nz = verts[v][2] - verts[u][2];
+    if (nx == 0.0 && ny == 0.0 && nz == 0.0) continue;         // duplicate vertex
+    auto h = [&](const P3& p) { return nx * p.x[0] + ny * p.x[1] + nz * p.x[2] + tol; };
+    next.clear();
+    const size_t m = poly.size();
+    for (size_t i = 0; i < m; i++) {
+      const P3& a = poly[i]; const P3& bb = poly[(i + 1) % m];
+      const double ha = h(a), hb = h(bb);
+      if (ha >= 0.0) next.push_back(a);
+      if ((ha >= 0.0) != (hb >= 0.0)) {
+        const double t = ha / (ha - hb);
+        P3 q; for (int j = 0; j < 3; j++) q.x[j] = a.x[j] + t * (bb.x[j] - a.x[j]);
+        next.push_back(q);
+      }
+    }
+    poly.swap(next);
+  }
+  return !poly.empty();
+}
 
 inline float clampf(double v, double lo, double hi) { return (float)std::fmin(hi, std::fmax(lo, v)); }
 
@@ -193,6 +236,40 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
         for (int c = 0; c < 3; c++) dst[c] = src >= 0 ? (float)m.vert[src][c] : 0.f;
       }
     }
+  // support-vertex candidate lists per (slot, cell of the floor direction in the link frame, leg)
+  {
+    // widening of a cell in its normalised coordinates (dominant component = 1) that covers the three tilted
+    // directions: a unit floor direction m has dominant component >= 1/sqrt(3); a tilted one is cos(t) m + sin(t) e
+    const double a = std::sin(std::fabs(m.multicontact_tilt)), cm = std::cos(m.multicontact_tilt) / std::sqrt(3.0);
+    const bool prune = cm - a > 0.2;
+    const double w_lo = prune ? 1.05 * a / (cm - a) + 1e-3 : 0.0, w_hi = prune ? 1.05 * ((cm + a) / (cm - a) - 1.0) + 1e-3 : 0.0;
+    std::vector<int> table((size_t)(nslot > 0 ? nslot : 1) * kSupportCells * 4, 0);
+    std::vector<unsigned char> idx;
+    for (int s = 0; s < nslot; s++) for (int l = 0; l < 4; l++) {
+      const OdgGeom& g = m.geom[per_leg[l][s]];
+      if (g.vert_count > 255) return "hull too large for the support-vertex candidate lists";
+      double ext = 0.0;
+      for (int k = 0; k < g.vert_count; k++) for (int c = 0; c < 3; c++) ext = std::fmax(ext, std::fabs(m.vert[g.vert_start + k][c]));
+      const double tol = 1e-7 + 1e-5 * ext;
+      for (int cell = 0; cell < kSupportCells; cell++) {
+        const int axis = cell >> 3, o = cell & 7;
+        const int sigma[3] = { (o & 1) ? -1 : 1, (o & 2) ? -1 : 1, (o & 4) ? -1 : 1 };
+        const size_t start = idx.size();
+        for (int k = 0; k < g.vert_count; k++)
+          if (!prune || hull_vertex_is_candidate(&m.vert[g.vert_start], g.vert_count, k, axis, sigma, w_lo, w_hi, tol))
+            idx.push_back((unsigned char)k);
+        if (start > 0xFFFF) return "support-vertex candidate lists too long";
+        table[((size_t)s * kSupportCells + cell) * 4 + l] = (int)start | ((int)(idx.size() - start) << 16);
+      }
+    }
+    while (out->gc.size() % 4) out->gc.push_back(0.f);
+    C.oct_off = (int)out->gc.size();
+    for (int v : table) { float f; std::memcpy(&f, &v, 4); out->gc.push_back(f); }
+    C.idx_off = (int)out->gc.size();
+    while (idx.size() % 16) idx.push_back(0);
+    for (size_t i = 0; i < idx.size(); i += 4) { float f; std::memcpy(&f, &idx[i], 4); out->gc.push_back(f); }
+    while (out->gc.size() % 4) out->gc.push_back(0.f);
+  }
   // three extra support directions tilted off -normal, 120 degrees apart (frame t1=+y, t2=-x)
   C.n_tilt = m.multicontact_tilt > 0 ? 3 : 0;
   for (int i = 0; i < 3; i++) {

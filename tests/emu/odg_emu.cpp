@@ -53,6 +53,24 @@ template <class F> static void run4(F f) {
 
 extern "C" {
 
+// Test hook for the support-vertex candidate lists (odg_prep.h): copies the hull of (slot, leg) as the kernel sees it
+// (float32, padded rows excluded) and the candidate indices of one direction cell. Returns the number of hull vertices;
+// *n_cand receives the list length.
+int emu_support_candidates(const Emu* e, int slot, int leg, int cell, float* verts_xyz, int* cand, int* n_cand) {
+  const odg::DevConst& C = e->prep.C;
+  const int nv = C.slot_nvert[slot], vs = C.slot_vstart[slot];
+  for (int k = 0; k < nv; k++)
+    for (int c = 0; c < 3; c++) verts_xyz[k * 3 + c] = e->prep.vert[((size_t)(vs + k) * 4 + leg) * 4 + c];
+  const float* gc = e->prep.gc.data();
+  const int ent = reinterpret_cast<const int*>(gc + C.oct_off)[(slot * odg::kSupportCells + cell) * 4 + leg];
+  const unsigned char* idx = reinterpret_cast<const unsigned char*>(gc + C.idx_off) + (ent & 0xFFFF);
+  *n_cand = ent >> 16;
+  for (int i = 0; i < *n_cand; i++) cand[i] = idx[i];
+  return nv;
+}
+int emu_num_slots(const Emu* e) { return e->prep.C.nslot; }
+float emu_tilt_dir(const Emu* e, int i, int c) { return e->prep.C.tilt_dir[i][c]; }
+
 const char* emu_last_error() { static thread_local std::string e; return e.c_str(); }
 
 Emu* emu_create(const OdgModel* m, const OdgEnvConfig* cfg, int N, uint64_t seed) {

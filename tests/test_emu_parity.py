@@ -158,3 +158,47 @@ def test_go1_observation_layout_48():
         assert np.allclose(o48[:, 6:9], np.where(n == 0, v, v / np.where(n == 0, 1, n)), atol=1e-6)
         a = rng.uniform(-0.3, 0.3, (4, 12)).astype(np.float32)
         o48, o45 = e48.step(a, info=False)[0], e45.step(a, info=False)[0]
+
+
+def test_support_vertex_candidate_lists_contain_every_winner():
+    """The collision pass scans only the hull vertices listed for the direction cell of the floor direction
+    (odg_prep.h: hull_vertex_is_candidate; 24 cells: dominant axis x signs). For random link orientations the first-index arg-extremum over the list
+    must be the one over the whole hull, for the floor direction and the three tilted ones — in float32, with the
+    kernel's expressions — and the lists must actually prune."""
+    import ctypes as C
+    from emu import lib
+    env = EmuEnv(1)
+    L = lib()
+    L.emu_support_candidates.restype = C.c_int
+    L.emu_num_slots.restype = C.c_int
+    L.emu_tilt_dir.restype = C.c_float
+    h = C.c_void_p(env.h)
+    tilt = np.array([[L.emu_tilt_dir(h, i, c) for c in range(3)] for i in range(3)], np.float32)
+    rng = np.random.default_rng(0)
+    total = listed = 0
+    for slot in range(L.emu_num_slots(h)):
+        for leg in range(4):
+            verts = np.zeros((400, 3), np.float32); cand = np.zeros(400, np.int32); n = C.c_int()
+            lists = []
+            for o in range(24):
+                nv = L.emu_support_candidates(h, slot, leg, o, verts.ctypes.data_as(C.c_void_p), cand.ctypes.data_as(C.c_void_p), C.byref(n))
+                lists.append(cand[:n.value].copy())
+                assert np.all(np.diff(lists[-1]) > 0)                      # index order, no duplicates
+                total += nv; listed += n.value
+            V = verts[:nv]
+            # random rotations (QR of a Gaussian matrix), plus near-axis-aligned ones where octants meet
+            for trial in range(300):
+                A = rng.normal(size=(3, 3)) if trial % 3 else np.eye(3) + 0.02 * rng.normal(size=(3, 3))
+                R, _ = np.linalg.qr(A)
+                R = (R * np.sign(np.linalg.det(R))).astype(np.float32)
+                rz = R[2]
+                ar = np.abs(rz)
+                axis = 0 if (ar[0] >= ar[1] and ar[0] >= ar[2]) else (1 if ar[1] >= ar[2] else 2)
+                o = axis * 8 + (int(rz[0] > 0) | int(rz[1] > 0) << 1 | int(rz[2] > 0) << 2)
+                c = lists[o]
+                z = V @ rz
+                assert c[np.argmin(z[c])] == np.argmin(z), (slot, leg, o)
+                for i in range(3):
+                    sc = V @ (R.T @ tilt[i])
+                    assert c[np.argmax(sc[c])] == np.argmax(sc), (slot, leg, o, i)
+    assert listed < 0.35 * total, (listed, total)
