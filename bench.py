@@ -103,6 +103,11 @@ def cpu_throughput(sample_envs, steps, warmup, procs):
     return n / dt, dt
 
 
+def workload_name(envs_per_gpu):
+    return (f"{envs_per_gpu} envs/GPU batched step, OpenDOG MJCF (our_robot), flat-plane foot contact, PD "
+            "position actuators, fused reward/obs/auto-reset (BASELINE.json configs[1])")
+
+
 def run_reference(args):
     """CPU arm: the oracle restatement (the reference's mujoco wheel is not installable here) on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -119,8 +124,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{ENVS_PER_GPU} envs batched step, OpenDOG MJCF walk env, frame_skip {FRAME_SKIP}",
-                   "frame_skip": FRAME_SKIP, "physics_steps_per_s": value * FRAME_SKIP},
+        "config": {"workload": workload_name(ENVS_PER_GPU), "envs_per_gpu": ENVS_PER_GPU, "frame_skip": FRAME_SKIP,
+                   "physics_steps_per_s": value * FRAME_SKIP,
+                   "note": "CPU arm: each step advances a bounded sample of the workload (see cpu_baseline.sample)"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": procs, "kind": "port",
                          "sample": f"{sample} oracle envs (one process per core, {sample // procs} envs each) x "
                                    f"{args.steps} env-steps; restatement of mj_step, not MuJoCo itself"},
@@ -278,8 +284,7 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{N} envs/GPU batched step, OpenDOG MJCF (our_robot), flat-plane foot contact, PD "
-                               "position actuators, fused reward/obs/auto-reset (BASELINE.json configs[1])",
+        "config": {"workload": workload_name(N),
                    "envs_per_gpu": N, "frame_skip": FRAME_SKIP, "physics_steps_per_s": value * FRAME_SKIP,
                    "l2": "flushed (256 MiB memset) between timed steps; per-step CUDA events summed",
                    "actions": "U(-1,1), fresh batch per step, pre-generated on device",
