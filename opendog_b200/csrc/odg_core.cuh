@@ -34,7 +34,7 @@
 struct float4 { float x, y, z, w; };
 float odg_emu_shfl_xor(float v, int m);     // provided by the emulator
 double odg_emu_shfl_xor_d(double v, int m);
-static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline float odg_rsqrt(float x) { return 1.0f / sqrtf(x); }
 static inline float odg_fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float odg_fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float odg_fsub_rn(float a, float b) { volatile float r = a - b; return r; }
@@ -51,6 +51,9 @@ static inline float odg_fdiv_fast(float a, float b) { return a / b; }
 #define odg_fsub_rn __fsub_rn
 #define odg_fdiv_rn __fdiv_rn
 #define odg_fdiv_fast __fdividef               // 2-ulp quotient without the IEEE slow-path call (step lengths, stiffnesses)
+// one MUFU.RSQ: every argument in this file is clamped to a normal number first, so the denormal pre/post-scaling that
+// rsqrtf() carries without -ftz (a compare and two predicated multiplies per call) is dead weight in the hot loops
+__device__ __forceinline__ float odg_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #define ODG_UNROLL _Pragma("unroll")
 #define ODG_NO_UNROLL _Pragma("unroll 1")
 #endif
@@ -308,7 +311,7 @@ ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, float dmk, 
   if (condim == 1) { fri = 0.f; Dt = 0.f; }
   const float U1 = z.x * fri, U2 = z.y * fri, N = z.z * mu;
   const float T2 = U1 * U1 + U2 * U2;
-  const float iT = rsqrtf(fmaxf(T2, 1e-20f));
+  const float iT = odg_rsqrt(fmaxf(T2, 1e-20f));
   const float T = T2 * iT;
   const bool top = N >= mu * T;                      // separating (T == 0: N >= 0)
   const bool bot = !top && (mu * N + T <= 0.f);      // sticking
@@ -363,7 +366,7 @@ ODG_DEV void cone_line4(V3 z0, V3 dz, float Dn, float Dt, float mu, float fri, f
     const float T2 = Ux * Ux + Uy * Uy;
     const float UV = Ux * Vx + Uy * Vy;
 #endif
-    const float iT = rsqrtf(fmaxf(T2, 1e-20f));
+    const float iT = odg_rsqrt(fmaxf(T2, 1e-20f));
     const float T = T2 * iT;
     const float Td = UV * iT;
     const float e = N - mu * T;                     // >= 0: separating (T == 0: N >= 0)
@@ -384,7 +387,7 @@ ODG_DEV void chol6_solve(float (&S)[6][6], float (&x)[6]) {
     // ~1e-2 the Schur complement can lose positive-definiteness in fp32; a floored pivot keeps the direction finite
     // (the line search then decides whether it is still a descent direction) instead of producing NaN
     s = fmaxf(s, 1e-6f * fabsf(djj) + 1e-20f);
-    float inv = rsqrtf(s);
+    float inv = odg_rsqrt(s);
     S[j][j] = inv;                                // store 1/L_jj
     ODG_UNROLL for (int i = j + 1; i < 6; i++) {
       float t = S[i][j];
@@ -431,7 +434,7 @@ ODG_DEV void chol_small(float (&A)[N][N], float (&iL)[N]) {
     float s = djj;
     ODG_UNROLL for (int k = 0; k < j; k++) s -= A[j][k] * A[j][k];
     s = fmaxf(s, 1e-6f * fabsf(djj) + 1e-20f);
-    iL[j] = rsqrtf(s);
+    iL[j] = odg_rsqrt(s);
     ODG_UNROLL for (int i = j + 1; i < N; i++) {
       float t = A[i][j];
       ODG_UNROLL for (int k = 0; k < j; k++) t -= A[i][k] * A[j][k];
@@ -471,7 +474,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
   {
     float n2 = bq[0] * bq[0] + bq[1] * bq[1] + bq[2] * bq[2] + bq[3] * bq[3];
     const bool degenerate = n2 < 1e-30f;
-    const float in = rsqrtf(fmaxf(n2, 1e-30f));
+    const float in = odg_rsqrt(fmaxf(n2, 1e-30f));
     bq[0] = degenerate ? 1.f : bq[0] * in; bq[1] = degenerate ? 0.f : bq[1] * in;
     bq[2] = degenerate ? 0.f : bq[2] * in; bq[3] = degenerate ? 0.f : bq[3] * in;
   }
@@ -1139,7 +1142,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       float nx = w * dx + x * dw + y * dz - z * dy;
       float ny = w * dy - x * dz + y * dw + z * dx;
       float nz = w * dz + x * dy - y * dx + z * dw;
-      float in = rsqrtf(nw * nw + nx * nx + ny * ny + nz * nz);
+      float in = odg_rsqrt(nw * nw + nx * nx + ny * ny + nz * nz);
       bq[0] = nw * in; bq[1] = nx * in; bq[2] = ny * in; bq[3] = nz * in;
     }
   }
