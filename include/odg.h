@@ -48,7 +48,7 @@ typedef struct OdgEnvConfig {
   int solver_iterations;     /* max Newton iterations per substep (MuJoCo default 100, tol 1e-8);
                                 the kernel exits early on convergence (mean ~5). default 30 */
   int ls_iterations;         /* line-search passes per Newton iteration; each pass evaluates phi' at 4 step
-                                lengths at once (first {0.5,1,2,4}, then 4 interior points of the bracket). default 4 */
+                                lengths at once (first {0.25,0.5,1,2}, then 4 interior points of the bracket). default 4 */
   float solver_tolerance;    /* the Newton iteration stops after a step whose inf-norm is <= tol * (1 + |qacc|_inf). Near
                                 the solution convergence is quadratic (measured: ... 1e-3, 6e-5, 3e-7), so the iterate after
                                 such a step is accurate to ~tol^2. default 1e-4 */

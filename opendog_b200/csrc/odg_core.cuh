@@ -1002,7 +1002,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       // pass, stop as soon as one evaluated point has |phi'| <= ls_tol*|phi'(0)|, else finish with the zero of the
       // chord on the last bracket
       const float ftol = C.ls_tol * fabsf(d10);
-      float al[4] = { 0.5f, 1.f, 2.f, 4.f }, f[4];
+      float al[4] = { 0.25f, 0.5f, 1.f, 2.f }, f[4];
       float lo = 0.f, flo = d10, hi = -1.f, fhi = 0.f;
       bool done = false;
       ODG_NO_UNROLL for (int ls = 0; ls < C.ls_iters && !done; ls++) {
