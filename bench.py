@@ -211,7 +211,7 @@ def run_gpu(args):
     for kv in args.cfg:
         k, v = kv.split("=")
         extra[k] = float(v) if "." in v or "e" in v else int(v)
-    env = BatchedWalkEnv(N, device=dev, seed=0, first_env_id=rank * N, info_keys=None, regroup=args.regroup, **extra)
+    env = BatchedWalkEnv(N, device=dev, seed=0, first_env_id=rank * N, info_keys=None, **extra)
     env.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -288,7 +288,6 @@ def run_gpu(args):
                    "envs_per_gpu": N, "frame_skip": FRAME_SKIP, "physics_steps_per_s": value * FRAME_SKIP,
                    "l2": "flushed (256 MiB memset) between timed steps; per-step CUDA events summed",
                    "actions": "U(-1,1), fresh batch per step, pre-generated on device",
-                   "regroup": int(env.cfg.regroup),
                    "solver": {"max_newton_iters": env.cfg.solver_iterations, "ls_iters": env.cfg.ls_iterations,
                               "tol": env.cfg.solver_tolerance}},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -312,9 +311,9 @@ def run_gpu(args):
                                           f"warm-up steps (robots landed; {dt:.1f} s); fp64 restatement of mj_step + "
                                           "reward code, not MuJoCo itself"}
     if rank == 0 and args.large_batch and world == 1:
-        line["large_batch"] = large_batch_probe(dev, args.large_batch, args.regroup, extra)
+        line["large_batch"] = large_batch_probe(dev, args.large_batch, extra)
     if rank == 0 and args.go1 and world == 1:
-        line["step_go1"] = large_batch_probe(dev, N, 0, None, model="go1")
+        line["step_go1"] = large_batch_probe(dev, N, None, model="go1")
     tr = profile_traffic(N)
     if tr:
         line["roofline"]["traffic"] = tr[0]
@@ -342,12 +341,12 @@ def run_gpu(args):
     return 0
 
 
-def large_batch_probe(dev, n_envs, regroup=1, extra=None, model="our_robot"):
+def large_batch_probe(dev, n_envs, extra=None, model="our_robot"):
     """Throughput at the batch size of BASELINE.json configs[3] (65536 envs/GPU), same timing hygiene; with
     model="go1": the 12-actuator model of configs[1]/[2] at the headline batch size."""
     import torch
     from opendog_b200.env import BatchedWalkEnv
-    env = BatchedWalkEnv(n_envs, model=model, device=dev, seed=0, info_keys=None, regroup=regroup, **(extra or {}))
+    env = BatchedWalkEnv(n_envs, model=model, device=dev, seed=0, info_keys=None, **(extra or {}))
     env.reset()
     acts = torch.rand(32, n_envs, env.act_dim, device=dev) * 2 - 1
     for i in range(20):                              # (robots dropped from the keyframe have landed, episodes are mixed)
@@ -494,7 +493,6 @@ def main():
     ap.add_argument("--mppi", type=int, default=1, help="N=1: also time one MPPI plan (1024 x 64); 0 = off")
     ap.add_argument("--train-probe", action="store_true", help="N=1: include the PPO epoch in the rollout probe")
     ap.add_argument("--cfg", action="append", default=[], help="OdgEnvConfig override key=value (experiments)")
-    ap.add_argument("--regroup", type=int, default=0, help="workload regrouping of envs into warps (OdgEnvConfig.regroup)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -58,9 +58,9 @@ typedef struct OdgEnvConfig {
   float reset_noise_scale;   /* reward_calc:106 -> 0.02 */
   int scale_actions;         /* 1 = apply ScaleActionWrapper.action (ScaleActionEnvironment.py:21-23)
                                 to actions in [-1,1]; 0 = actions are ctrl targets in rad */
-  int regroup;               /* 1 = before each step, regroup environments into warps by the solver work of their
-                                previous step (counting sort on device). Changes only the schedule, never the
-                                per-environment results. default 0 (measured: no gain on B200) */
+  int launch_lanes;          /* launch shape of the step kernel (schedule only: never changes a result bit, tests pin that).
+                                Active lanes per warp: 32, 16 or 8 = 8, 4 or 2 environments per warp; 0 = chosen from the
+                                batch size (8 environments per warp unless the batch has fewer warps than the GPU has SMs) */
   int first_env_id;          /* global id of env 0 of this handle (rank * num_envs): RNG streams are
                                 keyed by global env id so results do not depend on the sharding */
   int obs_layout;            /* 0 = WalkEnvironmentV0._get_obs (WalkEnvironment.py:115-136): 9 + 3*nu values
@@ -69,6 +69,9 @@ typedef struct OdgEnvConfig {
                                 (the "48" of BASELINE configs[2]): 12 + 3*nu values
                                 [2 v, 0.25 w, projected_gravity (reward_calc get_projected_gravity, its Euler-angle
                                 formula), 2 v_des, q - key_qpos[0,7:], 0.05 qd, last_action] */
+  int launch_block;          /* threads per block of the step kernel: 32, 64 or 128; 0 = 64 */
+  int launch_lockstep;       /* 1 = the warps of a block take Newton iterations in lockstep (one barrier per iteration;
+                                pays when the batch is several waves deep), 0 = never, -1 = chosen from the batch size */
 } OdgEnvConfig;
 
 /* Optional per-step outputs (any pointer may be NULL). WalkEnvironment.py:65-72 `info`. */

@@ -28,6 +28,18 @@ int odg_mppi_sample(const float* mean_dev, float sigma, int n_samples, int act_d
 int odg_mppi_accumulate(const float* reward_dev, const uint8_t* terminated_dev, int n_samples, float termination_cost,
                         float* cost_dev, uint8_t* alive_dev, void* stream);
 
+/* The whole rollout of a plan in ONE launch (what opendog_b200.mppi.MPPI runs): for every sample n of `sim`
+ * (created with auto_reset = 0; the caller has broadcast the shared start state with odg_set_state / odg_set_env_state)
+ * and t in [0, horizon): draw action[t][n][:] exactly as odg_mppi_sample does, take the fused environment step of
+ * odg_step, and accumulate cost[n] as odg_mppi_accumulate does (a terminated sample pays `termination_cost` once, stops
+ * stepping and only keeps drawing its action rows). State stays on the SM between the steps of a sample's horizon; no
+ * launch or grid-wide barrier separates them. mean_dev [T][A]; actions_dev [T][N][A]; cost_dev [N] (overwritten).
+ * `iteration_dev` (nullable) points to a device-side plan counter that overrides `iteration`: a CUDA graph that
+ * increments it replays with fresh noise every plan. */
+struct OdgSim;
+int odg_mppi_rollout(struct OdgSim* sim, const float* mean_dev, float sigma, int horizon, uint64_t seed, uint32_t iteration,
+                     const uint32_t* iteration_dev, float termination_cost, float* actions_dev, float* cost_dev, void* stream);
+
 /* Information-theoretic MPPI update, one block, fixed summation order (deterministic):
  *   w[n] = exp(-(cost[n] - min cost) / lambda);  mean_out[t][a] = sum_n w[n] action[t][n][a] / sum_n w[n]
  * actions_dev [T][N][A]; mean_out_dev [T][A]; stats_dev [4] f32 = (min cost, mean cost, sum w, argmin) nullable. */

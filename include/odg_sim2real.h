@@ -34,6 +34,11 @@ typedef struct OdgS2RConfig {
   int auto_reset;                   /* 1: a done env is reset inside odg_s2r_step (obs = reset obs) */
   double real_home_deg[8];          /* real_robot_home_deg_map in ACTUATOR_NAMES_ORDERED order  :95-102 */
   double joint_scale[8];            /* joint_scale_factors (all 1)                               :103 */
+  int max_steps;                    /* MAX_STEPS_PER_EPISODE = 250 (:68): the reference's training loop ends an episode
+                                       after this many policy steps (:539) and resets the env. With auto_reset = 1 this
+                                       layer plays that loop's role: an env whose counter reaches max_steps reports done = 1
+                                       with reason ODG_S2R_RUNNING ("max_steps", no penalty) and is reset. 0 = no cap;
+                                       ignored when auto_reset = 0 (the caller's own loop owns the cap, as in the reference) */
 } OdgS2RConfig;
 
 void odg_s2r_default_config(OdgS2RConfig* cfg);

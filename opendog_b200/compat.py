@@ -28,7 +28,8 @@ class BatchedQuadrupedEnv:
     state_dim = 3 + 8 + 8 + 1 + 2          # sim2real/train.py:164
     action_dim = 4
 
-    def __init__(self, num_envs: int, model: str = "our_robot", device=None, auto_reset: bool = True, **sim_config):
+    def __init__(self, num_envs: int, model: str = "our_robot", device=None, auto_reset: bool = True, max_steps: int = 250,
+                 **sim_config):
         # POLICY_DECISION_DT / timestep = 0.10 / 0.002 = 50 mj_step per policy step (sim2real/train.py:156)
         self.sim = BatchedWalkEnv(num_envs, model=model, device=device, info_keys=None, frame_skip=50, scale_actions=0,
                                   auto_reset=0, **sim_config)
@@ -36,6 +37,7 @@ class BatchedQuadrupedEnv:
         cfg = _lib.OdgS2RConfig()
         self.L.odg_s2r_default_config(C.byref(cfg))
         cfg.auto_reset = 1 if auto_reset else 0
+        cfg.max_steps = int(max_steps)     # MAX_STEPS_PER_EPISODE (sim2real/train.py:68,539); enforced only with auto_reset
         h = C.c_void_p()
         _lib.check(self.L.odg_s2r_create(self.sim._h, C.byref(self.sim._model), C.byref(cfg), C.byref(h)), "odg_s2r_create")
         self._h = h

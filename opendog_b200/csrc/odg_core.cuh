@@ -40,6 +40,10 @@ static inline float odg_fadd_rn(float a, float b) { volatile float r = a + b; re
 static inline float odg_fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float odg_fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline float odg_fdiv_fast(float a, float b) { return a / b; }
+#ifdef ODG_EMU_STATS
+// solver statistics of the host emulator (tools/emu_solver_stats.py): one record per Newton iteration of lane 0
+void odg_emu_stat(int it, float rel_step, float alpha, int ls_passes, int nc_leg, float d10);
+#endif
 #define ODG_UNROLL
 #define ODG_NO_UNROLL
 #else
@@ -131,7 +135,6 @@ struct SimPtrs {            // SoA state in HBM: x[i*N + env]
   int* step; int* gait_idx; int* gait_cnt; unsigned* episode;   // [N]
   unsigned char* fresh;                          // [N] last_action is the float64 zeros of reset_model
   int* work;                                     // [N] solver work of the last env-step (Newton iterations + line-search passes)
-  int* order;                                    // [N] env processed by each 4-lane slot (workload regrouping), or null
 };
 
 struct StepArgs {
@@ -997,6 +1000,9 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     smax = grp_max(smax, gm); amax = grp_max(amax, gm);
     const bool tiny = smax <= C.tol * (1.f + amax);
     float alpha = (tiny && d10 < 0.f) ? 1.f : 0.f;
+#ifdef ODG_EMU_STATS
+    const int ls_before = ls_evals;
+#endif
     if (d10 < 0.f && !tiny) {                       // else: negligible step, or not a descent direction (converged to rounding)
       // phi' is increasing (phi convex): bracket its zero with the first pass, shrink the bracket 5x per further
       // pass, stop as soon as one evaluated point has |phi'| <= ls_tol*|phi'(0)|, else finish with the zero of the
@@ -1044,6 +1050,9 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         alpha = (fhi < -0.1f * flo) ? hi : alpha;
       }
     }
+#ifdef ODG_EMU_STATS
+    if (lane0) odg_emu_stat(it, odg_fdiv_fast(smax, 1.f + amax), alpha, ls_evals - ls_before, nc, d10);
+#endif
     // ---- take the step, test convergence on the step size
     a_b.t = a_b.t + alpha * p_b.t; a_b.w = a_b.w + alpha * p_b.w;
     ODG_UNROLL for (int j = 0; j < NJL; j++) a_l[j] += alpha * p_l[j];
@@ -1180,12 +1189,15 @@ ODG_DEV int gait_call(int& idx, int& cnt, int paws_mask, float vx) {
   cnt = 0; idx = 0; return 0;
 }
 
+// What a caller that keeps stepping the same environment inside one kernel (MPPI rollouts) needs back from env_step.
+struct StepResult { float reward_unclipped; bool terminated, truncated; };
+
 // Full environment step for one 4-lane group: load state, frame_skip substeps, obs/reward/termination,
 // optional auto-reset, store state.
 template <int NJL>
-ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const float* ODG_RESTRICT s_gc,
-                      const float4* ODG_RESTRICT s_vert, const SimPtrs& P, const StepArgs& A,
-                      int env, int leg, unsigned gm, float* ODG_RESTRICT s_red) {
+ODG_DEV StepResult env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const float* ODG_RESTRICT s_gc,
+                            const float4* ODG_RESTRICT s_vert, const SimPtrs& P, const StepArgs& A,
+                            int env, int leg, unsigned gm, float* ODG_RESTRICT s_red) {
   const int N = P.N;
   const bool real = env < P.n;                     // padding environments never touch caller-owned buffers
   const int obs_dim = (C.obs_layout ? 12 : 9) + 3 * C.nu;
@@ -1233,8 +1245,8 @@ ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const f
       {
       const V3 ov = warm_v, ow = warm_wl; float ol[NJL];
       ODG_UNROLL for (int j = 0; j < NJL; j++) ol[j] = warm_l[j];
-      if (s >= 2 && !C.lockstep) {                  // (measured: +4 % without lockstep, -2 % with it, where the slowest of
-                                                    //  a block's 16 environments sets the pace)
+      if (s >= 2) {                                 // (in every launch shape, lockstep or not, so that a result never depends
+                                                    //  on the shape: measured +4 % free-running, -2 % under lockstep)
         warm_v = warm_v + (warm_v - pv); warm_wl = warm_wl + (warm_wl - pw);
         ODG_UNROLL for (int j = 0; j < NJL; j++) warm_l[j] += warm_l[j] - pl[j];
       }
@@ -1426,6 +1438,8 @@ ODG_DEV void env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const f
     if (A.mode == 0) { P.step[env] = step; P.fresh[env] = is_fresh ? 1 : 0; }
     if (do_reset) P.episode[env] = episode;
   }
+  StepResult res; res.reward_unclipped = (float)rr; res.terminated = terminated; res.truncated = truncated;
+  return res;
 }
 
 // reset_model (WalkEnvironment.py:138-151) for one 4-lane group

@@ -417,7 +417,12 @@ struct DevGuard {
   explicit DevGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
   ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
-double* g_gae_partial = nullptr; int g_gae_partial_cap = 0, g_gae_partial_dev = -1;
+// device that owns a caller buffer (entry points without a handle run where their tensors live)
+int device_of(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess || a.type != cudaMemoryTypeDevice) { cudaGetLastError(); return -1; }
+  return a.device;
+}
 }  // namespace
 
 extern "C" {
@@ -501,21 +506,26 @@ int odg_gae(const float* reward_dev, const float* value_dev, const uint8_t* done
     return set_error(ODG_ERR_INVALID, "odg_gae: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nblocks = (n + kGaeBlock - 1) / kGaeBlock;
-  int dev = 0;
-  CUDA_TRY(cudaGetDevice(&dev));
-  if (g_gae_partial_cap < nblocks || g_gae_partial_dev != dev) {
-    if (g_gae_partial) { cudaFree(g_gae_partial); g_gae_partial = nullptr; }
-    CUDA_TRY(cudaMalloc(&g_gae_partial, (size_t)2 * nblocks * sizeof(double)));
-    g_gae_partial_cap = nblocks; g_gae_partial_dev = dev;
-  }
-  k_gae<<<nblocks, kGaeBlock, 0, st>>>(reward_dev, value_dev, done_dev, T, n, gamma, lambda, adv_dev, ret_dev, g_gae_partial);
-  if (stats_dev) k_gae_finish<<<1, kGaeBlock, 0, st>>>(g_gae_partial, nblocks, (long long)T * n, stats_dev);
-  CUDA_TRY(cudaGetLastError());
+  const int dev = device_of(reward_dev);
+  if (dev < 0) return set_error(ODG_ERR_INVALID, "odg_gae: reward_dev is not device memory");
+  DevGuard guard(dev);
+  // per-block partial sums: a stream-ordered allocation that lives for this call only (no state shared between
+  // streams, threads or devices)
+  double* partial = nullptr;
+  CUDA_TRY(cudaMallocAsync(&partial, (size_t)2 * nblocks * sizeof(double), st));
+  k_gae<<<nblocks, kGaeBlock, 0, st>>>(reward_dev, value_dev, done_dev, T, n, gamma, lambda, adv_dev, ret_dev, partial);
+  if (stats_dev) k_gae_finish<<<1, kGaeBlock, 0, st>>>(partial, nblocks, (long long)T * n, stats_dev);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(partial, st);
+  if (e != cudaSuccess) return set_error(ODG_ERR_CUDA, std::string("odg_gae: ") + cudaGetErrorString(e));
   return ODG_OK;
 }
 
 int odg_normalize_advantages(float* adv_dev, long long count, const double* stats_dev, void* stream) {
   if (!adv_dev || !stats_dev || count < 1) return set_error(ODG_ERR_INVALID, "odg_normalize_advantages: bad arguments");
+  const int dev = device_of(adv_dev);
+  if (dev < 0) return set_error(ODG_ERR_INVALID, "odg_normalize_advantages: adv_dev is not device memory");
+  DevGuard guard(dev);
   k_adv_norm<<<(unsigned)((count + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(adv_dev, count, stats_dev);
   CUDA_TRY(cudaGetLastError());
   return ODG_OK;

@@ -34,30 +34,6 @@ namespace odg_internal { int set_error(int code, const std::string& msg) { retur
 namespace {
 
 
-// Stage the model constants of a persistent block into shared memory with 16-byte asynchronous copies (LDGSTS): every
-// thread issues all of its copies back to back and waits once, instead of a load -> store round trip per element (at
-// 4096 environments a block lives for a single tile, so this prologue is on the critical path of the step).
-__device__ __forceinline__ void stage_constants(float* smem, const float* __restrict__ g_lc, const float* __restrict__ g_gc,
-                                                const float* __restrict__ g_vert, SmemLayout L,
-                                                const float4** s_vert, const float** s_lc, const float** s_gc) {
-  // layout: [vert (16B aligned)][lc][gc]; all three sizes are multiples of 4 floats (host: SmemLayout)
-  float* slc = smem + L.vert_floats;
-  float* sgc = slc + L.lc_floats;
-  auto copy16 = [](float* dst, const float* src, int n_floats) {
-    for (int i = threadIdx.x * 4; i < n_floats; i += blockDim.x * 4) {
-      const unsigned d = (unsigned)__cvta_generic_to_shared(dst + i);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i) : "memory");
-    }
-  };
-  copy16(smem, g_vert, L.vert_floats);
-  copy16(slc, g_lc, L.lc_floats);
-  copy16(sgc, g_gc, L.gc_floats);
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  *s_vert = reinterpret_cast<const float4*>(smem); *s_lc = slc; *s_gc = sgc;
-}
-
 #ifndef ODG_MIN_BLOCKS
 #define ODG_MIN_BLOCKS 1
 #endif
@@ -84,7 +60,7 @@ __global__ void __launch_bounds__(ODG_MAX_BLOCK, ODG_MIN_BLOCKS) k_step(const __
   const int envs_per_block = (blockDim.x >> 5) * envs_per_warp;
   for (int base = blockIdx.x * envs_per_block; base < P.N; base += gridDim.x * envs_per_block) {
     const int slot = base + (threadIdx.x >> 5) * envs_per_warp + (lane >> 2);
-    if (slot < P.N) odg::env_step<NJL>(C, s_lc, s_gc, s_vert, P, A, P.order ? P.order[slot] : slot, leg, gm, s_red);
+    if (slot < P.N) odg::env_step<NJL>(C, s_lc, s_gc, s_vert, P, A, slot, leg, gm, s_red);
   }
 }
 
@@ -119,32 +95,6 @@ __global__ void k_fill(float* p, long long n, float v) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
-// ---- workload regrouping: counting sort of env ids by the solver work of their last step, so that the 8
-// environments sharing a warp need similar numbers of Newton / line-search passes (less divergence).
-constexpr int kWorkBins = 256;
-__global__ void k_work_hist(const int* __restrict__ work, int N, int* hist) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) atomicAdd(&hist[min(max(work[i], 0) >> 1, kWorkBins - 1)], 1);
-}
-__global__ void k_work_scan(int* hist) {          // one block of kWorkBins threads: exclusive scan in place
-  __shared__ int s[kWorkBins];
-  const int t = threadIdx.x;
-  s[t] = hist[t];
-  __syncthreads();
-  for (int d = 1; d < kWorkBins; d <<= 1) {
-    int v = t >= d ? s[t - d] : 0;
-    __syncthreads();
-    s[t] += v;
-    __syncthreads();
-  }
-  hist[t] = s[t] - hist[t];
-}
-__global__ void k_work_scatter(const int* __restrict__ work, int N, int Npad, int* offs, int* order) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) order[atomicAdd(&offs[min(max(work[i], 0) >> 1, kWorkBins - 1)], 1)] = i;
-  else if (i < Npad) order[i] = i;            // padding environments keep their own slots
-}
-
 template <typename T>
 __global__ void k_copy(T* dst, const T* src, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -177,31 +127,20 @@ int choose_launch(OdgSim* s) {
   // tiny batches (MPPI: 1024 samples) leave most schedulers empty: 2 environments per warp, so 4x the warps share the
   // work and fewer environments wait on the slowest one of their warp (40.5 vs 46.6 ms per 1024 x 64 plan)
   if (s->P.N / 8 < s->num_sms) lanes = 8;
-  if (const char* env = std::getenv("ODG_STEP_LANES")) { int v = std::atoi(env); if (v >= 4 && v <= 32 && v % 4 == 0) lanes = v; }
+  if (s->cfg_lanes) lanes = s->cfg_lanes;
   const long long warps = ((long long)s->P.N * 4 + lanes - 1) / lanes;
-  if (const char* env = std::getenv("ODG_STEP_BLOCK")) { int v = std::atoi(env); if (v == 32 || v == 64 || v == 128 || (v == 256 && ODG_MAX_BLOCK >= 256)) block = v; }
+  if (s->cfg_block) block = s->cfg_block;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev_occ, kern, block, s->smem_step));
   if (dev_occ < 1) dev_occ = 1;
   const long long wpb = block / 32, need = (warps + wpb - 1) / wpb, cap = (long long)s->num_sms * dev_occ;
   s->step_lanes = lanes; s->step_block = block;
   s->prep.C.lockstep = 2 * need > cap ? 1 : 0;    // measured: pays from ~8192 envs up (tools/tune_launch_shape.sh)
-  if (const char* env = std::getenv("ODG_LOCKSTEP")) s->prep.C.lockstep = std::atoi(env) ? 1 : 0;
+  if (s->cfg_lockstep >= 0) s->prep.C.lockstep = s->cfg_lockstep ? 1 : 0;
   s->step_grid = (int)(need < cap ? need : cap);
   return ODG_OK;
 }
 
 int launch_step(OdgSim* s, const StepArgs& A, cudaStream_t st) {
-  if (s->regroup && A.mode == 0) {
-    const int N = s->N, g = (N + 255) / 256;
-    CUDA_TRY(cudaMemsetAsync(s->d_hist, 0, kWorkBins * sizeof(int), st));
-    k_work_hist<<<g, 256, 0, st>>>(s->P.work, N, s->d_hist);
-    k_work_scan<<<1, kWorkBins, 0, st>>>(s->d_hist);
-    k_work_scatter<<<(s->P.N + 255) / 256, 256, 0, st>>>(s->P.work, N, s->P.N, s->d_hist, s->d_order);
-    s->launches += 3;
-    s->P.order = s->d_order;
-  } else {
-    s->P.order = nullptr;
-  }
   step_kernel_fn(s->prep.C)<<<s->step_grid, s->step_block, s->smem_step, st>>>(s->prep.C, s->P, A, s->d_lc, s->d_gc, s->d_vert, s->L, s->step_lanes);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -258,7 +197,7 @@ int odg_create(const OdgModel* model, const OdgEnvConfig* cfg_in, int num_envs, 
   const DevConst& C = s->prep.C;
   const size_t N = ((size_t)num_envs + 63) / 64 * 64;      // stride: whole blocks of up to 64 environments
   // one slab: qpos, qvel, warm, last_action, desvel (float) | step, gait_idx, gait_cnt, episode (i32) | fresh (u8)
-  const size_t nfloat = (size_t)(C.nq + 2 * C.nv + C.nu + 3) * N, nint = 6 * N + kWorkBins;
+  const size_t nfloat = (size_t)(C.nq + 2 * C.nv + C.nu + 3) * N, nint = 5 * N;
   const size_t bytes = nfloat * 4 + nint * 4 + N;
   if (cudaMalloc(&s->d_state, bytes) != cudaSuccess) { delete s; return fail(ODG_ERR_ALLOC, "cudaMalloc(state) failed"); }
   float* f = static_cast<float*>(s->d_state);
@@ -270,9 +209,8 @@ int odg_create(const OdgModel* model, const OdgEnvConfig* cfg_in, int num_envs, 
   s->P.desvel = f; f += 3 * N;
   int* ip = reinterpret_cast<int*>(f);
   s->P.step = ip; s->P.gait_idx = ip + N; s->P.gait_cnt = ip + 2 * N; s->P.episode = reinterpret_cast<unsigned*>(ip + 3 * N);
-  s->P.work = ip + 4 * N; s->d_order = ip + 5 * N; s->d_hist = ip + 6 * N;
-  s->P.order = nullptr;
-  s->P.fresh = reinterpret_cast<unsigned char*>(ip + 6 * N + kWorkBins);
+  s->P.work = ip + 4 * N;
+  s->P.fresh = reinterpret_cast<unsigned char*>(ip + 5 * N);
   auto upload = [&](float** dst, const std::vector<float>& v) -> cudaError_t {
     cudaError_t e = cudaMalloc(dst, v.size() * sizeof(float));
     if (e != cudaSuccess) return e;
@@ -283,7 +221,12 @@ int odg_create(const OdgModel* model, const OdgEnvConfig* cfg_in, int num_envs, 
   s->L.lc_floats = (int)s->prep.lc.size(); s->L.gc_floats = (int)s->prep.gc.size(); s->L.vert_floats = (int)s->prep.vert.size();
   s->smem_const = (size_t)(s->L.lc_floats + s->L.gc_floats + s->L.vert_floats) * sizeof(float);
   s->smem_step = s->smem_const + (size_t)ODG_MAX_BLOCK * odg::kRedStride * sizeof(float);
-  s->regroup = cfg.regroup;
+  if ((cfg.launch_lanes != 0 && cfg.launch_lanes != 8 && cfg.launch_lanes != 16 && cfg.launch_lanes != 32) ||
+      (cfg.launch_block != 0 && cfg.launch_block != 32 && cfg.launch_block != 64 && cfg.launch_block != 128 &&
+       !(cfg.launch_block == 256 && ODG_MAX_BLOCK >= 256)) || cfg.launch_lockstep < -1 || cfg.launch_lockstep > 1) {
+    odg_destroy(s); return fail(ODG_ERR_INVALID, "odg_create: bad launch_lanes / launch_block / launch_lockstep");
+  }
+  s->cfg_lanes = cfg.launch_lanes; s->cfg_block = cfg.launch_block; s->cfg_lockstep = cfg.launch_lockstep;
   CUDA_TRY(cudaMemset(s->P.work, 0, N * sizeof(int)));
   int rc = choose_launch(s);
   if (rc != ODG_OK) { odg_destroy(s); return rc; }

@@ -20,6 +20,7 @@ constexpr int kObs = 22;
 
 struct S2RConst {
   int N, stride, nq, nv, auto_reset;   // N environments, SoA stride of the simulator's state arrays
+  int max_steps;            // episode cap of the training loop (train.py:68,539), enforced when auto_reset
   int act_id[8];            // ctrl index of ACTUATOR_NAMES_ORDERED[o]  (FR, FL, BR, BL) x (tigh, knee)
   int qidx[8], vidx[8];     // qpos / qvel index of that actuator's joint
   double home[8];           // sim_keyframe_home_qpos_map
@@ -147,6 +148,8 @@ __global__ void k_s2r_post(const S2RConst C, const S2RState S, const odg::SimPtr
   if (!finite) { r -= 20.0; done = true; reason = ODG_S2R_MJ_ERROR; }
   if (fabs(roll) > lim || fabs(pitch) > lim || fabs(yaw) > lim) { r -= 5.0; done = true; reason = ODG_S2R_ORIENTATION_LIMIT; }
   if (!done && cpos > 0.05 && cneg > 0.75 * cpos) { r -= 5.0; done = true; reason = ODG_S2R_TOO_MUCH_BACKWARD; }
+  // the training loop's `for step_num in range(MAX_STEPS_PER_EPISODE)` (:539): episode over, no penalty, reason "max_steps"
+  if (!done && C.auto_reset && C.max_steps > 0 && counter >= C.max_steps) done = true;
   if (reward) reward[env] = (float)r;
   if (done_out) done_out[env] = done ? 1 : 0;
   if (reason_out) reason_out[env] = (unsigned char)reason;
@@ -185,6 +188,12 @@ __global__ void k_s2r_snapshot(const odg::SimPtrs P, int nq, int nv, float* sett
 
 }  // namespace
 
+struct DevScope {          // run an entry point on the handle's device, whatever the caller's current device is
+  int prev = -1;
+  explicit DevScope(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DevScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 struct OdgS2R {
   OdgSim* sim = nullptr;
   S2RConst C{};
@@ -198,7 +207,7 @@ extern "C" {
 void odg_s2r_default_config(OdgS2RConfig* c) {
   if (!c) return;
   c->action_amplitude_rad = 40.0 * 3.14159265358979323846 / 180.0;
-  c->settle_steps = 100; c->auto_reset = 0;
+  c->settle_steps = 100; c->auto_reset = 0; c->max_steps = 250;
   const double home[8] = { -45.0, 45.0, 45.0, 45.0, 45.0, -45.0, 45.0, -45.0 };   // FR_t FR_k FL_t FL_k BR_t BR_k BL_t BL_k
   for (int i = 0; i < 8; i++) { c->real_home_deg[i] = home[i]; c->joint_scale[i] = 1.0; }
 }
@@ -212,11 +221,13 @@ int odg_s2r_create(OdgSim* sim, const OdgModel* m, const OdgS2RConfig* cfg_in, O
   if (m->nu != 8 || m->njl != 2) return set_error(ODG_ERR_INVALID, "QuadrupedEnv needs the 8-actuator OpenDOG model");
   if (DC.scale_actions || DC.auto_reset) return set_error(ODG_ERR_INVALID, "create the OdgSim with scale_actions = 0 and auto_reset = 0");
   if (cfg.settle_steps % DC.frame_skip) return set_error(ODG_ERR_INVALID, "settle_steps must be a multiple of frame_skip");
+  if (cfg.max_steps < 0) return set_error(ODG_ERR_INVALID, "max_steps must be >= 0");
+  DevScope scope(sim->device);
   OdgS2R* e = new (std::nothrow) OdgS2R();
   if (!e) return set_error(ODG_ERR_ALLOC, "out of host memory");
   e->sim = sim;
   S2RConst& C = e->C;
-  C.N = sim->N; C.stride = sim->P.N; C.nq = DC.nq; C.nv = DC.nv; C.auto_reset = cfg.auto_reset; C.amp = cfg.action_amplitude_rad;
+  C.N = sim->N; C.stride = sim->P.N; C.nq = DC.nq; C.nv = DC.nv; C.auto_reset = cfg.auto_reset; C.max_steps = cfg.max_steps; C.amp = cfg.action_amplitude_rad;
   // ACTUATOR_NAMES_ORDERED = FR FL BR BL; model legs are in body order FL FR BL BR
   const int leg_of[4] = { 1, 0, 3, 2 };
   for (int o = 0; o < 8; o++) {
@@ -257,12 +268,14 @@ int odg_s2r_create(OdgSim* sim, const OdgModel* m, const OdgS2RConfig* cfg_in, O
 
 void odg_s2r_destroy(OdgS2R* e) {
   if (!e) return;
+  DevScope scope(e->sim->device);
   cudaFree(e->d_slab); cudaFree(e->d_settled); cudaFree(e->d_home_ctrl);
   delete e;
 }
 
 int odg_s2r_reset(OdgS2R* e, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   if (!e) return set_error(ODG_ERR_INVALID, "odg_s2r_reset: null handle");
+  DevScope scope(e->sim->device);
   const int N = e->C.N;
   k_s2r_reset<<<(N + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(e->C, e->S, e->sim->P, mask_dev, obs_dev, e->d_home_ctrl);
   e->sim->launches++;
@@ -273,6 +286,7 @@ int odg_s2r_reset(OdgS2R* e, const uint8_t* mask_dev, float* obs_dev, void* stre
 int odg_s2r_step(OdgS2R* e, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
                  uint8_t* reason_dev, float* sim_target_rad_dev, float* terminal_obs_dev, void* stream) {
   if (!e || !action_dev) return set_error(ODG_ERR_INVALID, "odg_s2r_step: null handle or action");
+  DevScope scope(e->sim->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int N = e->C.N;
   k_s2r_pre<<<(N + 127) / 128, 128, 0, st>>>(e->C, e->S, action_dev);
@@ -288,6 +302,7 @@ int odg_s2r_step(OdgS2R* e, const float* action_dev, float* obs_dev, float* rewa
 int odg_s2r_set_bookkeeping(OdgS2R* e, const int32_t* counter, const double* prev_x, const double* cum_pos,
                             const double* cum_neg, const double* prev_net, const float* last_cmd, void* stream) {
   if (!e) return set_error(ODG_ERR_INVALID, "odg_s2r_set_bookkeeping: null handle");
+  DevScope scope(e->sim->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t N = (size_t)e->C.N;
   if (counter) CUDA_TRY(cudaMemcpyAsync(e->S.counter, counter, N * 4, cudaMemcpyDeviceToDevice, st));

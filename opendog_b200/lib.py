@@ -25,7 +25,7 @@ SYMBOLS = [
     "odg_s2r_default_config", "odg_s2r_create", "odg_s2r_destroy", "odg_s2r_reset", "odg_s2r_step",
     "odg_s2r_set_bookkeeping",
     # MPPI (include/odg_mppi.h)
-    "odg_mppi_sample", "odg_mppi_accumulate", "odg_mppi_reduce",
+    "odg_mppi_sample", "odg_mppi_accumulate", "odg_mppi_reduce", "odg_mppi_rollout",
 ]
 
 
@@ -33,7 +33,8 @@ class OdgEnvConfig(C.Structure):
     _fields_ = [("task", C.c_int), ("frame_skip", C.c_int), ("max_episode_steps", C.c_int),
                 ("auto_reset", C.c_int), ("solver_iterations", C.c_int), ("ls_iterations", C.c_int),
                 ("solver_tolerance", C.c_float), ("ls_tolerance", C.c_float), ("reset_noise_scale", C.c_float),
-                ("scale_actions", C.c_int), ("regroup", C.c_int), ("first_env_id", C.c_int), ("obs_layout", C.c_int)]
+                ("scale_actions", C.c_int), ("launch_lanes", C.c_int), ("first_env_id", C.c_int), ("obs_layout", C.c_int),
+                ("launch_block", C.c_int), ("launch_lockstep", C.c_int)]
 
 
 _vp = C.c_void_p
@@ -53,7 +54,7 @@ class OdgPolicyWeights(C.Structure):
 
 class OdgS2RConfig(C.Structure):
     _fields_ = [("action_amplitude_rad", C.c_double), ("settle_steps", C.c_int), ("auto_reset", C.c_int),
-                ("real_home_deg", C.c_double * 8), ("joint_scale", C.c_double * 8)]
+                ("real_home_deg", C.c_double * 8), ("joint_scale", C.c_double * 8), ("max_steps", C.c_int)]
 
 
 class OdgError(RuntimeError):
@@ -109,6 +110,7 @@ def load():
     L.odg_s2r_set_bookkeeping.argtypes = [_vp] * 8
     L.odg_mppi_sample.argtypes = [_vp, C.c_float, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, _vp, _vp]
     L.odg_mppi_accumulate.argtypes = [_vp, _vp, C.c_int, C.c_float, _vp, _vp, _vp]
+    L.odg_mppi_rollout.argtypes = [_vp, _vp, C.c_float, C.c_int, C.c_uint64, C.c_uint32, _vp, C.c_float, _vp, _vp, _vp]
     L.odg_mppi_reduce.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp, _vp]
     L.odg_last_error.restype = C.c_char_p
     L.odg_version.restype = C.c_char_p

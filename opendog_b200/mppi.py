@@ -3,8 +3,10 @@
 no MPC code; the cost is minus the reference's walk reward (WalkEnvironment.py:81-109, taken BEFORE its max(0, .)
 clip, which would zero most of the signal) summed along the rollout.
 
-Per plan(): broadcast state -> horizon x (k_mppi_sample, k_step, k_mppi_accum) -> k_mppi_reduce; after the first
-call the whole sequence replays as one CUDA graph.
+Per plan(): broadcast the start state, ONE rollout launch (`odg_mppi_rollout`: every sample walks its whole horizon —
+sample the action row, fused env step, accumulate the cost — without leaving the SM) and one reduction launch
+(`odg_mppi_reduce`). The plan counter that keys the noise lives in device memory and is incremented on the stream, so
+a captured CUDA graph draws fresh noise on every replay.
 """
 from __future__ import annotations
 
@@ -19,7 +21,7 @@ from .env import BatchedWalkEnv, _ptr
 class MPPI:
     def __init__(self, num_samples: int = 1024, horizon: int = 64, sigma: float = 0.3, lam: float = 1.0,
                  termination_cost: float = 100.0, device=None, seed: int = 0, use_graph: bool = True, **sim_config):
-        self.env = BatchedWalkEnv(num_samples, device=device, seed=seed, info_keys=("reward_unclipped",), auto_reset=0, **sim_config)
+        self.env = BatchedWalkEnv(num_samples, device=device, seed=seed, info_keys=None, auto_reset=0, **sim_config)
         self.L, self.dev = self.env.L, self.env.device
         self.N, self.T, self.A = num_samples, horizon, self.env.act_dim
         self.sigma, self.lam, self.term_cost, self.seed = sigma, lam, termination_cost, seed
@@ -28,13 +30,13 @@ class MPPI:
         self.new_mean = torch.zeros(horizon, self.A, device=dev)
         self.actions = torch.zeros(horizon, num_samples, self.A, device=dev)
         self.cost = torch.zeros(num_samples, device=dev)
-        self.alive = torch.ones(num_samples, dtype=torch.uint8, device=dev)
         self.stats = torch.zeros(4, device=dev)
         # shared start state, broadcast to every sample at the start of a plan
         self.q0 = torch.zeros(num_samples, self.env.nq, device=dev)
         self.v0 = torch.zeros(num_samples, self.env.nv, device=dev)
         self.env_state0 = None
         self.iteration = 0
+        self.iteration_dev = torch.zeros(1, dtype=torch.int32, device=dev)     # plan counter keying the noise (Philox)
         self.use_graph, self.graph = use_graph, None
 
     def _st(self):
@@ -52,36 +54,34 @@ class MPPI:
                                desired_velocity=dv.reshape(1, -1).expand(self.N, -1).contiguous().to(self.dev),
                                fresh=torch.zeros(self.N, dtype=torch.uint8, device=self.dev))
 
-    def _body(self, iteration_tensor_free: int):
+    def _body(self):
         e, L, st = self.env, self.L, self._st()
         _lib.check(L.odg_set_state(e._h, _ptr(self.q0), _ptr(self.v0), None, st), "odg_set_state")
         s0 = self.env_state0
         _lib.check(L.odg_set_env_state(e._h, _ptr(s0["step"]), _ptr(s0["gait_index"]), _ptr(s0["gait_matches"]),
                                        _ptr(s0["last_action"]), _ptr(s0["desired_velocity"]), _ptr(s0["fresh"]), st),
                    "odg_set_env_state")
-        self.cost.zero_(); self.alive.fill_(1)
-        for t in range(self.T):
-            _lib.check(L.odg_mppi_sample(_ptr(self.mean[t]), self.sigma, self.N, self.A, C.c_uint64(self.seed),
-                                         iteration_tensor_free, t, _ptr(self.actions[t]), st), "odg_mppi_sample")
-            e.step_into(self.actions[t], None, e.reward, e.terminated, e.truncated)
-            _lib.check(L.odg_mppi_accumulate(_ptr(e.info["reward_unclipped"]), _ptr(e.terminated), self.N, self.term_cost, _ptr(self.cost),
-                                             _ptr(self.alive), st), "odg_mppi_accumulate")
+        _lib.check(L.odg_mppi_rollout(e._h, _ptr(self.mean), self.sigma, self.T, C.c_uint64(self.seed), 0, _ptr(self.iteration_dev),
+                                      self.term_cost, _ptr(self.actions), _ptr(self.cost), st), "odg_mppi_rollout")
         _lib.check(L.odg_mppi_reduce(_ptr(self.cost), _ptr(self.actions), self.T, self.N, self.A, self.lam,
                                      _ptr(self.new_mean), _ptr(self.stats), st), "odg_mppi_reduce")
+        self.iteration_dev.add_(1)
 
     def plan(self, update_mean: bool = True):
         """One MPPI iteration from the shared start state; returns the updated nominal sequence [T, A]."""
         assert self.env_state0 is not None, "call set_start first"
-        if self.use_graph and self.graph is not None:
-            self.graph.replay()          # NOTE: a replay reuses the captured iteration's noise stream
-        elif self.use_graph and self.iteration >= 1:
+        if not self.use_graph:
+            self._body()
+        elif self.graph is not None:
+            self.graph.replay()
+        elif self.iteration == 0:
+            self._body()                 # first plan runs eagerly: it is also the warm-up the capture needs
+        else:
             torch.cuda.synchronize(self.dev)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self._body(self.iteration)
+                self._body()
             self.graph.replay()          # capture only records: run it once
-        else:
-            self._body(self.iteration)
         self.iteration += 1
         if update_mean:
             self.mean.copy_(self.new_mean)
@@ -89,4 +89,4 @@ class MPPI:
 
     @property
     def kernels_per_plan(self) -> int:
-        return 3 * self.T + 6
+        return 9          # 2 + 5 state-broadcast transposes / copies, the rollout, the reduction, the counter

@@ -123,9 +123,8 @@ def gae(reward, value, done, gamma=0.99, lam=0.95, normalize=True, group=None):
     st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(L.odg_gae(_ptr(reward), _ptr(value), _ptr(done), T, N, gamma, lam, _ptr(adv), _ptr(ret), _ptr(stats), st),
                "odg_gae")
-    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized() and group is not False):
-        if torch.distributed.is_initialized():
-            torch.distributed.all_reduce(stats, group=group if group not in (None, True) else None)
+    from .train import allreduce_advantage_stats
+    allreduce_advantage_stats(stats, group)          # group=False: never; None / True: the default group when initialised
     if normalize:
         count = int(T * N)
         _lib.check(L.odg_normalize_advantages(_ptr(adv), count, _ptr(stats), st), "odg_normalize_advantages")

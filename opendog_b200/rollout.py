@@ -36,6 +36,8 @@ class Rollout:
         self.graph = None
         self.use_graph = use_graph
         self.obs[0].copy_(env.reset())
+        self._started = False              # row 0 holds the reset observation until the first horizon has been collected
+        self._warm = False
 
     def _body(self):
         T, pol, env = self.T, self.policy, self.env
@@ -48,26 +50,34 @@ class Rollout:
         self.step_base.add_(T + 1)
 
     def collect(self):
-        """One horizon of experience into the buffers. Returns self (buffers are [T(+1), N, ...])."""
-        if self.use_graph:
-            if self.graph is None:
-                self.obs[0].copy_(self.obs[self.T])
-                s = torch.cuda.Stream(device=self.env.device)
-                s.wait_stream(torch.cuda.current_stream(self.env.device))
-                with torch.cuda.stream(s):
-                    self._body()                                # warm-up outside capture (lazy module loads, allocs)
-                torch.cuda.current_stream(self.env.device).wait_stream(s)
-                torch.cuda.synchronize(self.env.device)
-                self.obs[0].copy_(self.obs[self.T])
-                self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph):
-                    self._body()
-                return self
+        """One horizon of experience into the buffers. Returns self (buffers are [T(+1), N, ...]).
+
+        The first call starts from the `env.reset()` observation stored by the constructor; every later call carries
+        the last observation of the previous horizon over into row 0. The buffers a call returns are exactly what
+        its own horizon produced: obs[t] is the observation action[t] / logp[t] / value[t] were computed from."""
+        dev = self.env.device
+        if self._started:
             self.obs[0].copy_(self.obs[self.T])
-            self.graph.replay()
-        else:
-            self.obs[0].copy_(self.obs[self.T])
+        self._started = True
+        if not self.use_graph:
             self._body()
+        elif self.graph is not None:
+            self.graph.replay()
+        elif not self._warm:
+            # first horizon: eager, on a side stream — real data, and at the same time the warm-up a capture needs
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s):
+                self._body()
+            torch.cuda.current_stream(dev).wait_stream(s)
+            self._warm = True
+        else:
+            # second horizon: capture (records only, executes nothing), then run it as the first replay
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body()
+            self.graph.replay()
         return self
 
     def advantages(self, normalize: bool = True, group=None):

@@ -336,8 +336,11 @@ static void add_contact(const OdgModel* m, OdgoData* d, int g, int vert, const d
   c->frame[2] = 1; c->frame[4] = 1; c->frame[6] = -1;
 }
 
+static void note_gap(double* slot, double v) { v = fabs(v); if (v < *slot) *slot = v; }
+
 void odgo_collision(const OdgModel* m, OdgoData* d) {
   d->ncon = 0;
+  d->gap_contact = d->gap_support = 1e30;
   const double tilt = m->multicontact_tilt;
   for (int g = 0; g < m->ngeom; g++) {
     const OdgGeom* G = &m->geom[g];
@@ -348,18 +351,22 @@ void odgo_collision(const OdgModel* m, OdgoData* d) {
       double c[3], p[3];
       m3_mulv(c, R, G->center); v3_add(c, c, x);
       double dist = c[2] - G->radius;
+      note_gap(&d->gap_contact, dist - G->margin);
       if (dist > G->margin) continue;
       v3_set(p, c[0], c[1], c[2] - G->radius);
       add_contact(m, d, g, -1, p, dist);
       continue;
     }
     /* support vertex in direction -normal */
-    int best = -1; double zmin = 0, pw[3], bestp[3] = {0, 0, 0};
+    int best = -1; double zmin = 0, z2 = 1e30, pw[3], bestp[3] = {0, 0, 0};
     for (int k = 0; k < G->vert_count; k++) {
       m3_mulv(pw, R, m->vert[G->vert_start + k]); v3_add(pw, pw, x);
-      if (best < 0 || pw[2] < zmin) { best = k; zmin = pw[2]; v3_copy(bestp, pw); }
+      if (best < 0 || pw[2] < zmin) { if (best >= 0) z2 = zmin; best = k; zmin = pw[2]; v3_copy(bestp, pw); }
+      else if (pw[2] < z2) z2 = pw[2];
     }
+    if (best >= 0) note_gap(&d->gap_contact, zmin - G->margin);
     if (best < 0 || zmin > G->margin) continue;
+    note_gap(&d->gap_support, z2 - zmin);
     add_contact(m, d, g, G->vert_start + best, bestp, zmin);
     /* up to three more support points, from directions tilted off -normal by `tilt`, 120 deg apart */
     int found[ODG_MAX_CON_PER_GEOM]; int nf = 1; found[0] = best;
@@ -367,14 +374,17 @@ void odgo_collision(const OdgModel* m, OdgoData* d) {
       double ang = 2.0 * ODG_PI * i / 3.0;
       /* tangent basis of the contact frame: t1 = (0,1,0), t2 = (-1,0,0) */
       double dir[3] = { -sin(tilt) * sin(ang), sin(tilt) * cos(ang), -cos(tilt) };
-      int bi = -1; double smax = 0, bp[3] = {0, 0, 0};
+      int bi = -1; double smax = 0, s2 = -1e30, bp[3] = {0, 0, 0};
       for (int k = 0; k < G->vert_count; k++) {
         m3_mulv(pw, R, m->vert[G->vert_start + k]); v3_add(pw, pw, x);
         double s = v3_dot(dir, pw);
-        if (bi < 0 || s > smax) { bi = k; smax = s; v3_copy(bp, pw); }
+        if (bi < 0 || s > smax) { if (bi >= 0) s2 = smax; bi = k; smax = s; v3_copy(bp, pw); }
+        else if (s > s2) s2 = s;
       }
+      note_gap(&d->gap_support, smax - s2);
       int dup = 0;
       for (int k = 0; k < nf; k++) dup |= (found[k] == bi);
+      if (!dup) note_gap(&d->gap_contact, bp[2] - G->margin);
       if (dup || bp[2] > G->margin) continue;
       found[nf++] = bi;
       add_contact(m, d, g, G->vert_start + bi, bp, bp[2]);
@@ -432,6 +442,7 @@ static void make_constraints(const OdgModel* m, OdgoData* d) {
   int nv = m->nv;
   double J[NV_MAX];
   d->nefc = 0;
+  d->gap_limit = 1e30;
   /* 1. dof friction loss */
   for (int i = 0; i < nv; i++) {
     double fl = i < 6 ? m->base_frictionloss[i] : m->frictionloss[(i - 6) / m->njl][(i - 6) % m->njl];
@@ -448,6 +459,7 @@ static void make_constraints(const OdgModel* m, OdgoData* d) {
       double q = d->qpos[7 + l * m->njl + j];
       for (int side = -1; side <= 1; side += 2) {
         double dist = side * (m->jnt_range[l][j][(side + 1) / 2] - q);
+        note_gap(&d->gap_limit, dist);
         if (dist < 0) {
           memset(J, 0, sizeof(J)); J[k] = -side;
           add_row(m, d, ODGO_ROW_LIMIT, k, J, dist, 0, 0, m->lim_solref, m->lim_solimp, m->dof_invweight0[l][j], 0);
@@ -930,8 +942,13 @@ void odgo_walk_step(OdgoWalkEnv* e, const float* action, double* obs, double* re
   odgo_walk_scale_action(action, scaled);
   e->step += 1;
   for (int i = 0; i < 8; i++) e->d.ctrl[i] = (double)scaled[i];
-  for (int s = 0; s < e->frame_skip; s++) odgo_step(e->m, &e->d);
+  double gap[3] = { 1e30, 1e30, 1e30 };
+  for (int s = 0; s < e->frame_skip; s++) {
+    odgo_step(e->m, &e->d);
+    gap[0] = fmin(gap[0], e->d.gap_contact); gap[1] = fmin(gap[1], e->d.gap_support); gap[2] = fmin(gap[2], e->d.gap_limit);
+  }
   walk_post(e, scaled, obs, reward, terminated, truncated, info);
+  if (info) for (int k = 0; k < 3; k++) info->min_gap[k] = gap[k];
 }
 
 void odgo_walk_evaluate(OdgoWalkEnv* e, const float* scaled, double* obs, double* reward, int* terminated,
@@ -939,6 +956,7 @@ void odgo_walk_evaluate(OdgoWalkEnv* e, const float* scaled, double* obs, double
   for (int i = 0; i < 8; i++) e->d.ctrl[i] = (double)scaled[i];
   odgo_forward(e->m, &e->d);
   walk_post(e, scaled, obs, reward, terminated, truncated, info);
+  if (info) { info->min_gap[0] = e->d.gap_contact; info->min_gap[1] = e->d.gap_support; info->min_gap[2] = e->d.gap_limit; }
 }
 
 void odgo_walk_step_autoreset(OdgoWalkEnv* e, const float* action, double* obs, double* reward, int* done,

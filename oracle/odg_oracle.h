@@ -60,6 +60,12 @@ typedef struct OdgoData {
   double efc_aref[ODGO_MAX_EFC], efc_R[ODGO_MAX_EFC], efc_D[ODGO_MAX_EFC];
   double efc_frictionloss[ODGO_MAX_EFC], efc_force[ODGO_MAX_EFC];
   double solver_cost, solver_gradnorm;
+  /* How close the last forward pass came to taking a DIFFERENT discrete decision (diagnostics for the parity tests:
+   * an fp32 implementation may legitimately decide the other way when one of these is at rounding level):
+   *   gap_contact  min |dist - margin| over every support point tested for inclusion (m)
+   *   gap_support  min lead of a winning support vertex over the runner-up of the same search (m)
+   *   gap_limit    min |q - bound| over limited joints (rad) */
+  double gap_contact, gap_support, gap_limit;
 } OdgoData;
 
 /* Walk-environment state that lives outside mjData in the reference (WalkEnvironmentV0 +
@@ -87,6 +93,7 @@ typedef struct OdgoWalkInfo {
   int paws_in_ground[4];
   int gait_first_call;       /* value used in the reward */
   double reward_terms[6];    /* lin_track, safe_range, gait, joint_cost, action_rate, y_cost (unweighted) */
+  double min_gap[3];         /* min over the substeps of this env-step of OdgoData.gap_contact / gap_support / gap_limit */
 } OdgoWalkInfo;
 
 int  odgo_sizeof_model(void);

@@ -47,6 +47,7 @@ class OdgoData(C.Structure):
         ("efc_aref", _d * MAX_EFC), ("efc_R", _d * MAX_EFC), ("efc_D", _d * MAX_EFC),
         ("efc_frictionloss", _d * MAX_EFC), ("efc_force", _d * MAX_EFC),
         ("solver_cost", _d), ("solver_gradnorm", _d),
+        ("gap_contact", _d), ("gap_support", _d), ("gap_limit", _d),
     ]
 
 
@@ -64,7 +65,7 @@ class OdgoWalkInfo(C.Structure):
         ("x_position", _d), ("y_position", _d), ("distance_from_origin", _d),
         ("paw_contact_forces", _d * 6 * 4), ("patterns_matches", _d),
         ("linear_vel_tracking_reward", _d), ("reward_ctrl", _d),
-        ("paws_in_ground", _i * 4), ("gait_first_call", _i), ("reward_terms", _d * 6),
+        ("paws_in_ground", _i * 4), ("gait_first_call", _i), ("reward_terms", _d * 6), ("min_gap", _d * 3),
     ]
 
 
@@ -139,6 +140,10 @@ class Sim:
     def xmat(self): return _np(self.d.xmat, (NB, 3, 3))
     @property
     def xipos(self): return _np(self.d.xipos, (NB, 3))
+    @property
+    def decision_gaps(self):
+        """(contact inclusion [m], support-vertex lead [m], joint-limit distance [rad]) of the last forward pass."""
+        return np.array([self.d.gap_contact, self.d.gap_support, self.d.gap_limit])
     @property
     def ncon(self): return self.d.ncon
     @property
@@ -216,7 +221,7 @@ class WalkEnv:
             patterns_matches=info.patterns_matches,
             linear_vel_tracking_reward=info.linear_vel_tracking_reward, reward_ctrl=info.reward_ctrl,
             paws_in_ground=np.array(info.paws_in_ground[:]), gait_first_call=info.gait_first_call,
-            reward_terms=np.array(info.reward_terms[:]),
+            reward_terms=np.array(info.reward_terms[:]), min_gap=np.array(info.min_gap[:]),
         )
         return obs, rew.value, t0.value, t1.value, term_obs, inf
 

@@ -79,8 +79,10 @@ class QuadrupedEnvOracle:
         for o in range(8):
             cmd[self.act_id[o]] = np.clip(self.home[o] + d[o], self.ctrlrange[o][0], self.ctrlrange[o][1])
         s.ctrl[:] = cmd
+        self.min_gap = np.full(3, 1e30)            # closest call of any discrete decision in this policy step (Sim.decision_gaps)
         for _ in range(self.n_sub):
             s.step()
+            self.min_gap = np.minimum(self.min_gap, s.decision_gaps)
         mj_err = not (np.isfinite(s.qpos).all() and np.isfinite(s.qvel).all())
         self.counter += 1
         x = float(s.qpos[0]); dx = x - self.prev_x

@@ -37,6 +37,19 @@ double odg_emu_shfl_xor_d(double v, int m) {
   g_buf[t_lane] = v; barrier(); double r = g_buf[t_lane ^ m]; barrier(); return r;
 }
 
+#ifdef ODG_EMU_STATS
+namespace { std::vector<float> g_stats; }
+void odg_emu_stat(int it, float rel_step, float alpha, int ls_passes, int nc_leg, float d10) {
+  g_stats.insert(g_stats.end(), { (float)it, rel_step, alpha, (float)ls_passes, (float)nc_leg, d10 });
+}
+extern "C" int emu_stats(float* out, int max_floats) {          // drains the record buffer (6 floats per record)
+  const int n = (int)g_stats.size() < max_floats ? (int)g_stats.size() : max_floats;
+  for (int i = 0; i < n; i++) out[i] = g_stats[i];
+  g_stats.clear();
+  return n;
+}
+#endif
+
 struct Emu {
   odg::Prepared prep;
   int N;
@@ -83,7 +96,7 @@ Emu* emu_create(const OdgModel* m, const OdgEnvConfig* cfg, int N, uint64_t seed
   e->last_action.assign((size_t)C.nu * N, 0.f); e->desvel.assign((size_t)3 * N, 0.f);
   e->work.assign(N, 0); e->step.assign(N, 0); e->gidx.assign(N, 0); e->gcnt.assign(N, 0); e->episode.assign(N, 0); e->fresh.assign(N, 1);
   e->P = odg::SimPtrs{ N, N, e->qpos.data(), e->qvel.data(), e->warm.data(), e->last_action.data(), e->desvel.data(),
-                       e->step.data(), e->gidx.data(), e->gcnt.data(), e->episode.data(), e->fresh.data(), e->work.data(), nullptr };
+                       e->step.data(), e->gidx.data(), e->gcnt.data(), e->episode.data(), e->fresh.data(), e->work.data() };
   for (int i = 0; i < N; i++) odg::env_init(C, e->P, i);
   return e;
 }

@@ -91,6 +91,69 @@ def test_walk_env_and_reset_indexing():
     assert ndone == 2 * N
 
 
+# An env-step may differ from the oracle beyond the stated tolerance ONLY when the fp32 kernel and the fp64 oracle took a
+# different DISCRETE decision in one of its substeps, and the oracle itself reports that decision as a coin toss at fp32
+# resolution: a support point within `FLIP_M` of the contact margin (the contact exists on one side only), or a support
+# vertex leading its runner-up by less than `FLIP_M` (the contact sits on a different hull vertex). Coordinates are
+# ~0.1 m, one float32 ulp there is 7.5e-9 m and the kinematic chain accumulates a few dozen roundings.
+FLIP_M = 1e-6
+
+
+def assert_info_matches(info, oi, i, names=None):
+    """`info` outputs of env i (reward_calc.py:339-370, WalkEnvironment.py:65-72) against the oracle's, stated tolerances."""
+    n = names or dict(paw="paw_forces", lin="lin_vel_reward", dist="distance")
+    assert abs(info["x_position"][i] - oi["x_position"]) <= 1e-5
+    assert abs(info["y_position"][i] - oi["y_position"]) <= 1e-5
+    assert abs(info[n["dist"]][i] - oi["distance_from_origin"]) <= 1e-5
+    assert abs(info[n["lin"]][i] - oi["linear_vel_tracking_reward"]) <= 2e-4
+    assert abs(info["reward_ctrl"][i] - oi["reward_ctrl"]) <= 1e-3 * max(1.0, oi["reward_ctrl"])
+    assert float(info["patterns_matches"][i]) == oi["patterns_matches"]
+    # get_paw_contact_forces (quirk C9): the force of the LAST contact of each paw in the calf frame. The split of a paw's
+    # load over its 3-4 coplanar contact points is statically indeterminate (only the regulariser picks it), so single
+    # contact forces carry a looser tolerance than their sum (1 %, test_single_step_*): 5 % of the largest paw force.
+    pf = np.asarray(info[n["paw"]][i], dtype=np.float64).reshape(4, 6)
+    ref = oi["paw_contact_forces"]
+    assert np.abs(pf - ref).max() <= 5e-2 * max(1.0, np.abs(ref).max()), (pf, ref)
+    assert not pf[:, 3:].any() and not ref[:, 3:].any()              # torque slots stay zero (mj_contactForce, condim 3)
+    for k in range(4):                                               # a paw off the ground reports zeros
+        if not oi["paws_in_ground"][k]:
+            assert not pf[k].any()
+
+
+def test_walk_info_outputs_and_outliers_are_decision_flips():
+    """Rows a9 / a4 of SURVEY section 8: every `info` output against the oracle, and every env-step outside the stated
+    tolerance must be explained by a decision the oracle reports as within FLIP_M of flipping."""
+    N, T = 6, 32
+    env = EmuEnv(N, seed=11, max_episode_steps=25)                   # (the reset drops the robot: it lands at step ~8)
+    ws = [WalkEnv(seed=11, env_id=i) for i in range(N)]
+    for w in ws:
+        w.e.max_steps = 25
+    env.reset(); [w.reset() for w in ws]
+    rng = np.random.default_rng(5)
+    n_out = n_contact_steps = 0
+    for t in range(T):
+        a = rng.uniform(-1, 1, (N, 8)).astype(np.float32)
+        obs, r, term, trunc, info = env.step(a)
+        res = [w.step_autoreset(a[i]) for i, w in enumerate(ws)]
+        for i in range(N):
+            oobs, orew, odone, _, otob, oi = res[i]
+            assert (term[i] or trunc[i]) == odone
+            mine = info["terminal_obs"][i] if odone else obs[i]
+            theirs = otob if odone else oobs
+            ok = (np.abs(mine - theirs).max() < 2e-4 and abs(r[i] - orew) < 2e-4
+                  and np.array_equal(info["paws_in_ground"][i], oi["paws_in_ground"]))
+            if ok:
+                assert_info_matches(info, oi, i)
+                n_contact_steps += int(oi["paws_in_ground"].any())
+            else:
+                n_out += 1
+                assert min(oi["min_gap"][0], oi["min_gap"][1]) < FLIP_M, (t, i, oi["min_gap"])
+        qp, qv, _ = env.get_state()
+        for i, w in enumerate(ws):
+            w.qpos[:] = qp[i]; w.qvel[:] = qv[i]
+    assert n_out <= 2 and n_contact_steps > N * T // 3
+
+
 def test_results_do_not_depend_on_sharding():
     """Envs are keyed by GLOBAL id: one handle of 4 envs == two handles of 2 (rank 0 / rank 1 shards)."""
     whole = EmuEnv(4, seed=9)

@@ -77,15 +77,40 @@ def test_plan_costs_match_env_rollout_and_graph_replay():
         _, _, _, info = e.step(acts[t])
         r = info["reward_unclipped"]
         term = e.terminated.bool()
-        ref = ref + torch.where(alive, -r + torch.where(term, torch.tensor(100.0, device="cuda"), torch.tensor(0.0, device="cuda")), torch.zeros_like(r))
+        stepped = torch.where(alive, ref - r, ref)                       # (same float32 order as the rollout kernel)
+        ref = torch.where(alive & term, stepped + 100.0, stepped)
         alive = alive & ~term
-    assert torch.equal(ref, cost) and cost.abs().min().item() > 0
+    assert torch.equal(ref, cost) and cost.abs().min().item() > 0, "fused rollout != the same sequences stepped one launch at a time"
     # softmin mean of the sampled sequences
     w = torch.exp(-(cost - cost.min()) / 1.0).double()
     refm = torch.einsum("n,tna->ta", w, acts.double()) / w.sum()
     assert (new_mean.double() - refm).abs().max().item() < 2e-5
-    # second call captures the graph, third replays it: same iteration index => identical plan
-    m.plan(update_mean=False); torch.cuda.synchronize(); c2 = m.cost.clone()
-    m.plan(update_mean=False); torch.cuda.synchronize()
-    assert torch.equal(m.cost, c2) and m.graph is not None
-    assert not torch.equal(c2, cost)              # iteration 1 drew different noise than iteration 0
+    # second call captures the graph, third replays it. The plan counter lives in device memory and is bumped inside the
+    # graph, so every replay draws fresh noise — the rows of plan k are the stand-alone sampler's with iteration = k.
+    import ctypes as C
+    from opendog_b200 import lib
+    m.plan(update_mean=False); torch.cuda.synchronize(); c2, a2 = m.cost.clone(), m.actions.clone()
+    m.plan(update_mean=False); torch.cuda.synchronize(); c3, a3 = m.cost.clone(), m.actions.clone()
+    assert m.graph is not None and int(m.iteration_dev) == 3
+    assert not torch.equal(c2, cost) and not torch.equal(c3, c2) and not torch.equal(a3, a2)
+    row = torch.empty(N, 8, device="cuda")
+    for it, acts_it in ((1, a2), (2, a3)):
+        lib.check(m.L.odg_mppi_sample(C.c_void_p(m.mean[5].data_ptr()), 0.3, N, 8, C.c_uint64(4), it, 5, C.c_void_p(row.data_ptr()), None), "sample")
+        assert torch.equal(row, acts_it[5])
+
+
+def test_reduce_accepts_the_documented_sample_limit():
+    """odg_mppi_reduce keeps [n_samples] weights in dynamic shared memory: 12000 samples need 48 KB on top of 8 KB of
+    static rows, i.e. the opt-in limit."""
+    import ctypes as C
+    from opendog_b200 import lib
+    L = lib.load()
+    T, N, A = 3, 12000, 8
+    cost = torch.rand(N, device="cuda"); act = torch.rand(T, N, A, device="cuda")
+    out = torch.empty(T, A, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    lib.check(L.odg_mppi_reduce(p(cost), p(act), T, N, A, 1.0, p(out), None, None), "reduce")
+    torch.cuda.synchronize()
+    w = torch.exp(-(cost - cost.min())).double()
+    ref = torch.einsum("n,tna->ta", w, act.double()) / w.sum()
+    assert (out.double() - ref).abs().max().item() < 2e-5

@@ -122,3 +122,33 @@ def test_rollout_graph_equals_eager_and_feeds_gae():
     for a, b in zip(*outs):
         assert torch.equal(a, b)
     assert outs[0][5].any(), "episodes should end (truncation at 30) inside the last collected horizon (steps 25-36)"
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_first_horizon_starts_from_the_reset_observation(use_graph):
+    """the first collect() must act on the `env.reset()` observation (not on a zero row), and in every horizon
+    it returns — eager, the eager warm-up of the graph path, the capture + first replay, later replays — obs[t] must be the
+    observation that action[t] / logp[t] were computed from."""
+    from opendog_b200.env import BatchedWalkEnv
+    from opendog_b200.policy import ActorCriticB200
+    from opendog_b200.rollout import Rollout
+    env = BatchedWalkEnv(160, seed=8, info_keys=None)
+    pol = ActorCriticB200(env.obs_dim, env.act_dim, 0.4, seed=3)
+    ro = Rollout(env, pol, horizon=6, use_graph=use_graph)
+    reset_obs = ro.obs[0].clone()
+    assert reset_obs.abs().sum().item() > 0
+    std = torch.exp(pol.action_log_std.detach()).reshape(-1)
+    last = None
+    for k in range(4):
+        ro.collect()
+        torch.cuda.synchronize()
+        if k == 0:
+            assert torch.equal(ro.obs[0], reset_obs), "row 0 of the first horizon is the reset observation"
+        else:
+            assert torch.equal(ro.obs[0], last), "row 0 carries the previous horizon's last observation"
+        for t in (0, ro.T - 1):
+            mean = pol.act(ro.obs[t].clone(), sample=False)[3]
+            z = (ro.action[t] - mean) / std
+            logp = (-0.5 * z * z - torch.log(std) - 0.5 * math.log(2 * math.pi)).sum(-1)
+            assert (logp - ro.logp[t]).abs().max().item() < 2e-3, (k, t)
+        last = ro.obs[ro.T].clone()

@@ -4,7 +4,7 @@ for v in "$@"; do
   if [ "$v" = default ]; then unset ODG_LIB_PATH; else export ODG_LIB_PATH=$PWD/build/variants/libodgsim_$v.so; fi
   for cfg in "4096 32 0" "65536 32 1"; do
     set -- $cfg
-    ODG_STEP_LANES=$2 ODG_LOCKSTEP=$3 python bench.py --steps 30 --warmup 12 --no-cpu-baseline --large-batch 0 --rollout-envs 0 --mppi 0 --go1 0 --envs-per-gpu $1 > gpurun_out/q10.log 2>&1
+    python bench.py --steps 30 --warmup 12 --no-cpu-baseline --large-batch 0 --rollout-envs 0 --mppi 0 --go1 0 --envs-per-gpu $1 --cfg launch_lanes=$2 --cfg launch_lockstep=$3 > gpurun_out/q10.log 2>&1
     python - "$v" $cfg <<'PY'
 import json,sys
 try:
