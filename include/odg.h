@@ -59,7 +59,7 @@ typedef struct OdgEnvConfig {
   int scale_actions;         /* 1 = apply ScaleActionWrapper.action (ScaleActionEnvironment.py:21-23)
                                 to actions in [-1,1]; 0 = actions are ctrl targets in rad */
   int launch_lanes;          /* launch shape of the step kernel (schedule only: never changes a result bit, tests pin that).
-                                Active lanes per warp: 32, 16 or 8 = 8, 4 or 2 environments per warp; 0 = chosen from the
+                                Active lanes per warp: 32, 16, 8 or 4 = 8, 4, 2 or 1 environments per warp; 0 = chosen from the
                                 batch size (8 environments per warp unless the batch has fewer warps than the GPU has SMs) */
   int first_env_id;          /* global id of env 0 of this handle (rank * num_envs): RNG streams are
                                 keyed by global env id so results do not depend on the sharding */

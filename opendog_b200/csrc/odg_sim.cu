@@ -221,7 +221,7 @@ int odg_create(const OdgModel* model, const OdgEnvConfig* cfg_in, int num_envs, 
   s->L.lc_floats = (int)s->prep.lc.size(); s->L.gc_floats = (int)s->prep.gc.size(); s->L.vert_floats = (int)s->prep.vert.size();
   s->smem_const = (size_t)(s->L.lc_floats + s->L.gc_floats + s->L.vert_floats) * sizeof(float);
   s->smem_step = s->smem_const + (size_t)ODG_MAX_BLOCK * odg::kRedStride * sizeof(float);
-  if ((cfg.launch_lanes != 0 && cfg.launch_lanes != 8 && cfg.launch_lanes != 16 && cfg.launch_lanes != 32) ||
+  if ((cfg.launch_lanes != 0 && cfg.launch_lanes != 4 && cfg.launch_lanes != 8 && cfg.launch_lanes != 16 && cfg.launch_lanes != 32) ||
       (cfg.launch_block != 0 && cfg.launch_block != 32 && cfg.launch_block != 64 && cfg.launch_block != 128 &&
        !(cfg.launch_block == 256 && ODG_MAX_BLOCK >= 256)) || cfg.launch_lockstep < -1 || cfg.launch_lockstep > 1) {
     odg_destroy(s); return fail(ODG_ERR_INVALID, "odg_create: bad launch_lanes / launch_block / launch_lockstep");
