@@ -38,21 +38,35 @@ METRIC = "env-steps/sec (device-timed) at 1/2/4/8 B200 vs ref mj_step on host co
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
+MUJOCO_SOLVER_DEFAULTS = dict(tolerance=1e-8, ls_tolerance=0.01, ls_iterations=50)     # mjOption defaults (mujoco 3.2.3)
+
+
 def _cpu_worker(conn, n_envs, seed, first_id):
+    """One worker = one host core stepping its own env set, like one SubprocVecEnv process (train/train.py:81-86), but
+    with the whole set advanced by ONE C call per env-step (no per-env Python or ctypes overhead in the timed loop)."""
+    import ctypes as C
     import numpy as np
-    from oracle.oracle import WalkEnv
+    from oracle.oracle import WalkEnv, OdgoWalkEnv, lib
+    L = lib()
+    # stop the Newton solver where MuJoCo's defaults stop; the oracle's own (parity) setting is ~1000x tighter and would
+    # make the CPU arm do several times the work mj_step does
+    L.odgo_set_solver.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
+    L.odgo_set_solver(MUJOCO_SOLVER_DEFAULTS["tolerance"], MUJOCO_SOLVER_DEFAULTS["ls_tolerance"],
+                      MUJOCO_SOLVER_DEFAULTS["ls_iterations"], 1)
     envs = [WalkEnv(seed=seed, env_id=first_id + i) for i in range(n_envs)]
     for e in envs:
         e.reset()
+    ptrs = (C.POINTER(OdgoWalkEnv) * n_envs)(*[C.pointer(e.e) for e in envs])
+    obs = np.zeros((n_envs, 33)); rew = np.zeros(n_envs); done = np.zeros(n_envs, np.int32)
     rng = np.random.default_rng(seed + first_id)
+    fp = lambda a, t: a.ctypes.data_as(C.POINTER(t))
     conn.send("ready")
     while True:
         msg = conn.recv()
         if msg is None:
             break
         a = rng.uniform(-1, 1, (n_envs, 8)).astype(np.float32)
-        for i, e in enumerate(envs):
-            e.step_autoreset(a[i])
+        L.odgo_walk_step_autoreset_batch(ptrs, n_envs, fp(a, C.c_float), fp(obs, C.c_double), fp(rew, C.c_double), fp(done, C.c_int))
         conn.send(n_envs)
     conn.close()
 
@@ -103,6 +117,25 @@ def cpu_throughput(sample_envs, steps, warmup, procs):
     return n / dt, dt
 
 
+def cpu_baseline(all_core_steps, one_core_steps, envs_per_core=16, warmup=12):
+    """The CPU arm on a bounded sample: all host cores (one process per core), then one core alone (SURVEY section 8d
+    config 1 asks for both). Returns the `cpu_baseline` object of the bench line."""
+    from oracle.oracle import build
+    build()
+    procs = os.cpu_count() or 1
+    v_all, dt_all = cpu_throughput(procs * envs_per_core, all_core_steps, warmup, procs)
+    v_one, dt_one = cpu_throughput(envs_per_core, one_core_steps, warmup, 1)
+    return {"value": v_all, "unit": "env-steps/s", "cores": procs, "kind": "port",
+            "one_core": {"value": v_one, "unit": "env-steps/s", "physics_steps_per_s": v_one * FRAME_SKIP},
+            "physics_steps_per_s_per_core": v_all * FRAME_SKIP / procs,
+            "solver": dict(MUJOCO_SOLVER_DEFAULTS, note="MuJoCo's default stopping rules; the parity oracle itself runs 1000x tighter"),
+            "build": "gcc -O3 -march=native -ffp-contract=off, one C call per worker per env-step",
+            "sample": f"all cores: {procs} processes x {envs_per_core} envs x {all_core_steps} env-steps ({dt_all:.1f} s); one core: "
+                      f"{envs_per_core} envs x {one_core_steps} env-steps ({dt_one:.1f} s); after {warmup} warm-up env-steps (robots "
+                      "landed). fp64 restatement of mj_step + the reference's reward code — NOT MuJoCo itself: mujoco==3.2.3 is "
+                      "not installable here or on the GPU box (profiles/r02_mujoco_probe.txt)"}, dt_all
+
+
 def workload_name(envs_per_gpu):
     return (f"{envs_per_gpu} envs/GPU batched step, OpenDOG MJCF (our_robot), flat-plane foot contact, PD "
             "position actuators, fused reward/obs/auto-reset (BASELINE.json configs[1])")
@@ -113,23 +146,17 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle.oracle import build
-    build()
-    procs = os.cpu_count() or 1
-    # bounded sample: the full 4096-env batch per step costs ~4 s / cores of CPU; keep the run in minutes
-    per_core_budget = 16
-    sample = min(ENVS_PER_GPU * args.gpus, max(procs, procs * per_core_budget))
-    value, dt = cpu_throughput(sample, args.steps, max(args.warmup, 12), procs)
+    # bounded sample: each "step" advances 16 envs per core (a 4096-env batch would cost ~0.25 s x 4096/16/cores per step)
+    cb, dt = cpu_baseline(all_core_steps=max(1, args.steps), one_core_steps=max(1, min(args.steps, 100)), warmup=max(args.warmup, 12))
+    value = cb["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(ENVS_PER_GPU), "envs_per_gpu": ENVS_PER_GPU, "frame_skip": FRAME_SKIP,
                    "physics_steps_per_s": value * FRAME_SKIP,
                    "note": "CPU arm: each step advances a bounded sample of the workload (see cpu_baseline.sample)"},
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": procs, "kind": "port",
-                         "sample": f"{sample} oracle envs (one process per core, {sample // procs} envs each) x "
-                                   f"{args.steps} env-steps; restatement of mj_step, not MuJoCo itself"},
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -301,15 +328,7 @@ def run_gpu(args):
         "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.oracle import build
-        build()
-        procs = os.cpu_count() or 1
-        sample = procs * 16
-        v, dt = cpu_throughput(sample, 600, 12, procs)
-        line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": procs, "kind": "port",
-                                "sample": f"{sample} oracle envs ({procs} processes x 16 envs) x 600 env-steps after 12 "
-                                          f"warm-up steps (robots landed; {dt:.1f} s); fp64 restatement of mj_step + "
-                                          "reward code, not MuJoCo itself"}
+        line["cpu_baseline"], _ = cpu_baseline(all_core_steps=1200, one_core_steps=600)
     if rank == 0 and args.large_batch and world == 1:
         line["large_batch"] = large_batch_probe(dev, args.large_batch, extra)
     if rank == 0 and args.go1 and world == 1:

@@ -137,6 +137,18 @@ struct SimPtrs {            // SoA state in HBM: x[i*N + env]
   int* work;                                     // [N] solver work of the last env-step (Newton iterations + line-search passes)
 };
 
+// MPPI mode of the step kernel (include/odg_mppi.h: odg_mppi_rollout): T > 0 turns one launch into a whole rollout —
+// every environment walks T env-steps, drawing its own action row before each one and accumulating its cost.
+struct MppiArgs {
+  int T;                          // horizon; 0 = ordinary step
+  float sigma, term_cost;
+  uint32_t seed_lo, seed_hi, iteration;
+  const uint32_t* iteration_dev;  // nullable: device-side plan counter (CUDA-graph replays draw fresh noise)
+  const float* mean;              // [T][A]
+  float* actions;                 // [T][n][A]
+  float* cost;                    // [n]
+};
+
 struct StepArgs {
   const float* action;      // [N][nu]
   float* obs;               // [N][obs_dim]
@@ -275,6 +287,31 @@ ODG_DEV void philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint
 }
 ODG_DEV float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
 constexpr uint32_t kStreamReset = 0x52534554u, kStreamDesvel = 0x44564c00u;
+
+// MPPI action row of one sample: action[a] = clamp(mean[a] + sigma * eps, -1, 1), eps from Philox4x32-10 keyed by
+// (seed, sample, iteration, t, block) turned into Box-Muller pairs. One definition for the stand-alone sampler kernel
+// and for the rollout mode of the step kernel.
+constexpr uint32_t kStreamMppi = 0x4d505049u;
+#ifndef ODG_HOST_EMU
+ODG_DEV void mppi_sample_row(const float* ODG_RESTRICT mean, float sigma, int n, int A, uint32_t seed_lo, uint32_t seed_hi,
+                             uint32_t iteration, uint32_t t, float* ODG_RESTRICT action) {
+  for (int blk = 0; blk * 4 < A; blk++) {
+    uint32_t r[4];
+    philox4x32(seed_lo, seed_hi, (uint32_t)n, iteration, (t << 8) | (uint32_t)blk, kStreamMppi, r);
+    for (int pr = 0; pr < 2; pr++) {
+      const float u1 = ((float)(r[2 * pr] >> 8) + 1.0f) * 5.9604644775390625e-08f;
+      const float u2 = u01(r[2 * pr + 1]);
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float sn, cs; sincosf(6.283185307179586f * u2, &sn, &cs);
+      const float e[2] = { rad * cs, rad * sn };
+      for (int q = 0; q < 2; q++) {
+        const int a = blk * 4 + pr * 2 + q;
+        if (a < A) action[(size_t)n * A + a] = fminf(1.f, fmaxf(-1.f, mean[a] + sigma * e[q]));
+      }
+    }
+  }
+}
+#endif
 
 // ---- solimp impedance (mj_makeImpedance::getimpedance); imp5 = d0,dmax,width,mid,power (pre-clamped on host)
 ODG_NOINLINE float impedance_pow(float x, float mid, float power) {      // generic power (reference models use 2)
@@ -1197,7 +1234,7 @@ struct StepResult { float reward_unclipped; bool terminated, truncated; };
 template <int NJL>
 ODG_DEV StepResult env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const float* ODG_RESTRICT s_gc,
                             const float4* ODG_RESTRICT s_vert, const SimPtrs& P, const StepArgs& A,
-                            int env, int leg, unsigned gm, float* ODG_RESTRICT s_red) {
+                            const float* action, int env, int leg, unsigned gm, float* ODG_RESTRICT s_red) {
   const int N = P.N;
   const bool real = env < P.n;                     // padding environments never touch caller-owned buffers
   const int obs_dim = (C.obs_layout ? 12 : 9) + 3 * C.nu;
@@ -1214,7 +1251,7 @@ ODG_DEV StepResult env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, c
     qd[j] = P.qvel[(6 + leg * NJL + j) * N + env];
     warm_l[j] = P.warm[(6 + leg * NJL + j) * N + env];
     const int u = (int)LCF(LC_UIDX, j);
-    float a = (LCF(LC_HASACT, j) != 0.f && real) ? A.action[env * C.nu + u] : 0.f;
+    float a = (LCF(LC_HASACT, j) != 0.f && real) ? action[env * C.nu + u] : 0.f;
     if (C.scale_actions && A.mode == 0) {
       // ScaleActionEnvironment.py:21-23 in float32, numpy evaluation order
       float lo = LCF(LC_SLO, j), hi = LCF(LC_SHI, j);

@@ -18,6 +18,7 @@
 #include <new>
 #include <string>
 
+#include "../../include/odg_mppi.h"
 #include "odg_sim_internal.h"
 
 namespace {
@@ -42,6 +43,7 @@ namespace {
 #endif
 template <int NJL>
 __global__ void __launch_bounds__(ODG_MAX_BLOCK, ODG_MIN_BLOCKS) k_step(const __grid_constant__ DevConst C, const SimPtrs P, const StepArgs A,
+                                              const __grid_constant__ odg::MppiArgs M,
                                               const float* __restrict__ g_lc, const float* __restrict__ g_gc,
                                               const float* __restrict__ g_vert, SmemLayout L, int lanes) {
   extern __shared__ __align__(16) float smem[];
@@ -58,9 +60,34 @@ __global__ void __launch_bounds__(ODG_MAX_BLOCK, ODG_MIN_BLOCKS) k_step(const __
   const unsigned gm = 0xFu << (lane & 28);
   const int envs_per_warp = lanes >> 2;
   const int envs_per_block = (blockDim.x >> 5) * envs_per_warp;
+  // Ordinary step: one env-step per environment. MPPI rollout (M.T > 0; odg_mppi_rollout): the SAME code walks a whole
+  // horizon per environment — draw the step's action row, take the env-step, add minus the unclipped reward to the
+  // sample's cost — so between the steps of a sample nothing waits on any other sample (no launch boundary, no grid-wide
+  // barrier), and a rollout is bit-identical to the same action rows stepped one launch at a time (one call site of
+  // env_step = one copy of its arithmetic). A sample that terminates pays once and only keeps drawing its action rows.
+  const int horizon = M.T > 0 ? M.T : 1;
+  const uint32_t iteration = (M.T > 0 && M.iteration_dev) ? *M.iteration_dev : M.iteration;
   for (int base = blockIdx.x * envs_per_block; base < P.N; base += gridDim.x * envs_per_block) {
-    const int slot = base + (threadIdx.x >> 5) * envs_per_warp + (lane >> 2);
-    if (slot < P.N) odg::env_step<NJL>(C, s_lc, s_gc, s_vert, P, A, slot, leg, gm, s_red);
+    const int env = base + (threadIdx.x >> 5) * envs_per_warp + (lane >> 2);
+    if (env >= P.N) continue;
+    float cost = 0.f;
+    bool alive = true;
+    for (int t = 0; t < horizon; t++) {
+      const float* action = A.action;
+      if (M.T > 0) {
+        float* row = M.actions + (size_t)t * P.n * C.nu;
+        if (leg == 0 && env < P.n)
+          odg::mppi_sample_row(M.mean + (size_t)t * C.nu, M.sigma, env, C.nu, M.seed_lo, M.seed_hi, iteration, (uint32_t)t, row);
+        __syncwarp(gm);                            // the group's other lanes read the row lane 0 just wrote
+        action = row;
+      }
+      if (alive) {
+        const odg::StepResult r = odg::env_step<NJL>(C, s_lc, s_gc, s_vert, P, A, action, env, leg, gm, s_red);
+        cost -= r.reward_unclipped;
+        if (r.terminated && M.T > 0) { cost += M.term_cost; alive = false; }
+      }
+    }
+    if (M.T > 0 && leg == 0 && env < P.n) M.cost[env] = cost;
   }
 }
 
@@ -106,7 +133,7 @@ __global__ void k_copy(T* dst, const T* src, long long n) {
 
 namespace {
 
-typedef void (*StepKernel)(const DevConst, const SimPtrs, const StepArgs, const float*, const float*, const float*, SmemLayout, int);
+typedef void (*StepKernel)(const DevConst, const SimPtrs, const StepArgs, const odg::MppiArgs, const float*, const float*, const float*, SmemLayout, int);
 StepKernel step_kernel_fn(const DevConst& C) {
   return C.njl == 2 ? k_step<2> : k_step<3>;
 }
@@ -141,7 +168,9 @@ int choose_launch(OdgSim* s) {
 }
 
 int launch_step(OdgSim* s, const StepArgs& A, cudaStream_t st) {
-  step_kernel_fn(s->prep.C)<<<s->step_grid, s->step_block, s->smem_step, st>>>(s->prep.C, s->P, A, s->d_lc, s->d_gc, s->d_vert, s->L, s->step_lanes);
+  odg::MppiArgs M;
+  std::memset(&M, 0, sizeof(M));
+  step_kernel_fn(s->prep.C)<<<s->step_grid, s->step_block, s->smem_step, st>>>(s->prep.C, s->P, A, M, s->d_lc, s->d_gc, s->d_vert, s->L, s->step_lanes);
   s->launches++;
   CUDA_TRY(cudaGetLastError());
   return ODG_OK;
@@ -277,6 +306,29 @@ int odg_step(OdgSim* s, const float* action_dev, float* obs_dev, float* reward_d
   StepArgs A;
   fill_args(&A, action_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, info, 0);
   return launch_step(s, A, static_cast<cudaStream_t>(stream));
+}
+
+int odg_mppi_rollout(OdgSim* s, const float* mean_dev, float sigma, int horizon, uint64_t seed, uint32_t iteration,
+                     const uint32_t* iteration_dev, float termination_cost, float* actions_dev, float* cost_dev, void* stream) {
+  if (!s || !mean_dev || !actions_dev || !cost_dev || horizon < 1 || !(sigma >= 0.f))
+    return fail(ODG_ERR_INVALID, "odg_mppi_rollout: bad arguments");
+  if (s->prep.C.auto_reset) return fail(ODG_ERR_INVALID, "odg_mppi_rollout: the handle must be created with auto_reset = 0");
+  DeviceGuard guard(s->device);
+  DevConst C = s->prep.C;
+  C.lockstep = 0;                                  // samples leave the horizon loop at different times: no block barriers
+  odg::MppiArgs M;
+  M.T = horizon; M.sigma = sigma; M.term_cost = termination_cost;
+  M.seed_lo = (uint32_t)seed; M.seed_hi = (uint32_t)(seed >> 32); M.iteration = iteration; M.iteration_dev = iteration_dev;
+  M.mean = mean_dev; M.actions = actions_dev; M.cost = cost_dev;
+  StepArgs A;
+  fill_args(&A, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+  // every sample gets its own 4-lane group for the whole horizon: one tile per block, never a second wave
+  const int epb = (s->step_block / 32) * (s->step_lanes / 4);
+  const int grid = (s->P.N + epb - 1) / epb;
+  step_kernel_fn(C)<<<grid, s->step_block, s->smem_step, static_cast<cudaStream_t>(stream)>>>(C, s->P, A, M, s->d_lc, s->d_gc, s->d_vert, s->L, s->step_lanes);
+  s->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ODG_OK;
 }
 
 int odg_evaluate(OdgSim* s, const float* ctrl_dev, float* obs_dev, float* reward_dev, uint8_t* terminated_dev,

@@ -336,11 +336,27 @@ static void add_contact(const OdgModel* m, OdgoData* d, int g, int vert, const d
   c->frame[2] = 1; c->frame[4] = 1; c->frame[6] = -1;
 }
 
+static __thread double g_world[ODG_MAX_VERT][3];          /* scratch: one hull in world coordinates */
 static void note_gap(double* slot, double v) { v = fabs(v); if (v < *slot) *slot = v; }
+
+static void bounding_spheres(const OdgModel* m, OdgoData* d) {
+  for (int g = 0; g < m->ngeom; g++) {
+    const OdgGeom* G = &m->geom[g];
+    double c[3] = {0, 0, 0}, r2 = 0;
+    for (int k = 0; k < G->vert_count; k++) for (int i = 0; i < 3; i++) c[i] += m->vert[G->vert_start + k][i] / G->vert_count;
+    for (int k = 0; k < G->vert_count; k++) {
+      double e[3]; v3_sub(e, m->vert[G->vert_start + k], c);
+      r2 = fmax(r2, v3_dot(e, e));
+    }
+    v3_copy(d->bs_center[g], c); d->bs_radius[g] = sqrt(r2) * (1 + 1e-12) + 1e-12;
+  }
+  d->bs_ready = 0x5ca1ab1e;
+}
 
 void odgo_collision(const OdgModel* m, OdgoData* d) {
   d->ncon = 0;
   d->gap_contact = d->gap_support = 1e30;
+  if (d->bs_ready != 0x5ca1ab1e) bounding_spheres(m, d);
   const double tilt = m->multicontact_tilt;
   for (int g = 0; g < m->ngeom; g++) {
     const OdgGeom* G = &m->geom[g];
@@ -357,10 +373,20 @@ void odgo_collision(const OdgModel* m, OdgoData* d) {
       add_contact(m, d, g, -1, p, dist);
       continue;
     }
-    /* support vertex in direction -normal */
+    {
+      /* broad phase (what mj_collision's bounding-volume test does for a geom far from the plane): the hull lies inside
+       * the sphere (center, radius) of its geom frame, so it cannot come within the margin if the sphere does not.
+       * Exact: never changes which contacts exist. */
+      double c[3];
+      m3_mulv(c, R, d->bs_center[g]);
+      if (c[2] + x[2] - d->bs_radius[g] > G->margin) continue;
+    }
+    /* world coordinates of the hull once; support vertex in direction -normal */
+    double (*W)[3] = g_world;
+    for (int k = 0; k < G->vert_count; k++) { m3_mulv(W[k], R, m->vert[G->vert_start + k]); v3_add(W[k], W[k], x); }
     int best = -1; double zmin = 0, z2 = 1e30, pw[3], bestp[3] = {0, 0, 0};
     for (int k = 0; k < G->vert_count; k++) {
-      m3_mulv(pw, R, m->vert[G->vert_start + k]); v3_add(pw, pw, x);
+      v3_copy(pw, W[k]);
       if (best < 0 || pw[2] < zmin) { if (best >= 0) z2 = zmin; best = k; zmin = pw[2]; v3_copy(bestp, pw); }
       else if (pw[2] < z2) z2 = pw[2];
     }
@@ -376,7 +402,7 @@ void odgo_collision(const OdgModel* m, OdgoData* d) {
       double dir[3] = { -sin(tilt) * sin(ang), sin(tilt) * cos(ang), -cos(tilt) };
       int bi = -1; double smax = 0, s2 = -1e30, bp[3] = {0, 0, 0};
       for (int k = 0; k < G->vert_count; k++) {
-        m3_mulv(pw, R, m->vert[G->vert_start + k]); v3_add(pw, pw, x);
+        v3_copy(pw, W[k]);
         double s = v3_dot(dir, pw);
         if (bi < 0 || s > smax) { if (bi >= 0) s2 = smax; bi = k; smax = s; v3_copy(bp, pw); }
         else if (s > s2) s2 = s;
@@ -591,7 +617,18 @@ static void line_derivs(const OdgModel* m, const OdgoData* d, const double* a, c
   *d1 = s1; *d2 = s2;
 }
 
-/* mj_fwdConstraint with the Newton solver, iterated to (much tighter than 1e-8) convergence */
+/* Stopping rules of the Newton solver. As an ORACLE the solve runs far past MuJoCo's defaults (scaled gradient < 1e-11,
+ * line search to 1e-14 of phi'(0)) so that the fp32 kernel is compared with the minimiser itself. As a CPU BASELINE
+ * (bench.py's cpu_baseline / --impl reference legs call odgo_set_solver) it stops where MuJoCo's defaults stop:
+ * mjOption.tolerance = 1e-8 on the scaled gradient OR the scaled cost improvement of the last iteration,
+ * ls_tolerance = 0.01, ls_iterations = 50 — otherwise the timed work would be several times what mj_step does. */
+static double g_tol = 1e-11, g_ls_tol = 1e-14;
+static int g_ls_iter = 100, g_improvement_exit = 0;
+void odgo_set_solver(double tolerance, double ls_tolerance, int ls_iterations, int improvement_exit) {
+  g_tol = tolerance; g_ls_tol = ls_tolerance; g_ls_iter = ls_iterations; g_improvement_exit = improvement_exit;
+}
+
+/* mj_fwdConstraint with the Newton solver */
 static void solve_constraints(const OdgModel* m, OdgoData* d) {
   int nv = m->nv;
   memcpy(d->qacc, d->qacc_smooth, nv * sizeof(double));
@@ -607,13 +644,16 @@ static void solve_constraints(const OdgModel* m, OdgoData* d) {
   double scale = 0;
   for (int i = 0; i < nv; i++) scale += d->M[i * nv + i];
   scale = 1.0 / fmax(MINVAL, scale);                       /* 1 / (meaninertia * nv) */
+  double prev_cost = 0;
   for (int it = 0; it < 100; it++) {
     double cost = total_cost(m, d, a, grad, H);
     double gn = 0;
     for (int i = 0; i < nv; i++) gn += grad[i] * grad[i];
     gn = sqrt(gn);
     d->solver_cost = cost; d->solver_gradnorm = gn * scale; d->solver_iter = it;
-    if (gn * scale < 1e-11) break;
+    if (gn * scale < g_tol) break;
+    if (g_improvement_exit && it > 0 && scale * (prev_cost - cost) < g_tol) break;
+    prev_cost = cost;
     if (chol_factor(H, nv, nv) != 0) break;
     for (int i = 0; i < nv; i++) p[i] = -grad[i];
     chol_solve(H, nv, nv, p);
@@ -633,9 +673,9 @@ static void solve_constraints(const OdgModel* m, OdgoData* d) {
     line_derivs(m, d, a, p, Jp_, jar0, g0, h0, 0.0, &d10, &d2);
     if (d10 >= 0) break;                                    /* not a descent direction: converged */
     double lo = 0, hi = -1, alpha = 1.0;
-    for (int ls = 0; ls < 100; ls++) {
+    for (int ls = 0; ls < g_ls_iter; ls++) {
       line_derivs(m, d, a, p, Jp_, jar0, g0, h0, alpha, &d1, &d2);
-      if (fabs(d1) <= 1e-14 * fabs(d10)) break;
+      if (fabs(d1) <= g_ls_tol * fabs(d10)) break;
       if (d1 < 0) lo = alpha; else hi = alpha;
       double next = alpha - d1 / d2;
       if (hi < 0) { if (!(next > lo)) next = 2 * alpha; }
@@ -957,6 +997,14 @@ void odgo_walk_evaluate(OdgoWalkEnv* e, const float* scaled, double* obs, double
   odgo_forward(e->m, &e->d);
   walk_post(e, scaled, obs, reward, terminated, truncated, info);
   if (info) { info->min_gap[0] = e->d.gap_contact; info->min_gap[1] = e->d.gap_support; info->min_gap[2] = e->d.gap_limit; }
+}
+
+/* a worker's whole env set in one call (no per-env foreign-function overhead): actions [n][8], obs [n][33] */
+void odgo_walk_step_autoreset_batch(OdgoWalkEnv** envs, int n, const float* actions, double* obs, double* reward, int* done) {
+  for (int i = 0; i < n; i++) {
+    int trunc = 0;
+    odgo_walk_step_autoreset(envs[i], actions + 8 * i, obs + 33 * i, reward + i, done + i, &trunc, 0, 0);
+  }
 }
 
 void odgo_walk_step_autoreset(OdgoWalkEnv* e, const float* action, double* obs, double* reward, int* done,

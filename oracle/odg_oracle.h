@@ -66,6 +66,9 @@ typedef struct OdgoData {
    *   gap_support  min lead of a winning support vertex over the runner-up of the same search (m)
    *   gap_limit    min |q - bound| over limited joints (rad) */
   double gap_contact, gap_support, gap_limit;
+  /* broad-phase cache: bounding sphere of every hull in its link frame (filled on first use; model constants) */
+  double bs_center[ODG_MAX_GEOM][3], bs_radius[ODG_MAX_GEOM];
+  int bs_ready;
 } OdgoData;
 
 /* Walk-environment state that lives outside mjData in the reference (WalkEnvironmentV0 +
@@ -111,6 +114,10 @@ void odgo_bias(const OdgModel* m, OdgoData* d);
 void odgo_collision(const OdgModel* m, OdgoData* d);
 double odgo_constraint_cost(const OdgModel* m, const OdgoData* d, const double* qacc);
 
+/* Newton stopping rules: oracle-tight by default; bench.py's CPU baseline legs switch to MuJoCo's defaults
+ * (tolerance 1e-8 on scaled gradient or improvement, ls_tolerance 0.01, ls_iterations 50). Process-wide. */
+void odgo_set_solver(double tolerance, double ls_tolerance, int ls_iterations, int improvement_exit);
+
 /* counter-based RNG shared bit-for-bit with the CUDA library */
 void odgo_philox4x32(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]);
 float odgo_u01(uint32_t x);
@@ -127,6 +134,8 @@ void odgo_walk_evaluate(OdgoWalkEnv* e, const float* scaled_action, double* obs3
 /* SB3 VecEnv worker semantics: step, and on done store the terminal obs and reset */
 void odgo_walk_step_autoreset(OdgoWalkEnv* e, const float* action, double* obs33, double* reward,
                               int* done, int* truncated, double* terminal_obs33, OdgoWalkInfo* info);
+
+void odgo_walk_step_autoreset_batch(OdgoWalkEnv** envs, int n, const float* actions, double* obs, double* reward, int* done);
 
 #ifdef __cplusplus
 }

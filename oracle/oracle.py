@@ -48,6 +48,7 @@ class OdgoData(C.Structure):
         ("efc_frictionloss", _d * MAX_EFC), ("efc_force", _d * MAX_EFC),
         ("solver_cost", _d), ("solver_gradnorm", _d),
         ("gap_contact", _d), ("gap_support", _d), ("gap_limit", _d),
+        ("bs_center", _d * 3 * MAX_GEOM), ("bs_radius", _d * MAX_GEOM), ("bs_ready", _i),
     ]
 
 
