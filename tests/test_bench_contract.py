@@ -21,7 +21,10 @@ def test_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0
     assert d["config"]["workload"].startswith("4096 envs/GPU batched step")
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "oracle envs" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "NOT MuJoCo itself" in cb["sample"]
+    # one core AND all cores, physics steps/s next to env-steps/s; MuJoCo's own stopping rules
+    assert cb["one_core"]["value"] > 0 and cb["one_core"]["physics_steps_per_s"] == 10 * cb["one_core"]["value"]
+    assert cb["physics_steps_per_s_per_core"] > 0 and cb["solver"]["tolerance"] == 1e-8 and cb["solver"]["ls_tolerance"] == 0.01
     assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
 
