@@ -234,6 +234,8 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     N = args.envs_per_gpu
     K, W = args.steps, max(args.warmup, 3)
+    SETTLE = 12          # untimed env-steps before anything is measured, whatever --warmup says: the reset drops the robots
+                         # 0.13 m (~8 env-steps of free fall, then the landing transient); timed steps are stance / impact physics
     extra = {}
     for kv in args.cfg:
         k, v = kv.split("=")
@@ -243,7 +245,7 @@ def run_gpu(args):
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     # synthetic inputs: a fresh U(-1,1) action batch per step, generated on the device OUTSIDE the timed region
-    actions = torch.rand(W + K, N, 8, device=dev, generator=gen) * 2 - 1
+    actions = torch.rand(SETTLE + W + K, N, 8, device=dev, generator=gen) * 2 - 1
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def barrier():
@@ -254,8 +256,11 @@ def run_gpu(args):
 
     sampler = ClockSampler(local)
     sampler.start()
-    # settle: let the robots land (reset drops them 0.13 m) so the timed steps are stance/impact physics
-    for i in range(W):
+    for i in range(SETTLE):
+        env.step(actions[i])
+    actions = actions[SETTLE:]
+    for i in range(W):                               # warm-up proper (same code path as the timed steps)
+        flush.zero_()
         env.step(actions[i])
     barrier()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
@@ -308,7 +313,7 @@ def run_gpu(args):
     # FP32 instruction-issue roofline: 148 SMs x 128 lanes x clock; ~6.4e5 lane-instructions per env-step
     alu_peak_lane_ips = 148 * 128 * (clocks.get("sm_mhz") or sm_max) * 1e6
     line = {
-        "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W, "settle_steps": SETTLE,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(N),
@@ -337,6 +342,16 @@ def run_gpu(args):
     if tr:
         line["roofline"]["traffic"] = tr[0]
         line["roofline"]["traffic_source"] = f"profiles/{tr[1]} (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+        if tr[3]:
+            # FP32 roofline with COUNTED work (SURVEY section 8d ii): thread-level 2 x FFMA + FADD + FMUL of one launch
+            # (ncu smsp__sass_thread_inst_executed_op_{ffma,fadd,fmul}_pred_on) / live launch time, against
+            # 148 SMs x 128 lanes x 2 flop x SM clock under load
+            clk = (clocks.get("sm_mhz") or sm_max) * 1e6
+            peak = 148 * 128 * 2 * clk / 1e12
+            ach = float(tr[3]) / launch_s / 1e12
+            line["roofline"]["fp32"] = {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                                        "counted_flops_per_launch": float(tr[3]), "counted_flops_per_env_step": float(tr[3]) / N,
+                                        "sm_clock_mhz": clk / 1e6}
         if tr[2]:
             # issue-slot view of the same launch: warp-instructions per launch (ncu) / live launch time vs 4 issue slots
             # per SM per cycle. This, not HBM, is the resource the kernel is bound by.
@@ -348,8 +363,24 @@ def run_gpu(args):
         line["mppi"] = mppi_probe(dev)
     if args.rollout_envs and (world > 1 or rank == 0):
         del env
-        line["rollout"] = rollout_probe(dev, args.rollout_envs if world == 1 else args.train_envs, args.horizon, rank, world,
-                                        dist, train=(world > 1 or args.train_probe))
+        if world == 1:
+            # BASELINE.json configs[2]: 16384 envs x horizon 24 with the policy on tensor cores, one GPU
+            line["rollout"] = rollout_probe(dev, args.rollout_envs, args.horizon, rank, world, dist, train=args.train_probe)
+        if args.train_envs:
+            # BASELINE.json configs[3] as first-class keys at EVERY N (the timed `value` above is the collective-free
+            # configs[1] step): 65536 envs per GPU, on-device rollout, GAE + advantage-statistics all-reduce, one PPO epoch
+            # with a flat-gradient all-reduce per minibatch. Weak scaling: efficiency at N = value(N) / (N x value(1)).
+            r = rollout_probe(dev, args.train_envs, args.horizon, rank, world, dist, train=True)
+            if world > 1:
+                line["rollout"] = r
+            line["configs3"] = {
+                "workload": f"{args.train_envs} envs/GPU x horizon {args.horizon} on {world} GPU(s) (BASELINE.json configs[3])",
+                "rollout_env_steps_per_s": r["env_steps_per_s_rollout"],
+                "train_iteration_env_steps_per_s": r["env_steps_per_s_train_iteration"],
+                "ms_rollout": r["ms_per_rollout"], "ms_gae_and_stats_allreduce": r["ms_gae_and_stats_allreduce"],
+                "ms_ppo_epoch": r["ms_ppo_epoch_with_grad_allreduce"],
+                "ms_grad_allreduce": r["ms_grad_allreduce_per_iteration"], "grad_allreduce": r["grad_allreduce"],
+                "ppo_update": r["ppo_update"], "scaling": "weak"}
         if world == 1 and args.go1:
             # BASELINE.json configs[2] names the 12-actuator model: Unitree Go1 through the same kernels (48-512-256-12)
             line["rollout_go1"] = rollout_probe(dev, args.rollout_envs, args.horizon, rank, world, dist, model="go1")
@@ -393,7 +424,8 @@ def profile_traffic(n_envs):
             d = json.load(open(f))
             t = d["kernels"][0].get("dram_traffic_bytes")
             if t:
-                best = (float(t), os.path.basename(f), d["kernels"][0].get("smsp__inst_executed.sum"))
+                best = (float(t), os.path.basename(f), d["kernels"][0].get("smsp__inst_executed.sum"),
+                        d["kernels"][0].get("fp32_flops_per_launch"))
         except Exception:
             pass
     return best
@@ -441,7 +473,7 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
-    opt = torch.optim.Adam(pol.parameters(), lr=1e-4)
+    opt = torch.optim.Adam(pol.parameters(), lr=1e-4, fused=True)
     for w in range(3):
         ro.collect()
         if w == 2:                       # untimed: first-use costs of the collectives and of autograd (NCCL lazy init)
@@ -453,18 +485,20 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
     sync()
     iters = 3
     e = [ev() for _ in range(4)]
-    t_roll = t_gae = t_upd = 0.0
+    t_roll = t_gae = t_upd = t_ar = 0.0
     for _ in range(iters):
+        timing = {}
         e[0].record(); ro.collect(); e[1].record()
         adv, ret, stats = ro.advantages(normalize=True)       # all-reduces [sum, sumsq, n] when world > 1
         e[2].record()
         if train:
             T, N = ro.T, n_envs
             ppo_update(pol, opt, ro.obs[:T].reshape(T * N, -1), ro.action.reshape(T * N, -1), ro.logp.reshape(-1),
-                       adv.reshape(-1), ret.reshape(-1), epochs=1, minibatches=4)
+                       adv.reshape(-1), ret.reshape(-1), epochs=1, minibatches=4, timing=timing)
         e[3].record()
         torch.cuda.synchronize(dev)
         t_roll += e[0].elapsed_time(e[1]); t_gae += e[1].elapsed_time(e[2]); t_upd += e[2].elapsed_time(e[3])
+        t_ar += sum(a.elapsed_time(b) for a, b in timing.get("allreduce", []))
     # the policy forward alone (same launches as inside the rollout)
     l0 = pol.launch_count
     e[0].record()
@@ -473,10 +507,10 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
     e[1].record()
     torch.cuda.synchronize(dev)
     t_mlp = e[0].elapsed_time(e[1]) / (pol.launch_count - l0)
-    t = torch.tensor([t_roll, t_gae, t_upd, t_mlp], device=dev, dtype=torch.float64)
+    t = torch.tensor([t_roll, t_gae, t_upd, t_mlp, t_ar], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_roll, t_gae, t_upd, t_mlp = [float(x) for x in t]
+    t_roll, t_gae, t_upd, t_mlp, t_ar = [float(x) for x in t]
     S, A = env.obs_dim, env.act_dim
     flops = 2.0 * (S * 512 + 512 * 256 + 256 * A) + 2.0 * (S * 512 + 512 * 256 + 256)      # actor + critic, per env
     pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
@@ -491,7 +525,14 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
                                "flops_per_env": flops, "note": "three skinny layers (K = 48/512/256) fused per 128-env CTA; weight streaming from L2 bound"},
            "kernels_per_rollout": ro.kernels_per_collect}
     if train:
+        n_param = sum(p.numel() for p in pol.parameters())
         out["ms_ppo_epoch_with_grad_allreduce"] = t_upd / iters
+        out["ms_grad_allreduce_per_iteration"] = t_ar / iters
+        out["grad_allreduce"] = {"calls_per_iteration": 4, "payload_bytes_per_call": 4 * n_param,
+                                 "ms_per_call": t_ar / iters / 4,
+                                 "share_of_train_iteration": t_ar / max(t_roll + t_gae + t_upd, 1e-9),
+                                 "note": "flat fp32 gradient buffer (pack + NCCL all-reduce + unpack), CUDA events on the training stream"}
+        out["ppo_update"] = "1 epoch x 4 minibatches, bf16 autocast forward/backward (fp32 master weights), torch Adam"
         out["env_steps_per_s_train_iteration"] = steps / ((t_roll + t_gae + t_upd) * 1e-3)
     return out
 

@@ -61,33 +61,48 @@ def allreduce_flat_grads(params, group=None, world: int | None = None):
 
 
 def ppo_update(policy, optimizer, obs, action, logp_old, adv, ret, clip: float = 0.2, vf_coef: float = 0.5,
-               ent_coef: float = 0.005, max_grad_norm: float = 0.5, epochs: int = 1, minibatches: int = 4, group=None):
+               ent_coef: float = 0.005, max_grad_norm: float = 0.5, epochs: int = 1, minibatches: int = 4, group=None,
+               autocast: bool = True, timing: dict | None = None):
     """Clipped-surrogate update with the hyper-parameters of train/train.py:117-130 (clip .2, ent .005,
     max_grad_norm .5). obs [B,S], action [B,A], logp_old/adv/ret [B]; minibatches are fixed contiguous slices.
     Gradients are averaged over ranks (one flat all-reduce per minibatch); afterwards the tensor-core copy of the
-    weights is refreshed. Returns the last minibatch's loss terms."""
-    # the update's GEMMs ([B, 33..512] x [512, 256] ...) run on the tensor cores as TF32 (fp32 accumulate); the fp32
-    # CUDA-core path is ~5x slower on B200 and the reference's own update is plain fp32 torch on whatever device it finds
+    weights is refreshed. Returns the last minibatch's loss terms.
+
+    `autocast` runs the differentiable forward / backward with bf16 operands on the tensor cores (fp32 master weights,
+    fp32 loss and optimiser) — the same operand precision as the rollout-time kernel that produced `logp_old`, so the
+    probability ratio compares like with like. `timing`, if given, receives CUDA events around every gradient
+    all-reduce (`timing["allreduce"]` = list of (start, end) pairs) so a caller can report the collective's share."""
+    # without autocast the GEMMs ([B, 33..512] x [512, 256] ...) run as TF32 (fp32 accumulate); the fp32 CUDA-core path is
+    # ~5x slower on B200 and the reference's own update is plain fp32 torch on whatever device it finds
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
     B = obs.shape[0]
     mb = (B + minibatches - 1) // minibatches
     params = [p for p in policy.parameters() if p.requires_grad]
+    use_ac = bool(autocast) and obs.is_cuda
     out = {}
     for _ in range(epochs):
         for i in range(minibatches):
             sl = slice(i * mb, min(B, (i + 1) * mb))
-            d, v = policy(obs[sl])
-            logp = d.log_prob(action[sl]).sum(-1)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=use_ac):
+                d, v = policy(obs[sl])
+            logp = d.log_prob(action[sl]).float().sum(-1)
             ratio = torch.exp(logp - logp_old[sl])
             a = adv[sl]
             pg = -torch.min(ratio * a, torch.clamp(ratio, 1 - clip, 1 + clip) * a).mean()
-            vf = torch.nn.functional.mse_loss(v.squeeze(-1), ret[sl])
-            ent = d.entropy().sum(-1).mean()
+            vf = torch.nn.functional.mse_loss(v.float().squeeze(-1), ret[sl])
+            ent = d.entropy().float().sum(-1).mean()
             loss = pg + vf_coef * vf - ent_coef * ent
             optimizer.zero_grad(set_to_none=True)
             loss.backward()
-            allreduce_flat_grads(params, group=group)
+            if timing is not None and obs.is_cuda:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                allreduce_flat_grads(params, group=group)
+                e1.record()
+                timing.setdefault("allreduce", []).append((e0, e1))
+            else:
+                allreduce_flat_grads(params, group=group)
             torch.nn.utils.clip_grad_norm_(params, max_grad_norm)
             optimizer.step()
             out = dict(loss=loss.detach(), pg=pg.detach(), vf=vf.detach(), entropy=ent.detach())

@@ -394,6 +394,9 @@ def test_large_handles_match_the_oracle_on_random_subsets(n):
     for t in range(34):
         env.step(torch.rand(n, 8, device="cuda", generator=g) * 2 - 1)
     rng = np.random.default_rng(n)
+    # spread the episode clocks over 19..24 so that about one environment in six is truncated by the compared step
+    # (random actions rarely tip the robot over within 34 steps, and terminal_obs / reset indexing need done envs)
+    env.set_env_state(step=torch.from_numpy(rng.integers(19, 25, n).astype(np.int32)))
     ids = np.sort(rng.choice(n, 256, replace=False))
     tid = torch.from_numpy(ids).cuda()
     q, v = [x[tid].cpu().numpy() for x in env.get_state()]
@@ -425,4 +428,4 @@ def test_large_handles_match_the_oracle_on_random_subsets(n):
             outliers += 1
             assert min(oi["min_gap"][0], oi["min_gap"][1]) < FLIP_M, f"env {gid}: outside tolerance without a decision flip {oi['min_gap']}"
     assert outliers <= 3, f"{outliers}/256 decision flips"
-    assert n_done >= 1 and n_contact >= 64, (n_done, n_contact)
+    assert n_done >= 16 and n_contact >= 64, (n_done, n_contact)

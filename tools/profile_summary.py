@@ -69,6 +69,17 @@ def main():
             scale_w = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit_w]
             d["dram_traffic_bytes"] = rd * scale + wr * scale_w
             md.append(f"| **DRAM traffic per launch (read+write)** | {d['dram_traffic_bytes']:.4g} | byte |")
+        # counted FP32 work (SURVEY section 8d ii): thread-level FFMA (x2), FADD, FMUL per launch = per-cycle rate x elapsed cycles
+        fp = {op: fnum(k.get(f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed", ("", ""))[1]) for op in ("ffma", "fadd", "fmul")}
+        # (smsp__ per_cycle_elapsed rates are per SM-clock cycle; sm__cycles_elapsed.max is the same clock)
+        cyc = fnum(k.get("sm__cycles_elapsed.max", k.get("smsp__cycles_elapsed.max", ("", "")))[1])
+        if all(v is not None for v in fp.values()) and cyc:
+            per_cycle = 2 * fp["ffma"] + fp["fadd"] + fp["fmul"]
+            d["fp32_flops_per_cycle"] = per_cycle
+            d["fp32_flops_per_launch"] = per_cycle * cyc
+            d["fp32_frac_of_peak_under_ncu"] = per_cycle / (148 * 128 * 2)
+            md.append(f"| **counted FP32 flops per launch (2 FFMA + FADD + FMUL, thread level)** | {d['fp32_flops_per_launch']:.4g} | flop |")
+            md.append(f"| FP32 flops per SM-cycle, chip-wide (peak 148 x 128 x 2 = 37888) | {per_cycle:.1f} = {100 * per_cycle / 37888:.2f} % | flop/cycle |")
         stalls = sorted(((fnum(v[1]) or 0.0, h) for h, v in k.items()
                          if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")),
                         reverse=True)[:8]
