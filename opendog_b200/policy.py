@@ -26,6 +26,8 @@ class ActorCriticB200(nn.Module):
         if not torch.cuda.is_available():
             raise _lib.OdgError("ActorCriticB200 needs a CUDA device: opendog_b200 has no CPU fallback")
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
         self.state_dim, self.action_dim, self.seed = state_dim, action_dim, seed
         self.actor = nn.Sequential(nn.Linear(state_dim, 512), nn.Tanh(), nn.Linear(512, 256), nn.Tanh(),
                                    nn.Linear(256, action_dim), nn.Tanh())
@@ -103,6 +105,25 @@ class ActorCriticB200(nn.Module):
         mean = self.actor(state)
         std = torch.exp(self.action_log_std.expand_as(mean))
         return torch.distributions.Normal(mean, std), self.critic(state)
+
+    # the update-phase forward on padded inputs: with the observation width rounded up to a multiple of 16 (33 -> 48,
+    # zero columns in x and W1) every GEMM of the forward and backward pass is tensor-core aligned in bf16; with K = 33
+    # cuBLAS falls back to legacy kernels that take a third of the whole PPO epoch (tools/prof_ppo.py)
+    @staticmethod
+    def pad_obs(state, multiple: int = 16):
+        k = (-state.shape[-1]) % multiple
+        return torch.nn.functional.pad(state, (0, k)) if k else state
+
+    def forward_padded(self, state_padded):
+        F = torch.nn.functional
+        k = state_padded.shape[-1] - self.state_dim
+        def run(net):
+            x = torch.tanh(F.linear(state_padded, F.pad(net[0].weight, (0, k)), net[0].bias))
+            x = torch.tanh(F.linear(x, net[2].weight, net[2].bias))
+            return F.linear(x, net[4].weight, net[4].bias)
+        mean = torch.tanh(run(self.actor))
+        std = torch.exp(self.action_log_std.expand_as(mean))
+        return torch.distributions.Normal(mean, std), run(self.critic)
 
 
 def gae(reward, value, done, gamma=0.99, lam=0.95, normalize=True, group=None):

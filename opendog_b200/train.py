@@ -80,12 +80,15 @@ def ppo_update(policy, optimizer, obs, action, logp_old, adv, ret, clip: float =
     mb = (B + minibatches - 1) // minibatches
     params = [p for p in policy.parameters() if p.requires_grad]
     use_ac = bool(autocast) and obs.is_cuda
+    padded = use_ac and hasattr(policy, "forward_padded")
+    if padded:
+        obs = policy.pad_obs(obs.to(torch.bfloat16))          # one cast + pad per update instead of one per minibatch
     out = {}
     for _ in range(epochs):
         for i in range(minibatches):
             sl = slice(i * mb, min(B, (i + 1) * mb))
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=use_ac):
-                d, v = policy(obs[sl])
+                d, v = policy.forward_padded(obs[sl]) if padded else policy(obs[sl])
             logp = d.log_prob(action[sl]).float().sum(-1)
             ratio = torch.exp(logp - logp_old[sl])
             a = adv[sl]
