@@ -476,7 +476,7 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
     opt = torch.optim.Adam(pol.parameters(), lr=1e-4, fused=True)
     for w in range(3):
         ro.collect()
-        if w == 2:                       # untimed: first-use costs of the collectives and of autograd (NCCL lazy init)
+        if w >= 1:                       # untimed, twice: first-use costs of the collectives, autograd and cuBLAS (lazy init, heuristics)
             adv, ret, stats = ro.advantages(normalize=True)
             if train:
                 T, N = ro.T, n_envs
@@ -486,6 +486,7 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
     iters = 3
     e = [ev() for _ in range(4)]
     t_roll = t_gae = t_upd = t_ar = 0.0
+    each = []
     for _ in range(iters):
         timing = {}
         e[0].record(); ro.collect(); e[1].record()
@@ -499,6 +500,7 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
         torch.cuda.synchronize(dev)
         t_roll += e[0].elapsed_time(e[1]); t_gae += e[1].elapsed_time(e[2]); t_upd += e[2].elapsed_time(e[3])
         t_ar += sum(a.elapsed_time(b) for a, b in timing.get("allreduce", []))
+        each.append([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])])
     # the policy forward alone (same launches as inside the rollout)
     l0 = pol.launch_count
     e[0].record()
@@ -527,6 +529,7 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
     if train:
         n_param = sum(p.numel() for p in pol.parameters())
         out["ms_ppo_epoch_with_grad_allreduce"] = t_upd / iters
+        out["ms_each_iteration_this_rank"] = [[round(x, 3) for x in row] for row in each]      # [rollout, gae, ppo] x iterations
         out["ms_grad_allreduce_per_iteration"] = t_ar / iters
         out["grad_allreduce"] = {"calls_per_iteration": 4, "payload_bytes_per_call": 4 * n_param,
                                  "ms_per_call": t_ar / iters / 4,
