@@ -329,7 +329,7 @@ def run_gpu(args):
                              "bound, not HBM bound (see alu)",
                      "alu": {"lane_instr_per_s_peak": alu_peak_lane_ips}},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * 8 * 4,
-                "d2h_bytes_per_step": N * (env.obs_dim * 4 + 4 + 1 + 1), "ms_per_step": e2e_ms / e2e_steps},
+                "d2h_bytes_per_step": int(env._out_bytes), "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -143,62 +143,239 @@ class QuadrupedEnv:
     def close(self): self._b.close()
 
 
-class WalkVecEnv:
-    """stable-baselines3 `VecEnv` protocol over `BatchedWalkEnv` (replaces `SubprocVecEnv`, train/train.py:81-86)."""
+def _gym_box(low, high, shape, dtype):
+    """A gymnasium Box when gymnasium is importable (SB3 needs the real thing), else a minimal stand-in."""
+    try:
+        from gymnasium.spaces import Box
+        return Box(low, high, shape, dtype)
+    except Exception:
+        class _Box:
+            def __init__(self, low, high, shape, dtype):
+                self.low = np.full(shape, low, dtype); self.high = np.full(shape, high, dtype)
+                self.shape, self.dtype = tuple(shape), np.dtype(dtype)
 
-    metadata = {"render_modes": ["human", "rgb_array", "depth_array"], "render_fps": 50}     # WalkEnvironment.py:28-31
+            def sample(self):
+                lo = np.where(np.isfinite(self.low), self.low, -1.0); hi = np.where(np.isfinite(self.high), self.high, 1.0)
+                return np.random.uniform(lo, hi).astype(self.dtype)
 
-    def __init__(self, num_envs: int, device=None, seed: int = 0, **config):
-        self.env = BatchedWalkEnv(num_envs, device=device, seed=seed, auto_reset=1, **config)
+            def contains(self, x):
+                x = np.asarray(x)
+                return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+            def __repr__(self):
+                return f"Box({self.low.min()}, {self.high.max()}, {self.shape}, {self.dtype})"
+        return _Box(low, high, shape, dtype)
+
+
+class _VecEnvProtocol:
+    """The abstract interface of `stable_baselines3.common.vec_env.VecEnv` (SB3 2.x), used as the base class when SB3
+    itself is not importable. With SB3 installed `WalkVecEnv` subclasses the real `VecEnv`, which is what
+    `PPO(..., env=vec_env)` requires: anything else is wrapped as a single gym env (`_wrap_env` -> `_patch_env`)."""
+
+    def __init__(self, num_envs, observation_space, action_space):
         self.num_envs = num_envs
-        self.observation_shape, self.action_shape = (self.env.obs_dim,), (self.env.act_dim,)
-        try:                                                        # real gymnasium spaces when importable
-            from gymnasium.spaces import Box
-            self.observation_space = Box(-np.inf, np.inf, self.observation_shape, np.float64)   # WalkEnvironment.py:46-48
-            self.action_space = Box(-1.0, 1.0, self.action_shape, np.float32)                    # ScaleActionEnvironment.py:19
-        except Exception:
-            self.observation_space = self.action_space = None
-        self._actions = None
-        self._h_act = torch.empty(num_envs, self.env.act_dim, pin_memory=True)
-
-    def reset(self):
-        return self.env.reset().double().cpu().numpy()
-
-    def step_async(self, actions):
-        self._actions = np.asarray(actions, dtype=np.float32)
-
-    def step_wait(self):
-        self._h_act.copy_(torch.from_numpy(self._actions))
-        obs, rew, done, info = self.env.step(self._h_act.to(self.env.device, non_blocking=True))
-        obs = obs.double().cpu().numpy(); rew = rew.double().cpu().numpy(); done = done.cpu().numpy()
-        trunc = self.env.truncated.cpu().numpy().astype(bool); term = self.env.terminated.cpu().numpy().astype(bool)
-        host = {k: v.cpu().numpy() for k, v in info.items()}
-        infos = []
-        for i in range(self.num_envs):
-            d = {"x_position": float(host["x_position"][i]), "y_position": float(host["y_position"][i]),
-                 "distance_from_origin": float(host["distance_from_origin"][i]),
-                 "patterns_matches": float(host["patterns_matches"][i]),
-                 "paw_contact_forces": {b: host["paw_contact_forces"][i, k].astype(np.float64) for k, b in enumerate((4, 7, 10, 13))},
-                 "linear_vel_tracking_reward": float(host["linear_vel_tracking_reward"][i]),
-                 "reward_ctrl": float(host["reward_ctrl"][i])}
-            if done[i]:
-                d["terminal_observation"] = host["terminal_obs"][i].astype(np.float64)
-                d["TimeLimit.truncated"] = bool(trunc[i] and not term[i])
-            infos.append(d)
-        return obs, rew, done, infos
+        self.observation_space, self.action_space = observation_space, action_space
+        self.reset_infos = [{} for _ in range(num_envs)]
+        self._seeds = [None for _ in range(num_envs)]
+        self._options = [{} for _ in range(num_envs)]
+        self.render_mode = None
 
     def step(self, actions):
         self.step_async(actions)
         return self.step_wait()
 
+    def _get_indices(self, indices):
+        if indices is None:
+            return range(self.num_envs)
+        if isinstance(indices, int):
+            return [indices]
+        return indices
+
+    def seed(self, seed=None):
+        if seed is None:
+            seed = int(np.random.randint(0, np.iinfo(np.uint32).max, dtype=np.uint32))
+        self._seeds = [seed + i for i in range(self.num_envs)]
+        return self._seeds
+
+    def set_options(self, options=None):
+        options = options or {}
+        self._options = [dict(options)] * self.num_envs if isinstance(options, dict) else list(options)
+
+    def _reset_seeds(self):
+        self._seeds = [None for _ in range(self.num_envs)]
+
+    def _reset_options(self):
+        self._options = [{} for _ in range(self.num_envs)]
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def getattr_depth_check(self, name, already_found):
+        return None
+
+
+def _vecenv_base():
+    try:
+        from stable_baselines3.common.vec_env import VecEnv
+        return VecEnv
+    except Exception:
+        return _VecEnvProtocol
+
+
+class LazyInfo(dict):
+    """One environment's `info` dict whose per-step entries (WalkEnvironment.py:65-72) are read from the step's host
+    arrays on access instead of being copied into N Python dicts every step. Entries that exist only for some
+    environments (`terminal_observation`, `TimeLimit.truncated`, `episode`) are ordinary dict items. Behaves like the
+    dict SB3's VecMonitor / callbacks expect: `in`, `[]`, `.get`, `.keys/.items`, `.copy()` (a plain dict), assignment."""
+    __slots__ = ("_rows", "_i")
+    PAWS = (4, 7, 10, 13)                                                   # paw body ids (reward_calc.py:58-63 order)
+
+    def __init__(self, rows, i):
+        super().__init__()
+        self._rows, self._i = rows, i
+
+    def _lazy(self, k):
+        a = self._rows[k][self._i]
+        if k == "paw_contact_forces":
+            return {b: a[j].astype(np.float64) for j, b in enumerate(self.PAWS)}
+        return float(a)
+
+    def __missing__(self, k):
+        if k in self._rows:
+            v = self._lazy(k)
+            dict.__setitem__(self, k, v)
+            return v
+        raise KeyError(k)
+
+    def __contains__(self, k):
+        return dict.__contains__(self, k) or k in self._rows
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+    def keys(self):
+        return list(dict.keys(self)) + [k for k in self._rows if not dict.__contains__(self, k)]
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return len(self.keys())
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def copy(self):
+        return dict(self.items())
+
+
+class WalkVecEnv(_vecenv_base()):
+    """`ScaleActionWrapper(WalkEnvironmentV0)` x num_envs behind the stable-baselines3 `VecEnv` interface, replacing
+    `make_vec_env(make_env_fn, n_envs, vec_env_cls=SubprocVecEnv)` of train/train.py:63-87. A real `VecEnv` subclass when
+    SB3 is importable, so `PPO("MlpPolicy", env=WalkVecEnv(n))` (train/train.py:117-130) takes it as is.
+
+    Per step: one pinned-host action copy in, one fused kernel, ONE device->host copy of the slab holding obs / reward /
+    flags / every info array; infos are `LazyInfo` views of that slab. Worker semantics of SB3 (auto-reset on done,
+    `terminal_observation`, `TimeLimit.truncated`) come from the kernel; the `Monitor(info_keywords=...)` wrapper each
+    reference env gets (train/train.py:69-70) is reproduced here: `info["episode"] = {"r", "l", "t", **keywords}` when an
+    episode ends, which is where SB3's `ep_rew_mean` / `ep_len_mean` come from."""
+
+    metadata = {"render_modes": ["human", "rgb_array", "depth_array"], "render_fps": 50}     # WalkEnvironment.py:28-31
+    INFO_KEYS = ("x_position", "y_position", "distance_from_origin", "paw_contact_forces", "patterns_matches",
+                 "linear_vel_tracking_reward", "reward_ctrl", "terminal_obs")
+
+    def __init__(self, num_envs: int, device=None, seed: int = 0,
+                 monitor_info_keywords=("x_position", "y_position", "distance_from_origin", "paw_contact_forces", "patterns_matches"),
+                 **config):
+        import time
+        self.env = BatchedWalkEnv(num_envs, device=device, seed=seed, auto_reset=1, info_keys=self.INFO_KEYS, **config)
+        obs_space = _gym_box(-np.inf, np.inf, (self.env.obs_dim,), np.float64)               # WalkEnvironment.py:46-48
+        act_space = _gym_box(-1.0, 1.0, (self.env.act_dim,), np.float32)                     # ScaleActionEnvironment.py:19
+        super().__init__(num_envs, obs_space, act_space)
+        self.observation_shape, self.action_shape = (self.env.obs_dim,), (self.env.act_dim,)
+        self.monitor_info_keywords = tuple(monitor_info_keywords or ())
+        self._actions = None
+        self._h_act = torch.empty(num_envs, self.env.act_dim, pin_memory=True)
+        self._t0 = time.time()
+        self._ep_ret = np.zeros(num_envs, np.float64)
+        self._ep_len = np.zeros(num_envs, np.int64)
+        self.render_mode = "rgb_array"
+
+    # ------------------------------------------------------------------ VecEnv interface
+    def reset(self):
+        obs = self.env.reset().double().cpu().numpy()
+        self._ep_ret[:] = 0; self._ep_len[:] = 0
+        self.reset_infos = [{} for _ in range(self.num_envs)]
+        if hasattr(self, "_reset_seeds"):
+            self._reset_seeds(); self._reset_options()
+        return obs
+
+    def step_async(self, actions):
+        self._actions = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.num_envs, self.env.act_dim)
+
+    def step_wait(self):
+        import time
+        self._h_act.copy_(torch.from_numpy(self._actions))
+        h_obs, h_rew, h_term, h_trunc, h_info = self.env.step_host(self._h_act, with_info=True)
+        obs = h_obs.numpy().astype(np.float64)                       # fresh arrays: SB3 keeps them across steps
+        rew = h_rew.numpy().astype(np.float64)
+        term = h_term.numpy().astype(bool); trunc = h_trunc.numpy().astype(bool)
+        done = term | trunc
+        rows = {k: v.numpy().copy() for k, v in h_info.items() if k != "terminal_obs"}
+        infos = [LazyInfo(rows, i) for i in range(self.num_envs)]
+        self._ep_ret += rew; self._ep_len += 1
+        if done.any():
+            tobs = h_info["terminal_obs"].numpy()
+            now = round(time.time() - self._t0, 6)
+            for i in np.flatnonzero(done):
+                d = infos[i]
+                d["terminal_observation"] = tobs[i].astype(np.float64)
+                d["TimeLimit.truncated"] = bool(trunc[i] and not term[i])
+                ep = {"r": round(float(self._ep_ret[i]), 6), "l": int(self._ep_len[i]), "t": now}     # Monitor.step
+                for k in self.monitor_info_keywords:
+                    ep[k] = d[k]
+                d["episode"] = ep
+            self._ep_ret[done] = 0; self._ep_len[done] = 0
+        return obs, rew, done, infos
+
     def close(self):
         self.env.close()
 
     def env_is_wrapped(self, wrapper_class, indices=None):
-        return [False] * self.num_envs
+        return [False for _ in self._get_indices(indices)]
 
-    def get_attr(self, name, indices=None):
-        return [getattr(self.env, name)] * self.num_envs
+    def get_attr(self, attr_name, indices=None):
+        """Attributes of the per-env objects the reference builds: `render_mode`, `metadata`, spaces; anything else is
+        looked up on the batched environment."""
+        own = {"render_mode": self.render_mode, "metadata": self.metadata, "observation_space": self.observation_space,
+               "action_space": self.action_space, "spec": None}
+        v = own[attr_name] if attr_name in own else getattr(self.env, attr_name)
+        return [v for _ in self._get_indices(indices)]
 
-    def seed(self, seed=None):
-        return [seed] * self.num_envs
+    def set_attr(self, attr_name, value, indices=None):
+        """Per-env attributes do not exist in a batched simulator: a config field of the whole batch can be set for ALL
+        envs at once (indices=None); anything narrower is refused rather than silently ignored."""
+        if indices is not None and len(list(self._get_indices(indices))) != self.num_envs:
+            raise NotImplementedError("WalkVecEnv.set_attr: attributes are shared by the whole batch")
+        if attr_name == "render_mode":
+            self.render_mode = value
+        else:
+            raise AttributeError(f"WalkVecEnv has no settable per-env attribute {attr_name!r}")
+
+    def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+        idx = list(self._get_indices(indices))
+        if method_name in ("get_wrapper_attr",) and method_args:
+            return self.get_attr(method_args[0], indices)
+        if method_name == "render":
+            return [None for _ in idx]
+        raise NotImplementedError(f"WalkVecEnv.env_method({method_name!r}): the batched simulator has no per-env Python object")
+
+    def get_images(self):
+        return [None for _ in range(self.num_envs)]           # no renderer on the GPU path (viewers are out of scope)
+
+    def render(self, mode=None):
+        return None

@@ -75,16 +75,6 @@ class BatchedWalkEnv:
         self.obs_dim = self.L.odg_obs_dim(h)
         self.act_dim = self.L.odg_act_dim(h)
         self.nq, self.nv = self.L.odg_nq(h), self.L.odg_nv(h)
-        N, dev = self.num_envs, self.device
-        # step outputs live in ONE device slab (obs | reward | terminated | truncated) so that a host-side caller
-        # fetches them with a single device->host copy (step_host)
-        nb = N * (self.obs_dim * 4 + 4 + 1 + 1)
-        self._out = torch.empty((nb + 3) // 4 * 4, dtype=torch.uint8, device=dev)
-        o = 0
-        self.obs = self._out[o:o + N * self.obs_dim * 4].view(torch.float32).view(N, self.obs_dim); o += N * self.obs_dim * 4
-        self.reward = self._out[o:o + N * 4].view(torch.float32); o += N * 4
-        self.terminated = self._out[o:o + N]; o += N
-        self.truncated = self._out[o:o + N]
         self._host = None
         self.info = {}
         self._info_struct = None
@@ -92,17 +82,48 @@ class BatchedWalkEnv:
 
     # ------------------------------------------------------------------ plumbing
     def set_info_keys(self, keys):
-        self.info = {}
+        """Choose the `info` tensors `step` fills and (re)allocate the output slab. Step outputs AND info tensors live in
+        ONE device buffer — [obs | reward | terminated | truncated | info arrays...], every array 16-byte aligned — so a
+        host-side caller fetches everything a step produced with a single device->host copy (`step_host`)."""
+        N, dev = self.num_envs, self.device
+        keys = tuple(keys or ())
+        al = lambda n: (n + 15) // 16 * 16
+        esz = {torch.float32: 4, torch.int32: 4, torch.uint8: 1}
+        parts = [("obs", torch.float32, (N, self.obs_dim)), ("reward", torch.float32, (N,)),
+                 ("terminated", torch.uint8, (N,)), ("truncated", torch.uint8, (N,))]
+        for k in keys:
+            dt, shp = _INFO_SPECS[k]
+            parts.append((k, dt, (N,) + tuple(shp(self))))
+        offs, o = [], 0
+        for _, dt, shp in parts:
+            offs.append(o)
+            n = esz[dt]
+            for d in shp:
+                n *= d
+            o += al(n)
+        self._slab = torch.zeros(o, dtype=torch.uint8, device=dev)
+        self._slab_layout = [(name, dt, shp, off) for (name, dt, shp), off in zip(parts, offs)]
+        self._out_bytes = offs[4] if len(parts) > 4 else o          # bytes of the [obs | reward | flags] prefix
+        views = {name: self._view(self._slab, dt, shp, off) for name, dt, shp, off in self._slab_layout}
+        self.obs, self.reward = views["obs"], views["reward"]
+        self.terminated, self.truncated = views["terminated"], views["truncated"]
+        self._out = self._slab[:self._out_bytes]
+        self._host = None
+        self.info = {k: views[k] for k in keys}
         if not keys:
             self._info_struct = None
             return
         s = _lib.OdgInfoPtrs()
         for k in keys:
-            dt, shp = _INFO_SPECS[k]
-            t = torch.zeros((self.num_envs,) + tuple(shp(self)), dtype=dt, device=self.device)
-            self.info[k] = t
-            setattr(s, k, t.data_ptr())
+            setattr(s, k, self.info[k].data_ptr())
         self._info_struct = s
+
+    @staticmethod
+    def _view(buf, dt, shp, off):
+        n = {torch.float32: 4, torch.int32: 4, torch.uint8: 1}[dt]
+        for d in shp:
+            n *= d
+        return buf[off:off + n].view(dt).view(shp)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -138,27 +159,29 @@ class BatchedWalkEnv:
         done = (self.terminated | self.truncated).bool()
         return self.obs, self.reward, done, self.info
 
-    def step_host(self, action_host: torch.Tensor):
+    def step_host(self, action_host: torch.Tensor, with_info: bool = False):
         """`step` for a caller whose policy lives on the HOST (SB3, the reference's loops): pinned host action in,
         pinned host (obs, reward, terminated, truncated) out — one H2D copy, one kernel, one D2H copy, one sync.
-        The returned arrays are views of an internal pinned buffer, valid until the next call."""
+        With `with_info` the same single D2H copy also brings every `info` array (they share the slab) and a dict of
+        host views is returned as a fifth element. The returned arrays are views of an internal pinned buffer, valid
+        until the next call."""
         N = self.num_envs
         if self._host is None:
-            self._host = dict(out=torch.empty_like(self._out, device="cpu").pin_memory(),
-                              act=torch.empty(N, self.act_dim).pin_memory(),
+            h = torch.empty_like(self._slab, device="cpu").pin_memory()
+            self._host = dict(slab=h, act=torch.empty(N, self.act_dim).pin_memory(),
                               dact=torch.empty(N, self.act_dim, device=self.device))
-            h, o = self._host["out"], 0
-            self._host["obs"] = h[o:o + N * self.obs_dim * 4].view(torch.float32).view(N, self.obs_dim); o += N * self.obs_dim * 4
-            self._host["reward"] = h[o:o + N * 4].view(torch.float32); o += N * 4
-            self._host["terminated"] = h[o:o + N]; o += N
-            self._host["truncated"] = h[o:o + N]
+            for name, dt, shp, off in self._slab_layout:
+                self._host[name] = self._view(h, dt, shp, off)
         H = self._host
         if action_host.data_ptr() != H["act"].data_ptr():
             H["act"].copy_(action_host)
         H["dact"].copy_(H["act"], non_blocking=True)
         self.step_into(H["dact"], self.obs, self.reward, self.terminated, self.truncated)
-        H["out"].copy_(self._out, non_blocking=True)
+        nb = self._slab.numel() if with_info else self._out_bytes
+        H["slab"][:nb].copy_(self._slab[:nb], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+        if with_info:
+            return H["obs"], H["reward"], H["terminated"], H["truncated"], {k: H[k] for k in self.info}
         return H["obs"], H["reward"], H["terminated"], H["truncated"]
 
     def step_into(self, action: torch.Tensor, obs, reward, terminated, truncated):

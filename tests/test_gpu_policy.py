@@ -152,3 +152,68 @@ def test_first_horizon_starts_from_the_reset_observation(use_graph):
             logp = (-0.5 * z * z - torch.log(std) - 0.5 * math.log(2 * math.pi)).sum(-1)
             assert (logp - ro.logp[t]).abs().max().item() < 2e-3, (k, t)
         last = ro.obs[ro.T].clone()
+
+
+def test_reference_checkpoint_loads_and_runs_through_the_kernel(tmp_path):
+    """SURVEY section 5 (checkpoint/resume): a `.pth` written by the reference's own trainer
+    (sim2real/train.py:587-588, `torch.save(agent.state_dict())`; fixture = its shipped
+    sim2real/output/pth/quadruped_ac_sym_ep3700.pth, 22 -> 512 -> 256 -> 4) loads unchanged into ActorCriticB200, the
+    tcgen05 forward reproduces the reference module's torch forward at the stated bf16 tolerances, and the deterministic
+    closed-loop rollout + JSON export of sim2real/train.py:600-636 runs on it with the structural invariants of the
+    symmetric-trot mapping (train.py:243-259) and the ctrlrange clip (:276)."""
+    import json
+    import os
+    import torch.nn as nn
+    from opendog_b200.compat import BatchedQuadrupedEnv
+    from opendog_b200.gait import export_walk_json, TRAIN_REAL_HOME_DEG
+    from opendog_b200.policy import ActorCriticB200
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_quadruped_ac_sym_ep3700.pth")
+    sd = torch.load(path, map_location="cpu", weights_only=True)
+
+    class RefActorCritic(nn.Module):                    # the reference module, restated (sim2real/train.py:132-149)
+        def __init__(self, s, a):
+            super().__init__()
+            self.actor = nn.Sequential(nn.Linear(s, 512), nn.Tanh(), nn.Linear(512, 256), nn.Tanh(), nn.Linear(256, a), nn.Tanh())
+            self.critic = nn.Sequential(nn.Linear(s, 512), nn.Tanh(), nn.Linear(512, 256), nn.Tanh(), nn.Linear(256, 1))
+            self.action_log_std = nn.Parameter(torch.zeros(1, a))
+    ref = RefActorCritic(22, 4)
+    ref.load_state_dict(sd)                             # strict: same keys, same shapes
+    pol = ActorCriticB200(22, 4, 0.4)
+    missing, unexpected = pol.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    pol.sync_weights()
+    env = BatchedQuadrupedEnv(256, auto_reset=True)
+    obs = env.reset().clone()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(6):                                  # observations the policy actually sees, plus random ones
+        x = obs if t % 2 == 0 else torch.randn(256, 22, device="cuda", generator=g)
+        mean, _, value, _ = pol.act(x, sample=False)
+        with torch.no_grad():
+            rm = ref.actor(x.cpu()); rv = ref.critic(x.cpu())[:, 0]
+            bm, bv = _ref_forward(ref, x.cpu(), True)
+        assert (mean.cpu() - rm).abs().max().item() < 3e-2 and (value.cpu() - rv).abs().max().item() < 3e-2
+        assert (mean.cpu() - bm).abs().max().item() < 4e-3 and (value.cpu() - bv).abs().max().item() < 4e-3
+        obs, _, _, _ = env.step(mean)
+        obs = obs.clone()
+    out = tmp_path / "walk.json"
+    env2 = BatchedQuadrupedEnv(4, auto_reset=False)
+    export_walk_json(pol, env2, str(out), num_steps=50)
+    steps = json.load(open(out))
+    assert len(steps) >= 5 and all(s["duration"] == 0.1 and len(s["targets_deg"]) == 8 for s in steps)
+    H = TRAIN_REAL_HOME_DEG
+    tol = 0.011                                         # targets are rounded to 2 decimals (train.py:628)
+    for k, s in enumerate(steps):
+        d = {n: s["targets_deg"][n] - H[n] for n in H}
+        # BL mirrors FR and BR mirrors FL on the thighs (train.py:243-247); thigh targets are clipped to ctrlrange
+        # [2.36, 2.8] around home 2.35619: delta in [+0.22, +25.43] degrees (our_robot.xml:14-15)
+        assert abs(d["BL_tigh_actuator"] - d["FR_tigh_actuator"]) <= tol and abs(d["BR_tigh_actuator"] - d["FL_tigh_actuator"]) <= tol
+        for n in ("FR_tigh_actuator", "FL_tigh_actuator"):
+            assert 0.21 <= d[n] <= 25.44
+        # the stance pair's knees stay home, the swinging pair's knees are antisymmetric (:249-259) up to the ctrlrange clip
+        # [-1.8, -1.2] around home -1.5708: delta in [-13.13, +21.25] degrees (our_robot.xml:19-20); phases alternate
+        swing, stance = (("FR_knee_actuator", "BL_knee_actuator"), ("FL_knee_actuator", "BR_knee_actuator"))[::1 if k % 2 == 0 else -1]
+        assert abs(d[stance[0]]) <= tol and abs(d[stance[1]]) <= tol
+        a, b = d[swing[0]], d[swing[1]]
+        assert -13.14 <= a <= 21.26 and -13.14 <= b <= 21.26
+        clipped = min(a, b) <= -13.12 or max(a, b) >= 21.24
+        assert abs(a + b) <= 2 * tol or clipped
