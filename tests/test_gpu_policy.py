@@ -191,8 +191,11 @@ def test_reference_checkpoint_loads_and_runs_through_the_kernel(tmp_path):
         with torch.no_grad():
             rm = ref.actor(x.cpu()); rv = ref.critic(x.cpu())[:, 0]
             bm, bv = _ref_forward(ref, x.cpu(), True)
-        assert (mean.cpu() - rm).abs().max().item() < 3e-2 and (value.cpu() - rv).abs().max().item() < 3e-2
-        assert (mean.cpu() - bm).abs().max().item() < 4e-3 and (value.cpu() - bv).abs().max().item() < 4e-3
+        # (a trained critic's values reach ~20 here, not O(1) as for a fresh network: bf16 rounding errors scale with the
+        #  magnitude of the partial sums, so the value tolerances are relative to the batch's largest |value|)
+        vs = max(1.0, rv.abs().max().item())
+        assert (mean.cpu() - rm).abs().max().item() < 3e-2 and (value.cpu() - rv).abs().max().item() < 3e-2 * vs
+        assert (mean.cpu() - bm).abs().max().item() < 4e-3 and (value.cpu() - bv).abs().max().item() < 4e-3 * vs
         obs, _, _, _ = env.step(mean)
         obs = obs.clone()
     out = tmp_path / "walk.json"
