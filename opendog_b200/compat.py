@@ -24,23 +24,31 @@ ACTUATOR_NAMES_ORDERED = ["FR_tigh_actuator", "FR_knee_actuator", "FL_tigh_actua
                           "BR_tigh_actuator", "BR_knee_actuator", "BL_tigh_actuator", "BL_knee_actuator"]
 
 
-class BatchedQuadrupedEnv:
-    state_dim = 3 + 8 + 8 + 1 + 2          # sim2real/train.py:164
-    action_dim = 4
+VARIANTS = {"train": 0, "terrain": 1}          # OdgS2RVariant: sim2real/train.py / sim2real/train2.py
 
-    def __init__(self, num_envs: int, model: str = "our_robot", device=None, auto_reset: bool = True, max_steps: int = 250,
-                 **sim_config):
-        # POLICY_DECISION_DT / timestep = 0.10 / 0.002 = 50 mj_step per policy step (sim2real/train.py:156)
-        self.sim = BatchedWalkEnv(num_envs, model=model, device=device, info_keys=None, frame_skip=50, scale_actions=0,
+
+class BatchedQuadrupedEnv:
+    """`QuadrupedEnv` for `num_envs` environments. variant "train" = sim2real/train.py:151-411 (4 actions, obs 22,
+    50 substeps per policy step); variant "terrain" = sim2real/train2.py:159-411 (8 actions, obs 12, 40 substeps)."""
+
+    def __init__(self, num_envs: int, model: str = "our_robot", device=None, auto_reset: bool = True, max_steps: int | None = None,
+                 variant: str = "train", **sim_config):
+        v = VARIANTS[variant]
+        # POLICY_DECISION_DT / timestep: 0.10 / 0.002 = 50 mj_step per policy step (train.py:156), 0.08 / 0.002 = 40 (train2.py:106,178)
+        self.sim = BatchedWalkEnv(num_envs, model=model, device=device, info_keys=None, frame_skip=(50, 40)[v], scale_actions=0,
                                   auto_reset=0, **sim_config)
         self.L, self.device, self.num_envs = self.sim.L, self.sim.device, self.sim.num_envs
+        self.variant = variant
         cfg = _lib.OdgS2RConfig()
-        self.L.odg_s2r_default_config(C.byref(cfg))
+        self.L.odg_s2r_default_config_for(C.byref(cfg), v)
         cfg.auto_reset = 1 if auto_reset else 0
-        cfg.max_steps = int(max_steps)     # MAX_STEPS_PER_EPISODE (sim2real/train.py:68,539); enforced only with auto_reset
+        self._auto_reset = bool(auto_reset)
+        if max_steps is not None:          # MAX_STEPS_PER_EPISODE: 250 (train.py:68) / 1000 (train2.py:88); enforced only with auto_reset
+            cfg.max_steps = int(max_steps)
         h = C.c_void_p()
         _lib.check(self.L.odg_s2r_create(self.sim._h, C.byref(self.sim._model), C.byref(cfg), C.byref(h)), "odg_s2r_create")
         self._h = h
+        self.state_dim, self.action_dim = self.L.odg_s2r_obs_dim(h), self.L.odg_s2r_act_dim(h)     # 22 / 4 (train.py:164), 12 / 8 (train2.py:186)
         N, dev = num_envs, self.device
         self.obs = torch.empty(N, self.state_dim, device=dev)
         self.reward = torch.empty(N, device=dev)
@@ -71,8 +79,8 @@ class BatchedQuadrupedEnv:
 
     def step(self, action: torch.Tensor):
         a = action.to(device=self.device, dtype=torch.float32).contiguous()
-        if a.shape != (self.num_envs, 4):
-            raise ValueError(f"action must be [{self.num_envs}, 4]")
+        if a.shape != (self.num_envs, self.action_dim):
+            raise ValueError(f"action must be [{self.num_envs}, {self.action_dim}]")
         _lib.check(self.L.odg_s2r_step(self._h, _ptr(a), _ptr(self.obs), _ptr(self.reward), _ptr(self.done), _ptr(self.reason),
                                        _ptr(self.sim_target_rad), _ptr(self.terminal_obs), self._stream()), "odg_s2r_step")
         info = {"sim_target_rad": self.sim_target_rad, "termination_reason": self.reason, "terminal_obs": self.terminal_obs}
@@ -85,6 +93,59 @@ class BatchedQuadrupedEnv:
                 f(prev_net, torch.float64), f(last_cmd, torch.float32)]
         _lib.check(self.L.odg_s2r_set_bookkeeping(self._h, *[_ptr(a) for a in args], self._stream()), "odg_s2r_set_bookkeeping")
         torch.cuda.current_stream(self.device).synchronize()
+
+
+class BatchedTerrainQuadrupedEnv(BatchedQuadrupedEnv):
+    """The terrain trainer's environment (sim2real/train2.py) with its per-episode height fields: every reset — explicit,
+    or the auto-reset of a finished episode — draws a new 100 x 100 terrain for that environment (`TERRAIN_GENERATION_EPISODIC`,
+    train2.py:108,307). As in the reference (which loads walking_scene.xml, whose hfield has no geom) the terrain is data
+    next to the physics, not part of it: `hfield_data` / `terrain_height` expose it."""
+
+    def __init__(self, num_envs: int, seed: int = 0, first_env_id: int = 0, **kw):
+        super().__init__(num_envs, variant="terrain", **kw)
+        t = C.c_void_p()
+        _lib.check(self.L.odg_terrain_create(num_envs, self.device.index, C.c_uint64(seed), first_env_id, C.byref(t)), "odg_terrain_create")
+        self._t = t
+        self._fields = None
+
+    def close(self):
+        if getattr(self, "_t", None):
+            self.L.odg_terrain_destroy(self._t)
+            self._t = None
+        super().close()
+
+    def reset(self, mask=None):
+        m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        _lib.check(self.L.odg_terrain_generate(self._t, _ptr(m), self._stream()), "odg_terrain_generate")
+        return super().reset(mask)
+
+    def step(self, action):
+        out = super().step(action)
+        if self._auto_reset:
+            _lib.check(self.L.odg_terrain_generate(self._t, _ptr(self.done), self._stream()), "odg_terrain_generate")
+        return out
+
+    @property
+    def hfield_data(self) -> torch.Tensor:
+        """[N, ncol * nrow] float32 view of the device fields, MuJoCo's `model.hfield_data` layout per environment."""
+        if self._fields is None:
+            iface = {"shape": (self.num_envs, 10000), "typestr": "<f4", "data": (int(self.L.odg_terrain_data(self._t)), False),
+                     "version": 3, "strides": None}
+            self._fields = torch.as_tensor(type("_Fields", (), {"__cuda_array_interface__": iface})(), device=self.device)
+        return self._fields
+
+    def terrain_height(self, xy: torch.Tensor) -> torch.Tensor:
+        """`get_terrain_height(x, y)` (train2.py:295-304) for one point per environment: xy [N, 2] -> [N]."""
+        q = xy.to(device=self.device, dtype=torch.float32).contiguous()
+        h = torch.empty(self.num_envs, device=self.device)
+        _lib.check(self.L.odg_terrain_height(self._t, _ptr(q), _ptr(h), self._stream()), "odg_terrain_height")
+        return h
+
+    def terrain_from_raw(self, raw: torch.Tensor, radius: torch.Tensor):
+        """Test hook: only the deterministic tail of the generator (blend, normalise, transpose) on given raw heights."""
+        r = raw.to(device=self.device, dtype=torch.float32).contiguous(); rad = radius.to(device=self.device, dtype=torch.float32).contiguous()
+        _lib.check(self.L.odg_terrain_from_raw(self._t, _ptr(r), _ptr(rad), self._stream()), "odg_terrain_from_raw")
+        return self.hfield_data
 
 
 class _DataView:
@@ -109,15 +170,17 @@ class _DataView:
 class QuadrupedEnv:
     """Single-environment numpy façade with the reference's constructor and 4-tuple API (sim2real/train.py:151)."""
 
+    _batched = BatchedQuadrupedEnv
+    sim_steps_per_policy_step = 50
+
     def __init__(self, model_path: str = "our_robot/walking_scene.xml"):
         if "walking_scene" not in str(model_path) and "our_robot" not in str(model_path):
             raise ValueError("QuadrupedEnv supports the OpenDOG walking scene")
-        self._b = BatchedQuadrupedEnv(1, auto_reset=False)
+        self._b = self._batched(1, auto_reset=False)
         self.state_dim, self.action_dim = self._b.state_dim, self._b.action_dim
         self.viewer = None
         self.model = self._b.sim.desc
         self.data = _DataView(self)
-        self.sim_steps_per_policy_step = 50
         self.episode_policy_step_counter = 0
 
     def reset(self):
@@ -127,7 +190,7 @@ class QuadrupedEnv:
     reset_to_home_keyframe = reset
 
     def step(self, policy_actions_scaled_neg1_to_1):
-        a = torch.as_tensor(np.asarray(policy_actions_scaled_neg1_to_1, dtype=np.float32).reshape(1, 4))
+        a = torch.as_tensor(np.asarray(policy_actions_scaled_neg1_to_1, dtype=np.float32).reshape(1, self.action_dim))
         obs, rew, done, info = self._b.step(a)
         self.episode_policy_step_counter += 1
         reason = int(self._b.reason[0])
@@ -141,6 +204,24 @@ class QuadrupedEnv:
     def close_viewer_internal(self): pass
     def sync_viewer_if_active(self): pass
     def close(self): self._b.close()
+
+
+class TerrainQuadrupedEnv(QuadrupedEnv):
+    """Single-environment numpy façade of the terrain trainer's `QuadrupedEnv` (sim2real/train2.py:159-411): 12-float
+    observation, 8 actions, the same 4-tuple API; `get_terrain_height(x, y)` and `hfield_data` as the reference exposes them."""
+    _batched = BatchedTerrainQuadrupedEnv
+    sim_steps_per_policy_step = 40
+
+    @property
+    def current_episode_steps(self):
+        return self.episode_policy_step_counter
+
+    def get_terrain_height(self, world_x, world_y):
+        return float(self._b.terrain_height(torch.tensor([[world_x, world_y]], dtype=torch.float32))[0])
+
+    @property
+    def hfield_data(self):
+        return self._b.hfield_data[0].cpu().numpy()
 
 
 def _gym_box(low, high, shape, dtype):

@@ -16,11 +16,13 @@ using odg_internal::set_error;
   do { cudaError_t e_ = (expr);                                                                \
        if (e_ != cudaSuccess) return set_error(ODG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
 
-constexpr int kObs = 22;
+constexpr int kObs = 22;          // largest observation (train.py: 22, train2.py: 12)
 
 struct S2RConst {
   int N, stride, nq, nv, auto_reset;   // N environments, SoA stride of the simulator's state arrays
   int max_steps;            // episode cap of the training loop (train.py:68,539), enforced when auto_reset
+  int variant, obs_dim, act_dim;   // OdgS2RVariant
+  double init_z_flat, settled_z;   // train2.py: initial_body_z_pos_on_flat (keyframe z), current_initial_body_z_pos (z after the settle)
   int act_id[8];            // ctrl index of ACTUATOR_NAMES_ORDERED[o]  (FR, FL, BR, BL) x (tigh, knee)
   int qidx[8], vidx[8];     // qpos / qvel index of that actuator's joint
   double home[8];           // sim_keyframe_home_qpos_map
@@ -53,6 +55,11 @@ __device__ void write_obs(const S2RConst& C, const float* qpos, const float* qve
   double yaw, pitch, roll;
   quat_to_ypr(qpos[3 * N + env], qpos[4 * N + env], qpos[5 * N + env], qpos[6 * N + env], yaw, pitch, roll);
   o[0] = (float)yaw; o[1] = (float)pitch; o[2] = (float)roll;
+  if (C.variant == ODG_S2R_TERRAIN) {              // train2.py:197-201: [yaw pitch roll, q_j - home (8), v_x]
+    for (int k = 0; k < 8; k++) o[3 + k] = (float)((double)qpos[C.qidx[k] * N + env] - C.home[k]);
+    o[11] = qvel[0 * N + env];
+    return;
+  }
   for (int k = 0; k < 8; k++) {
     o[3 + k] = (float)((double)qpos[C.qidx[k] * N + env] - C.home[k]);
     o[11 + k] = qvel[C.vidx[k] * N + env];
@@ -66,6 +73,13 @@ __device__ void write_obs(const S2RConst& C, const float* qpos, const float* qve
 __global__ void k_s2r_pre(const S2RConst C, const S2RState S, const float* __restrict__ action) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= C.N) return;
+  if (C.variant == ODG_S2R_TERRAIN) {              // train2.py:348-354: home + amplitude * a, clipped to ctrlrange
+    for (int o = 0; o < 8; o++) {
+      const double t = fmin(fmax(C.home[o] + (double)action[env * 8 + o] * C.amp, C.clo[o]), C.chi[o]);
+      S.ctrl[env * 8 + C.act_id[o]] = (float)t;
+    }
+    return;
+  }
   const int phase = S.counter[env] % 2;
   const double fr_t = (double)action[env * 4 + 0] * C.amp, k1 = (double)action[env * 4 + 1] * C.amp;
   const double fl_t = (double)action[env * 4 + 2] * C.amp, k2 = (double)action[env * 4 + 3] * C.amp;
@@ -107,6 +121,60 @@ __global__ void k_s2r_post(const S2RConst C, const S2RState S, const odg::SimPtr
   float o[kObs];
   write_obs(C, P.qpos, P.qvel, env, counter, o);
   const double vx = P.qvel[0 * N + env], vy = P.qvel[1 * N + env];
+  if (C.variant == ODG_S2R_TERRAIN) {
+    // train2.py:357-414
+    const double net = cpos - cneg, dnet = net - S.prev_net[env];
+    double r = 450.0 * vx;
+    if (dnet > 0.0005) r += 20.0 * dnet;
+    if (vx < -0.005) r += -9.0 * fabs(vx);
+    r += 0.005; r += 0.01;
+    r += -0.3 * fabs(vy);
+    r += -0.5 * fabs(vy);
+    r += -0.15 * fabs(y - C.init_y);
+    const double z = P.qpos[2 * N + env];
+    const double zs = z - C.settled_z, zi = z - C.init_z_flat;
+    double pz = 0.0;
+    if (zs < -0.03) pz -= (0.25 * 0.5) * (fabs(zs) - 0.03) * (fabs(zs) - 0.03);
+    if (fabs(zi) > 0.05) pz -= (0.25 * 0.25) * (fabs(zi) - 0.05) * (fabs(zi) - 0.05);
+    r += pz;
+    double yaw, pitch, roll;
+    quat_to_ypr(P.qpos[3 * N + env], P.qpos[4 * N + env], P.qpos[5 * N + env], P.qpos[6 * N + env], yaw, pitch, roll);
+    const double th = 15.0 * 0.017453292519943295, thy = 35.0 * 0.017453292519943295, lim = 35.0 * 0.017453292519943295;
+    double po = 0.0;
+    if (fabs(roll) > th) po += -0.08 * (fabs(roll) - th) * (fabs(roll) - th);
+    if (fabs(pitch) > th) po += -0.08 * (fabs(pitch) - th) * (fabs(pitch) - th);
+    if (fabs(yaw) > thy) po += -0.08 * (fabs(yaw) - thy) * (fabs(yaw) - thy);
+    r += po;
+    double dsq = 0.0;
+    for (int k = 0; k < 8; k++) {
+      const double d = (double)S.ctrl[env * 8 + C.act_id[k]] - (double)S.last_cmd[env * 8 + C.act_id[k]];
+      dsq += d * d;
+    }
+    r += -0.005 * dsq;
+    r += dx > 0 ? 70.0 * dx : (dx < 0.0005 ? -1.0 : 0.0);                     // reward_step_displacement (:363-366)
+    double jvm = 0.0;
+    for (int i = 7; i < 15 && i < C.nv; i++) jvm += fabs((double)P.qvel[i * N + env]);   // np.abs(qvel[7:15]): 7 of the 8 hinges (:398)
+    r += -0.05 * exp(-jvm * 5.0);
+    bool done = false; int reason = ODG_S2R_RUNNING;
+    if (!finite) { r -= 50.0; done = true; reason = ODG_S2R_MJ_ERROR; }
+    if (!done && (fabs(roll) > lim || fabs(pitch) > lim || fabs(yaw) > lim * 1.5)) { r -= 150.0; done = true; reason = ODG_S2R_ORIENTATION_LIMIT; }
+    if (!done && cpos > 0.05 && cneg > 0.85 * cpos) { r -= 50.0; done = true; reason = ODG_S2R_TOO_MUCH_BACKWARD; }
+    if (!done && C.auto_reset && C.max_steps > 0 && counter >= C.max_steps) done = true;
+    if (reward) reward[env] = (float)r;
+    if (done_out) done_out[env] = done ? 1 : 0;
+    if (reason_out) reason_out[env] = (unsigned char)reason;
+    if (sim_target) for (int u = 0; u < 8; u++) sim_target[env * 8 + u] = S.ctrl[env * 8 + u];
+    if (terminal_obs) for (int k = 0; k < C.obs_dim; k++) terminal_obs[env * C.obs_dim + k] = o[k];
+    S.counter[env] = counter; S.prev_x[env] = x; S.cum_pos[env] = cpos; S.cum_neg[env] = cneg; S.prev_net[env] = net;
+    for (int u = 0; u < 8; u++) S.last_cmd[env * 8 + u] = S.ctrl[env * 8 + u];
+    if (done && C.auto_reset) {
+      restore_settled(C, S, P, env);
+      for (int u = 0; u < 8; u++) S.last_cmd[env * 8 + u] = home_ctrl[u];
+      write_obs(C, P.qpos, P.qvel, env, 0, o);
+    }
+    if (obs) for (int k = 0; k < C.obs_dim; k++) obs[env * C.obs_dim + k] = o[k];
+    return;
+  }
   double r = 150.0 * vx;
   const double net = cpos - cneg, dnet = net - S.prev_net[env];
   if (dnet > 0.0005) r += 15.0 * dnet;
@@ -154,7 +222,7 @@ __global__ void k_s2r_post(const S2RConst C, const S2RState S, const odg::SimPtr
   if (done_out) done_out[env] = done ? 1 : 0;
   if (reason_out) reason_out[env] = (unsigned char)reason;
   if (sim_target) for (int u = 0; u < 8; u++) sim_target[env * 8 + u] = S.ctrl[env * 8 + u];
-  if (terminal_obs) for (int k = 0; k < kObs; k++) terminal_obs[env * kObs + k] = o[k];
+  if (terminal_obs) for (int k = 0; k < C.obs_dim; k++) terminal_obs[env * C.obs_dim + k] = o[k];
   // bookkeeping for the next step
   S.counter[env] = counter; S.prev_x[env] = x; S.cum_pos[env] = cpos; S.cum_neg[env] = cneg; S.prev_net[env] = net;
   for (int u = 0; u < 8; u++) S.last_cmd[env * 8 + u] = S.ctrl[env * 8 + u];
@@ -163,7 +231,7 @@ __global__ void k_s2r_post(const S2RConst C, const S2RState S, const odg::SimPtr
     for (int u = 0; u < 8; u++) S.last_cmd[env * 8 + u] = home_ctrl[u];
     write_obs(C, P.qpos, P.qvel, env, 0, o);
   }
-  if (obs) for (int k = 0; k < kObs; k++) obs[env * kObs + k] = o[k];
+  if (obs) for (int k = 0; k < C.obs_dim; k++) obs[env * C.obs_dim + k] = o[k];
 }
 
 __global__ void k_s2r_reset(const S2RConst C, const S2RState S, const odg::SimPtrs P, const unsigned char* __restrict__ mask,
@@ -173,7 +241,7 @@ __global__ void k_s2r_reset(const S2RConst C, const S2RState S, const odg::SimPt
   if (mask && !mask[env]) return;
   restore_settled(C, S, P, env);
   for (int u = 0; u < 8; u++) S.last_cmd[env * 8 + u] = home_ctrl[u];
-  if (obs) { float o[kObs]; write_obs(C, P.qpos, P.qvel, env, 0, o); for (int k = 0; k < kObs; k++) obs[env * kObs + k] = o[k]; }
+  if (obs) { float o[kObs]; write_obs(C, P.qpos, P.qvel, env, 0, o); for (int k = 0; k < C.obs_dim; k++) obs[env * C.obs_dim + k] = o[k]; }
 }
 __global__ void k_s2r_fill_ctrl(float* ctrl, const float* home_ctrl, int N) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -204,10 +272,22 @@ struct OdgS2R {
 
 extern "C" {
 
+void odg_s2r_default_config_for(OdgS2RConfig* c, int variant) {
+  if (!c) return;
+  odg_s2r_default_config(c);
+  if (variant == ODG_S2R_TERRAIN) {
+    c->variant = ODG_S2R_TERRAIN;
+    c->action_amplitude_rad = 50.0 * 3.14159265358979323846 / 180.0;     // ACTION_AMPLITUDE_DEG (train2.py:93)
+    c->max_steps = 1000;                                                  // MAX_STEPS_PER_EPISODE (train2.py:88)
+  }
+}
+int odg_s2r_obs_dim(const OdgS2R* e) { return e ? e->C.obs_dim : 0; }
+int odg_s2r_act_dim(const OdgS2R* e) { return e ? e->C.act_dim : 0; }
+
 void odg_s2r_default_config(OdgS2RConfig* c) {
   if (!c) return;
   c->action_amplitude_rad = 40.0 * 3.14159265358979323846 / 180.0;
-  c->settle_steps = 100; c->auto_reset = 0; c->max_steps = 250;
+  c->settle_steps = 100; c->auto_reset = 0; c->max_steps = 250; c->variant = ODG_S2R_TRAIN;
   const double home[8] = { -45.0, 45.0, 45.0, 45.0, 45.0, -45.0, 45.0, -45.0 };   // FR_t FR_k FL_t FL_k BR_t BR_k BL_t BL_k
   for (int i = 0; i < 8; i++) { c->real_home_deg[i] = home[i]; c->joint_scale[i] = 1.0; }
 }
@@ -220,7 +300,8 @@ int odg_s2r_create(OdgSim* sim, const OdgModel* m, const OdgS2RConfig* cfg_in, O
   const odg::DevConst& DC = sim->prep.C;
   if (m->nu != 8 || m->njl != 2) return set_error(ODG_ERR_INVALID, "QuadrupedEnv needs the 8-actuator OpenDOG model");
   if (DC.scale_actions || DC.auto_reset) return set_error(ODG_ERR_INVALID, "create the OdgSim with scale_actions = 0 and auto_reset = 0");
-  if (cfg.settle_steps % DC.frame_skip) return set_error(ODG_ERR_INVALID, "settle_steps must be a multiple of frame_skip");
+  if (cfg.settle_steps < 1) return set_error(ODG_ERR_INVALID, "settle_steps must be >= 1");
+  if (cfg.variant != ODG_S2R_TRAIN && cfg.variant != ODG_S2R_TERRAIN) return set_error(ODG_ERR_INVALID, "unknown OdgS2RVariant");
   if (cfg.max_steps < 0) return set_error(ODG_ERR_INVALID, "max_steps must be >= 0");
   DevScope scope(sim->device);
   OdgS2R* e = new (std::nothrow) OdgS2R();
@@ -228,6 +309,8 @@ int odg_s2r_create(OdgSim* sim, const OdgModel* m, const OdgS2RConfig* cfg_in, O
   e->sim = sim;
   S2RConst& C = e->C;
   C.N = sim->N; C.stride = sim->P.N; C.nq = DC.nq; C.nv = DC.nv; C.auto_reset = cfg.auto_reset; C.max_steps = cfg.max_steps; C.amp = cfg.action_amplitude_rad;
+  C.variant = cfg.variant; C.obs_dim = cfg.variant == ODG_S2R_TERRAIN ? 12 : 22; C.act_dim = cfg.variant == ODG_S2R_TERRAIN ? 8 : 4;
+  C.init_z_flat = m->key_qpos[2]; C.settled_z = m->key_qpos[2];
   // ACTUATOR_NAMES_ORDERED = FR FL BR BL; model legs are in body order FL FR BL BR
   const int leg_of[4] = { 1, 0, 3, 2 };
   for (int o = 0; o < 8; o++) {
@@ -256,12 +339,21 @@ int odg_s2r_create(OdgSim* sim, const OdgModel* m, const OdgS2RConfig* cfg_in, O
   CUDA_TRY(cudaMemcpy(e->d_home_ctrl, hc, sizeof(hc), cudaMemcpyHostToDevice));
   // settled reset state: keyframe (odg_create left every env there) + settle_steps x mj_step with ctrl = home
   k_s2r_fill_ctrl<<<(unsigned)((N * 8 + 255) / 256), 256>>>(e->S.ctrl, e->d_home_ctrl, sim->N);
-  for (int i = 0; i < cfg.settle_steps / DC.frame_skip; i++) {
+  {
+    // one launch with frame_skip = settle_steps (the policy-step length need not divide the settle: 100 vs 40 in train2.py)
+    const int fs = DC.frame_skip;
+    odg_set_frame_skip(sim, cfg.settle_steps);
     int rc = odg_step(sim, e->S.ctrl, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    odg_set_frame_skip(sim, fs);
     if (rc != ODG_OK) { odg_s2r_destroy(e); return rc; }
   }
   k_s2r_snapshot<<<1, 32>>>(sim->P, C.nq, C.nv, e->d_settled);
   CUDA_TRY(cudaDeviceSynchronize());
+  {
+    float z = 0.f;                                   // current_initial_body_z_pos (train2.py:318): trunk height after the settle
+    CUDA_TRY(cudaMemcpy(&z, e->d_settled + 2, sizeof(float), cudaMemcpyDeviceToHost));
+    C.settled_z = (double)z;
+  }
   *out = e;
   return odg_s2r_reset(e, nullptr, nullptr, nullptr);
 }

@@ -23,7 +23,10 @@ SYMBOLS = [
     "odg_normalize_advantages", "odg_policy_launch_count",
     # QuadrupedEnv surface (include/odg_sim2real.h)
     "odg_s2r_default_config", "odg_s2r_create", "odg_s2r_destroy", "odg_s2r_reset", "odg_s2r_step",
-    "odg_s2r_set_bookkeeping",
+    "odg_s2r_set_bookkeeping", "odg_s2r_default_config_for", "odg_s2r_obs_dim", "odg_s2r_act_dim",
+    # the terrain trainer's height fields (include/odg_sim2real.h)
+    "odg_terrain_create", "odg_terrain_destroy", "odg_terrain_generate", "odg_terrain_from_raw", "odg_terrain_height",
+    "odg_terrain_data",
     # MPPI (include/odg_mppi.h)
     "odg_mppi_sample", "odg_mppi_accumulate", "odg_mppi_reduce", "odg_mppi_rollout",
 ]
@@ -54,7 +57,7 @@ class OdgPolicyWeights(C.Structure):
 
 class OdgS2RConfig(C.Structure):
     _fields_ = [("action_amplitude_rad", C.c_double), ("settle_steps", C.c_int), ("auto_reset", C.c_int),
-                ("real_home_deg", C.c_double * 8), ("joint_scale", C.c_double * 8), ("max_steps", C.c_int)]
+                ("real_home_deg", C.c_double * 8), ("joint_scale", C.c_double * 8), ("max_steps", C.c_int), ("variant", C.c_int)]
 
 
 class OdgError(RuntimeError):
@@ -108,6 +111,18 @@ def load():
     L.odg_s2r_reset.argtypes = [_vp, _vp, _vp, _vp]
     L.odg_s2r_step.argtypes = [_vp] * 9
     L.odg_s2r_set_bookkeeping.argtypes = [_vp] * 8
+    L.odg_s2r_default_config_for.argtypes = [C.POINTER(OdgS2RConfig), C.c_int]
+    L.odg_s2r_default_config_for.restype = None
+    L.odg_s2r_obs_dim.argtypes = [_vp]
+    L.odg_s2r_act_dim.argtypes = [_vp]
+    L.odg_terrain_create.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(_vp)]
+    L.odg_terrain_destroy.argtypes = [_vp]
+    L.odg_terrain_destroy.restype = None
+    L.odg_terrain_generate.argtypes = [_vp, _vp, _vp]
+    L.odg_terrain_from_raw.argtypes = [_vp, _vp, _vp, _vp]
+    L.odg_terrain_height.argtypes = [_vp, _vp, _vp, _vp]
+    L.odg_terrain_data.argtypes = [_vp]
+    L.odg_terrain_data.restype = _vp
     L.odg_mppi_sample.argtypes = [_vp, C.c_float, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, _vp, _vp]
     L.odg_mppi_accumulate.argtypes = [_vp, _vp, C.c_int, C.c_float, _vp, _vp, _vp]
     L.odg_mppi_rollout.argtypes = [_vp, _vp, C.c_float, C.c_int, C.c_uint64, C.c_uint32, _vp, C.c_float, _vp, _vp, _vp]
