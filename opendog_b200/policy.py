@@ -21,7 +21,13 @@ def _ptr(t):
 
 
 class ActorCriticB200(nn.Module):
-    def __init__(self, state_dim: int, action_dim: int, action_std_init: float = 0.4, device=None, seed: int = 0):
+    """`hidden` = the two hidden widths: (512, 256) is sim2real/train.py:135-149 and the benchmark policy — its rollout-time
+    forward is the fused tcgen05 kernel; (1024, 512) is the terrain trainer's network (sim2real/train2.py:151-153), whose
+    128 x 1024 bf16 hidden tile does not fit one SM's shared memory next to the weight stages: `act` then runs the same
+    arithmetic (bf16 operands, fp32 accumulation) as library GEMMs through torch, on the device, with the same outputs."""
+
+    def __init__(self, state_dim: int, action_dim: int, action_std_init: float = 0.4, device=None, seed: int = 0,
+                 hidden=(512, 256)):
         super().__init__()
         if not torch.cuda.is_available():
             raise _lib.OdgError("ActorCriticB200 needs a CUDA device: opendog_b200 has no CPU fallback")
@@ -29,16 +35,24 @@ class ActorCriticB200(nn.Module):
         if self.dev.index is None:
             self.dev = torch.device("cuda", torch.cuda.current_device())
         self.state_dim, self.action_dim, self.seed = state_dim, action_dim, seed
-        self.actor = nn.Sequential(nn.Linear(state_dim, 512), nn.Tanh(), nn.Linear(512, 256), nn.Tanh(),
-                                   nn.Linear(256, action_dim), nn.Tanh())
-        self.critic = nn.Sequential(nn.Linear(state_dim, 512), nn.Tanh(), nn.Linear(512, 256), nn.Tanh(),
-                                    nn.Linear(256, 1))
+        h1, h2 = int(hidden[0]), int(hidden[1])
+        self.hidden = (h1, h2)
+        self.fused = self.hidden == (512, 256)
+        self.actor = nn.Sequential(nn.Linear(state_dim, h1), nn.Tanh(), nn.Linear(h1, h2), nn.Tanh(),
+                                   nn.Linear(h2, action_dim), nn.Tanh())
+        self.critic = nn.Sequential(nn.Linear(state_dim, h1), nn.Tanh(), nn.Linear(h1, h2), nn.Tanh(),
+                                    nn.Linear(h2, 1))
         self.action_log_std = nn.Parameter(torch.ones(1, action_dim) * math.log(action_std_init))
         self.to(self.dev)
         self.L = _lib.load()
-        h = C.c_void_p()
-        _lib.check(self.L.odg_policy_create(state_dim, action_dim, self.dev.index, C.byref(h)), "odg_policy_create")
-        self._h = h
+        self._h = None
+        self._launches = 0
+        self._gen = torch.Generator(device=self.dev)
+        self._gen.manual_seed(seed)
+        if self.fused:
+            h = C.c_void_p()
+            _lib.check(self.L.odg_policy_create(state_dim, action_dim, self.dev.index, C.byref(h)), "odg_policy_create")
+            self._h = h
         self._step = 0
         self.sync_weights()
 
@@ -55,11 +69,13 @@ class ActorCriticB200(nn.Module):
 
     @property
     def launch_count(self) -> int:
-        return int(self.L.odg_policy_launch_count(self._h))
+        return int(self.L.odg_policy_launch_count(self._h)) if self.fused else self._launches
 
     def sync_weights(self):
         """Re-pack the fp32 parameters into the kernel's bf16 operand layout (call after every optimiser step
         or load_state_dict)."""
+        if not self.fused:
+            return
         w = _lib.OdgPolicyWeights()
         keep = []
         for name, net in (("actor", self.actor), ("critic", self.critic)):
@@ -85,6 +101,8 @@ class ActorCriticB200(nn.Module):
             o = o.to(device=self.dev, dtype=torch.float32).contiguous()
         n = o.shape[0]
         out = out or {}
+        if not self.fused:
+            return self._act_library(o, sample, out)
         mean = out.get("mean") if out.get("mean") is not None else torch.empty(n, self.action_dim, device=self.dev)
         value = out.get("value") if out.get("value") is not None else torch.empty(n, device=self.dev)
         action = logp = None
@@ -97,6 +115,29 @@ class ActorCriticB200(nn.Module):
         _lib.check(self.L.odg_policy_forward(self._h, _ptr(o), n, _ptr(mean), _ptr(value), _ptr(action), _ptr(logp),
                                              C.c_uint64(self.seed), C.c_uint32(step & 0xFFFFFFFF), _ptr(step_base), first_row_id,
                                              self._stream()), "odg_policy_forward")
+        return (action if sample else mean), logp, value, mean
+
+    @torch.no_grad()
+    def _act_library(self, o, sample, out):
+        """Rollout-time forward for hidden sizes the fused kernel does not cover: bf16 operands, fp32 accumulation, on
+        the device (cuBLAS through torch). Same outputs as the kernel path; the noise comes from a torch generator."""
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            mean = self.actor(o).float()
+            value = self.critic(o).float().squeeze(-1)
+        self._launches += 1
+        ls = self.action_log_std.detach().reshape(-1)
+        action = logp = None
+        if sample:
+            eps = torch.randn(mean.shape, device=self.dev, generator=self._gen)
+            action = mean + torch.exp(ls) * eps
+            logp = (-0.5 * eps * eps - ls - 0.9189385332046727).sum(-1)
+        for k, v in (("mean", mean), ("value", value), ("action", action), ("logp", logp)):
+            if v is not None and out.get(k) is not None:
+                out[k].copy_(v)
+        pick = lambda k, v: out[k] if out.get(k) is not None else v
+        mean, value = pick("mean", mean), pick("value", value)
+        if sample:
+            action, logp = pick("action", action), pick("logp", logp)
         return (action if sample else mean), logp, value, mean
 
     # ------------------------------------------------------------------ differentiable forward (update phase)

@@ -112,3 +112,31 @@ def test_single_env_terrain_facade():
     assert np.allclose(info["sim_target_rad"], [2.36, -1.5708] * 4, atol=1e-6)      # home targets clipped to ctrlrange
     assert env.hfield_data.shape == (10000,) and 0.0 <= env.get_terrain_height(0.0, 0.0) <= 0.302
     env.close()
+
+
+def test_terrain_policy_network_and_rollout():
+    """The terrain trainer's ActorCritic (train2.py:149-157: 12 -> 1024 -> 512 -> 8, std 0.3) in the reference's
+    state_dict layout, driving the batched terrain environment through the on-device rollout."""
+    import torch.nn as nn
+    from opendog_b200.compat import BatchedTerrainQuadrupedEnv
+    from opendog_b200.policy import ActorCriticB200
+    pol = ActorCriticB200(12, 8, 0.3, hidden=(1024, 512), seed=2)
+    sd = pol.state_dict()
+    assert tuple(sd["actor.0.weight"].shape) == (1024, 12) and tuple(sd["actor.2.weight"].shape) == (512, 1024)
+    assert tuple(sd["actor.4.weight"].shape) == (8, 512) and tuple(sd["critic.4.weight"].shape) == (1, 512)
+    assert tuple(sd["action_log_std"].shape) == (1, 8) and abs(float(sd["action_log_std"][0, 0]) - np.log(0.3)) < 1e-6
+    env = BatchedTerrainQuadrupedEnv(512, auto_reset=True, seed=1)
+    obs = env.reset()
+    mean, _, value, _ = pol.act(obs, sample=False)
+    with torch.no_grad():
+        d, v = pol(obs)                                        # the reference module's fp32 forward
+    assert (mean - d.mean).abs().max().item() < 3e-2 and (value - v[:, 0]).abs().max().item() < 3e-2
+    ret = 0.0
+    for t in range(20):
+        a, logp, value, mean = pol.act(obs, sample=True)
+        z = (a - mean) / 0.3
+        assert torch.allclose(logp, (-0.5 * z * z - np.log(0.3) - 0.5 * np.log(2 * np.pi)).sum(-1), atol=1e-3)
+        obs, rew, done, info = env.step(a.clamp(-1, 1))
+        ret += float(rew.mean())
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    assert np.isfinite(ret)
