@@ -11,10 +11,19 @@ def test_udp_packet_matches_reference_schema():
     import msgpack
     from opendog_b200.env import BatchedWalkEnv
     from opendog_b200.telemetry import TelemetryServer
+    import numpy as np
+    from oracle.oracle import WalkEnv, scale_action
     env = BatchedWalkEnv(8, seed=1, info_keys=("paw_contact_forces", "ncon"))
     env.reset()
-    for _ in range(12):
+    for _ in range(11):
         env.step(torch.zeros(8, 8, device="cuda"))
+    # the VALUES of the packet, not only its schema: an oracle copy of environment 3 takes the last step alongside
+    q, v = [x.cpu().numpy() for x in env.get_state()]
+    w = WalkEnv(seed=1, env_id=3); w.reset()
+    w.qpos[:] = q[3]; w.qvel[:] = v[3]
+    act = np.linspace(-0.6, 0.6, 8).astype(np.float32)
+    env.step(torch.from_numpy(np.tile(act, (8, 1))).cuda())
+    oinfo = w.step(act)[4]
     srv = TelemetryServer(port=0)
     cli = socket.socket(socket.AF_INET, socket.SOCK_DGRAM); cli.settimeout(5.0)
     cli.sendto(b"hello", srv.address)
@@ -26,4 +35,9 @@ def test_udp_packet_matches_reference_schema():
     assert (d["num_qpos"], d["num_qvel"]) == (15, 14) and len(d["qpos_data"]) == 3 and len(d["qvel_data"]) == 3
     assert len(d["ctr_data"]) == 8 and len(d["contact_forces_data"]) == 24 and d["active_contacts"] >= 4
     assert 0.03 < d["qpos_data"][2] < 0.25                     # the robot has landed and stands
+    assert np.allclose(d["qpos_data"], w.qpos[:3], atol=1e-5) and np.allclose(d["qvel_data"], w.qvel[:3], atol=2e-4)
+    assert np.allclose(d["ctr_data"], scale_action(act), atol=1e-6)          # data.ctrl = the scaled targets (rad)
+    assert d["active_contacts"] == w.e.d.ncon
+    f = np.array(d["contact_forces_data"]).reshape(4, 6); ref = oinfo["paw_contact_forces"]      # reward_calc.py:351-370
+    assert np.abs(f - ref).max() <= 5e-2 * max(1.0, np.abs(ref).max()) and np.abs(ref).max() > 0.5
     srv.close(); cli.close()
