@@ -35,7 +35,10 @@ enum OdgStatus {
 };
 
 enum OdgTask {
-  ODG_TASK_WALK = 0          /* ScaleActionWrapper(WalkEnvironmentV0): obs 33, act 8 */
+  ODG_TASK_WALK = 0,         /* ScaleActionWrapper(WalkEnvironmentV0): obs 33, act 8 */
+  ODG_TASK_JUMP = 1          /* JumpEnvironmentV0 (environments/JumpEnvironment.py:70-119 + rewards/jump_environment_reward_calc.py)
+                                on the 12-actuator model: obs 21, act 12 = ctrl targets (use scale_actions = 0,
+                                reset_noise_scale = 0.1 as the reference does) */
 };
 
 /* Environment configuration. Defaults (odg_default_config) are the reference's constants. */
@@ -93,6 +96,10 @@ typedef struct OdgInfoPtrs {
   int32_t* solver_iters;         /* [N] Newton iterations used in the last substep */
   int32_t* ls_evals;             /* [N] line-search passes used in the last substep */
   float* reward_unclipped;       /* [N] rewards - costs BEFORE the max(0, .) clip of WalkEnvironment.py:84 (MPPI cost) */
+  /* 12-actuator model only (NULL elsewhere) */
+  float* cfrc_ext;               /* [N][13][6] data.cfrc_ext[1:] after do_simulation: per body [torque about the robot's
+                                    centre of mass, force], world axes (jump_environment_reward_calc.py:131-133) */
+  float* task_terms;             /* [N][10] jump task: compute_rewards' reward_info, weighted, in its key order */
 } OdgInfoPtrs;
 
 void odg_default_config(OdgEnvConfig* cfg);

@@ -22,11 +22,13 @@ extern "C" {
 #define ODG_MAX_NU 12
 #define ODG_MAX_NQ (7 + ODG_MAX_LEG * ODG_MAX_JL)
 #define ODG_MAX_NV (6 + ODG_MAX_LEG * ODG_MAX_JL)
-#define ODG_MAX_GEOM 32
+#define ODG_MAX_GEOM 48
 #define ODG_MAX_VERT 2048
 #define ODG_MAX_CON_PER_GEOM 4
 
-enum { ODG_GEOM_HULL = 0, ODG_GEOM_SPHERE = 1 };
+/* collision geoms against the floor plane: convex hull of a mesh (mjc_PlaneConvex), sphere (mjc_PlaneSphere), and the
+ * primitives of unitree_go1/go1.xml:26-60 — capsule (mjc_PlaneCapsule), cylinder (mjc_PlaneCylinder), box (mjc_PlaneBox) */
+enum { ODG_GEOM_HULL = 0, ODG_GEOM_SPHERE = 1, ODG_GEOM_CAPSULE = 2, ODG_GEOM_CYLINDER = 3, ODG_GEOM_BOX = 4 };
 
 typedef struct OdgGeom {
   int leg;                 /* owning leg, -1 = trunk */
@@ -35,10 +37,14 @@ typedef struct OdgGeom {
   int vert_start, vert_count; /* hull: slice of OdgModel.vert (link frame) */
   int mj_geom_id;          /* geom id in the MuJoCo model (floor plane is 0) */
   int mj_body_id;          /* body id in the MuJoCo model (paws: 4,7,10,13) */
-  int condim;              /* contact dim after mixing with the floor: max(condim_geom, condim_floor) */
-  double center[3];        /* sphere centre in the link frame */
+  int condim;              /* contact dim after mixing with the floor: max(condim_geom, condim_floor); 1, 3 or 6 */
+  double center[3];        /* geom position in the link frame (sphere centre; capsule / cylinder / box centre) */
   double radius;           /* sphere radius */
-  double friction;         /* sliding friction after mixing with the floor (element-wise max) */
+  double rot[9];           /* primitives: geom frame in the link frame, row-major (columns = geom axes) */
+  double size[3];          /* capsule / cylinder: radius, half-length (along the geom z axis); box: half extents */
+  double friction;         /* sliding friction after mixing with the floor (element-wise max, or the higher priority's) */
+  double friction_torsion; /* torsional and rolling friction (condim 6: go1.xml:61-64), same mixing */
+  double friction_roll;
   double margin;           /* includemargin = max(margin) - max(gap) */
   double solref[2];        /* contact solref after mixing */
   double solimp[5];        /* contact solimp after mixing */

@@ -72,8 +72,8 @@ __device__ __forceinline__ float odg_rsqrt(float x) { float r; asm("rsqrt.approx
 namespace odg {
 
 constexpr int kMaxJL = 3;
-constexpr int kMaxSlot = 8;          // collision geoms per leg
-constexpr int kMaxConLeg = 12;       // contacts per leg (<= 4 per geom)
+constexpr int kMaxSlot = 12;         // collision geoms per lane (a leg's own, plus its share of the trunk's)
+constexpr int kMaxConLeg = 12;       // contacts per lane (<= 4 per geom)
 constexpr int kMaxNU = 12;
 constexpr int kMaxNQ = 7 + 4 * kMaxJL;
 
@@ -93,7 +93,14 @@ enum LegConstField {
   LC_COUNT
 };
 // per-slot, per-leg constants: s_gc[(slot*GC_COUNT + f)*4 + leg]
-enum GeomConstField { GC_INVW, GC_CX, GC_CY, GC_CZ, GC_BX, GC_BY, GC_BZ, GC_BR, GC_HX, GC_HY, GC_HZ, GC_COUNT };
+enum GeomConstField { GC_INVW, GC_CX, GC_CY, GC_CZ, GC_BX, GC_BY, GC_BZ, GC_BR, GC_HX, GC_HY, GC_HZ,
+                      // primitives (capsule / cylinder / box; only the 3-joint-leg instantiation reads them): geom type of
+                      // THIS lane's geom in the slot (0 = none: front legs carry one hip cylinder less than rear legs, and
+                      // the trunk's colliders are dealt out over the four lanes), geom frame in the link frame, sizes
+                      GC_TYPE, GC_R0, GC_R1, GC_R2, GC_R3, GC_R4, GC_R5, GC_R6, GC_R7, GC_R8, GC_S0, GC_S1, GC_S2,
+                      GC_COUNT };
+// geom types as the kernel numbers them (model types + 1 where the lane-level table is used; 0 = empty slot)
+enum { PRIM_NONE = 0, PRIM_SPHERE = 2, PRIM_CAPSULE = 3, PRIM_CYLINDER = 4, PRIM_BOX = 5 };
 
 struct DevConst {
   int nleg, njl, nq, nv, nu, nslot, nvert_rows;
@@ -114,11 +121,17 @@ struct DevConst {
   float slot_margin[kMaxSlot], slot_K[kMaxSlot], slot_B[kMaxSlot], slot_imp[kMaxSlot][5];
   float slot_fri[kMaxSlot], slot_mu[kMaxSlot], slot_radius[kMaxSlot];
   float slot_dmk[kMaxSlot];                     // 1 / (mu^2 (1 + mu^2)): Dm = Dn * slot_dmk (cone surface stiffness)
+  // condim 6 (Go1 feet, go1.xml:61-64): torsional / rolling friction coefficients and the stiffness ratios of their rows,
+  // D_row = D_normal * ratio with ratio = impratio * mu_slide^2 / mu_row^2 (mj_makeImpedance); all 0 for condim < 6
+  float slot_frt[kMaxSlot], slot_frr[kMaxSlot], slot_dt_tor[kMaxSlot], slot_dt_roll[kMaxSlot];
+  int per_lane_geoms;                           // slots differ between lanes (type / presence from the GC_TYPE table)
   float tilt_dir[3][3];                         // extra support directions (world)
   int n_tilt;
   // env
   int frame_skip, max_steps, auto_reset, solver_iters, ls_iters, scale_actions, first_env_id;
   int obs_layout;                               // OdgEnvConfig::obs_layout
+  int task;                                     // OdgEnvConfig::task (0 walk, 1 jump: 3-joint-leg kernel only)
+  int obs_dim;                                  // walk: (obs_layout ? 12 : 9) + 3 nu; jump: 9 + nu
   float tol, ls_tol, noise;
   float key_qpos[kMaxNQ], key_ctrl[kMaxNU];
   float obs_joint_offset;                       // key_ctrl[0,7:] broadcast quirk (WalkEnvironment.py:116)
@@ -161,6 +174,8 @@ struct StepArgs {
   float* lin_vel_reward; float* reward_ctrl; float* terminal_obs; unsigned char* paws_in_ground;
   int* gait_reward; float* qacc; int* ncon; float* fn_sum; int* solver_iters; int* ls_evals;
   float* reward_raw;        // rewards - costs before the max(0, .) of WalkEnvironment.py:84
+  float* cfrc_ext;          // [N][1 + 4*njl][6] data.cfrc_ext of the robot's bodies (3-joint-leg kernel)
+  float* task_terms;        // [N][10] weighted reward / cost terms of the jump task (compute_rewards' reward_info)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -417,6 +432,72 @@ ODG_DEV void cone_line4(V3 z0, V3 dz, float Dn, float Dt, float mu, float fri, f
   }
 }
 
+// ---- condim-6 elliptic cone (sliding + torsional + rolling friction). z = (linear acceleration of the contact point,
+// angular acceleration of the geom's body), both in world axes minus their references; the plane's frame is
+// (n, t1, t2) = (+z, +y, -x), so the normal row is zl.z, the sliding rows zl.x / zl.y, the torsional row za.z and the
+// rolling rows za.x / za.y (the two sliding and the two rolling rows have equal coefficients: the signs and the order
+// within a pair do not matter). Index order here: 0,1 sliding, 2 normal, 3,4 rolling, 5 torsional.
+struct Cone6 { float sc[6], D[6]; float mu, Dm; };
+ODG_DEV Cone6 cone6_make(float Dn, float impratio, float mu, float fri, float dmk, float frt, float frr, float rt, float rr,
+                         int condim = 3) {
+  Cone6 k;
+  if (condim == 1) { fri = 0.f; impratio = 0.f; }            // frictionless: normal row only (see cone_eval)
+  k.sc[0] = fri; k.sc[1] = fri; k.sc[2] = mu; k.sc[3] = frr; k.sc[4] = frr; k.sc[5] = frt;
+  const float Dt = Dn * impratio;
+  k.D[0] = Dt; k.D[1] = Dt; k.D[2] = Dn; k.D[3] = Dn * rr; k.D[4] = Dn * rr; k.D[5] = Dn * rt;
+  k.mu = mu; k.Dm = Dn * dmk;
+  return k;
+}
+// gradient g (6) and Hessian H (6x6, symmetric, full storage) of the block's cost at z. Branch-free like cone_eval; a
+// row whose friction coefficient is 0 (condim 3 contact in the same kernel) has sc = D = 0 and drops out exactly.
+ODG_DEV void cone6_eval(const float (&z)[6], const Cone6& k, float (&g)[6], float (&H)[6][6]) {
+  float U[6];
+  ODG_UNROLL for (int i = 0; i < 6; i++) U[i] = z[i] * k.sc[i];
+  const float N = U[2], mu = k.mu;
+  const float T2 = U[0] * U[0] + U[1] * U[1] + U[3] * U[3] + U[4] * U[4] + U[5] * U[5];
+  const float iT = odg_rsqrt(fmaxf(T2, 1e-20f));
+  const float T = T2 * iT;
+  const bool top = N >= mu * T;
+  const bool bot = !top && (mu * N + T <= 0.f);
+  const bool mid = !top && !bot;
+  const float e = N - mu * T;
+  const float De = k.Dm * e, kap = -k.Dm * mu * e * iT;
+  float u[6], w[6];
+  ODG_UNROLL for (int i = 0; i < 6; i++) { u[i] = (i == 2) ? 0.f : U[i] * iT; w[i] = (i == 2) ? mu : -mu * u[i] * k.sc[i]; }
+  ODG_UNROLL for (int i = 0; i < 6; i++) g[i] = mid ? De * w[i] : (bot ? k.D[i] * z[i] : 0.f);
+  ODG_UNROLL for (int i = 0; i < 6; i++)
+    ODG_UNROLL for (int j = 0; j <= i; j++) {
+      // cone surface: Dm w w^T + kappa * S (I - u u^T) S on the tangential rows (PSD term by term, see cone_eval)
+      float hm = k.Dm * w[i] * w[j];
+      if (i != 2 && j != 2) hm += kap * k.sc[i] * k.sc[j] * ((i == j ? 1.f : 0.f) - u[i] * u[j]);
+      const float hb = (i == j) ? k.D[i] : 0.f;
+      const float h = mid ? hm : (bot ? hb : 0.f);
+      H[i][j] = h; H[j][i] = h;
+    }
+}
+template <int W>
+ODG_DEV void cone6_line(const float (&z0)[6], const float (&dz)[6], const Cone6& k, const float (&al)[W], float (&f)[W]) {
+  float cA = 0.f, cB = 0.f, cC = 0.f, qb1 = 0.f, qb2 = 0.f;
+  ODG_UNROLL for (int i = 0; i < 6; i++) {
+    qb1 += k.D[i] * z0[i] * dz[i]; qb2 += k.D[i] * dz[i] * dz[i];
+    if (i != 2) { const float a = z0[i] * k.sc[i], b = dz[i] * k.sc[i]; cA += a * a; cB += a * b; cC += b * b; }
+  }
+  const float N0 = z0[2] * k.mu, Nd = dz[2] * k.mu, mu = k.mu;
+  ODG_UNROLL for (int q = 0; q < W; q++) {
+    const float a = al[q];
+    const float N = N0 + a * Nd;
+    const float UV = cB + a * cC;
+    const float T2 = fmaxf(cA + a * (cB + UV), 0.f);
+    const float iT = odg_rsqrt(fmaxf(T2, 1e-20f));
+    const float T = T2 * iT, Td = UV * iT;
+    const float e = N - mu * T;
+    const float fmid = k.Dm * e * (Nd - mu * Td);
+    const float fbot = qb1 + a * qb2;
+    const bool bot = mu * N + T <= 0.f;
+    f[q] += e >= 0.f ? 0.f : (bot ? fbot : fmid);
+  }
+}
+
 // unrolled dense Cholesky solve of a 6x6 SPD system held in registers. S is overwritten by its factor.
 ODG_DEV void chol6_solve(float (&S)[6][6], float (&x)[6]) {
   ODG_UNROLL for (int j = 0; j < 6; j++) {
@@ -495,6 +576,9 @@ struct LastPass {
   float act[NJL];              // actuator forces
   Vec6 a_b; float a_l[NJL];    // qacc (trunk: linear, angular WORLD)
   int ncon, iters, ls_evals; float fn;
+  // mj_rnePostConstraint's cfrc_ext of this leg's bodies, [torque about the whole robot's centre of mass, force] in
+  // world axes, and this lane's share of the trunk's (3-joint legs only: the Go1 task rewards read them)
+  float cfrc[NJL == 3 ? NJL + 1 : 1][6];
 };
 
 #define LCF(f, j) s_lc[((j) * LC_COUNT + (f)) * 4 + leg]
@@ -639,6 +723,11 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
   // ------------------------------------------------------------------ collision: floor plane vs hulls
   V3 c_r[kMaxConLeg], c_aref[kMaxConLeg], c_z0[kMaxConLeg], c_dz[kMaxConLeg];     // cone rows of this leg's contacts
   float c_Dn[kMaxConLeg]; int c_slot[kMaxConLeg];
+  // 3-joint legs (Go1): every contact carries the three angular rows of condim 6 as well (torsional + rolling friction,
+  // go1.xml:61-64); contacts of condim-3 geoms have zero coefficients there and reduce to the 3-row cone exactly
+  constexpr bool kG = (NJL == 3);
+  constexpr int kConA = kG ? kMaxConLeg : 1;
+  V3 c_arefa[kConA], c_z0a[kConA], c_dza[kConA];
   int nc = 0;
   int foot_last = -1;
   auto add_contact = [&](float px, float py, float pz_mid, float dist, int s) {
@@ -653,6 +742,69 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     M3 Rl = R[0]; V3 pl = pos[0];
     ODG_UNROLL for (int j = 1; j < NJL; j++) if (link == j) { Rl = R[j]; pl = pos[j]; }
     const float margin = C.slot_margin[s];
+    if constexpr (kG) {
+      if (C.per_lane_geoms) {
+        // Primitive colliders against the plane (go1.xml:26-64): the lane's own geom of this slot. Trunk colliders
+        // (link -1) are dealt out over the four lanes. Restates mjc_PlaneSphere / PlaneCapsule / PlaneCylinder / PlaneBox
+        // (oracle/odg_oracle.c: odgo_collision holds the same rules in double).
+        if (link < 0) { Rl = R0; pl = mk3(0.f, 0.f, 0.f); }
+        const int type = (int)GCF(GC_TYPE, s);
+        if (type == PRIM_NONE) continue;
+        const V3 cc = pl + mul(Rl, mk3(GCF(GC_CX, s), GCF(GC_CY, s), GCF(GC_CZ, s)));
+        const float s0 = GCF(GC_S0, s), s1 = GCF(GC_S1, s), s2 = GCF(GC_S2, s);
+        const float cz = bp.z + cc.z;
+        if (cz - (s0 + s1 + s2) > margin) continue;              // (cull: no primitive reaches further than the sum of its sizes)
+        if (type == PRIM_SPHERE) {
+          const float dist = cz - s0;
+          if (dist <= margin) add_contact(cc.x, cc.y, cc.z - s0 - 0.5f * dist, dist, s);
+          continue;
+        }
+        M3 Gm; ODG_UNROLL for (int k = 0; k < 9; k++) Gm.m[k] = GCF(GC_R0 + k, s);
+        const M3 Mw = mul(Rl, Gm);
+        if (type == PRIM_CAPSULE) {
+          const V3 axc = col(Mw, 2);
+          for (int e = 0; e < 2; e++) {                          // +axis end first
+            const V3 pe = cc + ((e ? -s1 : s1) * axc);
+            const float dist = bp.z + pe.z - s0;
+            if (dist <= margin) add_contact(pe.x, pe.y, pe.z - s0 - 0.5f * dist, dist, s);
+          }
+        } else if (type == PRIM_BOX) {
+          int cnt = 0;
+          for (int i = 0; i < 8 && cnt < 4; i++) {                // corners in index order, the first four that qualify
+            const V3 cr = mul(Mw, mk3((i & 1) ? s0 : -s0, (i & 2) ? s1 : -s1, (i & 4) ? s2 : -s2));
+            if (cz + cr.z > margin || cr.z > 0.f) continue;
+            const float dist = cz + cr.z;
+            add_contact(cc.x + cr.x, cc.y + cr.y, cc.z + cr.z - 0.5f * dist, dist, s);
+            cnt++;
+          }
+        } else {                                                  // cylinder
+          V3 axc = col(Mw, 2);
+          float prjaxis = axc.z;
+          if (prjaxis > 0.f) { axc = -axc; prjaxis = -prjaxis; }
+          V3 vec = mk3(axc.x * prjaxis, axc.y * prjaxis, axc.z * prjaxis - 1.f);
+          const float len2 = dot(vec, vec);
+          if (len2 >= 1e-30f) vec = (s0 * odg_rsqrt(len2)) * vec; else vec = s0 * col(Mw, 0);
+          const float prjvec = vec.z, prjaxs = prjaxis * s1;
+          const V3 axs = s1 * axc;
+          const float d1 = cz + prjaxs + prjvec;
+          if (d1 <= margin) {
+            add_contact(cc.x + vec.x + axs.x, cc.y + vec.y + axs.y, cc.z + vec.z + axs.z - 0.5f * d1, d1, s);
+            const float d2 = cz - prjaxs + prjvec;
+            if (d2 <= margin) add_contact(cc.x + vec.x - axs.x, cc.y + vec.y - axs.y, cc.z + vec.z - axs.z - 0.5f * d2, d2, s);
+            const float d3 = cz + prjaxs - 0.5f * prjvec;
+            if (d3 <= margin) {
+              V3 v1 = cross(vec, axc);
+              const float l2 = dot(v1, v1);
+              v1 = (l2 > 0.f ? s0 * 0.8660254037844386f * odg_rsqrt(l2) : 0.f) * v1;
+              const V3 pm = cc + axs - 0.5f * vec;
+              add_contact(pm.x + v1.x, pm.y + v1.y, pm.z + v1.z - 0.5f * d3, d3, s);
+              add_contact(pm.x - v1.x, pm.y - v1.y, pm.z - v1.z - 0.5f * d3, d3, s);
+            }
+          }
+        }
+        continue;
+      }
+    }
     const float zoff = bp.z + pl.z;
     if (C.slot_type[s] == 1) {                     // sphere
       V3 cc = pl + mul(Rl, mk3(GCF(GC_CX, s), GCF(GC_CY, s), GCF(GC_CZ, s)));
@@ -761,6 +913,14 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       vc = vc + (on * qd[j]) * cross(ax[j], r - anc[j]);
     }
     c_aref[c] = mk3(-Bc * vc.x, -Bc * vc.y, -Bc * vc.z - Kc * imp * (dist - margin));
+    if constexpr (kG) {                             // torsional / rolling rows: aref = -B * (angular velocity of the body)
+      V3 wb = w0;
+      ODG_UNROLL for (int j = 0; j < NJL; j++) {
+        const float on = fminf(fmaxf((float)(link - j + 1), 0.f), 1.f);
+        wb = wb + (on * qd[j]) * ax[j];
+      }
+      c_arefa[c] = mk3(-Bc * wb.x, -Bc * wb.y, -Bc * wb.z);
+    }
   }
   // own-joint friction-loss and limit rows
   float aref_fl[NJL], lim_sgn[NJL], lim_aref[NJL], lim_D[NJL];
@@ -864,8 +1024,55 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       }
       V3 z = ap - c_aref[c];
       c_z0[c] = z;
-      V3 g; S3 H;
       const float Dn = c_Dn[c];
+      if constexpr (kG) {
+        // 6-row block: linear rows through the contact point's Jacobian (column of DoF d: cl_d), angular rows through
+        // the body's rotational Jacobian (column ca_d): trunk translation (e_i, 0), trunk rotation (e_k x r, e_k),
+        // joint j (cj[j], ax[j]) when the joint is above the contact's link
+        V3 aj[NJL];
+        V3 alb = a_b.w;
+        ODG_UNROLL for (int j = 0; j < NJL; j++) {
+          aj[j] = (j <= link) ? ax[j] : mk3(0.f, 0.f, 0.f);
+          alb = alb + a_l[j] * aj[j];
+        }
+        const V3 za = alb - c_arefa[c];
+        c_z0a[c] = za;
+        const Cone6 K6 = cone6_make(Dn, C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_frt[s], C.slot_frr[s],
+                                    C.slot_dt_tor[s], C.slot_dt_roll[s], C.slot_condim[s]);
+        const float z6[6] = { z.x, z.y, z.z, za.x, za.y, za.z };
+        float g6[6], H6[6][6];
+        cone6_eval(z6, K6, g6, H6);
+        const V3 gL = mk3(g6[0], g6[1], g6[2]), gA = mk3(g6[3], g6[4], g6[5]);
+        gb.t = gb.t + gL; gb.w = gb.w + cross(r, gL) + gA;
+        auto HLL = [&](V3 v) { return mk3(H6[0][0] * v.x + H6[0][1] * v.y + H6[0][2] * v.z, H6[1][0] * v.x + H6[1][1] * v.y + H6[1][2] * v.z,
+                                          H6[2][0] * v.x + H6[2][1] * v.y + H6[2][2] * v.z); };
+        auto HLA = [&](V3 v) { return mk3(H6[0][3] * v.x + H6[0][4] * v.y + H6[0][5] * v.z, H6[1][3] * v.x + H6[1][4] * v.y + H6[1][5] * v.z,
+                                          H6[2][3] * v.x + H6[2][4] * v.y + H6[2][5] * v.z); };
+        auto HAL = [&](V3 v) { return mk3(H6[3][0] * v.x + H6[3][1] * v.y + H6[3][2] * v.z, H6[4][0] * v.x + H6[4][1] * v.y + H6[4][2] * v.z,
+                                          H6[5][0] * v.x + H6[5][1] * v.y + H6[5][2] * v.z); };
+        auto HAA = [&](V3 v) { return mk3(H6[3][3] * v.x + H6[3][4] * v.y + H6[3][5] * v.z, H6[4][3] * v.x + H6[4][4] * v.y + H6[4][5] * v.z,
+                                          H6[5][3] * v.x + H6[5][4] * v.y + H6[5][5] * v.z); };
+        Htt.xx += H6[0][0]; Htt.xy += H6[0][1]; Htt.xz += H6[0][2]; Htt.yy += H6[1][1]; Htt.yz += H6[1][2]; Htt.zz += H6[2][2];
+        // trunk rotation k: linear column X_k = e_k x r, angular column e_k
+        const V3 Xk[3] = { mk3(0.f, -r.z, r.y), mk3(r.z, 0.f, -r.x), mk3(-r.y, r.x, 0.f) };
+        const V3 Ek[3] = { mk3(1.f, 0.f, 0.f), mk3(0.f, 1.f, 0.f), mk3(0.f, 0.f, 1.f) };
+        V3 hL[3], hA[3];                             // H * column k: linear / angular parts
+        ODG_UNROLL for (int k = 0; k < 3; k++) { hL[k] = HLL(Xk[k]) + HLA(Ek[k]); hA[k] = HAL(Xk[k]) + HAA(Ek[k]); }
+        ODG_UNROLL for (int k = 0; k < 3; k++) { Htw[0][k] += hL[k].x; Htw[1][k] += hL[k].y; Htw[2][k] += hL[k].z; }
+        Hww.xx += dot(Xk[0], hL[0]) + hA[0].x; Hww.xy += dot(Xk[0], hL[1]) + hA[1].x; Hww.xz += dot(Xk[0], hL[2]) + hA[2].x;
+        Hww.yy += dot(Xk[1], hL[1]) + hA[1].y; Hww.yz += dot(Xk[1], hL[2]) + hA[2].y; Hww.zz += dot(Xk[2], hL[2]) + hA[2].z;
+        ODG_UNROLL for (int j = 0; j < NJL; j++) {
+          const V3 hcL = HLL(cj[j]) + HLA(aj[j]), hcA = HAL(cj[j]) + HAA(aj[j]);
+          g_l[j] += dot(cj[j], gL) + dot(aj[j], gA);
+          Hlb[j].t = Hlb[j].t + hcL; Hlb[j].w = Hlb[j].w + cross(r, hcL) + hcA;
+          ODG_UNROLL for (int i = 0; i <= j; i++) {
+            float v = dot(cj[i], hcL) + dot(aj[i], hcA);
+            Hll[j][i] += v; if (i != j) Hll[i][j] += v;
+          }
+        }
+        continue;
+      }
+      V3 g; S3 H;
       cone_eval(z, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
       // (separated rows and rows with D = 0 come back as g = 0, H = 0 and add exactly 0 below)
       gb.t = gb.t + g; gb.w = gb.w + cross(r, g);
@@ -973,6 +1180,14 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         dz = dz + (on * p_l[j]) * cross(ax[j], r - anc[j]);
       }
       c_dz[c] = dz;
+      if constexpr (kG) {
+        V3 dza = p_b.w;
+        ODG_UNROLL for (int j = 0; j < NJL; j++) {
+          const float on = fminf(fmaxf((float)(link - j + 1), 0.f), 1.f);
+          dza = dza + (on * p_l[j]) * ax[j];
+        }
+        c_dza[c] = dza;
+      }
     }
     const float bf_zt = dot(bf_e, a_b.t) - bf_aref_t, bf_dzt = dot(bf_e, p_b.t);
     const float bf_zr = dot(bf_c, a_b.w) - bf_aref_r, bf_dzr = dot(bf_c, p_b.w);
@@ -1003,6 +1218,14 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       ODG_NO_UNROLL for (int c = 0; c < nc; c++) {               // (a row with D = 0 adds exactly 0: no skip, no branch)
         const int s = c_slot[c];
         const float Dn = c_Dn[c];
+        if constexpr (kG) {
+          const Cone6 K6 = cone6_make(Dn, C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_frt[s], C.slot_frr[s],
+                                      C.slot_dt_tor[s], C.slot_dt_roll[s], C.slot_condim[s]);
+          const V3 zl = c_z0[c], za = c_z0a[c], dl = c_dz[c], da = c_dza[c];
+          const float z6[6] = { zl.x, zl.y, zl.z, za.x, za.y, za.z }, d6[6] = { dl.x, dl.y, dl.z, da.x, da.y, da.z };
+          cone6_line<LW>(z6, d6, K6, al, f);
+          continue;
+        }
         cone_line4<LW>(c_z0[c], c_dz[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], al, f);
       }
       ODG_UNROLL for (int k = 0; k < LW; k++) f[k] = grp_sum(f[k], gm);
@@ -1104,6 +1327,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     out.ncon = nc; out.iters = iters; out.ls_evals = ls_evals; out.R_last = R[NJL - 1];
     out.foot_contact = foot_last >= 0 ? 1 : 0;
     out.foot_force = mk3(0.f, 0.f, 0.f);
+    if constexpr (kG) { ODG_UNROLL for (int q = 0; q <= NJL; q++) ODG_UNROLL for (int k = 0; k < 6; k++) out.cfrc[q][k] = 0.f; }
     float fn = 0.f;
     for (int c = 0; c < nc; c++) {
       const int s = c_slot[c];
@@ -1114,7 +1338,28 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       V3 ap = a_b.t + cross(a_b.w, r);
       ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) ap = ap + a_l[j] * cross(ax[j], r - anc[j]);
       V3 g; S3 H;
-      cone_eval(ap - c_aref[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
+      if constexpr (kG) {
+        V3 alb = a_b.w;
+        ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) alb = alb + a_l[j] * ax[j];
+        const V3 zl = ap - c_aref[c], za = alb - c_arefa[c];
+        const Cone6 K6 = cone6_make(Dn, C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_frt[s], C.slot_frr[s],
+                                    C.slot_dt_tor[s], C.slot_dt_roll[s], C.slot_condim[s]);
+        const float z6[6] = { zl.x, zl.y, zl.z, za.x, za.y, za.z };
+        float g6[6], H6[6][6];
+        cone6_eval(z6, K6, g6, H6);
+        g = mk3(g6[0], g6[1], g6[2]);
+        // wrench on the body: force -gL at the contact point, torque -gA; moved to the robot's centre of mass
+        const V3 fw = -g, tw = mk3(-g6[3], -g6[4], -g6[5]);
+        const V3 arm = r - odg_fdiv_rn(1.f, T.m) * T.h;
+        const V3 tq = tw + cross(arm, fw);
+        const int b = link < 0 ? NJL : link;
+        ODG_UNROLL for (int q = 0; q <= NJL; q++) if (q == b) {
+          out.cfrc[q][0] += tq.x; out.cfrc[q][1] += tq.y; out.cfrc[q][2] += tq.z;
+          out.cfrc[q][3] += fw.x; out.cfrc[q][4] += fw.y; out.cfrc[q][5] += fw.z;
+        }
+      } else {
+        cone_eval(ap - c_aref[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
+      }
       fn += -g.z;
       if (c == foot_last) out.foot_force = mk3(-g.z, -g.y, g.x);   // MuJoCo frame: n=+z, t1=+y, t2=-x
     }
@@ -1237,7 +1482,9 @@ ODG_DEV StepResult env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, c
                             const float* action, int env, int leg, unsigned gm, float* ODG_RESTRICT s_red) {
   const int N = P.N;
   const bool real = env < P.n;                     // padding environments never touch caller-owned buffers
-  const int obs_dim = (C.obs_layout ? 12 : 9) + 3 * C.nu;
+  const int obs_dim = C.obs_dim;
+  constexpr bool kG = (NJL == 3);
+  const bool jump = kG && C.task == 1;             // JumpEnvironmentV0 (environments/JumpEnvironment.py) on the Go1 model
   // ---- load
   V3 bp = mk3(P.qpos[0 * N + env], P.qpos[1 * N + env], P.qpos[2 * N + env]);
   float bq[4] = { P.qpos[3 * N + env], P.qpos[4 * N + env], P.qpos[5 * N + env], P.qpos[6 * N + env] };
@@ -1303,6 +1550,18 @@ ODG_DEV StepResult env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, c
   auto write_obs = [&](float* o, V3 v, V3 wl, const float (&quat)[4], const float (&qq)[NJL], const float (&qqd)[NJL],
                        const float (&la)[NJL]) {
     if (!o) return;
+    if (jump) {
+      // JumpEnvironment.py:95-117: [0.3 - x, 0.3 - z, v (3), v_z, projected_gravity (3), utils.last_action (12)], all
+      // scales 1. utils.last_action is never written by the environment (it stores self._last_action instead), so the
+      // last 12 entries are the zeros of its constructor.
+      if (leg == 0) {
+        o[0] = clip(0.3f - bp.x); o[1] = clip(0.3f - bp.z);
+        o[2] = clip(v.x); o[3] = clip(v.y); o[4] = clip(v.z); o[5] = clip(v.z);
+        float pg[3]; projected_gravity(C, quat, pg); o[6] = pg[0]; o[7] = pg[1]; o[8] = pg[2];
+      }
+      ODG_UNROLL for (int j = 0; j < NJL; j++) o[9 + leg * NJL + j] = 0.f;
+      return;
+    }
     if (leg == 0) {
       o[0] = clip(v.x * 2.0f); o[1] = clip(v.y * 2.0f); o[2] = clip(v.z * 2.0f);
       o[3] = clip(wl.x * 0.25f); o[4] = clip(wl.y * 0.25f); o[5] = clip(wl.z * 0.25f);
@@ -1373,11 +1632,54 @@ ODG_DEV StepResult env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, c
   const double rate = fresh ? rate_d : (double)rate_f;
   const double ycost = fabs((double)bp.y);
   const double costs = jc * 0.1 + rate * 0.01 + ycost;
-  const double rr = rewards - costs;
-  const float reward = (float)(rr > 0.0 ? rr : 0.0);
+  double rr = rewards - costs;
   const bool healthy = finite && (-lim < roll && roll < lim) && (-lim < pitch && pitch < lim) && (-lim < yaw && yaw < lim);
-  const bool terminated = !healthy;
+  bool terminated = !healthy;
   const bool truncated = step >= C.max_steps;
+  if constexpr (kG) {
+    if (jump) {
+      // JumpEnvironmentRewardCalc.compute_rewards (rewards/jump_environment_reward_calc.py:55-150), in double like the
+      // reference, term by term in its order of evaluation; static_stability (:140-150) for termination.
+      float c2 = 0.f;                                // ||cfrc_ext[[2,3,5,6,8,9,11,12]]||_F^2: hips and thighs of all legs
+      ODG_UNROLL for (int b = 0; b < 2; b++) ODG_UNROLL for (int k = 0; k < 6; k++) c2 += lp.cfrc[b][k] * lp.cfrc[b][k];
+      c2 = grp_sum(c2, gm);
+      const double x = (double)bp.x, y = (double)bp.y, z = (double)bp.z;
+      const double dx = 1.0 - x, dy = 0.0 - y;
+      const double dist = sqrt(dx * dx + dy * dy);
+      const double cube_h = 0.5;
+      const double t_lp = (z >= cube_h ? exp(-dist) : 0.0) * 3.0;
+      double jr = 0, jp = 0, jy = 0;
+      if (finite) euler_from_quat((double)bq[0], (double)bq[1], (double)bq[2], (double)bq[3], jr, jp, jy);
+      const double t_lo = exp(-(fabs(jr) + fabs(jp) + fabs(jy))) * 2.0;
+      const double vx = (double)bv.x, vy = (double)bv.y, vz = (double)bv.z;
+      const double t_cv = exp(-sqrt(vx * vx + vy * vy)) * 1.0;
+      const double t_hc = (z - cube_h > 0.0 ? z - cube_h : 0.0) * .2;
+      const double t_ps = -0.0 * 0.8;                // feet_air_time is never advanced by this calculator
+      const double e0 = (double)desvel.x - vx, e1 = (double)desvel.y - vy, e2 = (double)desvel.z - vz;
+      const double t_jv = exp(-((e0 * e0 + e1 * e1) + e2 * e2) / 0.45) * 1.0;
+      const double jrew = ((((t_lp + t_lo) + t_cv) + t_hc) + t_ps) + t_jv;
+      const double t_dl = (z < cube_h ? exp(dist) : 0.0) * 2.0;
+      const double t_vv = (z >= cube_h ? vz * vz : 0.0) * 1.5;
+      const double t_ob = (dist > 1.0 ? 1.0 : 0.0) * 3.0;
+      const double t_cc = (sqrtf(c2) > 0.1f ? 1.0 : 0.0) * 1.0;
+      const double jcost = ((t_dl + t_vv) + t_ob) + t_cc;
+      rr = jrew - jcost;
+      const double l20 = 20.0 * 3.14159265358979323846 / 180.0;
+      terminated = !(finite && (-l20 <= jy && jy <= l20) && (-l20 <= jr && jr <= l20));
+      if (A.want_info && A.task_terms && real && leg == 0) {
+        float* o = A.task_terms + (size_t)env * 10;
+        o[0] = (float)t_lp; o[1] = (float)t_lo; o[2] = (float)t_cv; o[3] = (float)t_hc; o[4] = (float)t_ps;
+        o[5] = (float)t_jv; o[6] = (float)t_dl; o[7] = (float)t_vv; o[8] = (float)t_ob; o[9] = (float)t_cc;
+      }
+    }
+    if (A.want_info && A.cfrc_ext && real) {
+      // body order of the MuJoCo model: trunk, then (hip, thigh, calf) per leg; the trunk row sums the four lanes' shares
+      float* o = A.cfrc_ext + (size_t)env * (1 + 4 * NJL) * 6;
+      ODG_UNROLL for (int b = 0; b < NJL; b++) ODG_UNROLL for (int k = 0; k < 6; k++) o[(1 + leg * NJL + b) * 6 + k] = lp.cfrc[b][k];
+      ODG_UNROLL for (int k = 0; k < 6; k++) { const float t = grp_sum(lp.cfrc[NJL][k], gm); if (leg == 0) o[k] = t; }
+    }
+  }
+  const float reward = (float)(rr > 0.0 ? rr : 0.0);
   // ---- info
   if (A.want_info && real) {
     if (A.paw_forces) {
@@ -1484,7 +1786,8 @@ template <int NJL>
 ODG_DEV void env_reset(const DevConst& C, const float* ODG_RESTRICT s_lc, const SimPtrs& P, float* obs_out,
                        int env, int leg, unsigned gm) {
   const int N = P.N;
-  const int obs_dim = (C.obs_layout ? 12 : 9) + 3 * C.nu;
+  const int obs_dim = C.obs_dim;
+  const bool jump = (NJL == 3) && C.task == 1;
   const unsigned episode = P.episode[env];
   grp_sync(gm);                                    // all lanes read the counter before lane 0 bumps it
   const uint32_t gid = (uint32_t)(C.first_env_id + env);
@@ -1507,7 +1810,8 @@ ODG_DEV void env_reset(const DevConst& C, const float* ODG_RESTRICT s_lc, const 
     P.qvel[(6 + leg * NJL + j) * N + env] = 0.f;
     P.warm[(6 + leg * NJL + j) * N + env] = 0.f;
     if (LCF(LC_HASACT, j) != 0.f) P.last_action[(int)LCF(LC_UIDX, j) * N + env] = 0.f;
-    if (obs) {
+    if (obs && jump) obs[9 + leg * NJL + j] = 0.f;
+    else if (obs) {
       obs[ob + leg * NJL + j] = clip(kq[qi] - (C.obs_layout ? LCF(LC_HOMEQ, j) : C.obs_joint_offset));
       obs[ob + C.nu + leg * NJL + j] = 0.f;
       if (LCF(LC_HASACT, j) != 0.f) obs[ob + 2 * C.nu + (int)LCF(LC_UIDX, j)] = 0.f;
@@ -1517,7 +1821,13 @@ ODG_DEV void env_reset(const DevConst& C, const float* ODG_RESTRICT s_lc, const 
     for (int i = 0; i < 7; i++) P.qpos[i * N + env] = kq[i];
     for (int i = 0; i < 6; i++) { P.qvel[i * N + env] = 0.f; P.warm[i * N + env] = 0.f; }
     P.step[env] = 0; P.fresh[env] = 1; P.episode[env] = episode + 1;
-    if (obs) {
+    if (obs && jump) {                               // JumpEnvironment.py:95-117 at zero velocity
+      obs[0] = clip(0.3f - kq[0]); obs[1] = clip(0.3f - kq[2]);
+      for (int i = 2; i < 6; i++) obs[i] = 0.f;
+      const float quat[4] = { kq[3], kq[4], kq[5], kq[6] };
+      float pg[3]; projected_gravity(C, quat, pg);
+      for (int i = 0; i < 3; i++) obs[6 + i] = pg[i];
+    } else if (obs) {
       for (int i = 0; i < 6; i++) obs[i] = 0.f;
       if (C.obs_layout) {
         const float quat[4] = { kq[3], kq[4], kq[5], kq[6] };
@@ -1538,8 +1848,14 @@ ODG_DEV void env_init(const DevConst& C, const SimPtrs& P, int env) {
   for (int u = 0; u < C.nu; u++) P.last_action[u * N + env] = 0.f;
   uint32_t r[4];
   philox4x32(C.seed_lo, C.seed_hi, (uint32_t)(C.first_env_id + env), 0u, 0u, kStreamDesvel, r);
-  P.desvel[0 * N + env] = odg_fadd_rn(0.5f, odg_fmul_rn(0.5f, u01(r[0])));
-  P.desvel[1 * N + env] = 0.f; P.desvel[2 * N + env] = 0.f;
+  if (C.task == 1) {      // jump_environment_reward_calc.py:33-35: U([1.20, -0, 1.20], [1.25, 0, 1.25]), sampled once
+    P.desvel[0 * N + env] = odg_fadd_rn(1.20f, odg_fmul_rn(0.05f, u01(r[0])));
+    P.desvel[1 * N + env] = 0.f;
+    P.desvel[2 * N + env] = odg_fadd_rn(1.20f, odg_fmul_rn(0.05f, u01(r[1])));
+  } else {
+    P.desvel[0 * N + env] = odg_fadd_rn(0.5f, odg_fmul_rn(0.5f, u01(r[0])));
+    P.desvel[1 * N + env] = 0.f; P.desvel[2 * N + env] = 0.f;
+  }
   P.step[env] = 0; P.gait_idx[env] = 0; P.gait_cnt[env] = 0; P.episode[env] = 0u; P.fresh[env] = 1;
 }
 

@@ -173,11 +173,31 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
   for (int i = 0; i < m.nq; i++) C.key_qpos[i] = (float)m.key_qpos[i];
   C.obs_joint_offset = (float)m.key_ctrl[m.nu - 1];       // key_ctrl[0, 7:] (WalkEnvironment.py:116)
   // collision slots: every leg must carry the same sequence of (link, type)
+  // per_leg[l][s] = model geom of lane l in slot s, or -1 (empty). Hull / sphere models (OpenDOG; Go1 feet only): every
+  // leg carries the same sequence. Models with primitive or trunk colliders (unitree_go1/go1.xml:26-64): slots are
+  // aligned link by link (a leg with fewer geoms on a link gets empty slots), and the trunk's colliders are dealt out
+  // over the four lanes in further slots with link -1; type and presence then come from the per-lane GC_TYPE table.
   std::vector<int> per_leg[4];
-  for (int g = 0; g < m.ngeom; g++) {
-    if (m.geom[g].leg < 0) return "trunk collision geoms are not supported by the kernel yet";
-    per_leg[m.geom[g].leg].push_back(g);
+  bool per_lane = false;
+  for (int g = 0; g < m.ngeom; g++)
+    if (m.geom[g].leg < 0 || m.geom[g].type >= ODG_GEOM_CAPSULE) per_lane = true;
+  if (!per_lane) {
+    for (int g = 0; g < m.ngeom; g++) per_leg[m.geom[g].leg].push_back(g);
+  } else {
+    if (m.njl != 3) return "primitive / trunk colliders are compiled into the 3-joint-leg kernel only";
+    for (int g = 0; g < m.ngeom; g++) if (m.geom[g].type == ODG_GEOM_HULL) return "hulls and primitive colliders cannot be mixed";
+    for (int link = 0; link < m.njl; link++) {
+      std::vector<int> on[4]; size_t n = 0;
+      for (int g = 0; g < m.ngeom; g++) if (m.geom[g].leg >= 0 && m.geom[g].link == link) on[m.geom[g].leg].push_back(g);
+      for (int l = 0; l < 4; l++) n = on[l].size() > n ? on[l].size() : n;
+      for (size_t k = 0; k < n; k++) for (int l = 0; l < 4; l++) per_leg[l].push_back(k < on[l].size() ? on[l][k] : -1);
+    }
+    std::vector<int> trunk;
+    for (int g = 0; g < m.ngeom; g++) if (m.geom[g].leg < 0) trunk.push_back(g);
+    for (size_t i = 0; i < trunk.size(); i += 4)
+      for (int l = 0; l < 4; l++) per_leg[l].push_back(i + l < trunk.size() ? trunk[i + l] : -1);
   }
+  C.per_lane_geoms = per_lane ? 1 : 0;
   const int nslot = (int)per_leg[0].size();
   if (nslot > kMaxSlot) return "too many collision geoms per leg";
   for (int l = 1; l < 4; l++) if ((int)per_leg[l].size() != nslot) return "legs differ in collision geoms";
@@ -185,13 +205,27 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
   out->gc.assign((size_t)(nslot > 0 ? nslot : 1) * GC_COUNT * 4, 0.f);
   int rows = 0;
   for (int s = 0; s < nslot; s++) {
-    const OdgGeom& g0 = m.geom[per_leg[0][s]];
+    int first = -1;
+    for (int l = 0; l < 4; l++) if (first < 0 && per_leg[l][s] >= 0) first = per_leg[l][s];
+    const OdgGeom& g0 = m.geom[first];
     int nv = 0;
     for (int l = 0; l < 4; l++) {
+      if (per_leg[l][s] < 0) continue;                 // empty slot on this lane: GC_TYPE stays 0
       const OdgGeom& g = m.geom[per_leg[l][s]];
-      if (g.link != g0.link || g.type != g0.type || g.condim != g0.condim || g.friction != g0.friction ||
-          g.margin != g0.margin) return "legs differ in collision geom parameters";
-      if (g.condim != 1 && g.condim != 3) return "contact condim must be 1 or 3";
+      if (g.link != g0.link || (!per_lane && g.type != g0.type) || g.condim != g0.condim || g.friction != g0.friction ||
+          g.friction_torsion != g0.friction_torsion || g.friction_roll != g0.friction_roll || g.margin != g0.margin)
+        return "legs differ in collision geom parameters";
+      for (int k = 0; k < 2; k++) if (g.solref[k] != g0.solref[k]) return "legs differ in collision geom parameters";
+      for (int k = 0; k < 5; k++) if (g.solimp[k] != g0.solimp[k]) return "legs differ in collision geom parameters";
+      if (g.condim != 1 && g.condim != 3 && !(g.condim == 6 && m.njl == 3))
+        return "contact condim must be 1 or 3 (6 in the 3-joint-leg kernel)";
+      if (per_lane) {
+        auto G = [&](int f) -> float& { return out->gc[((size_t)s * GC_COUNT + f) * 4 + l]; };
+        G(GC_TYPE) = (float)(g.type + 1);
+        for (int k = 0; k < 9; k++) G(GC_R0 + k) = (float)g.rot[k];
+        for (int k = 0; k < 3; k++) G(GC_S0 + k) = (float)g.size[k];
+        if (g.type == ODG_GEOM_SPHERE) G(GC_S0) = (float)g.radius;
+      }
       nv = g.vert_count > nv ? g.vert_count : nv;
       out->gc[((size_t)s * GC_COUNT + GC_INVW) * 4 + l] = (float)g.invweight0;
       out->gc[((size_t)s * GC_COUNT + GC_CX) * 4 + l] = (float)g.center[0];
@@ -216,19 +250,25 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
     C.slot_link[s] = g0.link; C.slot_type[s] = g0.type; C.slot_nvert[s] = nv; C.slot_vstart[s] = rows;
     C.slot_condim[s] = g0.condim;
     // reward_calc:93 body_feet_indices = [4, 7, 10, 13]: the last body of each leg chain
-    C.slot_isfoot[s] = (g0.mj_body_id == 1 + (njl + 1)) ? 1 : 0;
+    C.slot_isfoot[s] = (g0.leg >= 0 && g0.mj_body_id == 4 + 3 * g0.leg) ? 1 : 0;
     C.slot_margin[s] = (float)g0.margin; C.slot_radius[s] = (float)g0.radius;
     double K, B; solref_kb(m, g0.solref, g0.solimp, &K, &B);
     C.slot_K[s] = (float)K; C.slot_B[s] = (float)B; pack_imp(g0.solimp, C.slot_imp[s]);
     C.slot_fri[s] = (float)g0.friction;
     C.slot_mu[s] = (float)(g0.friction / std::sqrt(std::fmax(1e-15, m.impratio)));
     { const double mu = (double)C.slot_mu[s]; C.slot_dmk[s] = (float)(1.0 / std::fmax(1e-30, mu * mu * (1.0 + mu * mu))); }
+    if (g0.condim == 6) {                            // torsional / rolling rows: R_row = R_slide * mu_slide^2 / mu_row^2
+      const double f0 = std::fmax(1e-5, g0.friction), ft = std::fmax(1e-5, g0.friction_torsion), fr = std::fmax(1e-5, g0.friction_roll);
+      C.slot_frt[s] = (float)ft; C.slot_frr[s] = (float)fr;
+      C.slot_dt_tor[s] = (float)(m.impratio * ft * ft / (f0 * f0)); C.slot_dt_roll[s] = (float)(m.impratio * fr * fr / (f0 * f0));
+    }
     rows += nv;
   }
   C.nvert_rows = rows;
   out->vert.assign((size_t)(rows > 0 ? rows : 1) * 16, 0.f);
   for (int s = 0; s < nslot; s++)
     for (int l = 0; l < 4; l++) {
+      if (per_leg[l][s] < 0) continue;
       const OdgGeom& g = m.geom[per_leg[l][s]];
       for (int k = 0; k < C.slot_nvert[s]; k++) {
         int src = g.vert_count > 0 ? g.vert_start + (k < g.vert_count ? k : g.vert_count - 1) : -1;
@@ -246,7 +286,8 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
     std::vector<int> table((size_t)(nslot > 0 ? nslot : 1) * kSupportCells * 4, 0);
     std::vector<unsigned char> idx;
     for (int s = 0; s < nslot; s++) for (int l = 0; l < 4; l++) {
-      const OdgGeom& g = m.geom[per_leg[l][s]];
+      static const OdgGeom kEmpty = OdgGeom();
+      const OdgGeom& g = per_leg[l][s] >= 0 ? m.geom[per_leg[l][s]] : kEmpty;
       if (g.vert_count > 255) return "hull too large for the support-vertex candidate lists";
       double ext = 0.0;
       for (int k = 0; k < g.vert_count; k++) for (int c = 0; c < 3; c++) ext = std::fmax(ext, std::fabs(m.vert[g.vert_start + k][c]));
@@ -281,6 +322,10 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
   C.frame_skip = cfg.frame_skip; C.max_steps = cfg.max_episode_steps; C.auto_reset = cfg.auto_reset;
   C.solver_iters = cfg.solver_iterations; C.ls_iters = cfg.ls_iterations; C.scale_actions = cfg.scale_actions;
   C.obs_layout = cfg.obs_layout ? 1 : 0;
+  if (cfg.task != ODG_TASK_WALK && cfg.task != ODG_TASK_JUMP) return "unknown task";
+  if (cfg.task == ODG_TASK_JUMP && m.njl != 3) return "the jump task is defined on the 12-actuator (3 joints per leg) model";
+  C.task = cfg.task;
+  C.obs_dim = cfg.task == ODG_TASK_JUMP ? 9 + m.nu : (C.obs_layout ? 12 : 9) + 3 * m.nu;
   C.first_env_id = cfg.first_env_id; C.tol = cfg.solver_tolerance; C.ls_tol = cfg.ls_tolerance; C.noise = cfg.reset_noise_scale;
   C.seed_lo = (uint32_t)seed; C.seed_hi = (uint32_t)(seed >> 32);
   if (cfg.frame_skip < 1 || cfg.solver_iterations < 1 || cfg.ls_iterations < 1) return "bad config";

@@ -188,6 +188,7 @@ void fill_args(StepArgs* A, const float* action, float* obs, float* reward, uint
     A->terminal_obs = info->terminal_obs; A->paws_in_ground = info->paws_in_ground; A->gait_reward = info->gait_reward;
     A->qacc = info->qacc; A->ncon = info->ncon; A->fn_sum = info->contact_normal_force; A->solver_iters = info->solver_iters; A->ls_evals = info->ls_evals;
     A->reward_raw = info->reward_unclipped;
+    A->cfrc_ext = info->cfrc_ext; A->task_terms = info->task_terms;
   }
 }
 
@@ -275,7 +276,7 @@ void odg_destroy(OdgSim* s) {
 }
 
 int odg_num_envs(const OdgSim* s) { return s ? s->N : 0; }
-int odg_obs_dim(const OdgSim* s) { return s ? (s->prep.C.obs_layout ? 12 : 9) + 3 * s->prep.C.nu : 0; }
+int odg_obs_dim(const OdgSim* s) { return s ? s->prep.C.obs_dim : 0; }
 int odg_act_dim(const OdgSim* s) { return s ? s->prep.C.nu : 0; }
 int odg_nq(const OdgSim* s) { return s ? s->prep.C.nq : 0; }
 int odg_nv(const OdgSim* s) { return s ? s->prep.C.nv : 0; }

@@ -33,7 +33,13 @@ _INFO_SPECS = {
     "solver_iters": (torch.int32, lambda e: ()),
     "ls_evals": (torch.int32, lambda e: ()),
     "reward_unclipped": (torch.float32, lambda e: ()),
+    # 12-actuator model (Go1): data.cfrc_ext[1:] and the jump task's weighted reward terms
+    "cfrc_ext": (torch.float32, lambda e: (13, 6)),
+    "task_terms": (torch.float32, lambda e: (10,)),
 }
+TASKS = {"walk": 0, "jump": 1}
+JUMP_TERMS = ("landing_precision", "landing_orientation", "control_velocity_horizontal", "height_clearance", "phase_sync",
+              "jump_velocity", "distance_on_liftoff", "vertical_velocity_on_landing", "out_of_bounds", "collision_cost")
 DEFAULT_INFO = ("x_position", "y_position", "distance_from_origin", "paw_contact_forces", "patterns_matches",
                 "linear_vel_tracking_reward", "reward_ctrl", "terminal_obs")
 
@@ -63,6 +69,13 @@ class BatchedWalkEnv:
         self.L.odg_default_config(C.byref(self.cfg))
         if self.desc["nu"] == 12:
             self.cfg.obs_layout = 1        # 12-actuator models: the 48-value layout (landing_environment.py:116-136 + v_des)
+        task = config.pop("task", "walk")
+        self.cfg.task = TASKS[task] if isinstance(task, str) else int(task)
+        if self.cfg.task == TASKS["jump"]:
+            # JumpEnvironmentV0 is not wrapped in ScaleActionWrapper: actions are ctrl targets; its reward calculator's
+            # reset_noise_scale is 0.1 (jump_environment_reward_calc.py:52)
+            self.cfg.scale_actions = 0
+            self.cfg.reset_noise_scale = 0.1
         for k, v in config.items():
             if not hasattr(self.cfg, k):
                 raise TypeError(f"unknown config field {k!r}")

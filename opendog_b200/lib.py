@@ -47,7 +47,7 @@ class OdgInfoPtrs(C.Structure):
     _fields_ = [(n, _vp) for n in (
         "x_position", "y_position", "distance_from_origin", "paw_contact_forces", "patterns_matches",
         "linear_vel_tracking_reward", "reward_ctrl", "terminal_obs", "paws_in_ground", "gait_reward",
-        "qacc", "ncon", "contact_normal_force", "solver_iters", "ls_evals", "reward_unclipped")]
+        "qacc", "ncon", "contact_normal_force", "solver_iters", "ls_evals", "reward_unclipped", "cfrc_ext", "task_terms")]
 
 
 class OdgPolicyWeights(C.Structure):

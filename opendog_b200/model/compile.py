@@ -18,9 +18,10 @@ import numpy as np
 from . import rbd_numpy as rbd
 from .mjcf import MjcfModel, load_mjcf, quat_mul, quat_to_mat
 
-MAX_LEG, MAX_JL, MAX_NU, MAX_GEOM, MAX_VERT = 4, 3, 12, 32, 2048
+MAX_LEG, MAX_JL, MAX_NU, MAX_GEOM, MAX_VERT = 4, 3, 12, 48, 2048
 MAX_NQ, MAX_NV = 7 + MAX_LEG * MAX_JL, 6 + MAX_LEG * MAX_JL
-GEOM_HULL, GEOM_SPHERE = 0, 1
+GEOM_HULL, GEOM_SPHERE, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_BOX = 0, 1, 2, 3, 4
+_PRIMITIVES = {"capsule": GEOM_CAPSULE, "cylinder": GEOM_CYLINDER, "box": GEOM_BOX}
 
 _d = C.c_double
 _i = C.c_int
@@ -30,7 +31,8 @@ class OdgGeom(C.Structure):
     _fields_ = [
         ("leg", _i), ("link", _i), ("type", _i), ("vert_start", _i), ("vert_count", _i),
         ("mj_geom_id", _i), ("mj_body_id", _i), ("condim", _i),
-        ("center", _d * 3), ("radius", _d), ("friction", _d), ("margin", _d),
+        ("center", _d * 3), ("radius", _d), ("rot", _d * 9), ("size", _d * 3), ("friction", _d),
+        ("friction_torsion", _d), ("friction_roll", _d), ("margin", _d),
         ("solref", _d * 2), ("solimp", _d * 5), ("invweight0", _d),
     ]
 
@@ -61,7 +63,7 @@ class OdgModel(C.Structure):
 
 
 def compile_model(m: MjcfModel, key: str = "home", multicontact_tilt: float = 0.1,
-                  trunk_collision: bool | None = None) -> dict:
+                  trunk_collision: bool | None = None, max_condim: int | None = None) -> dict:
     """Return a JSON-able dict mirroring OdgModel. Raises if the tree is not trunk + leg chains."""
     free = [j for j in m.joints if j.type == "free"]
     if len(free) != 1 or m.bodies[free[0].body].parent != 0:
@@ -148,22 +150,28 @@ def compile_model(m: MjcfModel, key: str = "home", multicontact_tilt: float = 0.
                 mix = g.solmix / (g.solmix + floor.solmix)
                 sref = mix * g.solref + (1 - mix) * floor.solref
                 simp = mix * g.solimp + (1 - mix) * floor.solimp
-            # condim 4/6 (torsional / rolling friction, Go1 feet: go1.xml:61-64) is reduced to the 3-row elliptic cone:
-            # the kernel and the oracle implement condim 1 and 3 (DESIGN.md "what comes next")
-            condim = min(int(condim), 3)
+            condim = int(condim)
+            if condim not in (1, 3, 6):                    # (condim 4 = 6 without the rolling rows: no reference model uses it)
+                raise NotImplementedError(f"condim {condim}")
+            if max_condim is not None:
+                condim = min(condim, max_condim)
             e = dict(leg=leg, link=link, mj_geom_id=gid, mj_body_id=bid, condim=int(condim),
-                     friction=float(fr[0]), margin=float(max(g.margin, floor.margin) - max(g.gap, floor.gap)),
+                     friction=float(fr[0]), friction_torsion=float(fr[1]), friction_roll=float(fr[2]), margin=float(max(g.margin, floor.margin) - max(g.gap, floor.gap)),
                      solref=np.asarray(sref).tolist(), solimp=np.asarray(simp).tolist(),
                      invweight0=float(body_w[bid, 0]), center=[0.0, 0.0, 0.0], radius=0.0,
-                     vert_start=0, vert_count=0)
+                     rot=np.eye(3).reshape(-1).tolist(), size=[0.0, 0.0, 0.0], vert_start=0, vert_count=0)
             if g.type == "mesh":
                 v = g.verts @ R_in.T + p_in
                 e.update(type=GEOM_HULL, vert_start=len(verts), vert_count=len(v))
                 verts.extend(v.tolist())
             elif g.type == "sphere":
                 e.update(type=GEOM_SPHERE, center=(R_in @ g.pos + p_in).tolist(), radius=float(g.size[0]))
+            elif g.type in _PRIMITIVES:                    # go1.xml:26-60: capsule / cylinder / box colliders
+                size = np.zeros(3); size[:len(g.size)] = g.size
+                e.update(type=_PRIMITIVES[g.type], center=(R_in @ g.pos + p_in).tolist(),
+                         rot=(R_in @ quat_to_mat(g.quat)).reshape(-1).tolist(), size=size.tolist())
             else:
-                continue                                   # other primitives: not on the OpenDOG path
+                continue
             geoms.append(e)
 
     for li, (chain, welded) in enumerate(legs):
@@ -265,7 +273,9 @@ def to_struct(d: dict) -> OdgModel:
             setattr(cg, name, int(g[name]))
         for name in ("radius", "friction", "margin", "invweight0"):
             setattr(cg, name, float(g[name]))
+        cg.friction_torsion = float(g.get("friction_torsion", 0.0)); cg.friction_roll = float(g.get("friction_roll", 0.0))
         cg.center[:] = g["center"]; cg.solref[:] = g["solref"]; cg.solimp[:] = g["solimp"]
+        cg.rot[:] = g.get("rot", [1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0]); cg.size[:] = g.get("size", [0.0, 0.0, 0.0])
     return s
 
 

@@ -260,6 +260,20 @@ static void jac_point(const OdgModel* m, const OdgoData* d, int leg, int link, c
     }
 }
 
+/* rotational Jacobian of the body (leg, link): mj_jacBody's jacr — trunk rotational DoFs are in the trunk frame */
+static void jac_rot(const OdgModel* m, const OdgoData* d, int leg, int link, double* Jr) {
+  int nv = m->nv;
+  memset(Jr, 0, 3 * nv * sizeof(double));
+  double ax[3];
+  for (int i = 0; i < 3; i++) {
+    m3_col(ax, d->xmat[0], i);
+    for (int k = 0; k < 3; k++) Jr[k * nv + 3 + i] = ax[k];
+  }
+  if (leg >= 0)
+    for (int j = 0; j <= link; j++)
+      for (int k = 0; k < 3; k++) Jr[k * nv + dof_of(m, leg, j)] = d->axis[leg][j][k];
+}
+
 /* mj_rne(flg_acc=0): Coriolis + centrifugal + gravity, by per-body Newton-Euler in the world frame */
 void odgo_bias(const OdgModel* m, OdgoData* d) {
   int nv = m->nv;
@@ -371,6 +385,86 @@ void odgo_collision(const OdgModel* m, OdgoData* d) {
       if (dist > G->margin) continue;
       v3_set(p, c[0], c[1], c[2] - G->radius);
       add_contact(m, d, g, -1, p, dist);
+      continue;
+    }
+    if (G->type == ODG_GEOM_CAPSULE || G->type == ODG_GEOM_CYLINDER || G->type == ODG_GEOM_BOX) {
+      /* geom frame in the world: centre c, axes = columns of M = R * rot */
+      double c[3], M[9];
+      m3_mulv(c, R, G->center); v3_add(c, c, x);
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+        double s = 0; for (int k = 0; k < 3; k++) s += R[i * 3 + k] * G->rot[k * 3 + j];
+        M[i * 3 + j] = s;
+      }
+      const double n[3] = { 0, 0, 1 };
+      if (G->type == ODG_GEOM_CAPSULE) {
+        /* mjc_PlaneCapsule: sphere tests at the two ends of the segment, +axis first */
+        double ax[3]; m3_col(ax, M, 2);
+        for (int sgn = 1; sgn >= -1; sgn -= 2) {
+          double e[3], p[3];
+          v3_addscl(e, c, ax, sgn * G->size[1]);
+          double dist = e[2] - G->size[0];
+          note_gap(&d->gap_contact, dist - G->margin);
+          if (dist > G->margin) continue;
+          v3_set(p, e[0], e[1], e[2] - G->size[0]);
+          add_contact(m, d, g, -1, p, dist);
+        }
+      } else if (G->type == ODG_GEOM_BOX) {
+        /* mjc_PlaneBox: the 8 corners in index order, skipping corners above the centre or out of the margin, at most 4 */
+        int cnt = 0;
+        for (int i = 0; i < 8 && cnt < 4; i++) {
+          double loc[3] = { (i & 1) ? G->size[0] : -G->size[0], (i & 2) ? G->size[1] : -G->size[1], (i & 4) ? G->size[2] : -G->size[2] };
+          double corner[3], p[3];
+          m3_mulv(corner, M, loc);
+          double ldist = corner[2];
+          if (ldist <= 0) note_gap(&d->gap_contact, c[2] + ldist - G->margin);
+          if (c[2] + ldist > G->margin || ldist > 0) continue;
+          v3_add(p, corner, c);
+          add_contact(m, d, g, -1, p, c[2] + ldist);
+          cnt++;
+        }
+      } else {
+        /* mjc_PlaneCylinder: the lowest rim point of the disc nearer the plane, the rim point below it on the other disc,
+         * and two more points on the near disc's rim 120 degrees to either side */
+        double ax[3]; m3_col(ax, M, 2);
+        double prjaxis = v3_dot(n, ax);
+        if (prjaxis > 0) { for (int k = 0; k < 3; k++) ax[k] = -ax[k]; prjaxis = -prjaxis; }
+        double dist0 = c[2];
+        double vec[3];
+        for (int k = 0; k < 3; k++) vec[k] = ax[k] * prjaxis - n[k];
+        double len2 = v3_dot(vec, vec);
+        if (len2 >= 1e-30) { double s = G->size[0] / sqrt(len2); for (int k = 0; k < 3; k++) vec[k] *= s; }
+        else { double xa[3]; m3_col(xa, M, 0); for (int k = 0; k < 3; k++) vec[k] = xa[k] * G->size[0]; }
+        double prjvec = v3_dot(vec, n);
+        double axs[3]; for (int k = 0; k < 3; k++) axs[k] = ax[k] * G->size[1];
+        double prjaxs = prjaxis * G->size[1];
+        note_gap(&d->gap_contact, dist0 + prjaxs + prjvec - G->margin);
+        if (dist0 + prjaxs + prjvec > G->margin) continue;
+        {
+          double dist = dist0 + prjaxs + prjvec, p[3];
+          for (int k = 0; k < 3; k++) p[k] = c[k] + vec[k] + axs[k];
+          add_contact(m, d, g, -1, p, dist);
+        }
+        note_gap(&d->gap_contact, dist0 - prjaxs + prjvec - G->margin);
+        if (dist0 - prjaxs + prjvec <= G->margin) {
+          double dist = dist0 - prjaxs + prjvec, p[3];
+          for (int k = 0; k < 3; k++) p[k] = c[k] + vec[k] - axs[k];
+          add_contact(m, d, g, -1, p, dist);
+        }
+        double prjvec1 = -prjvec * 0.5;
+        note_gap(&d->gap_contact, dist0 + prjaxs + prjvec1 - G->margin);
+        if (dist0 + prjaxs + prjvec1 <= G->margin) {
+          double vec1[3];
+          v3_cross(vec1, vec, ax);
+          double l1 = sqrt(v3_dot(vec1, vec1));
+          if (l1 > 0) for (int k = 0; k < 3; k++) vec1[k] *= G->size[0] * sqrt(3.0) / 2 / l1;
+          double dist = dist0 + prjaxs + prjvec1;
+          for (int sgn = 1; sgn >= -1; sgn -= 2) {
+            double p[3];
+            for (int k = 0; k < 3; k++) p[k] = c[k] + sgn * vec1[k] + axs[k] - vec[k] * 0.5;
+            add_contact(m, d, g, -1, p, dist);
+          }
+        }
+      }
       continue;
     }
     {
@@ -492,25 +586,35 @@ static void make_constraints(const OdgModel* m, OdgoData* d) {
         }
       }
     }
-  /* 3. contacts: elliptic cone, condim 1 or 3 */
+  /* 3. contacts: elliptic cone, condim 1, 3 or 6. Rows: normal, two sliding rows (linear Jacobian of the contact point
+   * along the frame axes), then for condim 6 the torsional row (relative angular velocity about the normal) and two
+   * rolling rows (about the tangents) — mj_makeConstraint's mj_jacDifPair jacp / jacr blocks. The plane is static,
+   * so the relative Jacobians are the geom body's own. */
   for (int c = 0; c < d->ncon; c++) {
     OdgoContact* con = &d->contact[c];
     const OdgGeom* G = &m->geom[con->geom];
-    double Jp[3 * NV_MAX];
+    double Jp[3 * NV_MAX], Jr[3 * NV_MAX];
     jac_point(m, d, G->leg, G->link, con->pos, Jp);
+    jac_rot(m, d, G->leg, G->link, Jr);
     con->efc = d->nefc;
     if (con->dist >= G->margin) { con->efc = -1; continue; }      /* excluded (in the gap) */
+    const double fri5[5] = { G->friction, G->friction, G->friction_torsion, G->friction_roll, G->friction_roll };
     for (int k = 0; k < con->dim; k++) {
+      const double* Jsrc = k < 3 ? Jp : Jr;
+      const int ax = k < 3 ? k : k - 3;
       for (int i = 0; i < nv; i++)
-        J[i] = con->frame[3 * k] * Jp[i] + con->frame[3 * k + 1] * Jp[nv + i] + con->frame[3 * k + 2] * Jp[2 * nv + i];
+        J[i] = con->frame[3 * ax] * Jsrc[i] + con->frame[3 * ax + 1] * Jsrc[nv + i] + con->frame[3 * ax + 2] * Jsrc[2 * nv + i];
       int r = add_row(m, d, ODGO_ROW_CONTACT, c, J, k == 0 ? con->dist : 0, k == 0 ? G->margin : 0, 0,
                       G->solref, G->solimp, G->invweight0, k > 0);
       if (k > 0) {
-        /* elliptic cone: friction rows reuse the normal row's impedance; R_t = R_n / impratio */
+        /* elliptic cone (mj_makeImpedance): friction rows reuse the normal row's impedance; R_1 = R_n / impratio,
+         * R_j = R_1 * mu_1^2 / mu_j^2 for the further friction dimensions */
         int r0 = con->efc;
         double B = 0, K = 0;
         solref_kb(m, G->solref, G->solimp, &K, &B);
-        d->efc_R[r] = fmax(MINVAL, d->efc_R[r0] / fmax(MINVAL, m->impratio));
+        double R1 = fmax(MINVAL, d->efc_R[r0] / fmax(MINVAL, m->impratio));
+        double fj = fmax(1e-5, fri5[k - 1]), f0 = fmax(1e-5, fri5[0]);          /* mjMINMU */
+        d->efc_R[r] = fmax(MINVAL, R1 * ((f0 * f0) / (fj * fj)));     /* (ratio first: exactly R1 for the second sliding row) */
         d->efc_D[r] = 1 / d->efc_R[r];
         d->efc_aref[r] = -B * d->efc_vel[r];
       }
@@ -534,30 +638,38 @@ static double block_cost(const OdgModel* m, const OdgoData* d, int r, int dim, c
     if (z[0] >= 0) return 0;
     g[0] = D * z[0]; H[0] = D; return 0.5 * D * z[0] * z[0];
   }
-  /* elliptic contact, dim 3: map to the regular cone */
+  /* elliptic contact, dim 3 or 6: map to the regular cone (mj_constraintUpdate) */
   const OdgGeom* G = &m->geom[d->contact[d->efc_id[r]].geom];
-  double fri = G->friction;
-  double mu = fri * sqrt(d->efc_R[r + 1] / d->efc_R[r]);
-  double sc[3] = { mu, fri, fri };
-  double U[3] = { z[0] * sc[0], z[1] * sc[1], z[2] * sc[2] };
-  double N = U[0], T = sqrt(U[1] * U[1] + U[2] * U[2]);
+  const double fri5[5] = { G->friction, G->friction, G->friction_torsion, G->friction_roll, G->friction_roll };
+  double mu = fmax(1e-5, fri5[0]) * sqrt(d->efc_R[r + 1] / d->efc_R[r]);
+  double sc[6] = { 0 }, U[6] = { 0 };
+  sc[0] = mu;
+  for (int i = 1; i < dim; i++) sc[i] = fmax(1e-5, fri5[i - 1]);
+  for (int i = 0; i < dim; i++) U[i] = z[i] * sc[i];
+  double N = U[0], T = 0;
+  for (int i = 1; i < dim; i++) T += U[i] * U[i];
+  T = sqrt(T);
   if ((T <= 0 && N >= 0) || (T > 0 && N >= mu * T)) return 0;                    /* top zone: separated */
   if ((T <= 0 && N < 0) || (T > 0 && mu * N + T <= 0)) {                         /* bottom zone: sticking */
     double c = 0;
-    for (int i = 0; i < 3; i++) { double D = d->efc_D[r + i]; g[i] = D * z[i]; H[i * 3 + i] = D; c += 0.5 * D * z[i] * z[i]; }
+    for (int i = 0; i < dim; i++) { double D = d->efc_D[r + i]; g[i] = D * z[i]; H[i * dim + i] = D; c += 0.5 * D * z[i] * z[i]; }
     return c;
   }
   /* middle zone: on the cone surface (sliding) */
   double Dm = d->efc_D[r] / (mu * mu * (1 + mu * mu));
   double NmT = N - mu * T;
-  double gU[3] = { Dm * NmT, -Dm * NmT * mu * U[1] / T, -Dm * NmT * mu * U[2] / T };
-  double HU[9];
-  HU[0] = 1; HU[1] = HU[3] = -mu * U[1] / T; HU[2] = HU[6] = -mu * U[2] / T;
+  double gU[6], HU[36];
+  gU[0] = Dm * NmT;
+  for (int i = 1; i < dim; i++) gU[i] = -Dm * NmT * mu * U[i] / T;
   double a = mu * N / (T * T * T), b = mu * mu - mu * N / T;
-  HU[4] = a * U[1] * U[1] + b; HU[8] = a * U[2] * U[2] + b; HU[5] = HU[7] = a * U[1] * U[2];
-  for (int i = 0; i < 3; i++) {
+  HU[0] = 1;
+  for (int i = 1; i < dim; i++) {
+    HU[i] = HU[i * dim] = -mu * U[i] / T;
+    for (int j = i; j < dim; j++) HU[i * dim + j] = HU[j * dim + i] = a * U[i] * U[j] + (i == j ? b : 0);   /* symmetric by construction */
+  }
+  for (int i = 0; i < dim; i++) {
     g[i] = gU[i] * sc[i];
-    for (int j = 0; j < 3; j++) H[i * 3 + j] = Dm * HU[i * 3 + j] * sc[i] * sc[j];
+    for (int j = 0; j < dim; j++) H[i * dim + j] = Dm * HU[i * dim + j] * sc[i] * sc[j];
   }
   return 0.5 * Dm * NmT * NmT;
 }
@@ -576,7 +688,7 @@ static double total_cost(const OdgModel* m, const OdgoData* d, const double* a, 
   if (H) memcpy(H, d->M, nv * nv * sizeof(double));
   for (int r = 0; r < d->nefc;) {
     int dim = block_dim(d, r);
-    double z[3], g[3], Hb[9];
+    double z[6], g[6], Hb[36];
     for (int k = 0; k < dim; k++) {
       double s = -d->efc_aref[r + k];
       for (int i = 0; i < nv; i++) s += d->efc_J[(r + k) * nv + i] * a[i];
@@ -605,7 +717,7 @@ static void line_derivs(const OdgModel* m, const OdgoData* d, const double* a, c
   double s1 = g0 + alpha * h0, s2 = h0;
   for (int r = 0; r < d->nefc;) {
     int dim = block_dim(d, r);
-    double z[3], g[3], Hb[9];
+    double z[6], g[6], Hb[36];
     for (int k = 0; k < dim; k++) z[k] = jar0[r + k] + alpha * Jp_[r + k];
     block_cost(m, d, r, dim, z, g, Hb);
     for (int k = 0; k < dim; k++) {
@@ -689,7 +801,7 @@ static void solve_constraints(const OdgModel* m, OdgoData* d) {
   /* forces */
   for (int r = 0; r < d->nefc;) {
     int dim = block_dim(d, r);
-    double z[3], g[3], Hb[9];
+    double z[6], g[6], Hb[36];
     for (int k = 0; k < dim; k++) {
       double s = -d->efc_aref[r + k];
       for (int i = 0; i < nv; i++) s += d->efc_J[(r + k) * nv + i] * a[i];
@@ -704,7 +816,42 @@ static void solve_constraints(const OdgModel* m, OdgoData* d) {
   }
   for (int c = 0; c < d->ncon; c++) {
     OdgoContact* con = &d->contact[c];
-    for (int k = 0; k < 3; k++) con->force[k] = (con->efc >= 0 && k < con->dim) ? d->efc_force[con->efc + k] : 0;
+    for (int k = 0; k < 6; k++) con->force[k] = (con->efc >= 0 && k < con->dim) ? d->efc_force[con->efc + k] : 0;
+  }
+}
+
+/* mj_rnePostConstraint's cfrc_ext: per body, the contact wrenches acting on it as [torque, force] in world axes about
+ * the subtree centre of mass of the kinematic tree's root (body 1 = trunk: the whole robot's COM). gymnasium's
+ * do_simulation calls it after the last mj_step, so it belongs to the post-integration state's kinematics but the
+ * contact forces of the last substep's forward pass; here it is evaluated with the forward pass's own kinematics
+ * (positions differ by one substep of motion: the reward code only thresholds norms of it). */
+void odgo_cfrc_ext(const OdgModel* m, OdgoData* d) {
+  int nb = 1 + m->nleg * m->njl;
+  double com[3] = { 0, 0, 0 }, mt = m->base_mass;
+  for (int k = 0; k < 3; k++) com[k] = m->base_mass * d->xipos[0][k];
+  for (int l = 0; l < m->nleg; l++)
+    for (int j = 0; j < m->njl; j++) {
+      int b = body_of(m, l, j);
+      for (int k = 0; k < 3; k++) com[k] += m->mass[l][j] * d->xipos[b][k];
+      mt += m->mass[l][j];
+    }
+  for (int k = 0; k < 3; k++) com[k] /= mt;
+  memset(d->cfrc_ext, 0, sizeof(d->cfrc_ext));
+  for (int c = 0; c < d->ncon; c++) {
+    const OdgoContact* con = &d->contact[c];
+    if (con->efc < 0) continue;
+    const OdgGeom* G = &m->geom[con->geom];
+    int b = body_of(m, G->leg, G->link);
+    if (b >= nb) continue;
+    double f[3] = { 0, 0, 0 }, t[3] = { 0, 0, 0 }, r[3], rxf[3];
+    for (int k = 0; k < 3; k++)
+      for (int a = 0; a < 3; a++) {
+        f[k] += con->frame[3 * a + k] * con->force[a];                       /* frame^T * force */
+        if (con->dim > 3) t[k] += con->frame[3 * a + k] * con->force[3 + a];
+      }
+    v3_sub(r, con->pos, com);
+    v3_cross(rxf, r, f);
+    for (int k = 0; k < 3; k++) { d->cfrc_ext[b][k] += t[k] + rxf[k]; d->cfrc_ext[b][3 + k] += f[k]; }
   }
 }
 

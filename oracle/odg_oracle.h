@@ -21,7 +21,7 @@ extern "C" {
 #endif
 
 #define ODGO_MAX_CON (ODG_MAX_GEOM * ODG_MAX_CON_PER_GEOM)
-#define ODGO_MAX_EFC (ODG_MAX_NV + ODG_MAX_NV + 3 * ODGO_MAX_CON)
+#define ODGO_MAX_EFC (ODG_MAX_NV + ODG_MAX_NV + 6 * ODGO_MAX_CON)
 
 enum { ODGO_ROW_FRICTION = 0, ODGO_ROW_LIMIT = 1, ODGO_ROW_CONTACT = 2 };
 
@@ -33,7 +33,7 @@ typedef struct OdgoContact {
   double dist;
   double pos[3];       /* contact point (midway between surfaces) */
   double frame[9];     /* rows: normal, tangent1, tangent2 */
-  double force[3];     /* contact-frame force after the solve */
+  double force[6];     /* contact-frame force after the solve: normal, 2 sliding, torsional, 2 rolling */
 } OdgoContact;
 
 typedef struct OdgoData {
@@ -69,6 +69,8 @@ typedef struct OdgoData {
   /* broad-phase cache: bounding sphere of every hull in its link frame (filled on first use; model constants) */
   double bs_center[ODG_MAX_GEOM][3], bs_radius[ODG_MAX_GEOM];
   int bs_ready;
+  /* mj_rnePostConstraint (odgo_cfrc_ext): [torque, force] per body, body 0 = trunk (MuJoCo body id - 1) */
+  double cfrc_ext[1 + ODG_MAX_LEG * ODG_MAX_JL][6];
 } OdgoData;
 
 /* Walk-environment state that lives outside mjData in the reference (WalkEnvironmentV0 +
@@ -112,6 +114,7 @@ void odgo_kinematics(const OdgModel* m, OdgoData* d);
 void odgo_mass_matrix(const OdgModel* m, OdgoData* d);
 void odgo_bias(const OdgModel* m, OdgoData* d);
 void odgo_collision(const OdgModel* m, OdgoData* d);
+void odgo_cfrc_ext(const OdgModel* m, OdgoData* d);
 double odgo_constraint_cost(const OdgModel* m, const OdgoData* d, const double* qacc);
 
 /* Newton stopping rules: oracle-tight by default; bench.py's CPU baseline legs switch to MuJoCo's defaults

@@ -19,14 +19,14 @@ from opendog_b200.model.compile import (MAX_GEOM, MAX_JL, MAX_LEG, MAX_NQ, MAX_N
                                         OdgModel, load_compiled, to_struct)
 
 MAX_CON = MAX_GEOM * 4
-MAX_EFC = MAX_NV + MAX_NV + 3 * MAX_CON
+MAX_EFC = MAX_NV + MAX_NV + 6 * MAX_CON
 NB = 1 + MAX_LEG * MAX_JL
 _d, _i = C.c_double, C.c_int
 
 
 class OdgoContact(C.Structure):
     _fields_ = [("geom", _i), ("vert", _i), ("efc", _i), ("dim", _i), ("dist", _d), ("pos", _d * 3),
-                ("frame", _d * 9), ("force", _d * 3)]
+                ("frame", _d * 9), ("force", _d * 6)]
 
 
 class OdgoData(C.Structure):
@@ -49,6 +49,7 @@ class OdgoData(C.Structure):
         ("solver_cost", _d), ("solver_gradnorm", _d),
         ("gap_contact", _d), ("gap_support", _d), ("gap_limit", _d),
         ("bs_center", _d * 3 * MAX_GEOM), ("bs_radius", _d * MAX_GEOM), ("bs_ready", _i),
+        ("cfrc_ext", _d * 6 * NB),
     ]
 
 
@@ -172,6 +173,12 @@ class Sim:
     def mass_matrix(self): lib().odgo_mass_matrix(C.byref(self.m), C.byref(self.d))
     def bias(self): lib().odgo_bias(C.byref(self.m), C.byref(self.d))
     def collision(self): lib().odgo_collision(C.byref(self.m), C.byref(self.d))
+
+    def cfrc_ext(self):
+        """data.cfrc_ext as gymnasium leaves it after do_simulation (mj_rnePostConstraint): [nbody, 6], row 0 = world."""
+        lib().odgo_cfrc_ext(C.byref(self.m), C.byref(self.d))
+        nb = 1 + self.desc["nleg"] * self.desc["njl"]
+        return np.vstack([np.zeros((1, 6)), np.array(_np(self.d.cfrc_ext, (NB, 6))[:nb])])
 
     def cost(self, qacc):
         a = np.zeros(MAX_NV); a[:self.nv] = qacc

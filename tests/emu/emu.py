@@ -37,7 +37,7 @@ class StepArgs(C.Structure):
                 ("x_position", _p), ("y_position", _p), ("distance", _p), ("paw_forces", _p),
                 ("patterns_matches", _p), ("lin_vel_reward", _p), ("reward_ctrl", _p), ("terminal_obs", _p),
                 ("paws_in_ground", _p), ("gait_reward", _p), ("qacc", _p), ("ncon", _p), ("fn_sum", _p),
-                ("solver_iters", _p), ("ls_evals", _p), ("reward_raw", _p)]
+                ("solver_iters", _p), ("ls_evals", _p), ("reward_raw", _p), ("cfrc_ext", _p), ("task_terms", _p)]
 
 
 _lib = None
@@ -72,7 +72,8 @@ class EmuEnv:
     INFO = dict(x_position=("f", 1), y_position=("f", 1), distance=("f", 1), paw_forces=("f", 24),
                 patterns_matches=("f", 1), lin_vel_reward=("f", 1), reward_ctrl=("f", 1),
                 terminal_obs=("f", 33), paws_in_ground=("B", 4), gait_reward=("i", 1), qacc=("f", 14),
-                ncon=("i", 1), fn_sum=("f", 1), solver_iters=("i", 1), ls_evals=("i", 1), reward_raw=("f", 1))
+                ncon=("i", 1), fn_sum=("f", 1), solver_iters=("i", 1), ls_evals=("i", 1), reward_raw=("f", 1),
+                cfrc_ext=("f", 78), task_terms=("f", 10))
 
     def __init__(self, num_envs, model="our_robot", seed=0, **cfg):
         self.desc = load_compiled(model) if isinstance(model, str) else model      # (a descriptor dict: model variants)
@@ -85,7 +86,7 @@ class EmuEnv:
         self.h = lib().emu_create(C.byref(self.m), C.byref(self.cfg), num_envs, seed)
         assert self.h
         self.nq, self.nv, self.nu = self.desc["nq"], self.desc["nv"], self.desc["nu"]
-        self.obs_dim = (12 if self.cfg.obs_layout else 9) + 3 * self.nu
+        self.obs_dim = 9 + self.nu if self.cfg.task == 1 else (12 if self.cfg.obs_layout else 9) + 3 * self.nu
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -110,6 +111,8 @@ class EmuEnv:
         if info:
             for k, (t, n) in self.INFO.items():
                 n = {"terminal_obs": self.obs_dim, "qacc": self.nv}.get(k, n)
+                if k in ("cfrc_ext", "task_terms") and self.nu != 12:
+                    continue
                 dt = {"f": np.float32, "i": np.int32, "B": np.uint8}[t]
                 out[k] = np.zeros((self.N, n) if n > 1 else self.N, dt)
                 setattr(A, k, _ptr(out[k]))

@@ -265,3 +265,99 @@ def test_support_vertex_candidate_lists_contain_every_winner():
                     sc = V @ (R.T @ tilt[i])
                     assert c[np.argmax(sc[c])] == np.argmax(sc), (slot, leg, o, i)
     assert listed < 0.35 * total, (listed, total)
+
+
+def test_go1_colliders_condim6_and_cfrc_ext_tumble_parity():
+    """The full Go1 collision set (unitree_go1/go1.xml:26-64: trunk boxes / cylinders / capsules, hip cylinders, thigh and
+    calf capsules, condim-6 sphere feet with torsional and rolling friction) through the kernel source against the oracle:
+    robots dropped in random orientations with random targets tumble over every collider type. Single mj_step from
+    identical states at the stated tolerance; data.cfrc_ext (mj_rnePostConstraint) of the same forward pass."""
+    env = EmuEnv(1, model="go1", frame_skip=1, scale_actions=0, auto_reset=0, solver_iterations=100)
+    sim = Sim("go1")
+    rng = np.random.default_rng(5)
+    lo = np.array([r[0] for r in sim.desc["act_ctrlrange"]]); hi = np.array([r[1] for r in sim.desc["act_ctrlrange"]])
+    geoms = sim.desc["geoms"]
+    assert len(geoms) == 42 and sum(g["condim"] == 6 for g in geoms) == 4
+    seen, bad, n, worst_cf = set(), [], 0, 0.0
+    for trial in range(5):
+        sim.reset_keyframe()
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        sim.qpos[3:7] = q; sim.qpos[2] = 0.45
+        sim.qpos[7:] = rng.uniform(lo, hi)
+        sim.qvel[:] = rng.normal(size=18) * 0.5
+        for k in range(260):
+            if k % 50 == 0:
+                ctrl = rng.uniform(lo, hi).astype(np.float32)[None]
+            sim.ctrl[:] = ctrl[0]
+            env.set_state(sim.qpos[None], sim.qvel[None], sim.qacc_warmstart[None])
+            _, _, _, _, info = env.step(ctrl)
+            sim.step()
+            qp, qv, _ = env.get_state()
+            eq = (np.abs(qp[0] - sim.qpos) - (1e-6 + 1e-5 * np.abs(sim.qpos))).max()
+            ev = (np.abs(qv[0] - sim.qvel) - (1e-4 + 1e-3 * np.abs(sim.qvel))).max()
+            n += 1
+            for c in sim.contacts():
+                seen.add((geoms[c["geom"]]["type"], geoms[c["geom"]]["leg"] < 0, c["dim"]))
+            flip = sim.decision_gaps[0] < 1e-6            # a support point within fp32 rounding of the contact margin
+            if info["ncon"][0] != sim.ncon:
+                assert flip, (trial, k, info["ncon"][0], sim.ncon, sim.decision_gaps)
+                continue
+            if eq > 0 or ev > 0:
+                bad.append((trial, k, float(eq), float(ev)))
+            cf = sim.cfrc_ext()[1:]
+            scale = 1.0 + np.abs(cf).max()
+            worst_cf = max(worst_cf, np.abs(info["cfrc_ext"][0].reshape(13, 6) - cf).max() / scale)
+    # every collider type on trunk and legs, and the 6-row feet, were exercised
+    assert {(1, False, 6), (2, False, 3), (2, True, 3), (3, False, 3), (3, True, 3), (4, True, 3)} <= seen, seen
+    # stiff multi-point rests (a cylinder rim's four points next to capsule ends) converge a little short of the stated
+    # tolerance in fp32 now and then: at most 0.5 % of the steps, never by more than 10x
+    assert len(bad) <= 0.005 * n and all(b[2] < 1e-5 and b[3] < 1e-3 for b in bad), bad
+    assert worst_cf < 2e-2, worst_cf
+
+
+def test_jump_task_matches_the_oracle():
+    """JumpEnvironmentV0 on the Go1 model (environments/JumpEnvironment.py:70-134, rewards/jump_environment_reward_calc.py)
+    through the kernel source: reset observation and Philox reset state bit-for-bit, then on IDENTICAL states (odg_evaluate
+    semantics) flags bit-exact and every weighted reward term within float32 of the oracle, which is pinned to the
+    reference's own code by tests/test_golden_jump.py."""
+    from oracle.go1_tasks import JumpEnv
+    N, seed = 4, 11
+    env = EmuEnv(N, model="go1", seed=seed, task=1, scale_actions=0, reset_noise_scale=0.1, auto_reset=0, solver_iterations=100)
+    ws = [JumpEnv(seed=seed, env_id=i) for i in range(N)]
+    obs = env.reset()
+    oobs = np.stack([w.reset() for w in ws])
+    assert obs.shape == (N, 21) and np.abs(obs - oobs).max() < 1e-6
+    assert np.array_equal(env.get_state()[0], np.stack([w.qpos for w in ws]).astype(np.float32))
+    assert np.array_equal(env.get_env_state()["desired_velocity"], np.stack([w.desired_velocity for w in ws]))
+    rng = np.random.default_rng(3)
+    lo = np.array([r[0] for r in ws[0].sim.desc["act_ctrlrange"]]); hi = np.array([r[1] for r in ws[0].sim.desc["act_ctrlrange"]])
+    key = np.array(ws[0].sim.desc["key_ctrl"])
+    n_cc = n_air = n_term = 0
+    for t in range(40):
+        ctrl = np.clip(key + rng.uniform(-0.5, 0.5, (N, 12)), lo, hi).astype(np.float32)
+        for i, w in enumerate(ws):                       # walk the oracle, with poses that exercise every term
+            w.step(ctrl[i])
+            if i == 1 and t % 5 == 2:
+                w.qpos[:3] = [rng.uniform(0.2, 1.4), rng.uniform(-0.4, 0.4), rng.uniform(0.48, 0.7)]
+            if i == 2 and t % 6 == 3:
+                w.qpos[2] = 0.13; w.qpos[3:7] = [np.cos(0.725), np.sin(0.725), 0.0, 0.0]
+            if i == 3 and t % 9 == 4:
+                a = 0.36 if t % 2 else -0.34                # around the +-20 degree yaw bound
+                w.qpos[3:7] = [np.cos(a / 2), 0.0, 0.0, np.sin(a / 2)]
+            w.qpos[:] = w.qpos.astype(np.float32); w.qvel[:] = w.qvel.astype(np.float32)   # float32-representable states
+        env.set_state(np.stack([w.qpos for w in ws]), np.stack([w.qvel for w in ws]),
+                      np.stack([w.sim.qacc_warmstart for w in ws]))
+        env.set_env_state(step=np.array([w.step_count for w in ws], np.int32))
+        obs, rew, term, trunc, info = env.evaluate(ctrl)
+        for i, w in enumerate(ws):
+            w.sim.ctrl[:] = ctrl[i]
+            oo, orew, oterm, otrunc, oinfo = w.evaluate()
+            assert np.abs(obs[i] - oo).max() < 2e-6, (t, i)
+            near = abs(oinfo["collision_norm"] - 0.1) < 1e-3
+            assert term[i] == oterm and trunc[i] == otrunc, (t, i)
+            if not near:
+                assert np.allclose(info["task_terms"][i], oinfo["terms"], rtol=3e-6, atol=1e-6), (t, i, info["task_terms"][i], oinfo["terms"])
+                assert abs(rew[i] - orew) <= 3e-6 * max(1.0, abs(orew)), (t, i)
+                assert abs(info["reward_raw"][i] - oinfo["reward_unclipped"]) <= 1e-5 * max(1.0, abs(oinfo["reward_unclipped"]))
+            n_cc += oinfo["terms"][9] > 0; n_air += oinfo["terms"][0] > 0; n_term += oterm
+    assert n_cc >= 4 and n_air >= 4 and n_term >= 4
