@@ -380,6 +380,7 @@ def run_gpu(args):
                 "ms_rollout": r["ms_per_rollout"], "ms_gae_and_stats_allreduce": r["ms_gae_and_stats_allreduce"],
                 "ms_ppo_epoch": r["ms_ppo_epoch_with_grad_allreduce"],
                 "ms_grad_allreduce": r["ms_grad_allreduce_per_iteration"], "grad_allreduce": r["grad_allreduce"],
+                "ms_each_iteration": r["ms_each_iteration_this_rank"],      # [rollout, gae, ppo epoch] of every timed iteration, rank 0
                 "ppo_update": r["ppo_update"], "scaling": "weak"}
         if world == 1 and args.go1:
             # BASELINE.json configs[2] names the 12-actuator model: Unitree Go1 through the same kernels (48-512-256-12)
@@ -462,7 +463,7 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
     from opendog_b200.env import BatchedWalkEnv
     from opendog_b200.policy import ActorCriticB200
     from opendog_b200.rollout import Rollout
-    from opendog_b200.train import ppo_update
+    from opendog_b200.train import GraphedPPOUpdate, allreduce_flat_grads
     torch.manual_seed(0)
     env = BatchedWalkEnv(n_envs, model=model, device=dev, seed=0, first_env_id=rank * n_envs, info_keys=None)
     pol = ActorCriticB200(env.obs_dim, env.act_dim, 0.4, device=dev, seed=0)
@@ -473,15 +474,17 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
-    opt = torch.optim.Adam(pol.parameters(), lr=1e-4, fused=True)
+    opt = torch.optim.Adam(pol.parameters(), lr=1e-4, fused=True, capturable=True)
+    T, N = ro.T, n_envs
+    # the PPO epoch (4 minibatches: forward, loss, backward, flat-gradient all-reduce, clipping, fused Adam) is captured
+    # once as CUDA graphs and replayed: no launch / allocator / lazy-loading time inside the timed iterations
+    upd = GraphedPPOUpdate(pol, opt, T * N, env.obs_dim, env.act_dim, minibatches=4) if train else None
     for w in range(3):
         ro.collect()
-        if w >= 1:                       # untimed, twice: first-use costs of the collectives, autograd and cuBLAS (lazy init, heuristics)
+        if w >= 1:                       # untimed, twice: first-use costs of the collectives, autograd and cuBLAS, graph capture
             adv, ret, stats = ro.advantages(normalize=True)
             if train:
-                T, N = ro.T, n_envs
-                ppo_update(pol, opt, ro.obs[:T].reshape(T * N, -1), ro.action.reshape(T * N, -1), ro.logp.reshape(-1),
-                           adv.reshape(-1), ret.reshape(-1), epochs=1, minibatches=4)
+                upd(ro.obs[:T].reshape(T * N, -1), ro.action.reshape(T * N, -1), ro.logp.reshape(-1), adv.reshape(-1), ret.reshape(-1))
     sync()
     iters = 3
     e = [ev() for _ in range(4)]
@@ -493,14 +496,25 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
         adv, ret, stats = ro.advantages(normalize=True)       # all-reduces [sum, sumsq, n] when world > 1
         e[2].record()
         if train:
-            T, N = ro.T, n_envs
-            ppo_update(pol, opt, ro.obs[:T].reshape(T * N, -1), ro.action.reshape(T * N, -1), ro.logp.reshape(-1),
-                       adv.reshape(-1), ret.reshape(-1), epochs=1, minibatches=4, timing=timing)
+            upd(ro.obs[:T].reshape(T * N, -1), ro.action.reshape(T * N, -1), ro.logp.reshape(-1), adv.reshape(-1), ret.reshape(-1))
         e[3].record()
         torch.cuda.synchronize(dev)
         t_roll += e[0].elapsed_time(e[1]); t_gae += e[1].elapsed_time(e[2]); t_upd += e[2].elapsed_time(e[3])
         t_ar += sum(a.elapsed_time(b) for a, b in timing.get("allreduce", []))
         each.append([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])])
+    if train:
+        # the flat-gradient all-reduce alone (the captured epoch contains 4 of them): same buffer, same collective
+        params = [p for p in pol.parameters() if p.requires_grad]
+        for _ in range(2):
+            allreduce_flat_grads(params)
+        sync()
+        ea = [ev(), ev()]
+        ea[0].record()
+        for _ in range(4 * iters):
+            allreduce_flat_grads(params)
+        ea[1].record()
+        torch.cuda.synchronize(dev)
+        t_ar = ea[0].elapsed_time(ea[1])
     # the policy forward alone (same launches as inside the rollout)
     l0 = pol.launch_count
     e[0].record()
@@ -534,8 +548,8 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
         out["grad_allreduce"] = {"calls_per_iteration": 4, "payload_bytes_per_call": 4 * n_param,
                                  "ms_per_call": t_ar / iters / 4,
                                  "share_of_train_iteration": t_ar / max(t_roll + t_gae + t_upd, 1e-9),
-                                 "note": "flat fp32 gradient buffer (pack + NCCL all-reduce + unpack), CUDA events on the training stream"}
-        out["ppo_update"] = "1 epoch x 4 minibatches, bf16 autocast forward/backward (fp32 master weights), torch Adam"
+                                 "note": "flat fp32 gradient buffer (pack + NCCL all-reduce + unpack), timed alone right after the iterations (inside them it is part of the captured epoch)"}
+        out["ppo_update"] = "1 epoch x 4 minibatches replayed as CUDA graphs: bf16 autocast forward/backward (fp32 master weights), flat-gradient all-reduce, clipping, fused Adam"
         out["env_steps_per_s_train_iteration"] = steps / ((t_roll + t_gae + t_upd) * 1e-3)
     return out
 

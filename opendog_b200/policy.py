@@ -145,7 +145,7 @@ class ActorCriticB200(nn.Module):
         """Same signature as the reference module: (Normal(mean, std), value)."""
         mean = self.actor(state)
         std = torch.exp(self.action_log_std.expand_as(mean))
-        return torch.distributions.Normal(mean, std), self.critic(state)
+        return torch.distributions.Normal(mean, std, validate_args=False), self.critic(state)
 
     # the update-phase forward on padded inputs: with the observation width rounded up to a multiple of 16 (33 -> 48,
     # zero columns in x and W1) every GEMM of the forward and backward pass is tensor-core aligned in bf16; with K = 33
@@ -164,7 +164,9 @@ class ActorCriticB200(nn.Module):
             return F.linear(x, net[4].weight, net[4].bias)
         mean = torch.tanh(run(self.actor))
         std = torch.exp(self.action_log_std.expand_as(mean))
-        return torch.distributions.Normal(mean, std), run(self.critic)
+        # (validate_args=False: the argument check reads a flag back to the host — a device sync per forward, and illegal
+        #  inside a CUDA-graph capture)
+        return torch.distributions.Normal(mean, std, validate_args=False), run(self.critic)
 
 
 def gae(reward, value, done, gamma=0.99, lam=0.95, normalize=True, group=None):

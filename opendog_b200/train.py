@@ -112,3 +112,89 @@ def ppo_update(policy, optimizer, obs, action, logp_old, adv, ret, clip: float =
     if hasattr(policy, "sync_weights"):
         policy.sync_weights()
     return out
+
+
+class GraphedPPOUpdate:
+    """`ppo_update` captured once as a CUDA graph per minibatch and replayed: same arithmetic, same hyper-parameters, no
+    Python / launch / allocator time between the ~150 small kernels of a minibatch (forward, loss, backward, gradient
+    all-reduce, clipping, fused Adam). The inputs are copied into static buffers of the captured shape
+    (B = rows per update, fixed); the flat gradient all-reduce is captured with the rest (NCCL supports capture).
+    Falls back to the eager `ppo_update` if capture is impossible (e.g. a CPU run of the gloo tests)."""
+
+    def __init__(self, policy, optimizer, B: int, obs_dim: int, act_dim: int, minibatches: int = 4, clip: float = 0.2,
+                 vf_coef: float = 0.5, ent_coef: float = 0.005, max_grad_norm: float = 0.5, group=None):
+        self.policy, self.opt, self.B, self.mbs, self.group = policy, optimizer, int(B), int(minibatches), group
+        self.hp = dict(clip=clip, vf_coef=vf_coef, ent_coef=ent_coef, max_grad_norm=max_grad_norm)
+        dev = next(policy.parameters()).device
+        self.dev = dev
+        self.params = [p for p in policy.parameters() if p.requires_grad]
+        self.padded = hasattr(policy, "forward_padded")
+        k = (-obs_dim) % 16 if self.padded else 0
+        self.obs = torch.zeros(B, obs_dim + k, device=dev, dtype=torch.bfloat16 if self.padded else torch.float32)
+        self.obs_dim = obs_dim
+        self.action = torch.zeros(B, act_dim, device=dev)
+        self.logp_old, self.adv, self.ret = (torch.zeros(B, device=dev) for _ in range(3))
+        self.out = {k_: torch.zeros((), device=dev) for k_ in ("loss", "pg", "vf", "entropy")}
+        self.graphs = None
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+
+    def _minibatch(self, i):
+        mb = (self.B + self.mbs - 1) // self.mbs
+        sl = slice(i * mb, min(self.B, (i + 1) * mb))
+        hp = self.hp
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            d, v = self.policy.forward_padded(self.obs[sl]) if self.padded else self.policy(self.obs[sl])
+        logp = d.log_prob(self.action[sl]).float().sum(-1)
+        ratio = torch.exp(logp - self.logp_old[sl])
+        a = self.adv[sl]
+        pg = -torch.min(ratio * a, torch.clamp(ratio, 1 - hp["clip"], 1 + hp["clip"]) * a).mean()
+        vf = torch.nn.functional.mse_loss(v.float().squeeze(-1), self.ret[sl])
+        ent = d.entropy().float().sum(-1).mean()
+        loss = pg + hp["vf_coef"] * vf - hp["ent_coef"] * ent
+        self.opt.zero_grad(set_to_none=False)
+        loss.backward()
+        allreduce_flat_grads(self.params, group=self.group)
+        torch.nn.utils.clip_grad_norm_(self.params, hp["max_grad_norm"], foreach=True)
+        self.opt.step()
+        for k_, t in (("loss", loss), ("pg", pg), ("vf", vf), ("entropy", ent)):
+            self.out[k_].copy_(t.detach())
+
+    def _capture(self):
+        for p in self.params:                              # static gradient buffers
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):                         # warm-up outside capture (lazy inits, autotuning, optimizer state)
+            for i in range(self.mbs):
+                self._minibatch(i)
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        graphs = []
+        pool = None
+        for i in range(self.mbs):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                self._minibatch(i)
+            pool = g.pool()
+            graphs.append(g)
+        self.graphs = graphs
+
+    def load(self, obs, action, logp_old, adv, ret):
+        if self.padded:
+            self.obs[:, :self.obs_dim].copy_(obs)          # fp32 -> bf16 cast + zero-padded columns stay zero
+        else:
+            self.obs.copy_(obs)
+        self.action.copy_(action); self.logp_old.copy_(logp_old); self.adv.copy_(adv); self.ret.copy_(ret)
+
+    def __call__(self, obs, action, logp_old, adv, ret, epochs: int = 1):
+        self.load(obs, action, logp_old, adv, ret)
+        if self.graphs is None:
+            self._capture()                                # (its warm-up pass is a real update on this batch)
+        for _ in range(epochs):
+            for g in self.graphs:
+                g.replay()
+        if hasattr(self.policy, "sync_weights"):
+            self.policy.sync_weights()
+        return self.out

@@ -241,7 +241,7 @@ def test_go1_physics_parity_and_env():
             bad += 1             # a sphere foot within fp32 rounding of the 1 mm margin: the oracle must confirm it
             assert s.decision_gaps[0] < FLIP_M, f"Go1 state {i}: outside tolerance without a margin flip {s.decision_gaps}"
     assert bad <= max(2, N // 50), f"{bad}/{N} Go1 states outside the single-step tolerance"
-    assert ncon.max() == 4 and ncon.min() >= 1
+    assert ncon.max() >= 4 and ncon.min() >= 1          # four feet; now and then a calf capsule's end as well
     # the env surface on Go1
     e = BatchedWalkEnv(256, model="go1", seed=3, info_keys=None)
     obs = e.reset()

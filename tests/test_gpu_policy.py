@@ -220,3 +220,38 @@ def test_reference_checkpoint_loads_and_runs_through_the_kernel(tmp_path):
         assert -13.14 <= a <= 21.26 and -13.14 <= b <= 21.26
         clipped = min(a, b) <= -13.12 or max(a, b) >= 21.24
         assert abs(a + b) <= 2 * tol or clipped
+
+
+def test_graphed_ppo_update_equals_the_eager_update():
+    """train.GraphedPPOUpdate (the PPO epoch of BASELINE configs[3] replayed as CUDA graphs) against train.ppo_update on
+    the same batch from the same initial weights: same losses, same updated parameters (both run the bf16-autocast
+    forward / backward; the graph only removes launch and allocator time)."""
+    from opendog_b200.policy import ActorCriticB200
+    from opendog_b200.train import GraphedPPOUpdate, ppo_update
+    B, S, A = 8192, 33, 8
+    g = torch.Generator(device="cuda").manual_seed(1)
+    obs = torch.randn(B, S, device="cuda", generator=g); act = torch.randn(B, A, device="cuda", generator=g).clamp(-1, 1)
+    logp = torch.randn(B, device="cuda", generator=g) * 0.1 - 8
+    adv = torch.randn(B, device="cuda", generator=g); ret = torch.randn(B, device="cuda", generator=g)
+    pols, outs = [], []
+    for graphed in (False, True):
+        pol = ActorCriticB200(S, A, 0.4, seed=0)
+        torch.manual_seed(0)
+        for p in pol.parameters():
+            torch.nn.init.normal_(p, std=0.05)
+        opt = torch.optim.Adam(pol.parameters(), lr=1e-3, fused=True, capturable=True)
+        if graphed:
+            upd = GraphedPPOUpdate(pol, opt, B, S, A, minibatches=4)
+            for _ in range(3):                       # first call = capture (its warm-up pass is a real update), then replays
+                out = upd(obs, act, logp, adv, ret)
+        else:
+            for _ in range(3):
+                out = ppo_update(pol, opt, obs, act, logp, adv, ret, epochs=1, minibatches=4)
+        pols.append(pol); outs.append({k: float(v) for k, v in out.items()})
+    for k in outs[0]:
+        assert abs(outs[0][k] - outs[1][k]) <= 2e-3 * max(1.0, abs(outs[0][k])), (k, outs)
+    for (n0, p0), (_, p1) in zip(pols[0].named_parameters(), pols[1].named_parameters()):
+        assert torch.allclose(p0, p1, rtol=0, atol=3e-3), (n0, (p0 - p1).abs().max().item())
+    # the tensor-core copy of the weights was refreshed: the rollout-time forward sees the updated parameters
+    m0 = pols[0].act(obs[:256], sample=False)[3]; m1 = pols[1].act(obs[:256], sample=False)[3]
+    assert torch.allclose(m0, m1, atol=2e-2)
