@@ -35,17 +35,28 @@ using odg_internal::set_error;
 constexpr int kH1 = ODG_POLICY_H1, kH2 = ODG_POLICY_H2;
 constexpr int kM = 128;                  // environments (rows) per CTA = UMMA M
 constexpr int kNOut = 16;                // output layer padded to the smallest UMMA N
-constexpr int kK2Chunk = 64;             // columns of W2 streamed per chunk
-constexpr int kNumChunks = 2 + kH1 / kK2Chunk + 1;   // W1 halves, W2 k-chunks, W3  (= 11 per network)
+constexpr int kK2Chunk = 32;             // columns of W2 streamed per chunk (2 MMAs of K = 16)
+constexpr int kL1Rows = 128;             // rows of W1 per chunk (a quarter of the layer: N = 128 per MMA)
+constexpr int kL1Chunks = kH1 / kL1Rows, kL2Chunks = kH1 / kK2Chunk;
+constexpr int kRingChunks = kL1Chunks + kL2Chunks;      // chunks of a network that stream through the stage ring (W1, W2)
+constexpr int kNumChunks = kRingChunks + 1;             // + W3  (= 21 packed chunks per network)
+constexpr int kStages = 4;               // weight stages in flight (16 KB each)
+constexpr int kCluster = 2;              // CTAs per cluster: every weight chunk is fetched from L2 once per cluster and multicast
 constexpr uint32_t kStreamSample = 0x53414d50u;      // Philox stream id "SAMP"
+// thread roles: warps 0-7 = two epilogue warpgroups (TMEM lane quarter = warp & 3, column half = warp >> 2),
+// warp 8 = MMA issuer (one elected thread), warp 9 = weight producer (one elected thread, bulk async copies)
+constexpr int kEpiThreads = 256, kThreads = kEpiThreads + 64;
+constexpr int kIssuerTid = kEpiThreads, kProducerTid = kEpiThreads + 32;
 
 // ---- shared memory map (bytes)
 constexpr int kA0Bytes = kM * ODG_POLICY_MAX_STATE * 2;       // 16 KB  obs tile
 constexpr int kA1Bytes = kM * kH1 * 2;                         // 128 KB hidden 1 (hidden 2 aliases its first half)
-constexpr int kWBufBytes = 256 * kK2Chunk * 2;                 // 32 KB  one weight chunk
-constexpr int kOffA0 = 0, kOffA1 = kOffA0 + kA0Bytes, kOffW = kOffA1 + kA1Bytes, kOffBar = kOffW + 2 * kWBufBytes;
+constexpr int kWBufBytes = 16384;                              // one weight stage: 128 x 64 (W1), 256 x 32 (W2), 16 x 256 (W3)
+constexpr int kW3Bytes = kNOut * kH2 * 2;                      // 8 KB  output-layer weights: their own buffer, outside the ring
+constexpr int kOffA0 = 0, kOffA1 = kOffA0 + kA0Bytes, kOffW = kOffA1 + kA1Bytes, kOffW3 = kOffW + kStages * kWBufBytes;
+constexpr int kOffBar = kOffW3 + kW3Bytes;
 constexpr int kBiasFloats = kH1 + kH2 + kNOut;                  // per network: b1 | b2 | b3
-constexpr int kOffBias = kOffBar + 64;
+constexpr int kOffBias = kOffBar + 256;
 constexpr int kSmemBytes = kOffBias + 2 * kBiasFloats * 4;
 
 // byte offset of element (r, k) of an operand tile with kc columns in the canonical K-major no-swizzle layout:
@@ -58,8 +69,8 @@ __host__ __device__ inline int canon_off(int r, int k, int kc) {
 struct ChunkDesc { int rows, kc; int layer, row0, k0; };      // layer 0..2; rows x kc block of W_layer at (row0, k0)
 __host__ __device__ inline ChunkDesc chunk_desc(int c, int K0p) {
   ChunkDesc d;
-  if (c < 2) { d.rows = 256; d.kc = K0p; d.layer = 0; d.row0 = c * 256; d.k0 = 0; }
-  else if (c < 2 + kH1 / kK2Chunk) { d.rows = 256; d.kc = kK2Chunk; d.layer = 1; d.row0 = 0; d.k0 = (c - 2) * kK2Chunk; }
+  if (c < kL1Chunks) { d.rows = kL1Rows; d.kc = K0p; d.layer = 0; d.row0 = c * kL1Rows; d.k0 = 0; }
+  else if (c < kL1Chunks + kL2Chunks) { d.rows = 256; d.kc = kK2Chunk; d.layer = 1; d.row0 = 0; d.k0 = (c - kL1Chunks) * kK2Chunk; }
   else { d.rows = kNOut; d.kc = kH2; d.layer = 2; d.row0 = 0; d.k0 = 0; }
   return d;
 }
@@ -74,6 +85,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(b)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
   uint32_t ok;
   asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
@@ -85,9 +99,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(b, parity)) if (clock64() - t0 > 4000000000ll) __trap();
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+// the same copy delivered to the same shared-memory offset (data and mbarrier) of every CTA of the cluster in `mask`
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -110,7 +129,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+// arrive on the mbarrier at the same offset in every CTA of the cluster in `mask` once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               :: "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
@@ -119,8 +143,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
@@ -135,9 +159,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-#ifdef ODG_MLP_TIMING
+#ifdef ODG_MLP_TIMING            // clock64 stamps of CTA 0 (tools/mlp_time.py): [0,16) epilogue thread 0, [16,32) issuer, [32,40) producer
 __device__ long long g_mlp_t[64];
-#define MLP_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_mlp_t[i] = clock64(); } while (0)
+#define MLP_STAMP(i) do { if (blockIdx.x == 0) g_mlp_t[i] = clock64(); } while (0)
 #else
 #define MLP_STAMP(i) do { } while (0)
 #endif
@@ -151,182 +175,256 @@ struct MlpParams {
   uint32_t seed_lo, seed_hi, step; const uint32_t* step_base; int first_row;
 };
 
-// hidden-layer epilogue: D[row][0..ncols) (TMEM, fp32) + bias -> tanh -> bf16 -> A operand tile with `kc_out` columns,
-// written at columns [kofs, kofs + ncols)
-__device__ __forceinline__ void epilogue_hidden(uint32_t taddr_row, int ncols, const float* __restrict__ bias,
+// hidden-layer epilogue of one thread: D[row][c0 .. c0 + ncols) (TMEM, fp32) + bias -> tanh -> bf16 -> A operand tile
+// with `kc_out` columns, written at columns [kofs + c0, ...). Two 32-column TMEM loads are in flight at a time.
+__device__ __forceinline__ void epilogue_hidden(uint32_t taddr_row, int c0, int ncols, const float* __restrict__ bias,
                                                 uint8_t* a_out, int kc_out, int kofs, int row) {
-  for (int cb = 0; cb < ncols; cb += 32) {
-    uint32_t v[32];
-    tmem_ld32(taddr_row + cb, v);
+  for (int cb = c0; cb < c0 + ncols; cb += 64) {
+    uint32_t va[32], vb[32];
+    tmem_ld32_nowait(taddr_row + cb, va);
+    tmem_ld32_nowait(taddr_row + cb + 32, vb);
+    tmem_ld_wait();
 #pragma unroll
-    for (int g = 0; g < 4; g++) {
-      uint32_t w[4];
+    for (int half = 0; half < 2; half++) {
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int col = cb + g * 8 + i * 2;
-        float x0 = tanh_fast(__uint_as_float(v[g * 8 + i * 2]) + bias[col]);
-        float x1 = tanh_fast(__uint_as_float(v[g * 8 + i * 2 + 1]) + bias[col + 1]);
-        w[i] = pack_bf16(x0, x1);
+      for (int g = 0; g < 4; g++) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int col = cb + half * 32 + g * 8 + i * 2;
+          const uint32_t r0 = half ? vb[g * 8 + i * 2] : va[g * 8 + i * 2], r1 = half ? vb[g * 8 + i * 2 + 1] : va[g * 8 + i * 2 + 1];
+          w[i] = pack_bf16(tanh_fast(__uint_as_float(r0) + bias[col]), tanh_fast(__uint_as_float(r1) + bias[col + 1]));
+        }
+        *reinterpret_cast<uint4*>(a_out + canon_off(row, kofs + cb + half * 32 + g * 8, kc_out)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      *reinterpret_cast<uint4*>(a_out + canon_off(row, kofs + cb + g * 8, kc_out)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
 }
 
-__global__ void __launch_bounds__(kM, 1) k_mlp(const MlpParams P) {
+// Warp-specialised forward. Per network the work is four accumulator stages, alternating between the two halves of
+// the 512 TMEM columns, so the MMAs of stage i+1 run while the epilogue warps drain stage i:
+//   stage 0  layer 1, outputs   0..255  -> region 0     stage 2  layer 2 (16 K-chunks)   -> region 0
+//   stage 1  layer 1, outputs 256..511  -> region 1     stage 3  layer 3 (N = 16)        -> region 1
+// Barriers (all single-CTA mbarriers):
+//   w3_full / w3_free       the output layer's weights have their own 8 KB buffer (in the ring they would hold a stage
+//                           from the end of layer 2's stream until layer 3 is issued and stall the next network's stream)
+//   w_full[s] / w_free[s]   weight stage s landed (bulk copy multicast by the cluster CTA that owns the chunk) / the MMAs
+//                           that read it have retired in BOTH CTAs of the cluster (multicast commits, count 2)
+//   acc_full[r]             the MMAs of the stage that accumulates into TMEM region r retired
+//   acc_free[r]             the 256 epilogue threads have drained region r (tcgen05.ld done)
+//   a_ready[0..2]           hidden-1 columns 0..255 / 256..511 / hidden-2 written to shared memory (the A operand of the
+//                           next layer); layer 2's first 8 K-chunks only need the first half of hidden 1
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) k_mlp(const MlpParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA0 = smem + kOffA0; uint8_t* sA1 = smem + kOffA1;
-  uint8_t* sW[2] = { smem + kOffW, smem + kOffW + kWBufBytes };
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + kOffBar);       // [2] weight chunk landed in buffer b
-  uint64_t* bar_free = bar_w + 2;                                       // [2] the MMAs that read buffer b have retired
-  uint64_t* bar_acc = bar_w + 4;                                        // the accumulator of a layer is complete
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_w + 6);
+  uint8_t* sW = smem + kOffW;
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + kOffBar);      // [kStages]
+  uint64_t* w_free = w_full + kStages;                                  // [kStages]
+  uint64_t* acc_full = w_free + kStages;                                // [2]
+  uint64_t* acc_free = acc_full + 2;                                    // [2]
+  uint64_t* a_ready = acc_free + 2;                                     // [3]
+  uint64_t* w3_full = a_ready + 3;
+  uint64_t* w3_free = w3_full + 1;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(w3_free + 1);
+  uint8_t* sW3 = smem + kOffW3;
   float* s_bias = reinterpret_cast<float*>(smem + kOffBias);            // both networks' biases (epilogue broadcasts)
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int row = tid;                                                  // TMEM lane = row of the tile
-  const int grow = blockIdx.x * kM + row;                               // row in the batch
   const int K0p = P.K0p;
-  const int total_chunks = 2 * kNumChunks;
+  const int total_chunks = 2 * kRingChunks;
 
   if (tid == 0) {
-    mbar_init(&bar_w[0], 1); mbar_init(&bar_w[1], 1); mbar_init(&bar_free[0], 1); mbar_init(&bar_free[1], 1); mbar_init(bar_acc, 1);
+    for (int i = 0; i < kStages; i++) { mbar_init(&w_full[i], 1); mbar_init(&w_free[i], kCluster); }
+    for (int i = 0; i < 2; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], kEpiThreads); }
+    for (int i = 0; i < 3; i++) mbar_init(&a_ready[i], kEpiThreads);
+    mbar_init(w3_full, 1); mbar_init(w3_free, kCluster);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(s_tmem)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < 2 * kBiasFloats; i += kM) s_bias[i] = P.bias[i / kBiasFloats][i % kBiasFloats];
-  // obs tile -> bf16 A0 (rows past the batch and columns past S are zero)
-  {
-    const float* o = P.obs + (size_t)grow * P.S;
-    for (int k8 = 0; k8 < K0p; k8 += 8) {
+  __syncthreads();
+  cluster_sync_all();                                  // the peer's barriers are initialised before anything arrives on them
+  constexpr uint16_t kAllCtas = (uint16_t)((1u << kCluster) - 1);
+  const uint32_t crank = cluster_ctarank();
+  // one weight chunk: every CTA arms its own barrier, the chunk's owner fetches it once and multicasts it to the cluster
+  auto send = [&](uint8_t* dst, uint64_t* bar, int net, int packed_chunk, bool owner) {
+    const uint32_t bytes = (uint32_t)chunk_bytes(packed_chunk, K0p);
+    mbar_expect_tx(bar, bytes);
+    if (owner) bulk_g2s_multicast(dst, P.wpack[net] + chunk_offset(packed_chunk, K0p), bytes, bar, kAllCtas);
+  };
+  if (tid == kProducerTid) {                           // the first stages fill while the other warps stage biases and observations
+    MLP_STAMP(32);
+    for (int c = 0; c < kStages; c++) send(sW + c * kWBufBytes, &w_full[c], 0, c, (uint32_t)(c % kCluster) == crank);
+    send(sW3, w3_full, 0, kRingChunks, crank == 0);
+  }
+  for (int i = tid; i < 2 * kBiasFloats; i += kThreads) s_bias[i] = P.bias[i / kBiasFloats][i % kBiasFloats];
+  // obs tile -> bf16 A0 (rows past the batch and columns past S are zero): 256 threads, two per row
+  if (tid < kEpiThreads) {
+    const int r = tid & (kM - 1), g = blockIdx.x * kM + r;
+    const float* o = P.obs + (size_t)g * P.S;
+    for (int k8 = (tid >> 7) * 8; k8 < K0p; k8 += 16) {
       uint32_t w[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         const int k = k8 + 2 * i;
-        float x0 = (grow < P.n && k < P.S) ? o[k] : 0.f;
-        float x1 = (grow < P.n && k + 1 < P.S) ? o[k + 1] : 0.f;
+        float x0 = (g < P.n && k < P.S) ? o[k] : 0.f;
+        float x1 = (g < P.n && k + 1 < P.S) ? o[k + 1] : 0.f;
         w[i] = pack_bf16(x0, x1);
       }
-      *reinterpret_cast<uint4*>(sA0 + canon_off(row, k8, K0p)) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(sA0 + canon_off(r, k8, K0p)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  MLP_STAMP(0);
   const uint32_t tmem = *s_tmem;
-  const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's lane quarter
-  constexpr uint32_t kD1 = 0, kD2 = 256;                                // accumulator columns: layer 1 / 3 at 0, layer 2 at 256
 
-  // weight chunk c of the flat sequence (actor chunks, then critic chunks) -> buffer c & 1
-  auto prefetch = [&](int c) {
-    const int net = c / kNumChunks, cc = c % kNumChunks;
-    const uint32_t bytes = (uint32_t)chunk_bytes(cc, K0p);
-    mbar_expect_tx(&bar_w[c & 1], bytes);
-    bulk_g2s(sW[c & 1], P.wpack[net] + chunk_offset(cc, K0p), bytes, &bar_w[c & 1]);
-  };
-  if (tid == 0) prefetch(0);
-
-  int c = 0;                                                            // flat chunk counter (uniform across threads)
-  int n_acc = 0;                                                        // accumulators completed so far (bar_acc phase)
-  // One chunk, issued by thread 0 only: wait for its weights, issue `ksteps` MMAs (K = 16 each)
-  // D[.., ncols] (+)= A[128 x 16k] * W_chunk^T, commit them to the buffer's "free" barrier (and, for the last chunk of
-  // a layer, to the accumulator barrier), then prefetch the next chunk into the other buffer as soon as the MMAs that
-  // read it (chunk c-1) have retired. MMAs of consecutive chunks queue back to back in the tensor pipe; nobody waits for
-  // an individual chunk. The other 127 threads only wait for the accumulator (`wait_acc`).
-  auto run_chunk = [&](uint32_t a_saddr, uint32_t a_sbo, int ksteps, uint32_t dcol, int ncols, bool accumulate, bool last) {
-    if (tid == 0) {
-      mbar_wait(&bar_w[c & 1], (uint32_t)((c >> 1) & 1));
+  if (tid == kProducerTid) {
+    // ---- weight producer: the flat ring sequence (actor W1 + W2 chunks, then the critic's) through kStages buffers
+    for (int c = kStages; c < total_chunks; c++) {
+      if (c == kL1Chunks) MLP_STAMP(33);
+      if (c == kRingChunks) MLP_STAMP(34);
+      if (c == kRingChunks + kL1Chunks) MLP_STAMP(35);
+      const int st = c % kStages;
+      mbar_wait(&w_free[st], (uint32_t)((c / kStages - 1) & 1));          // freed by every CTA of the cluster
+      send(sW + st * kWBufBytes, &w_full[st], c / kRingChunks, c % kRingChunks, (uint32_t)(c % kCluster) == crank);
+      if (c == total_chunks - kStages) {               // the critic's W3, long after the actor's layer 3 has retired
+        mbar_wait(w3_free, 0u);
+        send(sW3, w3_full, 1, kRingChunks, crank == 0);
+      }
+    }
+    MLP_STAMP(36);
+  } else if (tid == kIssuerTid) {
+    // ---- MMA issuer
+    int c = 0;
+    uint32_t ph_free[2] = { 0, 0 }, ph_ready[3] = { 0, 0, 0 };
+    auto mma_chunk = [&](uint32_t a_saddr, uint32_t a_sbo, int ksteps, uint32_t dcol, int ncols, bool accumulate) {
+      const int st = c % kStages;
+      mbar_wait(&w_full[st], (uint32_t)((c / kStages) & 1));
       tc_fence_after();
-      const ChunkDesc d = chunk_desc(c % kNumChunks, K0p);
-      const uint32_t b_saddr = smem_u32(sW[c & 1]), b_sbo = (uint32_t)(d.kc >> 3) * 128u;
+      const ChunkDesc d = chunk_desc(c % kRingChunks, K0p);
+      const uint32_t b_saddr = smem_u32(sW + st * kWBufBytes), b_sbo = (uint32_t)(d.kc >> 3) * 128u;
       const uint32_t idesc = make_idesc(kM, ncols);
       for (int k = 0; k < ksteps; k++)
         umma_bf16(tmem + dcol, make_desc(a_saddr + k * 256, 128, a_sbo), make_desc(b_saddr + k * 256, 128, b_sbo), idesc,
                   (accumulate || k > 0) ? 1u : 0u);
-      umma_commit(&bar_free[c & 1]);
-      if (last) umma_commit(bar_acc);
-      if (c + 1 < total_chunks) {
-        if (c >= 1) mbar_wait(&bar_free[(c + 1) & 1], (uint32_t)(((c - 1) >> 1) & 1));   // chunk c-1 read that buffer
-        prefetch(c + 1);
+      umma_commit_multicast(&w_free[st], kAllCtas);
+      c++;
+    };
+    for (int net = 0; net < 2; net++) {
+      for (int h = 0; h < 2; h++) {                                      // stages 0, 1: layer 1 halves -> regions 0, 1
+        if (net > 0) { mbar_wait(&acc_free[h], ph_free[h]); ph_free[h] ^= 1; tc_fence_after(); }
+        for (int q = 0; q < 2; q++)
+          mma_chunk(smem_u32(sA0), (uint32_t)(K0p >> 3) * 128u, K0p / 16, (uint32_t)(h * 256 + q * kL1Rows), kL1Rows, false);
+        umma_commit(&acc_full[h]);
+        MLP_STAMP(16 + net * 8 + h);
       }
-    }
-    c++;
-  };
-  auto wait_acc = [&]() { mbar_wait(bar_acc, (uint32_t)(n_acc & 1)); tc_fence_after(); n_acc++; };
-  // all tcgen05.ld of an accumulator region done + A operand writes visible to the async proxy, before the next MMAs
-  auto sync_after_epilogue = [&]() { fence_async_smem(); tc_fence_before(); __syncthreads(); tc_fence_after(); };
-
-  float outv[kNOut];
-  for (int net = 0; net < 2; net++) {
-    const float* b1 = s_bias + net * kBiasFloats; const float* b2 = b1 + kH1; const float* b3 = b2 + kH2;
-    for (int h = 0; h < 2; h++) {                                        // layer 1, two 256-wide halves
-      run_chunk(smem_u32(sA0), (uint32_t)(K0p >> 3) * 128u, K0p / 16, kD1, 256, false, true);
-      wait_acc();
-      MLP_STAMP(1 + net * 12 + h * 2);
-      epilogue_hidden(tmem_row + kD1, 256, b1 + h * 256, sA1, kH1, h * 256, row);
-      sync_after_epilogue();
-      MLP_STAMP(2 + net * 12 + h * 2);
-    }
-    for (int kc = 0; kc < kH1 / kK2Chunk; kc++)                          // layer 2, K streamed in 64-column chunks
-      run_chunk(smem_u32(sA1) + kc * (kK2Chunk / 8) * 128, (uint32_t)(kH1 >> 3) * 128u, kK2Chunk / 16, kD2, 256, kc > 0,
-                kc == kH1 / kK2Chunk - 1);
-    wait_acc();
-    MLP_STAMP(5 + net * 12);
-    epilogue_hidden(tmem_row + kD2, 256, b2, sA1, kH2, 0, row);          // hidden 2 overwrites hidden 1 (all its MMAs retired)
-    sync_after_epilogue();
-    MLP_STAMP(6 + net * 12);
-    run_chunk(smem_u32(sA1), (uint32_t)(kH2 >> 3) * 128u, kH2 / 16, kD1, kNOut, false, true);   // output layer
-    wait_acc();
-    MLP_STAMP(7 + net * 12);
-    {
-      uint32_t v[16];
-      tmem_ld16(tmem_row + kD1, v);
-      if (net == 0) {
-#pragma unroll
-        for (int a = 0; a < kNOut; a++) outv[a] = tanhf(__uint_as_float(v[a]) + b3[a]);   // actor: Tanh head
-      } else if (grow < P.n && P.value) {
-        P.value[grow] = __uint_as_float(v[0]) + b3[0];
+      mbar_wait(&acc_free[0], ph_free[0]); ph_free[0] ^= 1;               // stage 2: layer 2 -> region 0
+      for (int kc = 0; kc < kL2Chunks; kc++) {
+        if (kc == 0) { mbar_wait(&a_ready[0], ph_ready[0]); ph_ready[0] ^= 1; tc_fence_after(); }
+        if (kc == kL2Chunks / 2) { MLP_STAMP(16 + net * 8 + 2); mbar_wait(&a_ready[1], ph_ready[1]); ph_ready[1] ^= 1; tc_fence_after(); }
+        mma_chunk(smem_u32(sA1) + kc * (kK2Chunk / 8) * 128, (uint32_t)(kH1 >> 3) * 128u, kK2Chunk / 16, 0u, 256, kc > 0);
       }
+      umma_commit(&acc_full[0]);
+      MLP_STAMP(16 + net * 8 + 3);
+      mbar_wait(&acc_free[1], ph_free[1]); ph_free[1] ^= 1;               // stage 3: layer 3 -> region 1
+      mbar_wait(&a_ready[2], ph_ready[2]); ph_ready[2] ^= 1; tc_fence_after();
+      mbar_wait(w3_full, (uint32_t)net);
+      tc_fence_after();
+      for (int k = 0; k < kH2 / 16; k++)
+        umma_bf16(tmem + 256u, make_desc(smem_u32(sA1) + k * 256, 128, (uint32_t)(kH2 >> 3) * 128u),
+                  make_desc(smem_u32(sW3) + k * 256, 128, (uint32_t)(kH2 >> 3) * 128u), make_idesc(kM, kNOut), k > 0 ? 1u : 0u);
+      umma_commit_multicast(w3_free, kAllCtas);
+      umma_commit(&acc_full[1]);
+      MLP_STAMP(16 + net * 8 + 4);
     }
-    sync_after_epilogue();
-  }
-  MLP_STAMP(30);
-  // ---- Normal(mean, exp(log_std)): sample + log-prob  (sim2real/train.py:542-543)
-  if (grow < P.n) {
-    const uint32_t step_ctr = P.step + (P.step_base ? __ldg(P.step_base) : 0u);
-    float lp = 0.f;
+  } else if (tid < kEpiThreads) {
+    // ---- epilogue warpgroups: thread = (row, column half)
+    const int row = tid & (kM - 1), ch = tid >> 7;
+    const int grow = blockIdx.x * kM + row;
+    const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t ph_full[2] = { 0, 0 };
+    auto wait_full = [&](int r) { mbar_wait(&acc_full[r], ph_full[r]); ph_full[r] ^= 1; tc_fence_after(); };
+    // region drained (+ A operand written and visible to the async proxy): let the issuer go on
+    auto release = [&](int r, int ready) {
+      tc_fence_before();
+      if (ready >= 0) { fence_async_smem(); mbar_arrive(&a_ready[ready]); }
+      mbar_arrive(&acc_free[r]);
+    };
+    float outv[kNOut];
+    // ---- Normal(mean, exp(log_std)): sample + log-prob  (sim2real/train.py:542-543). Runs in the epilogue warps' idle time
+    // while the critic's layer-2 weights stream in.
+    auto sample_actor = [&]() {
+      if (!(ch == 0 && grow < P.n)) return;
+      const uint32_t step_ctr = P.step + (P.step_base ? __ldg(P.step_base) : 0u);
+      float lp = 0.f;
 #pragma unroll
-    for (int blk = 0; blk < kNOut / 4; blk++) {
-      if (blk * 4 >= P.A) break;
-      uint32_t r[4];
-      odg::philox4x32(P.seed_lo, P.seed_hi, (uint32_t)(P.first_row + grow), step_ctr, (uint32_t)blk, kStreamSample, r);
+      for (int blk = 0; blk < kNOut / 4; blk++) {
+        if (blk * 4 >= P.A) break;
+        uint32_t r[4];
+        odg::philox4x32(P.seed_lo, P.seed_hi, (uint32_t)(P.first_row + grow), step_ctr, (uint32_t)blk, kStreamSample, r);
 #pragma unroll
-      for (int pr = 0; pr < 2; pr++) {                                  // Box-Muller: 2 uniforms -> 2 normals
-        const float u1 = ((float)(r[2 * pr] >> 8) + 1.0f) * 5.9604644775390625e-08f;     // (0, 1]
-        const float u2 = odg::u01(r[2 * pr + 1]);
-        const float rad = sqrtf(-2.0f * logf(u1));
-        float sn, cs; sincosf(6.283185307179586f * u2, &sn, &cs);
-        const float e[2] = { rad * cs, rad * sn };
+        for (int pr = 0; pr < 2; pr++) {                                  // Box-Muller: 2 uniforms -> 2 normals
+          const float u1 = ((float)(r[2 * pr] >> 8) + 1.0f) * 5.9604644775390625e-08f;     // (0, 1]
+          const float u2 = odg::u01(r[2 * pr + 1]);
+          const float rad = sqrtf(-2.0f * logf(u1));
+          float sn, cs; sincosf(6.283185307179586f * u2, &sn, &cs);
+          const float e[2] = { rad * cs, rad * sn };
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
-          const int a = blk * 4 + pr * 2 + q;
-          if (a < P.A) {
-            const float ls = __ldg(P.log_std + a);
-            if (P.mean) P.mean[(size_t)grow * P.A + a] = outv[a];
-            if (P.action) P.action[(size_t)grow * P.A + a] = outv[a] + expf(ls) * e[q];
-            lp += -0.5f * e[q] * e[q] - ls - 0.9189385332046727f;
+          for (int q = 0; q < 2; q++) {
+            const int a = blk * 4 + pr * 2 + q;
+            if (a < P.A) {
+              const float ls = __ldg(P.log_std + a);
+              if (P.mean) P.mean[(size_t)grow * P.A + a] = outv[a];
+              if (P.action) P.action[(size_t)grow * P.A + a] = outv[a] + expf(ls) * e[q];
+              lp += -0.5f * e[q] * e[q] - ls - 0.9189385332046727f;
+            }
           }
         }
       }
+      if (P.logp) P.logp[grow] = lp;
+    };
+    if (tid == 0) MLP_STAMP(0);
+    for (int net = 0; net < 2; net++) {
+      const float* b1 = s_bias + net * kBiasFloats; const float* b2 = b1 + kH1; const float* b3 = b2 + kH2;
+      for (int h = 0; h < 2; h++) {
+        wait_full(h);
+        if (tid == 0) MLP_STAMP(1 + net * 7 + h * 2);
+        epilogue_hidden(tmem_row + h * 256, ch * 128, 128, b1 + h * 256, sA1, kH1, h * 256, row);
+        release(h, h);
+        if (tid == 0) MLP_STAMP(2 + net * 7 + h * 2);
+        if (net == 1 && h == 1) sample_actor();
+      }
+      wait_full(0);                                                      // every layer-2 MMA retired: hidden 2 may overwrite hidden 1
+      if (tid == 0) MLP_STAMP(5 + net * 7);
+      epilogue_hidden(tmem_row, ch * 128, 128, b2, sA1, kH2, 0, row);
+      release(0, 2);
+      if (tid == 0) MLP_STAMP(6 + net * 7);
+      wait_full(1);
+      if (tid == 0) MLP_STAMP(7 + net * 7);
+      if (ch == 0) {
+        uint32_t v[16];
+        tmem_ld16(tmem_row + 256, v);
+        if (net == 0) {
+#pragma unroll
+          for (int a = 0; a < kNOut; a++) outv[a] = tanhf(__uint_as_float(v[a]) + b3[a]);   // actor: Tanh head
+        } else if (grow < P.n && P.value) {
+          P.value[grow] = __uint_as_float(v[0]) + b3[0];
+        }
+      }
+      release(1, -1);
     }
-    if (P.logp) P.logp[grow] = lp;
+    if (tid == 0) MLP_STAMP(15);
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
+  }
+  cluster_sync_all();                                  // no CTA leaves while its peer may still signal its barriers
 }
 
 // fp32 [out][in] weights -> bf16 chunks. One thread per destination element pair.
@@ -472,7 +570,7 @@ int odg_policy_load(OdgPolicy* p, const OdgPolicyWeights* w, void* stream) {
     const float* const* B = net == 0 ? w->actor_b : w->critic_b;
     for (int i = 0; i < 3; i++) if (!W[i] || !B[i]) return set_error(ODG_ERR_INVALID, "odg_policy_load: missing weight pointer");
     const int nout = net == 0 ? p->A : 1;
-    const int max_elems = 256 * (p->K0p > kK2Chunk ? p->K0p : kK2Chunk);
+    const int max_elems = kWBufBytes / 2;                            // elements of the largest chunk
     dim3 grid((max_elems + 255) / 256, kNumChunks);
     k_pack<<<grid, 256, 0, st>>>(W[0], W[1], W[2], p->S, nout, p->K0p, p->d_wpack[net]);
     k_pack_bias<<<(kH1 + kH2 + kNOut + 255) / 256, 256, 0, st>>>(B[0], B[1], B[2], nout, p->d_bias[net]);
@@ -494,7 +592,8 @@ int odg_policy_forward(OdgPolicy* p, const float* obs_dev, int n, float* mean_de
   P.wpack[0] = p->d_wpack[0]; P.wpack[1] = p->d_wpack[1]; P.bias[0] = p->d_bias[0]; P.bias[1] = p->d_bias[1];
   P.log_std = p->d_log_std; P.mean = mean_dev; P.value = value_dev; P.action = action_dev; P.logp = logp_dev;
   P.seed_lo = (uint32_t)seed; P.seed_hi = (uint32_t)(seed >> 32); P.step = step; P.step_base = step_base_dev; P.first_row = first_row_id;
-  k_mlp<<<(n + kM - 1) / kM, kM, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(P);
+  const int ctas = ((n + kM - 1) / kM + kCluster - 1) / kCluster * kCluster;       // whole clusters; surplus rows are masked
+  k_mlp<<<ctas, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(P);
   p->launches++;
   CUDA_TRY(cudaGetLastError());
   return ODG_OK;

@@ -190,9 +190,10 @@ class GraphedPPOUpdate:
 
     def __call__(self, obs, action, logp_old, adv, ret, epochs: int = 1):
         self.load(obs, action, logp_old, adv, ret)
-        if self.graphs is None:
-            self._capture()                                # (its warm-up pass is a real update on this batch)
-        for _ in range(epochs):
+        first = self.graphs is None
+        if first:
+            self._capture()                                # its eager warm-up pass is this call's first epoch
+        for _ in range(epochs - 1 if first else epochs):
             for g in self.graphs:
                 g.replay()
         if hasattr(self.policy, "sync_weights"):
