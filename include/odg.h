@@ -75,6 +75,10 @@ typedef struct OdgEnvConfig {
   int launch_block;          /* threads per block of the step kernel: 32, 64 or 128; 0 = 64 */
   int launch_lockstep;       /* 1 = the warps of a block take Newton iterations in lockstep (one barrier per iteration;
                                 pays when the batch is several waves deep), 0 = never, -1 = chosen from the batch size */
+  int launch_fat;            /* 1 = the instantiation of the step kernel that keeps per-contact Jacobian columns and line-search
+                                coefficients in local memory instead of recomputing them (pays when a warp has a scheduler
+                                to itself), 0 = the lean one, -1 = chosen from the batch size. Schedule only: results are
+                                bit-identical */
 } OdgEnvConfig;
 
 /* Optional per-step outputs (any pointer may be NULL). WalkEnvironment.py:65-72 `info`. */

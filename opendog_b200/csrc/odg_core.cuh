@@ -40,6 +40,7 @@ static inline float odg_fadd_rn(float a, float b) { volatile float r = a + b; re
 static inline float odg_fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float odg_fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline float odg_fdiv_fast(float a, float b) { return a / b; }
+static inline float odg_fma_rn(float a, float b, float c) { return fmaf(a, b, c); }
 #ifdef ODG_EMU_STATS
 // solver statistics of the host emulator (tools/emu_solver_stats.py): one record per Newton iteration of lane 0
 void odg_emu_stat(int it, float rel_step, float alpha, int ls_passes, int nc_leg, float d10);
@@ -54,6 +55,7 @@ void odg_emu_stat(int it, float rel_step, float alpha, int ls_passes, int nc_leg
 #define odg_fadd_rn __fadd_rn
 #define odg_fsub_rn __fsub_rn
 #define odg_fdiv_rn __fdiv_rn
+#define odg_fma_rn __fmaf_rn
 #define odg_fdiv_fast __fdividef               // 2-ulp quotient without the IEEE slow-path call (step lengths, stiffnesses)
 // one MUFU.RSQ: every argument in this file is clamped to a normal number first, so the denormal pre/post-scaling that
 // rsqrtf() carries without -ftz (a compare and two predicated multiplies per call) is dead weight in the hot loops
@@ -64,9 +66,6 @@ __device__ __forceinline__ float odg_rsqrt(float x) { float r; asm("rsqrt.approx
 
 #ifndef ODG_LS_WIDTH
 #define ODG_LS_WIDTH 4
-#endif
-#ifndef ODG_CONE_QUADRATIC
-#define ODG_CONE_QUADRATIC 1
 #endif
 
 namespace odg {
@@ -186,7 +185,10 @@ ODG_DEV V3 operator-(V3 a, V3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); 
 ODG_DEV V3 operator*(float s, V3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
 ODG_DEV V3 operator-(V3 a) { return mk3(-a.x, -a.y, -a.z); }
 ODG_DEV float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-ODG_DEV V3 cross(V3 a, V3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+// (explicit fused form: `a.y * b.z - a.z * b.y` may be contracted either way round, and the two instantiations of the step
+//  kernel — one stores a contact's Jacobian columns, one recomputes them — must produce the same bits at every site)
+ODG_DEV float cross1(float a, float b, float c, float d) { return odg_fma_rn(a, b, -odg_fmul_rn(c, d)); }      // a*b - c*d
+ODG_DEV V3 cross(V3 a, V3 b) { return mk3(cross1(a.y, b.z, a.z, b.y), cross1(a.z, b.x, a.x, b.z), cross1(a.x, b.y, a.y, b.x)); }
 ODG_DEV float comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 
 struct M3 { float m[9]; };   // row-major
@@ -394,40 +396,45 @@ ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, float dmk, 
   return top ? 0 : (bot ? 1 : 2);
 }
 
-// phi' contribution of one contact block at four step lengths: f[k] += d/dalpha cost(z0 + al[k]*dz). Branch-free
-// zone selection so the four evaluations interleave.
-template <int W>
-ODG_DEV void cone_line4(V3 z0, V3 dz, float Dn, float Dt, float mu, float fri, float dmk, int condim, const float (&al)[W], float (&f)[W]) {
+// Line search over one contact block, in two parts. `cone_line_prep` (once per Newton iteration, when the search
+// direction is known) reduces the block to nine numbers: |U(alpha)|^2 = cA + 2 alpha cB + alpha^2 cC and U.V = cB + alpha cC
+// as polynomials in the step length (U, V = scaled tangential parts of z0, dz), the normal part N0 + alpha Nd, the
+// sticking-zone quadratic q1 + alpha q2, the cone-surface stiffness Dm and mu. `cone_line_eval` (every pass of the search)
+// adds d/dalpha cost(z0 + al[k] dz) at W step lengths from those nine numbers alone — no per-slot constants, no vector
+// arithmetic in the search's inner loop. Branch-free zone selection so the W evaluations interleave. The line search only
+// positions the step; the solution the iteration converges to does not depend on it.
+struct LineCoef { float N0, Nd, cA, cB, cC, q1, q2, Dm, mu; };
+ODG_DEV LineCoef cone_line_prep(V3 z0, V3 dz, float Dn, float Dt, float mu, float fri, float dmk, int condim) {
   // a frictionless (condim 1) row is the same cone with no tangential part: fri = Dt = 0 gives T = 0, zone = (N >= 0 ?
   // top : bottom) and phi' = Dn * dz.z * min(z.z, 0) without a branch
   if (condim == 1) { fri = 0.f; Dt = 0.f; }
-  const float U0x = z0.x * fri, U0y = z0.y * fri, Vx = dz.x * fri, Vy = dz.y * fri, N0 = z0.z * mu, Nd = dz.z * mu;
-  const float Dm = Dn * dmk;
-  const float qb1 = Dt * (z0.x * dz.x + z0.y * dz.y) + Dn * z0.z * dz.z;      // sticking zone: phi' = qb1 + alpha*qb2
-  const float qb2 = Dt * (dz.x * dz.x + dz.y * dz.y) + Dn * dz.z * dz.z;
-#if ODG_CONE_QUADRATIC
-  // |U(alpha)|^2 and U.V as polynomials in alpha (three coefficients per contact instead of two vector updates per
-  // step length). The line search only positions the step; the solution the iteration converges to does not depend on it.
-  const float cA = U0x * U0x + U0y * U0y, cB = U0x * Vx + U0y * Vy, cC = Vx * Vx + Vy * Vy;
-#endif
+  // (explicitly rounded / fused operations: the lean instantiation of the step kernel inlines this into every pass of
+  //  the search, the other one into the preparation loop, and both must produce the same bits)
+  const float U0x = odg_fmul_rn(z0.x, fri), U0y = odg_fmul_rn(z0.y, fri), Vx = odg_fmul_rn(dz.x, fri), Vy = odg_fmul_rn(dz.y, fri);
+  LineCoef k;
+  k.N0 = odg_fmul_rn(z0.z, mu); k.Nd = odg_fmul_rn(dz.z, mu);
+  k.Dm = odg_fmul_rn(Dn, dmk); k.mu = mu;
+  const float zt = odg_fma_rn(z0.x, dz.x, odg_fmul_rn(z0.y, dz.y)), dt = odg_fma_rn(dz.x, dz.x, odg_fmul_rn(dz.y, dz.y));
+  k.q1 = odg_fma_rn(Dt, zt, odg_fmul_rn(odg_fmul_rn(Dn, z0.z), dz.z));      // sticking zone: phi' = q1 + alpha*q2
+  k.q2 = odg_fma_rn(Dt, dt, odg_fmul_rn(odg_fmul_rn(Dn, dz.z), dz.z));
+  k.cA = odg_fma_rn(U0x, U0x, odg_fmul_rn(U0y, U0y)); k.cB = odg_fma_rn(U0x, Vx, odg_fmul_rn(U0y, Vy));
+  k.cC = odg_fma_rn(Vx, Vx, odg_fmul_rn(Vy, Vy));
+  return k;
+}
+template <int W>
+ODG_DEV void cone_line_eval(const LineCoef& c, const float (&al)[W], float (&f)[W]) {
   ODG_UNROLL for (int k = 0; k < W; k++) {
     const float a = al[k];
-    const float N = N0 + a * Nd;
-#if ODG_CONE_QUADRATIC
-    const float UV = cB + a * cC;
-    const float T2 = fmaxf(cA + a * (cB + UV), 0.f);
-#else
-    const float Ux = U0x + a * Vx, Uy = U0y + a * Vy;
-    const float T2 = Ux * Ux + Uy * Uy;
-    const float UV = Ux * Vx + Uy * Vy;
-#endif
+    const float N = c.N0 + a * c.Nd;
+    const float UV = c.cB + a * c.cC;
+    const float T2 = fmaxf(c.cA + a * (c.cB + UV), 0.f);
     const float iT = odg_rsqrt(fmaxf(T2, 1e-20f));
     const float T = T2 * iT;
     const float Td = UV * iT;
-    const float e = N - mu * T;                     // >= 0: separating (T == 0: N >= 0)
-    const float fmid = Dm * e * (Nd - mu * Td);
-    const float fbot = qb1 + a * qb2;
-    const bool bot = mu * N + T <= 0.f;             // sticking
+    const float e = N - c.mu * T;                   // >= 0: separating (T == 0: N >= 0)
+    const float fmid = c.Dm * e * (c.Nd - c.mu * Td);
+    const float fbot = c.q1 + a * c.q2;
+    const bool bot = c.mu * N + T <= 0.f;           // sticking
     f[k] += e >= 0.f ? 0.f : (bot ? fbot : fmid);
   }
 }
@@ -475,27 +482,18 @@ ODG_DEV void cone6_eval(const float (&z)[6], const Cone6& k, float (&g)[6], floa
       H[i][j] = h; H[j][i] = h;
     }
 }
-template <int W>
-ODG_DEV void cone6_line(const float (&z0)[6], const float (&dz)[6], const Cone6& k, const float (&al)[W], float (&f)[W]) {
-  float cA = 0.f, cB = 0.f, cC = 0.f, qb1 = 0.f, qb2 = 0.f;
-  ODG_UNROLL for (int i = 0; i < 6; i++) {
-    qb1 += k.D[i] * z0[i] * dz[i]; qb2 += k.D[i] * dz[i] * dz[i];
-    if (i != 2) { const float a = z0[i] * k.sc[i], b = dz[i] * k.sc[i]; cA += a * a; cB += a * b; cC += b * b; }
+ODG_DEV LineCoef cone6_line_prep(const float (&z0)[6], const float (&dz)[6], const Cone6& k) {
+  LineCoef c;
+  c.cA = 0.f; c.cB = 0.f; c.cC = 0.f; c.q1 = 0.f; c.q2 = 0.f;
+  ODG_UNROLL for (int i = 0; i < 6; i++) {           // (explicit fused operations, as in cone_line_prep)
+    c.q1 = odg_fma_rn(odg_fmul_rn(k.D[i], z0[i]), dz[i], c.q1); c.q2 = odg_fma_rn(odg_fmul_rn(k.D[i], dz[i]), dz[i], c.q2);
+    if (i != 2) {
+      const float a = odg_fmul_rn(z0[i], k.sc[i]), b = odg_fmul_rn(dz[i], k.sc[i]);
+      c.cA = odg_fma_rn(a, a, c.cA); c.cB = odg_fma_rn(a, b, c.cB); c.cC = odg_fma_rn(b, b, c.cC);
+    }
   }
-  const float N0 = z0[2] * k.mu, Nd = dz[2] * k.mu, mu = k.mu;
-  ODG_UNROLL for (int q = 0; q < W; q++) {
-    const float a = al[q];
-    const float N = N0 + a * Nd;
-    const float UV = cB + a * cC;
-    const float T2 = fmaxf(cA + a * (cB + UV), 0.f);
-    const float iT = odg_rsqrt(fmaxf(T2, 1e-20f));
-    const float T = T2 * iT, Td = UV * iT;
-    const float e = N - mu * T;
-    const float fmid = k.Dm * e * (Nd - mu * Td);
-    const float fbot = qb1 + a * qb2;
-    const bool bot = mu * N + T <= 0.f;
-    f[q] += e >= 0.f ? 0.f : (bot ? fbot : fmid);
-  }
+  c.N0 = odg_fmul_rn(z0[2], k.mu); c.Nd = odg_fmul_rn(dz[2], k.mu); c.mu = k.mu; c.Dm = k.Dm;
+  return c;
 }
 
 // unrolled dense Cholesky solve of a 6x6 SPD system held in registers. S is overwritten by its factor.
@@ -587,7 +585,12 @@ struct LastPass {
 // One mj_step (or one mj_forward when integrate == false) for the 4-lane group of one environment.
 // Every contact is an elliptic-cone block against the plane z = 0; a frictionless (condim 1) row is the same block
 // with no tangential part (cone_eval / cone_line4).
-template <int NJL>
+// FAT = keep more per-contact data in (L1-cached) local memory instead of recomputing it: the joints' Jacobian columns at
+// the contact point (once per substep) and the nine line-search coefficients (once per Newton iteration). Same
+// arithmetic either way (results are bit-identical: the GPU suite compares a FAT handle with a lean one). It pays when
+// a warp has a scheduler to itself (+6.5 % at 4096 envs) and costs when 8 warps per SM share the L1 — 26 instead of 14
+// words per contact no longer fit (-18 % at 65536 envs) — so the host picks per batch size like it picks lockstep.
+template <int NJL, bool FAT>
 ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const float* ODG_RESTRICT s_gc,
                      const float4* ODG_RESTRICT s_vert, int leg, unsigned gm,
                      V3& bp, float (&bq)[4], V3& bv, V3& bwl, float (&q)[NJL], float (&qd)[NJL],
@@ -721,13 +724,17 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     tau_l[j] = f - cbias[j] - LCF(LC_DAMP, j) * qd[j];
   }
   // ------------------------------------------------------------------ collision: floor plane vs hulls
-  V3 c_r[kMaxConLeg], c_aref[kMaxConLeg], c_z0[kMaxConLeg], c_dz[kMaxConLeg];     // cone rows of this leg's contacts
+  V3 c_r[kMaxConLeg], c_aref[kMaxConLeg], c_z0[kMaxConLeg];     // cone rows of this leg's contacts
+  LineCoef c_lc[FAT ? kMaxConLeg : 1];                            // FAT: their line-search coefficients for the current direction
+  V3 c_dz[FAT ? 1 : kMaxConLeg];                                  // lean: the direction's row values (coefficients are re-derived per pass)
+  V3 c_cj[FAT ? kMaxConLeg : 1][NJL];                                       // Jacobian columns of this leg's joints at the contact point
+                                                                  // (zero for joints below the contact's link)
   float c_Dn[kMaxConLeg]; int c_slot[kMaxConLeg];
   // 3-joint legs (Go1): every contact carries the three angular rows of condim 6 as well (torsional + rolling friction,
   // go1.xml:61-64); contacts of condim-3 geoms have zero coefficients there and reduce to the 3-row cone exactly
   constexpr bool kG = (NJL == 3);
   constexpr int kConA = kG ? kMaxConLeg : 1;
-  V3 c_arefa[kConA], c_z0a[kConA], c_dza[kConA];
+  V3 c_arefa[kConA], c_z0a[kConA], c_dza[(kG && !FAT) ? kMaxConLeg : 1];
   int nc = 0;
   int foot_last = -1;
   auto add_contact = [&](float px, float py, float pz_mid, float dist, int s) {
@@ -909,8 +916,9 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     const V3 r = c_r[c];
     V3 vc = bv + cross(w0, r);
     ODG_UNROLL for (int j = 0; j < NJL; j++) {
-      const float on = fminf(fmaxf((float)(link - j + 1), 0.f), 1.f);
-      vc = vc + (on * qd[j]) * cross(ax[j], r - anc[j]);
+      const V3 cjv = (j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f);
+      if (FAT) c_cj[c][j] = cjv;
+      vc = vc + qd[j] * cjv;
     }
     c_aref[c] = mk3(-Bc * vc.x, -Bc * vc.y, -Bc * vc.z - Kc * imp * (dist - margin));
     if constexpr (kG) {                             // torsional / rolling rows: aref = -B * (angular velocity of the body)
@@ -1019,7 +1027,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       V3 cj[NJL];
       V3 ap = a_b.t + cross(a_b.w, r);
       ODG_UNROLL for (int j = 0; j < NJL; j++) {
-        cj[j] = (j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f);
+        cj[j] = FAT ? c_cj[c][j] : ((j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f));
         ap = ap + a_l[j] * cj[j];
       }
       V3 z = ap - c_aref[c];
@@ -1171,23 +1179,35 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         Hq += p_l[j] * s;
       }
     }
+    // the nine line-search coefficients of contact c for the direction whose row values are (dz, dza)
+    auto line_coef = [&](int c, V3 dz, V3 dza) {
+      const int s = c_slot[c];
+      const float Dn = c_Dn[c];
+      if constexpr (kG) {
+        const Cone6 K6 = cone6_make(Dn, C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_frt[s], C.slot_frr[s],
+                                    C.slot_dt_tor[s], C.slot_dt_roll[s], C.slot_condim[s]);
+        const V3 zl = c_z0[c], za = c_z0a[c];
+        const float z6[6] = { zl.x, zl.y, zl.z, za.x, za.y, za.z }, d6[6] = { dz.x, dz.y, dz.z, dza.x, dza.y, dza.z };
+        return cone6_line_prep(z6, d6, K6);
+      } else {
+        return cone_line_prep(c_z0[c], dz, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s]);
+      }
+    };
     ODG_NO_UNROLL for (int c = 0; c < nc; c++) {
       const int link = C.slot_link[c_slot[c]];
       const V3 r = c_r[c];
       V3 dz = p_b.t + cross(p_b.w, r);
-      ODG_UNROLL for (int j = 0; j < NJL; j++) {    // joints below the contact's link do not move it: arithmetic mask
-        const float on = fminf(fmaxf((float)(link - j + 1), 0.f), 1.f);
-        dz = dz + (on * p_l[j]) * cross(ax[j], r - anc[j]);
-      }
-      c_dz[c] = dz;
+      ODG_UNROLL for (int j = 0; j < NJL; j++)       // (zero columns below the contact's link)
+        dz = dz + p_l[j] * (FAT ? c_cj[c][j] : ((j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f)));
+      V3 dza = p_b.w;
       if constexpr (kG) {
-        V3 dza = p_b.w;
         ODG_UNROLL for (int j = 0; j < NJL; j++) {
           const float on = fminf(fmaxf((float)(link - j + 1), 0.f), 1.f);
           dza = dza + (on * p_l[j]) * ax[j];
         }
-        c_dza[c] = dza;
       }
+      if constexpr (FAT) c_lc[c] = line_coef(c, dz, dza);
+      else { c_dz[c] = dz; if constexpr (kG) c_dza[c] = dza; }
     }
     const float bf_zt = dot(bf_e, a_b.t) - bf_aref_t, bf_dzt = dot(bf_e, p_b.t);
     const float bf_zr = dot(bf_c, a_b.w) - bf_aref_r, bf_dzr = dot(bf_c, p_b.w);
@@ -1216,17 +1236,8 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(fmaxf(bf_Dt * (bf_zt + al[k] * bf_dzt), -bf_ft), bf_ft) * bf_dzt;
       ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(fmaxf(bf_Dr * (bf_zr + al[k] * bf_dzr), -bf_fr), bf_fr) * bf_dzr;
       ODG_NO_UNROLL for (int c = 0; c < nc; c++) {               // (a row with D = 0 adds exactly 0: no skip, no branch)
-        const int s = c_slot[c];
-        const float Dn = c_Dn[c];
-        if constexpr (kG) {
-          const Cone6 K6 = cone6_make(Dn, C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_frt[s], C.slot_frr[s],
-                                      C.slot_dt_tor[s], C.slot_dt_roll[s], C.slot_condim[s]);
-          const V3 zl = c_z0[c], za = c_z0a[c], dl = c_dz[c], da = c_dza[c];
-          const float z6[6] = { zl.x, zl.y, zl.z, za.x, za.y, za.z }, d6[6] = { dl.x, dl.y, dl.z, da.x, da.y, da.z };
-          cone6_line<LW>(z6, d6, K6, al, f);
-          continue;
-        }
-        cone_line4<LW>(c_z0[c], c_dz[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], al, f);
+        if constexpr (FAT) cone_line_eval<LW>(c_lc[c], al, f);
+        else cone_line_eval<LW>(line_coef(c, c_dz[c], kG ? c_dza[c] : mk3(0.f, 0.f, 0.f)), al, f);
       }
       ODG_UNROLL for (int k = 0; k < LW; k++) f[k] = grp_sum(f[k], gm);
     };
@@ -1336,7 +1347,8 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       if (Dn == 0.f) continue;
       const V3 r = c_r[c];
       V3 ap = a_b.t + cross(a_b.w, r);
-      ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) ap = ap + a_l[j] * cross(ax[j], r - anc[j]);
+      ODG_UNROLL for (int j = 0; j < NJL; j++)
+        ap = ap + a_l[j] * (FAT ? c_cj[c][j] : ((j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f)));
       V3 g; S3 H;
       if constexpr (kG) {
         V3 alb = a_b.w;
@@ -1476,7 +1488,7 @@ struct StepResult { float reward_unclipped; bool terminated, truncated; };
 
 // Full environment step for one 4-lane group: load state, frame_skip substeps, obs/reward/termination,
 // optional auto-reset, store state.
-template <int NJL>
+template <int NJL, bool FAT>
 ODG_DEV StepResult env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, const float* ODG_RESTRICT s_gc,
                             const float4* ODG_RESTRICT s_vert, const SimPtrs& P, const StepArgs& A,
                             const float* action, int env, int leg, unsigned gm, float* ODG_RESTRICT s_red) {
@@ -1537,7 +1549,7 @@ ODG_DEV StepResult env_step(const DevConst& C, const float* ODG_RESTRICT s_lc, c
       pv = ov; pw = ow;
       ODG_UNROLL for (int j = 0; j < NJL; j++) pl[j] = ol[j];
       }
-      substep<NJL>(C, s_lc, s_gc, s_vert, leg, gm, bp, bq, bv, bwl, q, qd, ctrl, warm_v, warm_wl, warm_l,
+      substep<NJL, FAT>(C, s_lc, s_gc, s_vert, leg, gm, bp, bq, bv, bwl, q, qd, ctrl, warm_v, warm_wl, warm_l,
                         stepping, s == nsub - 1, lp, work, s_red);
     }
   }

@@ -335,7 +335,7 @@ inline std::string prepare(const OdgModel& m, const OdgEnvConfig& cfg, uint64_t 
 inline void default_config(OdgEnvConfig* c) {
   c->task = ODG_TASK_WALK; c->frame_skip = 10; c->max_episode_steps = 750; c->auto_reset = 1;
   c->solver_iterations = 30; c->ls_iterations = 4; c->solver_tolerance = 1e-4f; c->ls_tolerance = 0.1f; c->reset_noise_scale = 0.02f;
-  c->scale_actions = 1; c->launch_lanes = 0; c->first_env_id = 0; c->obs_layout = 0; c->launch_block = 0; c->launch_lockstep = -1;
+  c->scale_actions = 1; c->launch_lanes = 0; c->first_env_id = 0; c->obs_layout = 0; c->launch_block = 0; c->launch_lockstep = -1; c->launch_fat = -1;
 }
 
 }  // namespace odg

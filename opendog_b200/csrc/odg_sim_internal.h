@@ -15,7 +15,8 @@ struct OdgSim {
   SmemLayout L{};
   size_t smem_step = 0, smem_const = 0;
   int step_block = 128, step_grid = 1, step_lanes = 32;
-  int cfg_lanes = 0, cfg_block = 0, cfg_lockstep = -1;   // OdgEnvConfig::launch_*
+  int cfg_lanes = 0, cfg_block = 0, cfg_lockstep = -1, cfg_fat = -1;   // OdgEnvConfig::launch_*
+  int step_fat = 1;                                       // which instantiation of the step kernel launch_step uses
   long long launches = 0;
 };
 

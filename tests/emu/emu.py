@@ -25,7 +25,7 @@ class OdgEnvConfig(C.Structure):
                 ("auto_reset", C.c_int), ("solver_iterations", C.c_int), ("ls_iterations", C.c_int),
                 ("solver_tolerance", C.c_float), ("ls_tolerance", C.c_float), ("reset_noise_scale", C.c_float),
                 ("scale_actions", C.c_int), ("launch_lanes", C.c_int), ("first_env_id", C.c_int), ("obs_layout", C.c_int),
-                ("launch_block", C.c_int), ("launch_lockstep", C.c_int)]
+                ("launch_block", C.c_int), ("launch_lockstep", C.c_int), ("launch_fat", C.c_int)]
 
 
 _p = C.c_void_p

@@ -17,7 +17,8 @@ from test_emu_parity import FLIP_M, assert_info_matches  # noqa: E402  (shared t
 # (2 / 4 environments per warp, one- and four-warp blocks). Every oracle comparison below runs under each of them.
 SHAPES = {
     "auto": {},
-    "lockstep": dict(launch_lanes=32, launch_block=64, launch_lockstep=1),
+    "lockstep": dict(launch_lanes=32, launch_block=64, launch_lockstep=1, launch_fat=0),      # what every large batch gets
+    "lean": dict(launch_fat=0),
     "2-per-warp": dict(launch_lanes=8, launch_block=128, launch_lockstep=0),
     "4-per-warp-lockstep": dict(launch_lanes=16, launch_block=32, launch_lockstep=1),
 }
@@ -429,3 +430,23 @@ def test_large_handles_match_the_oracle_on_random_subsets(n):
             assert min(oi["min_gap"][0], oi["min_gap"][1]) < FLIP_M, f"env {gid}: outside tolerance without a decision flip {oi['min_gap']}"
     assert outliers <= 3, f"{outliers}/256 decision flips"
     assert n_done >= 16 and n_contact >= 64, (n_done, n_contact)
+
+
+@pytest.mark.parametrize("model", ["our_robot", "go1"])
+def test_fat_and_lean_step_kernels_are_bit_identical(model):
+    """OdgEnvConfig::launch_fat only moves per-contact data between registers / recomputation and local memory (odg_core.cuh:
+    substep<NJL, FAT>): same arithmetic, so observations, rewards, flags and states agree bit for bit, step after step,
+    through contacts, terminations and auto-resets."""
+    from opendog_b200.env import BatchedWalkEnv
+    n = 512
+    envs = [BatchedWalkEnv(n, model=model, seed=5, info_keys=None, launch_fat=f, max_episode_steps=15) for f in (0, 1)]
+    o = [e.reset().clone() for e in envs]
+    assert torch.equal(o[0], o[1])
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for t in range(25):
+        a = (torch.rand(n, envs[0].act_dim, device="cuda", generator=g) * 2 - 1) * (1.0 if model == "our_robot" else 0.6)
+        out = [e.step(a) for e in envs]
+        for k in range(3):
+            assert torch.equal(out[0][k], out[1][k]), (model, t, k)
+    for a_, b_ in zip(envs[0].get_state(), envs[1].get_state()):
+        assert torch.equal(a_, b_)

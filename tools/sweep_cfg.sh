@@ -3,7 +3,7 @@
 for N in 4096 65536; do
   for cfg in "$@"; do
     args=""; for kv in $cfg; do [ "$kv" = "-" ] || args="$args --cfg $kv"; done
-    python bench.py --steps 30 --warmup 5 --no-cpu-baseline --large-batch 0 --rollout-envs 0 --mppi 0 --go1 0 --envs-per-gpu $N $args > gpurun_out/sweep.log 2>&1
+    python bench.py --steps 30 --warmup 5 --no-cpu-baseline --large-batch 0 --rollout-envs 0 --train-envs 0 --mppi 0 --go1 0 --envs-per-gpu $N $args > gpurun_out/sweep.log 2>&1
     python - "$N" "$cfg" <<'PY'
 import json,sys
 try:
