@@ -179,6 +179,13 @@ class BatchedWalkEnv:
         host views is returned as a fifth element. The returned arrays are views of an internal pinned buffer, valid
         until the next call."""
         N = self.num_envs
+        torch.cuda.nvtx.range_push("odg.step_host")
+        try:
+            return self._step_host(action_host, with_info, N)
+        finally:
+            torch.cuda.nvtx.range_pop()
+
+    def _step_host(self, action_host, with_info, N):
         if self._host is None:
             h = torch.empty_like(self._slab, device="cpu").pin_memory()
             self._host = dict(slab=h, act=torch.empty(N, self.act_dim).pin_memory(),

@@ -56,6 +56,13 @@ class Rollout:
         the last observation of the previous horizon over into row 0. The buffers a call returns are exactly what
         its own horizon produced: obs[t] is the observation action[t] / logp[t] / value[t] were computed from."""
         dev = self.env.device
+        torch.cuda.nvtx.range_push("odg.rollout.collect")          # timeline ranges for nsys / ncu --nvtx (SURVEY section 5: profiling)
+        try:
+            return self._collect(dev)
+        finally:
+            torch.cuda.nvtx.range_pop()
+
+    def _collect(self, dev):
         if self._started:
             self.obs[0].copy_(self.obs[self.T])
         self._started = True
@@ -82,7 +89,8 @@ class Rollout:
 
     def advantages(self, normalize: bool = True, group=None):
         """GAE over the collected horizon (sim2real/train.py:557-564). Returns (adv [T,N], returns [T,N], stats)."""
-        return gae(self.reward, self.value, self.done, self.gamma, self.lam, normalize=normalize, group=group)
+        with torch.cuda.nvtx.range("odg.rollout.gae"):
+            return gae(self.reward, self.value, self.done, self.gamma, self.lam, normalize=normalize, group=group)
 
     @property
     def kernels_per_collect(self) -> int:

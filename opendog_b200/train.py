@@ -189,6 +189,7 @@ class GraphedPPOUpdate:
         self.action.copy_(action); self.logp_old.copy_(logp_old); self.adv.copy_(adv); self.ret.copy_(ret)
 
     def __call__(self, obs, action, logp_old, adv, ret, epochs: int = 1):
+        torch.cuda.nvtx.range_push("odg.ppo_epoch")
         self.load(obs, action, logp_old, adv, ret)
         first = self.graphs is None
         if first:
@@ -198,4 +199,5 @@ class GraphedPPOUpdate:
                 g.replay()
         if hasattr(self.policy, "sync_weights"):
             self.policy.sync_weights()
+        torch.cuda.nvtx.range_pop()
         return self.out
