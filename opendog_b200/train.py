@@ -123,6 +123,8 @@ class GraphedPPOUpdate:
 
     def __init__(self, policy, optimizer, B: int, obs_dim: int, act_dim: int, minibatches: int = 4, clip: float = 0.2,
                  vf_coef: float = 0.5, ent_coef: float = 0.005, max_grad_norm: float = 0.5, group=None):
+        if not all(g.get("capturable", False) for g in optimizer.param_groups):
+            raise ValueError("GraphedPPOUpdate needs an optimizer created with capturable=True (its step is captured in a CUDA graph)")
         self.policy, self.opt, self.B, self.mbs, self.group = policy, optimizer, int(B), int(minibatches), group
         self.hp = dict(clip=clip, vf_coef=vf_coef, ent_coef=ent_coef, max_grad_norm=max_grad_norm)
         dev = next(policy.parameters()).device
