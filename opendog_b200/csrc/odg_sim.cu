@@ -160,6 +160,9 @@ int choose_launch(OdgSim* s) {
   if (s->P.N / 8 < s->num_sms) lanes = 8;
   if (s->cfg_lanes) lanes = s->cfg_lanes;
   const long long warps = ((long long)s->P.N * 4 + lanes - 1) / lanes;
+  // a batch that 64-thread blocks would spread unevenly (more blocks than SMs, fewer than two per SM) but 128-thread blocks
+  // place one per SM — one warp per scheduler everywhere — takes the larger block: 4096 envs = 128 blocks, +1.5 %
+  if (lanes == 32 && (warps + 1) / 2 > s->num_sms && (warps + 3) / 4 <= s->num_sms) block = 128;
   if (s->cfg_block) block = s->cfg_block;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev_occ, kern, block, s->smem_step));
   if (dev_occ < 1) dev_occ = 1;
