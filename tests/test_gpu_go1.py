@@ -124,3 +124,26 @@ def test_jump_task_matches_the_oracle_and_auto_resets():
             assert (st[d] == 0).all()
             assert (o[d][:, 2:6] == 0).all()                                      # reset obs: zero velocities
     assert dones >= 256 * 2
+
+
+@pytest.mark.parametrize("n", [1, 3, 65, 1000])
+def test_ragged_batch_sizes_on_every_model_and_task(n):
+    """Batch sizes that do not fill a warp, a block or a wave (the state arrays are padded to whole blocks and the padding
+    environments never touch caller buffers): every model / task steps, stays finite, and the first environment of a
+    ragged handle is bit-identical to the same environment in a 64-env handle."""
+    from opendog_b200.env import BatchedWalkEnv
+    g = torch.Generator(device="cuda").manual_seed(n)
+    for kw in (dict(), dict(model="go1"), dict(model="go1", task="jump")):
+        e = BatchedWalkEnv(n, seed=1, info_keys=None, **kw)
+        ref = BatchedWalkEnv(64, seed=1, info_keys=None, **kw)
+        o, o64 = e.reset(), ref.reset()
+        assert torch.equal(o[0], o64[0])
+        for t in range(4):
+            a64 = (torch.rand(64, e.act_dim, device="cuda", generator=g) * 2 - 1) * (0.3 if kw else 1.0)
+            if kw.get("task") == "jump":
+                a64 = torch.tensor(e.desc["key_ctrl"], device="cuda").expand(64, -1) + a64
+            a = a64[:n] if n <= 64 else torch.cat([a64, a64[:1].expand(n - 64, -1)]).contiguous()
+            o, r, d, _ = e.step(a.contiguous())
+            o64, r64, d64, _ = ref.step(a64.contiguous())
+            assert torch.isfinite(o).all() and torch.isfinite(r).all(), (n, kw, t)
+            assert torch.equal(o[0], o64[0]) and torch.equal(r[0], r64[0]) and torch.equal(d[0], d64[0]), (n, kw, t)
