@@ -26,6 +26,7 @@
 
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #ifdef ODG_HOST_EMU
 #define ODG_DEV inline
@@ -190,6 +191,17 @@ ODG_DEV float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 ODG_DEV float cross1(float a, float b, float c, float d) { return odg_fma_rn(a, b, -odg_fmul_rn(c, d)); }      // a*b - c*d
 ODG_DEV V3 cross(V3 a, V3 b) { return mk3(cross1(a.y, b.z, a.z, b.y), cross1(a.z, b.x, a.x, b.z), cross1(a.x, b.y, a.y, b.x)); }
 ODG_DEV float comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+// 16-byte records for per-contact data in local memory: one 128-bit load / store instead of three or four 32-bit ones
+ODG_DEV float4 mk4(V3 v, float w) { float4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = w; return r; }
+ODG_DEV V3 xyz(float4 q) { return mk3(q.x, q.y, q.z); }
+#ifdef ODG_HOST_EMU
+static inline float odg_int_bits(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline int odg_float_bits(float f) { int i; memcpy(&i, &f, 4); return i; }
+#else
+#define odg_int_bits __int_as_float
+#define odg_float_bits __float_as_int
+#endif
 
 struct M3 { float m[9]; };   // row-major
 ODG_DEV V3 mul(const M3& R, V3 v) {
@@ -724,23 +736,24 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     tau_l[j] = f - cbias[j] - LCF(LC_DAMP, j) * qd[j];
   }
   // ------------------------------------------------------------------ collision: floor plane vs hulls
-  V3 c_r[kMaxConLeg], c_aref[kMaxConLeg], c_z0[kMaxConLeg];     // cone rows of this leg's contacts
-  LineCoef c_lc[FAT ? kMaxConLeg : 1];                            // FAT: their line-search coefficients for the current direction
-  V3 c_dz[FAT ? 1 : kMaxConLeg];                                  // lean: the direction's row values (coefficients are re-derived per pass)
-  V3 c_cj[FAT ? kMaxConLeg : 1][NJL];                                       // Jacobian columns of this leg's joints at the contact point
+  // cone rows of this leg's contacts, as 16-byte records: (r, Dn) — Dn holds the distance until the rows are built —,
+  // (aref, slot index bits), (z0, -)
+  float4 c_ra[kMaxConLeg], c_af[kMaxConLeg], c_z0[kMaxConLeg];
+  float4 c_lc[FAT ? kMaxConLeg : 1][3];                           // FAT: their line-search coefficients (LineCoef) for the current direction
+  float4 c_dz[FAT ? 1 : kMaxConLeg];                              // lean: the direction's row values (coefficients are re-derived per pass)
+  float4 c_cj[FAT ? kMaxConLeg : 1][NJL];                                       // Jacobian columns of this leg's joints at the contact point
                                                                   // (zero for joints below the contact's link)
-  float c_Dn[kMaxConLeg]; int c_slot[kMaxConLeg];
   // 3-joint legs (Go1): every contact carries the three angular rows of condim 6 as well (torsional + rolling friction,
   // go1.xml:61-64); contacts of condim-3 geoms have zero coefficients there and reduce to the 3-row cone exactly
   constexpr bool kG = (NJL == 3);
   constexpr int kConA = kG ? kMaxConLeg : 1;
-  V3 c_arefa[kConA], c_z0a[kConA], c_dza[(kG && !FAT) ? kMaxConLeg : 1];
+  float4 c_arefa[kConA], c_z0a[kConA], c_dza[(kG && !FAT) ? kMaxConLeg : 1];
   int nc = 0;
   int foot_last = -1;
   auto add_contact = [&](float px, float py, float pz_mid, float dist, int s) {
     if (nc >= kMaxConLeg) return;
-    c_r[nc] = mk3(px, py, pz_mid);
-    c_Dn[nc] = dist; c_slot[nc] = s;
+    c_ra[nc] = mk4(mk3(px, py, pz_mid), dist);
+    c_af[nc] = mk4(mk3(0.f, 0.f, 0.f), odg_int_bits(s));
     if (C.slot_isfoot[s]) foot_last = nc;
     nc++;
   };
@@ -902,32 +915,33 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     }
   }
   // ------------------------------------------------------------------ constraint rows (mj_makeConstraint/Impedance)
-  // contacts: c_Dn currently holds dist; turn into D_n and build aref
+  // contacts: c_ra.w currently holds dist; turn into D_n and build aref
   for (int c = 0; c < nc; c++) {
-    const int s = c_slot[c];
+    const float4 ra = c_ra[c];
+    const int s = odg_float_bits(c_af[c].w);
     const int link = C.slot_link[s];
-    const float dist = c_Dn[c];
+    const float dist = ra.w;
     const float margin = C.slot_margin[s];
     float active = dist < margin ? 1.f : 0.f;       // excluded if in the gap (gap = 0: never for dist==margin only)
     float imp = impedance(C.slot_imp[s], dist - margin);
     float Rn = fmaxf(1e-15f, odg_fdiv_fast(1.f - imp, imp) * GCF(GC_INVW, s));
-    c_Dn[c] = odg_fdiv_fast(active, Rn);
     const float Bc = C.slot_B[s], Kc = C.slot_K[s];
-    const V3 r = c_r[c];
+    const V3 r = xyz(ra);
+    c_ra[c] = mk4(r, odg_fdiv_fast(active, Rn));
     V3 vc = bv + cross(w0, r);
     ODG_UNROLL for (int j = 0; j < NJL; j++) {
       const V3 cjv = (j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f);
-      if (FAT) c_cj[c][j] = cjv;
+      if (FAT) c_cj[c][j] = mk4(cjv, 0.f);
       vc = vc + qd[j] * cjv;
     }
-    c_aref[c] = mk3(-Bc * vc.x, -Bc * vc.y, -Bc * vc.z - Kc * imp * (dist - margin));
+    c_af[c] = mk4(mk3(-Bc * vc.x, -Bc * vc.y, -Bc * vc.z - Kc * imp * (dist - margin)), odg_int_bits(s));
     if constexpr (kG) {                             // torsional / rolling rows: aref = -B * (angular velocity of the body)
       V3 wb = w0;
       ODG_UNROLL for (int j = 0; j < NJL; j++) {
         const float on = fminf(fmaxf((float)(link - j + 1), 0.f), 1.f);
         wb = wb + (on * qd[j]) * ax[j];
       }
-      c_arefa[c] = mk3(-Bc * wb.x, -Bc * wb.y, -Bc * wb.z);
+      c_arefa[c] = mk4(mk3(-Bc * wb.x, -Bc * wb.y, -Bc * wb.z), 0.f);
     }
   }
   // own-joint friction-loss and limit rows
@@ -1021,18 +1035,19 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     }
     // contacts
     ODG_NO_UNROLL for (int c = 0; c < nc; c++) {
-      const int s = c_slot[c];
+      const float4 ra = c_ra[c], af = c_af[c];
+      const int s = odg_float_bits(af.w);
       const int link = C.slot_link[s];
-      const V3 r = c_r[c];
+      const V3 r = xyz(ra);
       V3 cj[NJL];
       V3 ap = a_b.t + cross(a_b.w, r);
       ODG_UNROLL for (int j = 0; j < NJL; j++) {
-        cj[j] = FAT ? c_cj[c][j] : ((j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f));
+        cj[j] = FAT ? xyz(c_cj[c][j]) : ((j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f));
         ap = ap + a_l[j] * cj[j];
       }
-      V3 z = ap - c_aref[c];
-      c_z0[c] = z;
-      const float Dn = c_Dn[c];
+      V3 z = ap - xyz(af);
+      c_z0[c] = mk4(z, 0.f);
+      const float Dn = ra.w;
       if constexpr (kG) {
         // 6-row block: linear rows through the contact point's Jacobian (column of DoF d: cl_d), angular rows through
         // the body's rotational Jacobian (column ca_d): trunk translation (e_i, 0), trunk rotation (e_k x r, e_k),
@@ -1043,8 +1058,8 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
           aj[j] = (j <= link) ? ax[j] : mk3(0.f, 0.f, 0.f);
           alb = alb + a_l[j] * aj[j];
         }
-        const V3 za = alb - c_arefa[c];
-        c_z0a[c] = za;
+        const V3 za = alb - xyz(c_arefa[c]);
+        c_z0a[c] = mk4(za, 0.f);
         const Cone6 K6 = cone6_make(Dn, C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_frt[s], C.slot_frr[s],
                                     C.slot_dt_tor[s], C.slot_dt_roll[s], C.slot_condim[s]);
         const float z6[6] = { z.x, z.y, z.z, za.x, za.y, za.z };
@@ -1181,24 +1196,24 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     }
     // the nine line-search coefficients of contact c for the direction whose row values are (dz, dza)
     auto line_coef = [&](int c, V3 dz, V3 dza) {
-      const int s = c_slot[c];
-      const float Dn = c_Dn[c];
+      const int s = odg_float_bits(c_af[c].w);
+      const float Dn = c_ra[c].w;
       if constexpr (kG) {
         const Cone6 K6 = cone6_make(Dn, C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_frt[s], C.slot_frr[s],
                                     C.slot_dt_tor[s], C.slot_dt_roll[s], C.slot_condim[s]);
-        const V3 zl = c_z0[c], za = c_z0a[c];
+        const V3 zl = xyz(c_z0[c]), za = xyz(c_z0a[c]);
         const float z6[6] = { zl.x, zl.y, zl.z, za.x, za.y, za.z }, d6[6] = { dz.x, dz.y, dz.z, dza.x, dza.y, dza.z };
         return cone6_line_prep(z6, d6, K6);
       } else {
-        return cone_line_prep(c_z0[c], dz, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s]);
+        return cone_line_prep(xyz(c_z0[c]), dz, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s]);
       }
     };
     ODG_NO_UNROLL for (int c = 0; c < nc; c++) {
-      const int link = C.slot_link[c_slot[c]];
-      const V3 r = c_r[c];
+      const int link = C.slot_link[odg_float_bits(c_af[c].w)];
+      const V3 r = xyz(c_ra[c]);
       V3 dz = p_b.t + cross(p_b.w, r);
       ODG_UNROLL for (int j = 0; j < NJL; j++)       // (zero columns below the contact's link)
-        dz = dz + p_l[j] * (FAT ? c_cj[c][j] : ((j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f)));
+        dz = dz + p_l[j] * (FAT ? xyz(c_cj[c][j]) : ((j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f)));
       V3 dza = p_b.w;
       if constexpr (kG) {
         ODG_UNROLL for (int j = 0; j < NJL; j++) {
@@ -1206,8 +1221,13 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
           dza = dza + (on * p_l[j]) * ax[j];
         }
       }
-      if constexpr (FAT) c_lc[c] = line_coef(c, dz, dza);
-      else { c_dz[c] = dz; if constexpr (kG) c_dza[c] = dza; }
+      if constexpr (FAT) {
+        const LineCoef k = line_coef(c, dz, dza);
+        float4 q;
+        q.x = k.N0; q.y = k.Nd; q.z = k.cA; q.w = k.cB; c_lc[c][0] = q;
+        q.x = k.cC; q.y = k.q1; q.z = k.q2; q.w = k.Dm; c_lc[c][1] = q;
+        q.x = k.mu; q.y = 0.f; q.z = 0.f; q.w = 0.f; c_lc[c][2] = q;
+      } else { c_dz[c] = mk4(dz, 0.f); if constexpr (kG) c_dza[c] = mk4(dza, 0.f); }
     }
     const float bf_zt = dot(bf_e, a_b.t) - bf_aref_t, bf_dzt = dot(bf_e, p_b.t);
     const float bf_zr = dot(bf_c, a_b.w) - bf_aref_r, bf_dzr = dot(bf_c, p_b.w);
@@ -1236,8 +1256,14 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(fmaxf(bf_Dt * (bf_zt + al[k] * bf_dzt), -bf_ft), bf_ft) * bf_dzt;
       ODG_UNROLL for (int k = 0; k < LW; k++) f[k] += fminf(fmaxf(bf_Dr * (bf_zr + al[k] * bf_dzr), -bf_fr), bf_fr) * bf_dzr;
       ODG_NO_UNROLL for (int c = 0; c < nc; c++) {               // (a row with D = 0 adds exactly 0: no skip, no branch)
-        if constexpr (FAT) cone_line_eval<LW>(c_lc[c], al, f);
-        else cone_line_eval<LW>(line_coef(c, c_dz[c], kG ? c_dza[c] : mk3(0.f, 0.f, 0.f)), al, f);
+        if constexpr (FAT) {
+          const float4 q0 = c_lc[c][0], q1 = c_lc[c][1], q2 = c_lc[c][2];
+          LineCoef k;
+          k.N0 = q0.x; k.Nd = q0.y; k.cA = q0.z; k.cB = q0.w; k.cC = q1.x; k.q1 = q1.y; k.q2 = q1.z; k.Dm = q1.w; k.mu = q2.x;
+          cone_line_eval<LW>(k, al, f);
+        } else {
+          cone_line_eval<LW>(line_coef(c, xyz(c_dz[c]), kG ? xyz(c_dza[c]) : mk3(0.f, 0.f, 0.f)), al, f);
+        }
       }
       ODG_UNROLL for (int k = 0; k < LW; k++) f[k] = grp_sum(f[k], gm);
     };
@@ -1341,19 +1367,19 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     if constexpr (kG) { ODG_UNROLL for (int q = 0; q <= NJL; q++) ODG_UNROLL for (int k = 0; k < 6; k++) out.cfrc[q][k] = 0.f; }
     float fn = 0.f;
     for (int c = 0; c < nc; c++) {
-      const int s = c_slot[c];
+      const int s = odg_float_bits(c_af[c].w);
       const int link = C.slot_link[s];
-      const float Dn = c_Dn[c];
+      const float Dn = c_ra[c].w;
       if (Dn == 0.f) continue;
-      const V3 r = c_r[c];
+      const V3 r = xyz(c_ra[c]);
       V3 ap = a_b.t + cross(a_b.w, r);
       ODG_UNROLL for (int j = 0; j < NJL; j++)
-        ap = ap + a_l[j] * (FAT ? c_cj[c][j] : ((j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f)));
+        ap = ap + a_l[j] * (FAT ? xyz(c_cj[c][j]) : ((j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f)));
       V3 g; S3 H;
       if constexpr (kG) {
         V3 alb = a_b.w;
         ODG_UNROLL for (int j = 0; j < NJL; j++) if (j <= link) alb = alb + a_l[j] * ax[j];
-        const V3 zl = ap - c_aref[c], za = alb - c_arefa[c];
+        const V3 zl = ap - xyz(c_af[c]), za = alb - xyz(c_arefa[c]);
         const Cone6 K6 = cone6_make(Dn, C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_frt[s], C.slot_frr[s],
                                     C.slot_dt_tor[s], C.slot_dt_roll[s], C.slot_condim[s]);
         const float z6[6] = { zl.x, zl.y, zl.z, za.x, za.y, za.z };
@@ -1370,7 +1396,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
           out.cfrc[q][3] += fw.x; out.cfrc[q][4] += fw.y; out.cfrc[q][5] += fw.z;
         }
       } else {
-        cone_eval(ap - c_aref[c], Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
+        cone_eval(ap - xyz(c_af[c]), Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
       }
       fn += -g.z;
       if (c == foot_last) out.foot_force = mk3(-g.z, -g.y, g.x);   // MuJoCo frame: n=+z, t1=+y, t2=-x
