@@ -746,6 +746,10 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
   // 3-joint legs (Go1): every contact carries the three angular rows of condim 6 as well (torsional + rolling friction,
   // go1.xml:61-64); contacts of condim-3 geoms have zero coefficients there and reduce to the 3-row cone exactly
   constexpr bool kG = (NJL == 3);
+  // FAT with 3-row cones: the spare words of a contact's records carry its cone constants — mu and the friction coefficient
+  // (0 for a frictionless row) next to the two Jacobian columns, 1 / (mu^2 (1 + mu^2)) in place of the slot index once
+  // the rows are built — so the iteration's loops need no per-slot constant lookups (dependent constant-bank loads)
+  constexpr bool kStash = FAT && !kG && NJL >= 2;
   constexpr int kConA = kG ? kMaxConLeg : 1;
   float4 c_arefa[kConA], c_z0a[kConA], c_dza[(kG && !FAT) ? kMaxConLeg : 1];
   int nc = 0;
@@ -931,10 +935,10 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     V3 vc = bv + cross(w0, r);
     ODG_UNROLL for (int j = 0; j < NJL; j++) {
       const V3 cjv = (j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f);
-      if (FAT) c_cj[c][j] = mk4(cjv, 0.f);
+      if (FAT) c_cj[c][j] = mk4(cjv, j == 0 ? C.slot_mu[s] : (C.slot_condim[s] == 1 ? 0.f : C.slot_fri[s]));
       vc = vc + qd[j] * cjv;
     }
-    c_af[c] = mk4(mk3(-Bc * vc.x, -Bc * vc.y, -Bc * vc.z - Kc * imp * (dist - margin)), odg_int_bits(s));
+    c_af[c] = mk4(mk3(-Bc * vc.x, -Bc * vc.y, -Bc * vc.z - Kc * imp * (dist - margin)), kStash ? C.slot_dmk[s] : odg_int_bits(s));
     if constexpr (kG) {                             // torsional / rolling rows: aref = -B * (angular velocity of the body)
       V3 wb = w0;
       ODG_UNROLL for (int j = 0; j < NJL; j++) {
@@ -1036,13 +1040,15 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     // contacts
     ODG_NO_UNROLL for (int c = 0; c < nc; c++) {
       const float4 ra = c_ra[c], af = c_af[c];
-      const int s = odg_float_bits(af.w);
+      const int s = kStash ? 0 : odg_float_bits(af.w);
       const int link = C.slot_link[s];
       const V3 r = xyz(ra);
       V3 cj[NJL];
+      float cjw[NJL];                               // (kStash: mu, friction)
       V3 ap = a_b.t + cross(a_b.w, r);
       ODG_UNROLL for (int j = 0; j < NJL; j++) {
-        cj[j] = FAT ? xyz(c_cj[c][j]) : ((j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f));
+        const float4 q = FAT ? c_cj[c][j] : mk4(((j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f)), 0.f);
+        cj[j] = xyz(q); cjw[j] = q.w;
         ap = ap + a_l[j] * cj[j];
       }
       V3 z = ap - xyz(af);
@@ -1096,7 +1102,8 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         continue;
       }
       V3 g; S3 H;
-      cone_eval(z, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
+      if constexpr (kStash) cone_eval(z, Dn, cjw[1] != 0.f ? Dn * C.impratio : 0.f, cjw[0], cjw[1], af.w, 3, g, H);
+      else cone_eval(z, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
       // (separated rows and rows with D = 0 come back as g = 0, H = 0 and add exactly 0 below)
       gb.t = gb.t + g; gb.w = gb.w + cross(r, g);
       // H * X, X = -[r]x : column i of X is e_i x r
@@ -1196,7 +1203,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     }
     // the nine line-search coefficients of contact c for the direction whose row values are (dz, dza)
     auto line_coef = [&](int c, V3 dz, V3 dza) {
-      const int s = odg_float_bits(c_af[c].w);
+      const int s = kStash ? 0 : odg_float_bits(c_af[c].w);
       const float Dn = c_ra[c].w;
       if constexpr (kG) {
         const Cone6 K6 = cone6_make(Dn, C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_frt[s], C.slot_frr[s],
@@ -1204,12 +1211,15 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         const V3 zl = xyz(c_z0[c]), za = xyz(c_z0a[c]);
         const float z6[6] = { zl.x, zl.y, zl.z, za.x, za.y, za.z }, d6[6] = { dz.x, dz.y, dz.z, dza.x, dza.y, dza.z };
         return cone6_line_prep(z6, d6, K6);
+      } else if constexpr (kStash) {
+        const float mu = c_cj[c][0].w, fri = c_cj[c][1].w;
+        return cone_line_prep(xyz(c_z0[c]), dz, Dn, fri != 0.f ? Dn * C.impratio : 0.f, mu, fri, c_af[c].w, 3);
       } else {
         return cone_line_prep(xyz(c_z0[c]), dz, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s]);
       }
     };
     ODG_NO_UNROLL for (int c = 0; c < nc; c++) {
-      const int link = C.slot_link[odg_float_bits(c_af[c].w)];
+      const int link = kStash ? 0 : C.slot_link[odg_float_bits(c_af[c].w)];
       const V3 r = xyz(c_ra[c]);
       V3 dz = p_b.t + cross(p_b.w, r);
       ODG_UNROLL for (int j = 0; j < NJL; j++)       // (zero columns below the contact's link)
@@ -1367,7 +1377,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     if constexpr (kG) { ODG_UNROLL for (int q = 0; q <= NJL; q++) ODG_UNROLL for (int k = 0; k < 6; k++) out.cfrc[q][k] = 0.f; }
     float fn = 0.f;
     for (int c = 0; c < nc; c++) {
-      const int s = odg_float_bits(c_af[c].w);
+      const int s = kStash ? 0 : odg_float_bits(c_af[c].w);
       const int link = C.slot_link[s];
       const float Dn = c_ra[c].w;
       if (Dn == 0.f) continue;
@@ -1396,7 +1406,12 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
           out.cfrc[q][3] += fw.x; out.cfrc[q][4] += fw.y; out.cfrc[q][5] += fw.z;
         }
       } else {
-        cone_eval(ap - xyz(c_af[c]), Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
+        if constexpr (kStash) {
+          const float mu = c_cj[c][0].w, fri = c_cj[c][1].w;
+          cone_eval(ap - xyz(c_af[c]), Dn, fri != 0.f ? Dn * C.impratio : 0.f, mu, fri, c_af[c].w, 3, g, H);
+        } else {
+          cone_eval(ap - xyz(c_af[c]), Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
+        }
       }
       fn += -g.z;
       if (c == foot_last) out.foot_force = mk3(-g.z, -g.y, g.x);   // MuJoCo frame: n=+z, t1=+y, t2=-x
