@@ -277,24 +277,35 @@ ODG_DEV void grp_sync(unsigned gmask) { __syncwarp(gmask); }
 #endif
 ODG_DEV float grp_sum(float v, unsigned gm) { v += grp_xor(v, 1, gm); v += grp_xor(v, 2, gm); return v; }
 ODG_DEV float grp_sum21(float v, unsigned gm) { v += grp_xor(v, 2, gm); v += grp_xor(v, 1, gm); return v; }
-// Sum of 28 values over the 4 lanes of a group through shared memory: one 112-byte row per lane (stride kRedStride
-// floats, so the float4 accesses of the 8 groups of a warp fall on different banks), summed in lane order 0,1,2,3 by
-// every lane (bit-identical results in all 4). 7 STS.128 + 28 LDS.128 + 84 FADD instead of 56 shuffles, each of which
-// costs a WARPSYNC/collective region under a partial mask: the Newton body is instruction-fetch bound.
-constexpr int kRedVals = 28, kRedStride = 36;
+// Sum of 28 values over the 4 lanes of a group through shared memory, in two stages: every lane stores its 28 values as
+// one row (stride kRedStride floats), then lane l sums columns [8l, 8l + 8) of the four rows — in lane order 0,1,2,3, so
+// the result does not depend on who computes it — back into row 0 (nobody else reads those columns), which all four lanes
+// then read. The rows must not grow: at 65536 envs four blocks per SM sit just under a shared-memory carve-out step, and
+// the next step takes 32 KB of L1 away from the local-memory traffic (-25 %). 7 + 2 STS.128,
+// 8 + 7 LDS.128 and 24 FADD per lane instead of 28 LDS.128 + 84 FADD when every lane sums everything (or 56 shuffles, each
+// of which costs a WARPSYNC / collective region under a partial mask): the Newton body is instruction-fetch bound.
+constexpr int kRedVals = 28, kRedStride = 36, kRedGroup = 4 * kRedStride;     // 4 rows per group
 constexpr int kSupportCells = 24;     // direction cells of the support-vertex candidate lists: dominant axis (3) x signs (8)
 ODG_DEV void grp_sum28(float (&v)[kRedVals], float* ODG_RESTRICT s_red, int leg, unsigned gm) {
   grp_sync(gm);                                    // earlier readers of the rows are done
   float4* mine = reinterpret_cast<float4*>(s_red + leg * kRedStride);
   ODG_UNROLL for (int k = 0; k < kRedVals / 4; k++) { float4 t; t.x = v[4 * k]; t.y = v[4 * k + 1]; t.z = v[4 * k + 2]; t.w = v[4 * k + 3]; mine[k] = t; }
   grp_sync(gm);
-  ODG_UNROLL for (int k = 0; k < kRedVals / 4; k++) {
+  float4* res = reinterpret_cast<float4*>(s_red);
+  ODG_UNROLL for (int h = 0; h < 2; h++) {         // (columns 28..31 are padding: whatever they hold is summed and never read)
+    const int k = 2 * leg + h;
     const float4 a = reinterpret_cast<const float4*>(s_red)[k];
     const float4 b = reinterpret_cast<const float4*>(s_red + kRedStride)[k];
     const float4 c = reinterpret_cast<const float4*>(s_red + 2 * kRedStride)[k];
     const float4 d = reinterpret_cast<const float4*>(s_red + 3 * kRedStride)[k];
-    v[4 * k] = ((a.x + b.x) + c.x) + d.x; v[4 * k + 1] = ((a.y + b.y) + c.y) + d.y;
-    v[4 * k + 2] = ((a.z + b.z) + c.z) + d.z; v[4 * k + 3] = ((a.w + b.w) + c.w) + d.w;
+    float4 t;
+    t.x = ((a.x + b.x) + c.x) + d.x; t.y = ((a.y + b.y) + c.y) + d.y; t.z = ((a.z + b.z) + c.z) + d.z; t.w = ((a.w + b.w) + c.w) + d.w;
+    res[k] = t;
+  }
+  grp_sync(gm);
+  ODG_UNROLL for (int k = 0; k < kRedVals / 4; k++) {
+    const float4 t = res[k];
+    v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
   }
 }
 ODG_DEV float grp_max(float v, unsigned gm) { v = fmaxf(v, grp_xor(v, 1, gm)); v = fmaxf(v, grp_xor(v, 2, gm)); return v; }

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(ODG_MAX_BLOCK, ODG_MIN_BLOCKS) k_step(const __
   const int leg = threadIdx.x & 3;
   const int lane = threadIdx.x & 31;
   // per-group reduction rows (odg_core.cuh: grp_sum28) follow the staged constants
-  float* s_red = smem + L.vert_floats + L.lc_floats + L.gc_floats + (threadIdx.x >> 2) * (4 * odg::kRedStride);
+  float* s_red = smem + L.vert_floats + L.lc_floats + L.gc_floats + (threadIdx.x >> 2) * odg::kRedGroup;
   if (lane >= lanes) return;
   const unsigned gm = 0xFu << (lane & 28);
   const int envs_per_warp = lanes >> 2;
@@ -261,7 +261,7 @@ int odg_create(const OdgModel* model, const OdgEnvConfig* cfg_in, int num_envs, 
       upload(&s->d_vert, s->prep.vert) != cudaSuccess) { odg_destroy(s); return fail(ODG_ERR_ALLOC, "constant upload failed"); }
   s->L.lc_floats = (int)s->prep.lc.size(); s->L.gc_floats = (int)s->prep.gc.size(); s->L.vert_floats = (int)s->prep.vert.size();
   s->smem_const = (size_t)(s->L.lc_floats + s->L.gc_floats + s->L.vert_floats) * sizeof(float);
-  s->smem_step = s->smem_const + (size_t)ODG_MAX_BLOCK * odg::kRedStride * sizeof(float);
+  s->smem_step = s->smem_const + (size_t)(ODG_MAX_BLOCK / 4) * odg::kRedGroup * sizeof(float);
   if ((cfg.launch_lanes != 0 && cfg.launch_lanes != 4 && cfg.launch_lanes != 8 && cfg.launch_lanes != 16 && cfg.launch_lanes != 32) ||
       (cfg.launch_block != 0 && cfg.launch_block != 32 && cfg.launch_block != 64 && cfg.launch_block != 128 &&
        !(cfg.launch_block == 256 && ODG_MAX_BLOCK >= 256)) || cfg.launch_lockstep < -1 || cfg.launch_lockstep > 1 ||

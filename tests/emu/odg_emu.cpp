@@ -116,7 +116,7 @@ void emu_step(Emu* e, const odg::StepArgs* A) {
   odg::StepArgs a = *A;
   run4([=](int l) {
     const float4* sv = reinterpret_cast<const float4*>(e->prep.vert.data());
-    alignas(16) static float s_red[4 * odg::kRedStride];     // the group's shared-memory reduction rows
+    alignas(16) static float s_red[odg::kRedGroup];     // the group's shared-memory reduction rows
     for (int i = 0; i < e->N; i++) {
       if (e->prep.C.njl == 2) odg::env_step<2, true>(e->prep.C, e->prep.lc.data(), e->prep.gc.data(), sv, e->P, a, a.action, i, l, 0xFu, s_red);
       else odg::env_step<3, true>(e->prep.C, e->prep.lc.data(), e->prep.gc.data(), sv, e->P, a, a.action, i, l, 0xFu, s_red);
