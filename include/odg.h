@@ -74,7 +74,9 @@ typedef struct OdgEnvConfig {
                                 formula), 2 v_des, q - key_qpos[0,7:], 0.05 qd, last_action] */
   int launch_block;          /* threads per block of the step kernel: 32, 64 or 128; 0 = 64 */
   int launch_lockstep;       /* 1 = the warps of a block take Newton iterations in lockstep (one barrier per iteration;
-                                pays when the batch is several waves deep), 0 = never, -1 = chosen from the batch size */
+                                pays when the batch is several waves deep), 2 = pairs of warps inside 128-thread blocks do
+                                (named barriers; needs launch_lanes 32 and launch_block 128 or 0), 0 = never, -1 = chosen
+                                from the batch size */
   int launch_fat;            /* 1 = the instantiation of the step kernel that keeps per-contact Jacobian columns and line-search
                                 coefficients in local memory instead of recomputing them (pays when a warp has a scheduler
                                 to itself), 0 = the lean one, -1 = chosen from the batch size. Schedule only: results are

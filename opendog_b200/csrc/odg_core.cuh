@@ -185,7 +185,11 @@ ODG_DEV V3 operator+(V3 a, V3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); 
 ODG_DEV V3 operator-(V3 a, V3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
 ODG_DEV V3 operator*(float s, V3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
 ODG_DEV V3 operator-(V3 a) { return mk3(-a.x, -a.y, -a.z); }
-ODG_DEV float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// (sums of products in one fixed fused order — see cross(): the order must not depend on the code around the call)
+ODG_DEV float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+  return odg_fma_rn(az, bz, odg_fma_rn(ay, by, odg_fmul_rn(ax, bx)));
+}
+ODG_DEV float dot(V3 a, V3 b) { return dot3(a.x, a.y, a.z, b.x, b.y, b.z); }
 // (explicit fused form: `a.y * b.z - a.z * b.y` may be contracted either way round, and the two instantiations of the step
 //  kernel — one stores a contact's Jacobian columns, one recomputes them — must produce the same bits at every site)
 ODG_DEV float cross1(float a, float b, float c, float d) { return odg_fma_rn(a, b, -odg_fmul_rn(c, d)); }      // a*b - c*d
@@ -205,12 +209,12 @@ static inline int odg_float_bits(float f) { int i; memcpy(&i, &f, 4); return i; 
 
 struct M3 { float m[9]; };   // row-major
 ODG_DEV V3 mul(const M3& R, V3 v) {
-  return mk3(R.m[0] * v.x + R.m[1] * v.y + R.m[2] * v.z, R.m[3] * v.x + R.m[4] * v.y + R.m[5] * v.z,
-             R.m[6] * v.x + R.m[7] * v.y + R.m[8] * v.z);
+  return mk3(dot3(R.m[0], R.m[1], R.m[2], v.x, v.y, v.z), dot3(R.m[3], R.m[4], R.m[5], v.x, v.y, v.z),
+             dot3(R.m[6], R.m[7], R.m[8], v.x, v.y, v.z));
 }
 ODG_DEV V3 tmul(const M3& R, V3 v) {
-  return mk3(R.m[0] * v.x + R.m[3] * v.y + R.m[6] * v.z, R.m[1] * v.x + R.m[4] * v.y + R.m[7] * v.z,
-             R.m[2] * v.x + R.m[5] * v.y + R.m[8] * v.z);
+  return mk3(dot3(R.m[0], R.m[3], R.m[6], v.x, v.y, v.z), dot3(R.m[1], R.m[4], R.m[7], v.x, v.y, v.z),
+             dot3(R.m[2], R.m[5], R.m[8], v.x, v.y, v.z));
 }
 ODG_DEV M3 mul(const M3& A, const M3& B) {
   M3 C;
@@ -224,8 +228,8 @@ ODG_DEV V3 col(const M3& R, int k) { return mk3(R.m[k], R.m[3 + k], R.m[6 + k]);
 // symmetric 3x3: xx xy xz yy yz zz
 struct S3 { float xx, xy, xz, yy, yz, zz; };
 ODG_DEV V3 mul(const S3& A, V3 v) {
-  return mk3(A.xx * v.x + A.xy * v.y + A.xz * v.z, A.xy * v.x + A.yy * v.y + A.yz * v.z,
-             A.xz * v.x + A.yz * v.y + A.zz * v.z);
+  return mk3(dot3(A.xx, A.xy, A.xz, v.x, v.y, v.z), dot3(A.xy, A.yy, A.yz, v.x, v.y, v.z),
+             dot3(A.xz, A.yz, A.zz, v.x, v.y, v.z));
 }
 ODG_DEV S3 zero_s3() { S3 s; s.xx = s.xy = s.xz = s.yy = s.yz = s.zz = 0.f; return s; }
 ODG_DEV void add_outer(S3& A, V3 a, V3 b) {   // A += sym part of a b^T + b a^T scaled 0.5 ... used only with a==b scaled
@@ -390,7 +394,9 @@ ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, float dmk, 
   // A frictionless (condim 1) row is the same cone with fri = Dt = 0: T = 0, zone = (N >= 0 ? top : bottom).
   if (condim == 1) { fri = 0.f; Dt = 0.f; }
   const float U1 = z.x * fri, U2 = z.y * fri, N = z.z * mu;
-  const float T2 = U1 * U1 + U2 * U2;
+  // (sums of two products are written with explicit fused operations: "a*b + c*d" can be contracted either way round,
+  //  and the two instantiations of the step kernel inline this function into differently shaped code)
+  const float T2 = odg_fma_rn(U1, U1, odg_fmul_rn(U2, U2));
   const float iT = odg_rsqrt(fmaxf(T2, 1e-20f));
   const float T = T2 * iT;
   const bool top = N >= mu * T;                      // separating (T == 0: N >= 0)
@@ -410,10 +416,11 @@ ODG_DEV int cone_eval(V3 z, float Dn, float Dt, float mu, float fri, float dmk, 
   g.x = mid ? De * w.x : (bot ? Dt * z.x : 0.f);
   g.y = mid ? De * w.y : (bot ? Dt * z.y : 0.f);
   g.z = mid ? De * w.z : (bot ? Dn * z.z : 0.f);
-  H.xx = mid ? Dm * w.x * w.x + kap * vx * vx : (bot ? Dt : 0.f);
-  H.yy = mid ? Dm * w.y * w.y + kap * vy * vy : (bot ? Dt : 0.f);
+  const float Dwx = Dm * w.x, Dwy = Dm * w.y, kvx = kap * vx;
+  H.xx = mid ? odg_fma_rn(Dwx, w.x, odg_fmul_rn(kvx, vx)) : (bot ? Dt : 0.f);
+  H.yy = mid ? odg_fma_rn(Dwy, w.y, odg_fmul_rn(odg_fmul_rn(kap, vy), vy)) : (bot ? Dt : 0.f);
   H.zz = mid ? Dm * w.z * w.z : (bot ? Dn : 0.f);
-  H.xy = mid ? Dm * w.x * w.y + kap * vx * vy : 0.f;
+  H.xy = mid ? odg_fma_rn(Dwx, w.y, odg_fmul_rn(kvx, vy)) : 0.f;
   H.xz = mid ? Dm * w.x * w.z : 0.f;
   H.yz = mid ? Dm * w.y * w.z : 0.f;
   return top ? 0 : (bot ? 1 : 2);
@@ -1000,7 +1007,17 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     // although 13 % of the samples then sit here) and costs a little when every warp has a scheduler to itself
     // (-2 % at 4096), so the host enables it per batch size (DevConst::lockstep).
     if (C.lockstep) {
-      if (!__syncthreads_or(conv ? 0 : 1)) break;
+      // lockstep == 2: PAIRS of warps inside a larger block (named barrier 1 + pair index, 64 threads): the pairing that
+      // is fastest, with the block's constants staged once for two pairs — half the shared memory per SM, which keeps
+      // four pairs under a smaller carve-out and leaves the L1 to the local-memory traffic
+      int any;
+      if (C.lockstep == 2) {
+        asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 q, %1, 0;\n bar.red.or.pred p, %2, 64, q;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(any) : "r"(conv ? 0u : 1u), "r"(1u + (threadIdx.x >> 6)) : "memory");
+      } else {
+        any = __syncthreads_or(conv ? 0 : 1);
+      }
+      if (!any) break;
       if (conv) continue;
     } else if (conv) break;
 #else

@@ -143,36 +143,51 @@ StepKernel step_kernel_fn(const DevConst& C, bool fat) {
 const void* step_kernel(const DevConst& C, bool fat) { return (const void*)step_kernel_fn(C, fat); }
 
 int choose_launch(OdgSim* s) {
-  // 4 lanes per env, persistent blocks (constants staged once per block).
-  int dev_occ = 0;
+  // 4 lanes per env, persistent blocks (constants staged once per block). Shared memory per block = the staged constants
+  // + one reduction area per 4-lane group of THIS block size: how much shared memory the resident blocks of an SM take
+  // decides the carve-out and with it how much L1 is left for the kernel's local-memory traffic (per-contact records) —
+  // at 65536 envs one carve-out step (32 KB of L1) is worth 25 % of the throughput.
   const void* kern = step_kernel(s->prep.C, false);
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_step));
-  CUDA_TRY(cudaFuncSetAttribute(step_kernel(s->prep.C, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_step));
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev_occ, kern, 128, s->smem_step));
-  if (dev_occ < 1) dev_occ = 1;
-  // Measured on B200 (tools/tune_launch_shape.sh): 64-thread blocks (2 warps walking the Newton loop in lockstep, 4 blocks per
-  // SM) with 8 environments per warp are fastest at 4096 and at 65536 environments; fewer environments per warp or
-  // one-warp blocks lose more to instruction fetch than they gain in divergence.
+  auto smem_for = [&](int block) { return s->smem_const + (size_t)(block / 4) * odg::kRedGroup * sizeof(float); };
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(ODG_MAX_BLOCK)));
+  CUDA_TRY(cudaFuncSetAttribute(step_kernel(s->prep.C, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(ODG_MAX_BLOCK)));
+  // Measured on B200 (tools/tune_launch_shape.sh, tools/tune_4096.sh, tools/tune_fat.sh): 8 environments per warp; fewer
+  // environments per warp or one-warp blocks lose more to instruction fetch than they gain in divergence.
   int lanes = 32;
-  int block = 64;
   // tiny batches (MPPI: 1024 samples) leave most schedulers empty: 2 environments per warp, so 4x the warps share the
   // work and fewer environments wait on the slowest one of their warp (40.5 vs 46.6 ms per 1024 x 64 plan)
   if (s->P.N / 8 < s->num_sms) lanes = 8;
   if (s->cfg_lanes) lanes = s->cfg_lanes;
   const long long warps = ((long long)s->P.N * 4 + lanes - 1) / lanes;
-  // a batch that 64-thread blocks would spread unevenly (more blocks than SMs, fewer than two per SM) but 128-thread blocks
-  // place one per SM — one warp per scheduler everywhere — takes the larger block: 4096 envs = 128 blocks, +1.5 %
+  auto occupancy = [&](int block, int* occ) -> cudaError_t {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, block, smem_for(block));
+    if (*occ < 1) *occ = 1;
+    return e;
+  };
+  // is the batch more than half a wave of two-warp blocks? (measured: lockstep and the lean instantiation pay from ~8192 envs up)
+  int occ64 = 1;
+  CUDA_TRY(occupancy(64, &occ64));
+  const bool deep = 2 * ((warps + 1) / 2) > (long long)s->num_sms * occ64;
+  int block = 64;
+  // a small batch that 64-thread blocks would spread unevenly (more blocks than SMs, fewer than two per SM) but 128-thread
+  // blocks place one per SM — one warp per scheduler everywhere — takes the larger block: 4096 envs = 128 blocks, +1.5 %
   if (lanes == 32 && (warps + 1) / 2 > s->num_sms && (warps + 3) / 4 <= s->num_sms) block = 128;
+  // lockstep: 0 = free-running warps, 1 = all warps of a block take Newton iterations together, 2 = PAIRS of warps inside
+  // 128-thread blocks (named barriers): the fastest pairing with the constants staged once for two pairs. Deep batches
+  // get 2, shallow ones 0.
+  int lockstep = deep ? (lanes == 32 ? 2 : 1) : 0;
+  if (s->cfg_lockstep >= 0) lockstep = s->cfg_lockstep;
+  if (lockstep == 2 && !s->cfg_block) block = 128;
   if (s->cfg_block) block = s->cfg_block;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev_occ, kern, block, s->smem_step));
-  if (dev_occ < 1) dev_occ = 1;
-  const long long wpb = block / 32, need = (warps + wpb - 1) / wpb, cap = (long long)s->num_sms * dev_occ;
-  s->step_lanes = lanes; s->step_block = block;
-  s->prep.C.lockstep = 2 * need > cap ? 1 : 0;    // measured: pays from ~8192 envs up (tools/tune_launch_shape.sh)
-  if (s->cfg_lockstep >= 0) s->prep.C.lockstep = s->cfg_lockstep ? 1 : 0;
+  if (lockstep == 2 && (block != 128 || lanes != 32)) lockstep = 1;      // pairs need whole warps in 128-thread blocks
+  int occ = 1;
+  CUDA_TRY(occupancy(block, &occ));
+  const long long wpb = block / 32, need = (warps + wpb - 1) / wpb, cap = (long long)s->num_sms * occ;
+  s->step_lanes = lanes; s->step_block = block; s->smem_step = smem_for(block);
+  s->prep.C.lockstep = lockstep;
   // the local-memory-heavier instantiation wherever a warp has a scheduler (and its share of the L1) nearly to itself:
-  // the same batches that run without lockstep (measured: +6.5 % at 4096 envs, -18 % at 65536)
-  s->step_fat = 2 * need > cap ? 0 : 1;
+  // the shallow batches (measured: +6.5 % at 4096 envs, -18 % at 65536)
+  s->step_fat = deep ? 0 : 1;
   if (s->cfg_fat >= 0) s->step_fat = s->cfg_fat ? 1 : 0;
   s->step_grid = (int)(need < cap ? need : cap);
   return ODG_OK;
@@ -261,10 +276,9 @@ int odg_create(const OdgModel* model, const OdgEnvConfig* cfg_in, int num_envs, 
       upload(&s->d_vert, s->prep.vert) != cudaSuccess) { odg_destroy(s); return fail(ODG_ERR_ALLOC, "constant upload failed"); }
   s->L.lc_floats = (int)s->prep.lc.size(); s->L.gc_floats = (int)s->prep.gc.size(); s->L.vert_floats = (int)s->prep.vert.size();
   s->smem_const = (size_t)(s->L.lc_floats + s->L.gc_floats + s->L.vert_floats) * sizeof(float);
-  s->smem_step = s->smem_const + (size_t)(ODG_MAX_BLOCK / 4) * odg::kRedGroup * sizeof(float);
   if ((cfg.launch_lanes != 0 && cfg.launch_lanes != 4 && cfg.launch_lanes != 8 && cfg.launch_lanes != 16 && cfg.launch_lanes != 32) ||
       (cfg.launch_block != 0 && cfg.launch_block != 32 && cfg.launch_block != 64 && cfg.launch_block != 128 &&
-       !(cfg.launch_block == 256 && ODG_MAX_BLOCK >= 256)) || cfg.launch_lockstep < -1 || cfg.launch_lockstep > 1 ||
+       !(cfg.launch_block == 256 && ODG_MAX_BLOCK >= 256)) || cfg.launch_lockstep < -1 || cfg.launch_lockstep > 2 ||
       cfg.launch_fat < -1 || cfg.launch_fat > 1) {
     odg_destroy(s); return fail(ODG_ERR_INVALID, "odg_create: bad launch_lanes / launch_block / launch_lockstep / launch_fat");
   }
