@@ -194,6 +194,12 @@ ODG_DEV float dot(V3 a, V3 b) { return dot3(a.x, a.y, a.z, b.x, b.y, b.z); }
 //  kernel — one stores a contact's Jacobian columns, one recomputes them — must produce the same bits at every site)
 ODG_DEV float cross1(float a, float b, float c, float d) { return odg_fma_rn(a, b, -odg_fmul_rn(c, d)); }      // a*b - c*d
 ODG_DEV V3 cross(V3 a, V3 b) { return mk3(cross1(a.y, b.z, a.z, b.y), cross1(a.z, b.x, a.x, b.z), cross1(a.x, b.y, a.y, b.x)); }
+// accumulating forms, one fused multiply-add per product: acc + a.b and acc + a x b
+ODG_DEV float dot_acc(float acc, V3 a, V3 b) { return odg_fma_rn(a.z, b.z, odg_fma_rn(a.y, b.y, odg_fma_rn(a.x, b.x, acc))); }
+ODG_DEV float cross1_acc(float acc, float a, float b, float c, float d) { return odg_fma_rn(a, b, odg_fma_rn(-c, d, acc)); }
+ODG_DEV V3 cross_acc(V3 acc, V3 a, V3 b) {
+  return mk3(cross1_acc(acc.x, a.y, b.z, a.z, b.y), cross1_acc(acc.y, a.z, b.x, a.x, b.z), cross1_acc(acc.z, a.x, b.y, a.y, b.x));
+}
 ODG_DEV float comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 
 // 16-byte records for per-contact data in local memory: one 128-bit load / store instead of three or four 32-bit ones
@@ -1073,7 +1079,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       const V3 r = xyz(ra);
       V3 cj[NJL];
       float cjw[NJL];                               // (kStash: mu, friction)
-      V3 ap = a_b.t + cross(a_b.w, r);
+      V3 ap = cross_acc(a_b.t, a_b.w, r);
       ODG_UNROLL for (int j = 0; j < NJL; j++) {
         const float4 q = FAT ? c_cj[c][j] : mk4(((j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f)), 0.f);
         cj[j] = xyz(q); cjw[j] = q.w;
@@ -1133,7 +1139,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       if constexpr (kStash) cone_eval(z, Dn, cjw[1] != 0.f ? Dn * C.impratio : 0.f, cjw[0], cjw[1], af.w, 3, g, H);
       else cone_eval(z, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
       // (separated rows and rows with D = 0 come back as g = 0, H = 0 and add exactly 0 below)
-      gb.t = gb.t + g; gb.w = gb.w + cross(r, g);
+      gb.t = gb.t + g; gb.w = cross_acc(gb.w, r, g);
       // H * X, X = -[r]x : column i of X is e_i x r
       V3 X0 = mk3(0.f, -r.z, r.y), X1 = mk3(r.z, 0.f, -r.x), X2 = mk3(-r.y, r.x, 0.f);
       V3 HX0 = mul(H, X0), HX1 = mul(H, X1), HX2 = mul(H, X2);
@@ -1141,16 +1147,13 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       Htw[0][0] += HX0.x; Htw[1][0] += HX0.y; Htw[2][0] += HX0.z;
       Htw[0][1] += HX1.x; Htw[1][1] += HX1.y; Htw[2][1] += HX1.z;
       Htw[0][2] += HX2.x; Htw[1][2] += HX2.y; Htw[2][2] += HX2.z;
-      Hww.xx += dot(X0, HX0); Hww.xy += dot(X0, HX1); Hww.xz += dot(X0, HX2);
-      Hww.yy += dot(X1, HX1); Hww.yz += dot(X1, HX2); Hww.zz += dot(X2, HX2);
+      Hww.xx = dot_acc(Hww.xx, X0, HX0); Hww.xy = dot_acc(Hww.xy, X0, HX1); Hww.xz = dot_acc(Hww.xz, X0, HX2);
+      Hww.yy = dot_acc(Hww.yy, X1, HX1); Hww.yz = dot_acc(Hww.yz, X1, HX2); Hww.zz = dot_acc(Hww.zz, X2, HX2);
       ODG_UNROLL for (int j = 0; j < NJL; j++) {    // (cj[j] = 0 for joints below the contact's link: adds exactly 0)
         V3 hc = mul(H, cj[j]);
-        g_l[j] += dot(cj[j], g);
-        Hlb[j].t = Hlb[j].t + hc; Hlb[j].w = Hlb[j].w + cross(r, hc);
-        ODG_UNROLL for (int i = 0; i <= j; i++) {
-          float v = dot(cj[i], hc);
-          Hll[j][i] += v; if (i != j) Hll[i][j] += v;
-        }
+        g_l[j] = dot_acc(g_l[j], cj[j], g);
+        Hlb[j].t = Hlb[j].t + hc; Hlb[j].w = cross_acc(Hlb[j].w, r, hc);
+        ODG_UNROLL for (int i = 0; i <= j; i++) Hll[j][i] = dot_acc(Hll[j][i], cj[i], hc);   // (lower triangle: all chol_small reads)
       }
     }
     // ---- eliminate the leg block: Schur complement on the trunk
@@ -1249,7 +1252,7 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     ODG_NO_UNROLL for (int c = 0; c < nc; c++) {
       const int link = kStash ? 0 : C.slot_link[odg_float_bits(c_af[c].w)];
       const V3 r = xyz(c_ra[c]);
-      V3 dz = p_b.t + cross(p_b.w, r);
+      V3 dz = cross_acc(p_b.t, p_b.w, r);
       ODG_UNROLL for (int j = 0; j < NJL; j++)       // (zero columns below the contact's link)
         dz = dz + p_l[j] * (FAT ? xyz(c_cj[c][j]) : ((j <= link) ? cross(ax[j], r - anc[j]) : mk3(0.f, 0.f, 0.f)));
       V3 dza = p_b.w;
