@@ -1140,15 +1140,19 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
       else cone_eval(z, Dn, Dn * C.impratio, C.slot_mu[s], C.slot_fri[s], C.slot_dmk[s], C.slot_condim[s], g, H);
       // (separated rows and rows with D = 0 come back as g = 0, H = 0 and add exactly 0 below)
       gb.t = gb.t + g; gb.w = cross_acc(gb.w, r, g);
-      // H * X, X = -[r]x : column i of X is e_i x r
-      V3 X0 = mk3(0.f, -r.z, r.y), X1 = mk3(r.z, 0.f, -r.x), X2 = mk3(-r.y, r.x, 0.f);
-      V3 HX0 = mul(H, X0), HX1 = mul(H, X1), HX2 = mul(H, X2);
+      // H * X, X = -[r]x : column i of X is e_i x r = (0, -r.z, r.y), (r.z, 0, -r.x), (-r.y, r.x, 0). Written out with the
+      // zeros dropped: every entry of H X and of X^T (H X) is one "a*b - c*d".
+      const V3 HX0 = mk3(cross1(H.xz, r.y, H.xy, r.z), cross1(H.yz, r.y, H.yy, r.z), cross1(H.zz, r.y, H.yz, r.z));
+      const V3 HX1 = mk3(cross1(H.xx, r.z, H.xz, r.x), cross1(H.xy, r.z, H.yz, r.x), cross1(H.xz, r.z, H.zz, r.x));
+      const V3 HX2 = mk3(cross1(H.xy, r.x, H.xx, r.y), cross1(H.yy, r.x, H.xy, r.y), cross1(H.yz, r.x, H.xz, r.y));
       Htt.xx += H.xx; Htt.xy += H.xy; Htt.xz += H.xz; Htt.yy += H.yy; Htt.yz += H.yz; Htt.zz += H.zz;
       Htw[0][0] += HX0.x; Htw[1][0] += HX0.y; Htw[2][0] += HX0.z;
       Htw[0][1] += HX1.x; Htw[1][1] += HX1.y; Htw[2][1] += HX1.z;
       Htw[0][2] += HX2.x; Htw[1][2] += HX2.y; Htw[2][2] += HX2.z;
-      Hww.xx = dot_acc(Hww.xx, X0, HX0); Hww.xy = dot_acc(Hww.xy, X0, HX1); Hww.xz = dot_acc(Hww.xz, X0, HX2);
-      Hww.yy = dot_acc(Hww.yy, X1, HX1); Hww.yz = dot_acc(Hww.yz, X1, HX2); Hww.zz = dot_acc(Hww.zz, X2, HX2);
+      // X0 . v = r.y v.z - r.z v.y,  X1 . v = r.z v.x - r.x v.z,  X2 . v = r.x v.y - r.y v.x
+      Hww.xx = cross1_acc(Hww.xx, r.y, HX0.z, r.z, HX0.y); Hww.xy = cross1_acc(Hww.xy, r.y, HX1.z, r.z, HX1.y);
+      Hww.xz = cross1_acc(Hww.xz, r.y, HX2.z, r.z, HX2.y); Hww.yy = cross1_acc(Hww.yy, r.z, HX1.x, r.x, HX1.z);
+      Hww.yz = cross1_acc(Hww.yz, r.z, HX2.x, r.x, HX2.z); Hww.zz = cross1_acc(Hww.zz, r.x, HX2.y, r.y, HX2.x);
       ODG_UNROLL for (int j = 0; j < NJL; j++) {    // (cj[j] = 0 for joints below the contact's link: adds exactly 0)
         V3 hc = mul(H, cj[j]);
         g_l[j] = dot_acc(g_l[j], cj[j], g);
