@@ -318,6 +318,19 @@ ODG_DEV void grp_sum28(float (&v)[kRedVals], float* ODG_RESTRICT s_red, int leg,
     v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
   }
 }
+// One sum and two maxima over the 4 lanes of a group in a single shared-memory round (the rows of grp_sum28): one
+// STS.128 + four LDS.128 instead of six partial-mask shuffles.
+ODG_DEV void grp_sum_max2(float& sum, float& m0, float& m1, float* ODG_RESTRICT s_red, int leg, unsigned gm) {
+  grp_sync(gm);                                    // earlier readers of the rows are done
+  float4 t; t.x = sum; t.y = m0; t.z = m1; t.w = 0.f;
+  *reinterpret_cast<float4*>(s_red + leg * kRedStride) = t;
+  grp_sync(gm);
+  const float4 a = *reinterpret_cast<const float4*>(s_red), b = *reinterpret_cast<const float4*>(s_red + kRedStride);
+  const float4 c = *reinterpret_cast<const float4*>(s_red + 2 * kRedStride), d = *reinterpret_cast<const float4*>(s_red + 3 * kRedStride);
+  sum = ((a.x + b.x) + c.x) + d.x;
+  m0 = fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y));
+  m1 = fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z));
+}
 ODG_DEV float grp_max(float v, unsigned gm) { v = fmaxf(v, grp_xor(v, 1, gm)); v = fmaxf(v, grp_xor(v, 2, gm)); return v; }
 ODG_DEV V3 grp_sum(V3 v, unsigned gm) { return mk3(grp_sum(v.x, gm), grp_sum(v.y, gm), grp_sum(v.z, gm)); }
 ODG_DEV float grp_bcast(float v, int src_leg, int leg, unsigned gm) {   // value of lane `src_leg` to all 4
@@ -1279,7 +1292,13 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
     // phi'(0) = p . grad  (lane-partials of the trunk gradient were kept in gb)
     float d10 = dot6(gb, p_b);
     ODG_UNROLL for (int j = 0; j < NJL; j++) d10 += p_l[j] * g_l[j];
-    d10 = grp_sum(d10, gm);
+    // size of the full Newton step relative to the iterate: when it is already negligible this is the last iteration
+    // and the step is taken without a line search
+    float amax = 0.f, smax = 0.f;
+    smax = fmaxf(fmaxf(fabsf(p_b.t.x), fabsf(p_b.t.y)), fmaxf(fabsf(p_b.t.z), fmaxf(fabsf(p_b.w.x), fmaxf(fabsf(p_b.w.y), fabsf(p_b.w.z)))));
+    amax = fmaxf(fmaxf(fabsf(a_b.t.x), fabsf(a_b.t.y)), fmaxf(fabsf(a_b.t.z), fmaxf(fabsf(a_b.w.x), fmaxf(fabsf(a_b.w.y), fabsf(a_b.w.z)))));
+    ODG_UNROLL for (int j = 0; j < NJL; j++) { smax = fmaxf(smax, fabsf(p_l[j])); amax = fmaxf(amax, fabsf(a_l[j])); }
+    grp_sum_max2(d10, smax, amax, s_red, leg, gm);
     // phi'(alpha) at four step lengths at once (lane-partial sums, then one group reduction per value). The four
     // evaluations are independent, which gives the scheduler 4-way ILP in the kernel's hottest loop, and the
     // number of passes is fixed (<= C.ls_iters), so environments sharing a warp do not diverge here.
@@ -1333,13 +1352,6 @@ ODG_DEV void substep(const DevConst& C, const float* ODG_RESTRICT s_lc, const fl
         }
       }
     };
-    // size of the full Newton step relative to the iterate: when it is already negligible this is the last iteration
-    // and the step is taken without a line search
-    float amax = 0.f, smax = 0.f;
-    smax = fmaxf(fmaxf(fabsf(p_b.t.x), fabsf(p_b.t.y)), fmaxf(fabsf(p_b.t.z), fmaxf(fabsf(p_b.w.x), fmaxf(fabsf(p_b.w.y), fabsf(p_b.w.z)))));
-    amax = fmaxf(fmaxf(fabsf(a_b.t.x), fabsf(a_b.t.y)), fmaxf(fabsf(a_b.t.z), fmaxf(fabsf(a_b.w.x), fmaxf(fabsf(a_b.w.y), fabsf(a_b.w.z)))));
-    ODG_UNROLL for (int j = 0; j < NJL; j++) { smax = fmaxf(smax, fabsf(p_l[j])); amax = fmaxf(amax, fabsf(a_l[j])); }
-    smax = grp_max(smax, gm); amax = grp_max(amax, gm);
     const bool tiny = smax <= C.tol * (1.f + amax);
     float alpha = (tiny && d10 < 0.f) ? 1.f : 0.f;
 #ifdef ODG_EMU_STATS
