@@ -266,6 +266,9 @@ def run_gpu(args):
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     launches0 = env.launch_count
+    import gc
+    gc.collect()
+    gc.disable()                                     # no collector pauses between the launches of the timed region
     barrier()
     t_wall0 = time.perf_counter()
     for i in range(K):
@@ -297,6 +300,7 @@ def run_gpu(args):
         h_obs, h_rew, h_term, h_trunc = env.step_host(host_actions[i])
     e1.record()
     barrier()
+    gc.enable()
     e2e_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     # ---- max over ranks
@@ -370,7 +374,7 @@ def run_gpu(args):
             # BASELINE.json configs[3] as first-class keys at EVERY N (the timed `value` above is the collective-free
             # configs[1] step): 65536 envs per GPU, on-device rollout, GAE + advantage-statistics all-reduce, one PPO epoch
             # with a flat-gradient all-reduce per minibatch. Weak scaling: efficiency at N = value(N) / (N x value(1)).
-            r = rollout_probe(dev, args.train_envs, args.horizon, rank, world, dist, train=True)
+            r = rollout_probe(dev, args.train_envs, args.horizon, rank, world, dist, train=True, iters=args.train_iters)
             if world > 1:
                 line["rollout"] = r
             line["configs3"] = {
@@ -381,6 +385,7 @@ def run_gpu(args):
                 "ms_ppo_epoch": r["ms_ppo_epoch_with_grad_allreduce"],
                 "ms_grad_allreduce": r["ms_grad_allreduce_per_iteration"], "grad_allreduce": r["grad_allreduce"],
                 "ms_each_iteration": r["ms_each_iteration_this_rank"],      # [rollout, gae, ppo epoch] of every timed iteration, rank 0
+                "ms_host": r.get("ms_host_in_ppo_call_each_iteration"),
                 "ppo_update": r["ppo_update"], "scaling": "weak"}
         if world == 1 and args.go1:
             # BASELINE.json configs[2] names the 12-actuator model: Unitree Go1 through the same kernels (48-512-256-12)
@@ -455,7 +460,7 @@ def mppi_probe(dev, samples=1024, horizon=64):
             "kernels_per_plan": m.kernels_per_plan, "min_cost": float(m.stats[0]), "mean_cost": float(m.stats[1])}
 
 
-def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="our_robot"):
+def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="our_robot", iters=3):
     """BASELINE.json configs[2]/[3]: on-device PPO rollout (policy MLP on tensor cores + fused env step, one CUDA
     graph per horizon), GAE, and — with `train` — the advantage-statistics all-reduce and one PPO epoch with a flat
     gradient all-reduce per minibatch. Device-timed, max over ranks."""
@@ -464,7 +469,13 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
     from opendog_b200.policy import ActorCriticB200
     from opendog_b200.rollout import Rollout
     from opendog_b200.train import GraphedPPOUpdate, allreduce_flat_grads
+    import gc
     torch.manual_seed(0)
+    # objects of earlier probes (CUDA graphs, their private memory pools) die when Python's cycle collector gets round to
+    # them; if that happens inside a timed iteration, the cudaFree calls stall the host between two graph launches and the
+    # device idles (seen as one 40-500 ms "PPO epoch" among 14.5 ms ones). Collect now, and keep the collector off while timing.
+    gc.collect()
+    torch.cuda.empty_cache()
     env = BatchedWalkEnv(n_envs, model=model, device=dev, seed=0, first_env_id=rank * n_envs, info_keys=None)
     pol = ActorCriticB200(env.obs_dim, env.act_dim, 0.4, device=dev, seed=0)
     ro = Rollout(env, pol, horizon=horizon, use_graph=True, first_row_id=rank * n_envs)
@@ -479,29 +490,35 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
     # the PPO epoch (4 minibatches: forward, loss, backward, flat-gradient all-reduce, clipping, fused Adam) is captured
     # once as CUDA graphs and replayed: no launch / allocator / lazy-loading time inside the timed iterations
     upd = GraphedPPOUpdate(pol, opt, T * N, env.obs_dim, env.act_dim, minibatches=4) if train else None
-    for w in range(3):
+    for w in range(5):
         ro.collect()
-        if w >= 1:                       # untimed, twice: first-use costs of the collectives, autograd and cuBLAS, graph capture
+        if w >= 1:                       # untimed, four times: first-use costs of the collectives, autograd and cuBLAS, graph capture
             adv, ret, stats = ro.advantages(normalize=True)
             if train:
                 upd(ro.obs[:T].reshape(T * N, -1), ro.action.reshape(T * N, -1), ro.logp.reshape(-1), adv.reshape(-1), ret.reshape(-1))
+    gc.collect()
+    gc.disable()
     sync()
-    iters = 3
     e = [ev() for _ in range(4)]
     t_roll = t_gae = t_upd = t_ar = 0.0
     each = []
+    host_ms = []
     for _ in range(iters):
         timing = {}
         e[0].record(); ro.collect(); e[1].record()
         adv, ret, stats = ro.advantages(normalize=True)       # all-reduces [sum, sumsq, n] when world > 1
         e[2].record()
+        h0 = time.perf_counter()
         if train:
             upd(ro.obs[:T].reshape(T * N, -1), ro.action.reshape(T * N, -1), ro.logp.reshape(-1), adv.reshape(-1), ret.reshape(-1))
+        h1 = time.perf_counter()
         e[3].record()
         torch.cuda.synchronize(dev)
+        host_ms.append((h1 - h0) * 1e3)
         t_roll += e[0].elapsed_time(e[1]); t_gae += e[1].elapsed_time(e[2]); t_upd += e[2].elapsed_time(e[3])
         t_ar += sum(a.elapsed_time(b) for a, b in timing.get("allreduce", []))
         each.append([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])])
+    gc.enable()
     if train:
         # the flat-gradient all-reduce alone (the captured epoch contains 4 of them): same buffer, same collective
         params = [p for p in pol.parameters() if p.requires_grad]
@@ -544,6 +561,7 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
         n_param = sum(p.numel() for p in pol.parameters())
         out["ms_ppo_epoch_with_grad_allreduce"] = t_upd / iters
         out["ms_each_iteration_this_rank"] = [[round(x, 3) for x in row] for row in each]      # [rollout, gae, ppo] x iterations
+        out["ms_host_in_ppo_call_each_iteration"] = [round(x, 3) for x in host_ms]   # host time spent inside the (asynchronous) update call
         out["ms_grad_allreduce_per_iteration"] = t_ar / iters
         out["grad_allreduce"] = {"calls_per_iteration": 4, "payload_bytes_per_call": 4 * n_param,
                                  "ms_per_call": t_ar / iters / 4,
@@ -566,6 +584,7 @@ def main():
     ap.add_argument("--rollout-envs", type=int, default=16384, help="N=1: also time the on-device PPO rollout (0 = off)")
     ap.add_argument("--train-envs", type=int, default=65536, help="N>1: envs per GPU of the train-iteration probe")
     ap.add_argument("--horizon", type=int, default=24)
+    ap.add_argument("--train-iters", type=int, default=3, help="timed iterations of the train-iteration probe")
     ap.add_argument("--go1", type=int, default=1, help="N=1: also time the rollout on the 12-actuator Go1 model; 0 = off")
     ap.add_argument("--mppi", type=int, default=1, help="N=1: also time one MPPI plan (1024 x 64); 0 = off")
     ap.add_argument("--train-probe", action="store_true", help="N=1: include the PPO epoch in the rollout probe")
