@@ -57,3 +57,41 @@ class TelemetryServer:
 
     def close(self):
         self.sock.close()
+
+
+class CustomMetrics:
+    """The scalars `train/train.py:20-44` (`CustomLoggingCallback`) writes to TensorBoard — the mean of `x_position`,
+    `y_position`, `distance_from_origin` and `patterns_matches` over every environment and every step since the last
+    record, recorded every 100 calls — for a batched environment: the per-step `info` tensors are summed on the device
+    (one small kernel per key and step, no host copy), and `on_step` returns `{"custom/<key>": mean}` once every `every`
+    calls (one 4-float D2H) and `None` otherwise. `record` is called with that dict if given (e.g. an SB3 logger's
+    `record` wrapped as `lambda d: [logger.record(k, v) for k, v in d.items()]`)."""
+
+    KEYS = ("x_position", "y_position", "distance_from_origin", "patterns_matches")
+
+    def __init__(self, every: int = 100, keys=KEYS, record=None):
+        self.every, self.keys, self.record = int(every), tuple(keys), record
+        self.n_calls = 0
+        self._sum = None
+        self._count = 0
+
+    def on_step(self, info: dict):
+        import torch
+        self.n_calls += 1
+        vals = [info[k] for k in self.keys if k in info]
+        if vals:
+            present = [k for k in self.keys if k in info]
+            if self._sum is None or self._present != present:
+                self._present = present
+                self._sum = torch.zeros(len(present), dtype=torch.float64, device=vals[0].device)
+                self._count = 0
+            self._sum += torch.stack([v.reshape(-1).double().sum() for v in vals])
+            self._count += vals[0].numel()
+        if self.n_calls % self.every != 0 or self._sum is None or self._count == 0:
+            return None
+        means = (self._sum / self._count).cpu().tolist()
+        out = {f"custom/{k}": m for k, m in zip(self._present, means)}
+        self._sum.zero_(); self._count = 0
+        if self.record is not None:
+            self.record(out)
+        return out

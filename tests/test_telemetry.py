@@ -41,3 +41,28 @@ def test_udp_packet_matches_reference_schema():
     f = np.array(d["contact_forces_data"]).reshape(4, 6); ref = oinfo["paw_contact_forces"]      # reward_calc.py:351-370
     assert np.abs(f - ref).max() <= 5e-2 * max(1.0, np.abs(ref).max()) and np.abs(ref).max() > 0.5
     srv.close(); cli.close()
+
+
+def test_custom_metrics_equal_the_reference_callback_arithmetic():
+    """train/train.py:20-44: every `info[key]` of every environment is appended to a list, and every 100 calls the mean
+    of the list is recorded and the list cleared. Same numbers from per-step [N] tensors (CPU tensors here: the class
+    only needs torch)."""
+    import numpy as np
+    from opendog_b200.telemetry import CustomMetrics
+    rng = np.random.default_rng(0)
+    N, every = 7, 5
+    cm = CustomMetrics(every=every)
+    lists = {k: [] for k in CustomMetrics.KEYS}
+    for call in range(1, 13):
+        info = {k: torch.from_numpy(rng.normal(size=N).astype(np.float32)) for k in CustomMetrics.KEYS}
+        info["unrelated"] = torch.zeros(N)
+        for k in CustomMetrics.KEYS:                       # the reference: one append per environment and key
+            lists[k] += [float(x) for x in info[k]]
+        out = cm.on_step(info)
+        if call % every == 0:
+            assert set(out) == {f"custom/{k}" for k in CustomMetrics.KEYS}
+            for k in CustomMetrics.KEYS:
+                assert abs(out[f"custom/{k}"] - np.mean(lists[k])) < 1e-6
+                lists[k].clear()
+        else:
+            assert out is None
