@@ -17,6 +17,7 @@
 #ifndef ODG_H
 #define ODG_H
 
+#include <stddef.h>
 #include <stdint.h>
 #include "odg_model.h"
 
@@ -133,6 +134,17 @@ int odg_reset(OdgSim* sim, const uint8_t* mask_dev, float* obs_dev, void* stream
  * SB3 auto-reset when cfg.auto_reset). action_dev: [N][act_dim]. */
 int odg_step(OdgSim* sim, const float* action_dev, float* obs_dev, float* reward_dev,
              uint8_t* terminated_dev, uint8_t* truncated_dev, const OdgInfoPtrs* info, void* stream);
+
+/* `odg_step` for a caller whose policy lives on the HOST (stable-baselines3's numpy rollout loop, train/train.py:117-158;
+ * the batch-1 loop of sim2real/train.py:537-549): ONE call = host actions in, host results out. Copies
+ * action_host [N][act_dim] (any host memory; through action_pinned — a page-locked staging buffer of the same size, or
+ * NULL when action_host is page-locked itself) to action_dev, takes the step into obs_dev / reward_dev / terminated_dev /
+ * truncated_dev (+ info), copies `out_bytes` bytes from out_dev to out_host (page-locked; the caller lays its output
+ * tensors out in one device slab so that one copy brings all of them), and waits for the stream: when it returns, out_host
+ * holds the step's results. out_dev / out_host may be NULL (no copy back). */
+int odg_step_host(OdgSim* sim, const float* action_host, float* action_pinned, float* action_dev,
+                  float* obs_dev, float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev,
+                  const OdgInfoPtrs* info, const void* out_dev, void* out_host, size_t out_bytes, void* stream);
 
 /* Test hook: one `mj_forward` on the current state (no integration), then the same
  * obs/reward/termination code as odg_step, with `ctrl_dev` [N][act_dim] already in ctrl units.

@@ -335,6 +335,26 @@ int odg_step(OdgSim* s, const float* action_dev, float* obs_dev, float* reward_d
   return launch_step(s, A, static_cast<cudaStream_t>(stream));
 }
 
+int odg_step_host(OdgSim* s, const float* action_host, float* action_pinned, float* action_dev, float* obs_dev,
+                  float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev, const OdgInfoPtrs* info,
+                  const void* out_dev, void* out_host, size_t out_bytes, void* stream) {
+  if (!s || !action_host || !action_dev) return fail(ODG_ERR_INVALID, "odg_step_host: null handle or action");
+  if ((out_dev == nullptr) != (out_host == nullptr)) return fail(ODG_ERR_INVALID, "odg_step_host: out_dev and out_host go together");
+  DeviceGuard guard(s->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t abytes = (size_t)s->N * s->prep.C.nu * sizeof(float);
+  const float* src = action_host;
+  if (action_pinned && action_pinned != action_host) { std::memcpy(action_pinned, action_host, abytes); src = action_pinned; }
+  CUDA_TRY(cudaMemcpyAsync(action_dev, src, abytes, cudaMemcpyHostToDevice, st));
+  StepArgs A;
+  fill_args(&A, action_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, info, 0);
+  int rc = launch_step(s, A, st);
+  if (rc != ODG_OK) return rc;
+  if (out_dev && out_bytes) CUDA_TRY(cudaMemcpyAsync(out_host, out_dev, out_bytes, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return ODG_OK;
+}
+
 int odg_mppi_rollout(OdgSim* s, const float* mean_dev, float sigma, int horizon, uint64_t seed, uint32_t iteration,
                      const uint32_t* iteration_dev, float termination_cost, float* actions_dev, float* cost_dev, void* stream) {
   if (!s || !mean_dev || !actions_dev || !cost_dev || horizon < 1 || !(sigma >= 0.f))

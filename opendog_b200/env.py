@@ -193,13 +193,19 @@ class BatchedWalkEnv:
             for name, dt, shp, off in self._slab_layout:
                 self._host[name] = self._view(h, dt, shp, off)
         H = self._host
-        if action_host.data_ptr() != H["act"].data_ptr():
-            H["act"].copy_(action_host)
-        H["dact"].copy_(H["act"], non_blocking=True)
-        self.step_into(H["dact"], self.obs, self.reward, self.terminated, self.truncated)
+        a = action_host
+        if a.device.type != "cpu" or a.dtype != torch.float32 or not a.is_contiguous():
+            a = a.to(device="cpu", dtype=torch.float32).contiguous()
+        if a.shape != (N, self.act_dim):
+            raise ValueError(f"action must be [{N}, {self.act_dim}]")
         nb = self._slab.numel() if with_info else self._out_bytes
-        H["slab"][:nb].copy_(self._slab[:nb], non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        info = C.byref(self._info_struct) if self._info_struct is not None else None
+        # one C call: (memcpy to the page-locked staging buffer unless the caller's tensor is it) -> H2D -> step kernel ->
+        # one D2H of the output slab -> stream synchronize (include/odg.h: odg_step_host)
+        staged = a.data_ptr() == H["act"].data_ptr() or a.is_pinned()
+        _lib.check(self.L.odg_step_host(self._h, _ptr(a), None if staged else _ptr(H["act"]), _ptr(H["dact"]), _ptr(self.obs),
+                                        _ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated), info,
+                                        _ptr(self._slab), _ptr(H["slab"]), nb, self._stream()), "odg_step_host")
         if with_info:
             return H["obs"], H["reward"], H["terminated"], H["truncated"], {k: H[k] for k in self.info}
         return H["obs"], H["reward"], H["terminated"], H["truncated"]

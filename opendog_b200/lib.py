@@ -18,6 +18,7 @@ SYMBOLS = [
     "odg_default_config", "odg_create", "odg_destroy", "odg_num_envs", "odg_obs_dim", "odg_act_dim",
     "odg_nq", "odg_nv", "odg_reset", "odg_step", "odg_evaluate", "odg_get_state", "odg_set_state",
     "odg_get_env_state", "odg_set_env_state", "odg_launch_count", "odg_last_error", "odg_version", "odg_set_frame_skip",
+    "odg_step_host",
     # rollout / policy entry points (include/odg_policy.h)
     "odg_policy_create", "odg_policy_destroy", "odg_policy_load", "odg_policy_forward", "odg_gae",
     "odg_normalize_advantages", "odg_policy_launch_count",
@@ -89,6 +90,7 @@ def load():
     L.odg_launch_count.restype = C.c_longlong
     L.odg_reset.argtypes = [_vp, _vp, _vp, _vp]
     L.odg_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(OdgInfoPtrs), _vp]
+    L.odg_step_host.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(OdgInfoPtrs), _vp, _vp, C.c_size_t, _vp]
     L.odg_evaluate.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(OdgInfoPtrs), _vp]
     L.odg_get_state.argtypes = [_vp, _vp, _vp, _vp]
     L.odg_set_state.argtypes = [_vp, _vp, _vp, _vp, _vp]

@@ -450,3 +450,30 @@ def test_fat_and_lean_step_kernels_are_bit_identical(model):
             assert torch.equal(out[0][k], out[1][k]), (model, t, k)
     for a_, b_ in zip(envs[0].get_state(), envs[1].get_state()):
         assert torch.equal(a_, b_)
+
+
+def test_step_host_equals_step_with_device_tensors():
+    """`step_host` (include/odg.h: odg_step_host — host actions in, host results out, one C call) against `step` on
+    CUDA tensors: same seeds, same actions, identical observations, rewards, flags and info through terminations and
+    auto-resets; pageable, page-locked and non-contiguous / float64 action tensors all take the same path."""
+    from opendog_b200.env import BatchedWalkEnv
+    n = 300
+    keys = ("x_position", "paw_contact_forces", "terminal_obs")
+    a_env = BatchedWalkEnv(n, seed=11, info_keys=keys, max_episode_steps=9)
+    b_env = BatchedWalkEnv(n, seed=11, info_keys=keys, max_episode_steps=9)
+    assert torch.equal(a_env.reset(), b_env.reset())
+    g = torch.Generator().manual_seed(3)
+    for t in range(24):
+        act = torch.rand(n, 8, generator=g) * 2 - 1
+        host_in = act if t % 3 == 0 else (act.pin_memory() if t % 3 == 1 else act.double())      # pageable / pinned / needs conversion
+        l0 = a_env.launch_count
+        out = a_env.step_host(host_in, with_info=(t % 2 == 0))
+        assert a_env.launch_count - l0 == 1                                      # one kernel per host step
+        obs, rew, done, info = b_env.step(act.cuda())
+        assert torch.equal(out[0], obs.cpu()) and torch.equal(out[1], rew.cpu())
+        assert torch.equal((out[2] | out[3]).bool(), done.cpu().bool())
+        if t % 2 == 0:
+            for k in keys:
+                assert torch.equal(out[4][k], info[k].cpu()), k
+    for x, y in zip(a_env.get_state(), b_env.get_state()):
+        assert torch.equal(x, y)
