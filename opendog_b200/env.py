@@ -192,6 +192,9 @@ class BatchedWalkEnv:
                               dact=torch.empty(N, self.act_dim, device=self.device))
             for name, dt, shp, off in self._slab_layout:
                 self._host[name] = self._view(h, dt, shp, off)
+            # the call's fixed pointer arguments, built once (this method runs once per env-step of a host-side loop)
+            self._host["args"] = (_ptr(self._host["act"]), _ptr(self._host["dact"]), _ptr(self.obs), _ptr(self.reward),
+                                  _ptr(self.terminated), _ptr(self.truncated), _ptr(self._slab), _ptr(h))
         H = self._host
         a = action_host
         if a.device.type != "cpu" or a.dtype != torch.float32 or not a.is_contiguous():
@@ -203,9 +206,9 @@ class BatchedWalkEnv:
         # one C call: (memcpy to the page-locked staging buffer unless the caller's tensor is it) -> H2D -> step kernel ->
         # one D2H of the output slab -> stream synchronize (include/odg.h: odg_step_host)
         staged = a.data_ptr() == H["act"].data_ptr() or a.is_pinned()
-        _lib.check(self.L.odg_step_host(self._h, _ptr(a), None if staged else _ptr(H["act"]), _ptr(H["dact"]), _ptr(self.obs),
-                                        _ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated), info,
-                                        _ptr(self._slab), _ptr(H["slab"]), nb, self._stream()), "odg_step_host")
+        p_act, p_dact, p_obs, p_rew, p_term, p_trunc, p_slab, p_hslab = H["args"]
+        _lib.check(self.L.odg_step_host(self._h, _ptr(a), None if staged else p_act, p_dact, p_obs, p_rew, p_term, p_trunc, info,
+                                        p_slab, p_hslab, nb, self._stream()), "odg_step_host")
         if with_info:
             return H["obs"], H["reward"], H["terminated"], H["truncated"], {k: H[k] for k in self.info}
         return H["obs"], H["reward"], H["terminated"], H["truncated"]
