@@ -67,6 +67,54 @@ def load_walk_json(path_or_list, desc, real_home=RUN_REAL_HOME_DEG, scale=RUN_SC
     return np.array(tg), np.array(du)
 
 
+# sim2real/main.py:19-38 (the hand-coded trot's sim -> real map): the exporter's home table, scale factors all 1
+MAIN_REAL_HOME_DEG = dict(TRAIN_REAL_HOME_DEG)
+MAIN_SCALE = {k: 1.0 for k in MAIN_REAL_HOME_DEG}
+
+
+def hand_coded_trot(desc, real_home=MAIN_REAL_HOME_DEG, scale=MAIN_SCALE, num_steps=12, phase_duration=0.40,
+                    initial_hold=1.0, final_hold=1.0):
+    """`create_control_sequence` (sim2real/main.py:63-151), the reference's open-loop trot: hold the keyframe's ctrl for
+    1 s, then 12 phases of 0.4 s in which one diagonal pair (FR + BL on even phases, FL + BR on odd ones) swings — thigh
+    +0.10 rad, knee flexed by -0.50 (front) / -0.35 (back) — while the other pair stands — thigh -0.10, knee extended by
+    +0.15 (front) / +0.20 (back) —, every target clamped to the actuator's ctrlrange (:118-128), then 1 s at home: 6.8 s =
+    3400 substeps of PD targets. Returns (targets_rad [14, nu] in ctrl order, targets_deg [14, nu] = the real-robot
+    commands of main.py:130-136, durations [14])."""
+    names = list(desc["act_names"])
+    home = np.array(desc["key_ctrl"], dtype=np.float64)
+    lo = np.array([r[0] for r in desc["act_ctrlrange"]]); hi = np.array([r[1] for r in desc["act_ctrlrange"]])
+    idx = {n: names.index(n + "_actuator") for n in ("FR_tigh", "FR_knee", "BR_tigh", "BR_knee", "FL_tigh", "FL_knee", "BL_tigh", "BL_knee")}
+    swing_thigh, stance_thigh = 0.10, -0.10
+    swing_knee = {"F": -0.50, "B": -0.35}
+    stance_knee = {"F": 0.15, "B": 0.2}
+    rows, durs = [home.copy()], [initial_hold]
+    for step in range(num_steps):
+        swing = ("FR", "BL") if step % 2 == 0 else ("FL", "BR")
+        row = home.copy()
+        for leg in ("FR", "BR", "FL", "BL"):
+            sw = leg in swing
+            row[idx[leg + "_tigh"]] = home[idx[leg + "_tigh"]] + (swing_thigh if sw else stance_thigh)
+            row[idx[leg + "_knee"]] = home[idx[leg + "_knee"]] + (swing_knee if sw else stance_knee)[leg[0]]
+        rows.append(np.clip(row, lo, hi)); durs.append(phase_duration)
+    rows.append(home.copy()); durs.append(final_hold)
+    rad = np.array(rows)
+    deg = np.array([[sim_rad_to_real_deg(float(r[u]), float(home[u]), real_home[n], scale[n]) for u, n in enumerate(names)] for r in rad])
+    return rad, deg, np.array(durs)
+
+
+def trot_json(desc, path=None, **kw):
+    """The gait file main.py:236-252 writes for the robot: degrees rounded to 2 decimals, durations to 3."""
+    rad, deg, durs = hand_coded_trot(desc, **kw)
+    # (the reference's dicts are keyed in its ACTUATOR_NAMES order for the hold steps and in assignment order for the phases;
+    #  consumers index by name)
+    seq = [{"duration": round(float(d), 3), "targets_deg": {n: round(float(row[u]), 2) for u, n in enumerate(desc["act_names"])}}
+           for row, d in zip(deg, durs)]
+    if path:
+        with open(path, "w") as f:
+            json.dump(seq, f, indent=2)
+    return seq
+
+
 def segment_substeps(durations, timestep):
     """How many mj_step calls run.py spends on each sequence step: it advances when `data.time >= start + duration`,
     checked BEFORE each step with data.time accumulated in float64 (run.py:286-330)."""
