@@ -87,6 +87,7 @@ def test_c_abi_error_behaviour():
     assert L.odg_create(C.byref(m), None, 4, 0, 0, None) == INVALID
     assert L.odg_step(None, None, None, None, None, None, None, None) == INVALID and b"odg_step" in L.odg_last_error()
     assert L.odg_evaluate(None, None, None, None, None, None, None, None) == INVALID
+    assert L.odg_step_host(None, None, None, None, None, None, None, None, None, None, None, 0, None) == INVALID and b"odg_step_host" in L.odg_last_error()
     assert L.odg_reset(None, None, None, None) == INVALID and b"odg_reset" in L.odg_last_error()
     assert L.odg_get_state(None, None, None, None) == INVALID
     assert L.odg_set_frame_skip(None, 10) == INVALID
