@@ -136,6 +136,16 @@ def cpu_baseline(all_core_steps, one_core_steps, envs_per_core=16, warmup=12):
                       "not installable here or on the GPU box (profiles/r02_mujoco_probe.txt)"}, dt_all
 
 
+def workload_config(envs_per_gpu):
+    """The `config` object of BOTH arms (ours and --impl reference): the workload and the timing rules, no measured values —
+    so the two lines name the same configuration key for key. Arm-specific facts sit next to it (`physics_steps_per_s`,
+    `solver`, `cpu_baseline.sample`)."""
+    return {"workload": workload_name(envs_per_gpu), "envs_per_gpu": envs_per_gpu, "frame_skip": FRAME_SKIP,
+            "l2": "GPU arm: flushed (256 MiB memset) between timed steps, per-step CUDA events summed; CPU arm: host caches, wall clock",
+            "actions": "U(-1,1), a fresh batch every step (GPU arm: pre-generated on the device; CPU arm: drawn in each worker)",
+            "cpu_arm": "every step advances a bounded sample of the workload (cpu_baseline.sample); throughput per env-step is what is compared"}
+
+
 def workload_name(envs_per_gpu):
     return (f"{envs_per_gpu} envs/GPU batched step, OpenDOG MJCF (our_robot), flat-plane foot contact, PD "
             "position actuators, fused reward/obs/auto-reset (BASELINE.json configs[1])")
@@ -153,9 +163,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(ENVS_PER_GPU), "envs_per_gpu": ENVS_PER_GPU, "frame_skip": FRAME_SKIP,
-                   "physics_steps_per_s": value * FRAME_SKIP,
-                   "note": "CPU arm: each step advances a bounded sample of the workload (see cpu_baseline.sample)"},
+        "config": workload_config(ENVS_PER_GPU), "physics_steps_per_s": value * FRAME_SKIP,
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -320,12 +328,8 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W, "settle_steps": SETTLE,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(N),
-                   "envs_per_gpu": N, "frame_skip": FRAME_SKIP, "physics_steps_per_s": value * FRAME_SKIP,
-                   "l2": "flushed (256 MiB memset) between timed steps; per-step CUDA events summed",
-                   "actions": "U(-1,1), fresh batch per step, pre-generated on device",
-                   "solver": {"max_newton_iters": env.cfg.solver_iterations, "ls_iters": env.cfg.ls_iterations,
-                              "tol": env.cfg.solver_tolerance}},
+        "config": workload_config(N), "physics_steps_per_s": value * FRAME_SKIP,
+        "solver": {"max_newton_iters": env.cfg.solver_iterations, "ls_iters": env.cfg.ls_iterations, "tol": env.cfg.solver_tolerance},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,

@@ -20,6 +20,10 @@ def test_reference_arm_prints_the_contract_line():
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1 and d["higher_is_better"] is True
     assert d["value"] > 0 and d["ms_per_step"] > 0
     assert d["config"]["workload"].startswith("4096 envs/GPU batched step")
+    # both arms print the SAME config object (no measured values in it): the driver compares the two lines' configs
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(4096) and d["physics_steps_per_s"] == 10 * d["value"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "NOT MuJoCo itself" in cb["sample"]
     # one core AND all cores, physics steps/s next to env-steps/s; MuJoCo's own stopping rules
