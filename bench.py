@@ -385,6 +385,7 @@ def run_gpu(args):
                 "workload": f"{args.train_envs} envs/GPU x horizon {args.horizon} on {world} GPU(s) (BASELINE.json configs[3])",
                 "rollout_env_steps_per_s": r["env_steps_per_s_rollout"],
                 "train_iteration_env_steps_per_s": r["env_steps_per_s_train_iteration"],
+                "train_iteration_env_steps_per_s_median_iteration": r["env_steps_per_s_train_iteration_median"],
                 "ms_rollout": r["ms_per_rollout"], "ms_gae_and_stats_allreduce": r["ms_gae_and_stats_allreduce"],
                 "ms_ppo_epoch": r["ms_ppo_epoch_with_grad_allreduce"],
                 "ms_grad_allreduce": r["ms_grad_allreduce_per_iteration"], "grad_allreduce": r["grad_allreduce"],
@@ -573,6 +574,10 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
                                  "note": "flat fp32 gradient buffer (pack + NCCL all-reduce + unpack), timed alone right after the iterations (inside them it is part of the captured epoch)"}
         out["ppo_update"] = "1 epoch x 4 minibatches replayed as CUDA graphs: bf16 autocast forward/backward (fp32 master weights), flat-gradient all-reduce, clipping, fused Adam"
         out["env_steps_per_s_train_iteration"] = steps / ((t_roll + t_gae + t_upd) * 1e-3)
+        # the same from the MEDIAN iteration of this rank (an iteration in which one rank's host starts its rollout late shows up
+        # on every other rank as time spent waiting in the epoch's first all-reduce: ms_each_iteration)
+        med = sorted(sum(row) for row in each)[len(each) // 2]
+        out["env_steps_per_s_train_iteration_median"] = n_envs * world * horizon / (med * 1e-3)
     return out
 
 
@@ -588,7 +593,7 @@ def main():
     ap.add_argument("--rollout-envs", type=int, default=16384, help="N=1: also time the on-device PPO rollout (0 = off)")
     ap.add_argument("--train-envs", type=int, default=65536, help="N>1: envs per GPU of the train-iteration probe")
     ap.add_argument("--horizon", type=int, default=24)
-    ap.add_argument("--train-iters", type=int, default=3, help="timed iterations of the train-iteration probe")
+    ap.add_argument("--train-iters", type=int, default=5, help="timed iterations of the train-iteration probe")
     ap.add_argument("--go1", type=int, default=1, help="N=1: also time the rollout on the 12-actuator Go1 model; 0 = off")
     ap.add_argument("--mppi", type=int, default=1, help="N=1: also time one MPPI plan (1024 x 64); 0 = off")
     ap.add_argument("--train-probe", action="store_true", help="N=1: include the PPO epoch in the rollout probe")
