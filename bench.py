@@ -504,12 +504,15 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
     gc.collect()
     gc.disable()
     sync()
-    e = [ev() for _ in range(4)]
+    # No host synchronisation inside the timed iterations (a training loop has none either): the host enqueues an iteration
+    # while the device is still busy with the previous one, so a late host — on ANY rank: every rank waits for the
+    # slowest one in the epoch's first all-reduce — costs nothing unless it is later than the ~100 ms of queued work.
+    E = [[ev() for _ in range(4)] for _ in range(iters)]
     t_roll = t_gae = t_upd = t_ar = 0.0
     each = []
     host_ms = []
-    for _ in range(iters):
-        timing = {}
+    for it in range(iters):
+        e = E[it]
         e[0].record(); ro.collect(); e[1].record()
         adv, ret, stats = ro.advantages(normalize=True)       # all-reduces [sum, sumsq, n] when world > 1
         e[2].record()
@@ -518,12 +521,13 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
             upd(ro.obs[:T].reshape(T * N, -1), ro.action.reshape(T * N, -1), ro.logp.reshape(-1), adv.reshape(-1), ret.reshape(-1))
         h1 = time.perf_counter()
         e[3].record()
-        torch.cuda.synchronize(dev)
         host_ms.append((h1 - h0) * 1e3)
+    torch.cuda.synchronize(dev)
+    for e in E:
         t_roll += e[0].elapsed_time(e[1]); t_gae += e[1].elapsed_time(e[2]); t_upd += e[2].elapsed_time(e[3])
-        t_ar += sum(a.elapsed_time(b) for a, b in timing.get("allreduce", []))
         each.append([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])])
     gc.enable()
+    e = E[0]
     if train:
         # the flat-gradient all-reduce alone (the captured epoch contains 4 of them): same buffer, same collective
         params = [p for p in pol.parameters() if p.requires_grad]
@@ -566,7 +570,7 @@ def rollout_probe(dev, n_envs, horizon, rank, world, dist, train=False, model="o
         n_param = sum(p.numel() for p in pol.parameters())
         out["ms_ppo_epoch_with_grad_allreduce"] = t_upd / iters
         out["ms_each_iteration_this_rank"] = [[round(x, 3) for x in row] for row in each]      # [rollout, gae, ppo] x iterations
-        out["ms_host_in_ppo_call_each_iteration"] = [round(x, 3) for x in host_ms]   # host time spent inside the (asynchronous) update call
+        out["ms_host_in_ppo_call_each_iteration"] = [round(x, 3) for x in host_ms]   # host time spent inside the (asynchronous) update call: enqueue only
         out["ms_grad_allreduce_per_iteration"] = t_ar / iters
         out["grad_allreduce"] = {"calls_per_iteration": 4, "payload_bytes_per_call": 4 * n_param,
                                  "ms_per_call": t_ar / iters / 4,

@@ -89,7 +89,7 @@ class ActorCriticB200(nn.Module):
         keep.append(ls)
         w.action_log_std = ls.data_ptr()
         _lib.check(self.L.odg_policy_load(self._h, C.byref(w), self._stream()), "odg_policy_load")
-        torch.cuda.current_stream(self.dev).synchronize()      # `keep` must outlive the packing kernels
+        self._pack_keep = keep       # the packing kernels run asynchronously: their fp32 sources stay referenced until the next call
 
     # ------------------------------------------------------------------ rollout-time forward (tensor cores)
     def act(self, obs: torch.Tensor, sample: bool = True, out=None, first_row_id: int = 0, step: int | None = None,
