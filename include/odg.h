@@ -79,9 +79,9 @@ typedef struct OdgEnvConfig {
                                 (named barriers; needs launch_lanes 32 and launch_block 128 or 0), 0 = never, -1 = chosen
                                 from the batch size */
   int launch_fat;            /* 1 = the instantiation of the step kernel that keeps per-contact Jacobian columns and line-search
-                                coefficients in local memory instead of recomputing them (pays when a warp has a scheduler
-                                to itself), 0 = the lean one, -1 = chosen from the batch size. Schedule only: results are
-                                bit-identical */
+                                coefficients in local memory instead of recomputing them, 0 = the lean one, -1 = chosen by the
+                                library (the former at every batch size as of the end of round 2). Schedule only: results
+                                are bit-identical */
 } OdgEnvConfig;
 
 /* Optional per-step outputs (any pointer may be NULL). WalkEnvironment.py:65-72 `info`. */

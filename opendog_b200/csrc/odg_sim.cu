@@ -176,6 +176,9 @@ int choose_launch(OdgSim* s) {
   // 128-thread blocks (named barriers): the fastest pairing with the constants staged once for two pairs. Deep batches
   // get 2, shallow ones 0.
   int lockstep = deep ? (lanes == 32 ? 2 : 1) : 0;
+  // 3-joint legs (Go1: 17 k instructions, instruction fetch is its top stall even at one warp per scheduler): pairs whenever
+  // warps are whole (measured, tools/tune_go1.sh: +11 % at 4096 envs, +10 % at 16384, +12 % at 65536 together with FAT)
+  if (s->prep.C.njl == 3 && lanes == 32) lockstep = 2;
   if (s->cfg_lockstep >= 0) lockstep = s->cfg_lockstep;
   if (lockstep == 2 && !s->cfg_block) block = 128;
   if (s->cfg_block) block = s->cfg_block;
@@ -185,9 +188,12 @@ int choose_launch(OdgSim* s) {
   const long long wpb = block / 32, need = (warps + wpb - 1) / wpb, cap = (long long)s->num_sms * occ;
   s->step_lanes = lanes; s->step_block = block; s->smem_step = smem_for(block);
   s->prep.C.lockstep = lockstep;
-  // the local-memory-heavier instantiation wherever a warp has a scheduler (and its share of the L1) nearly to itself:
-  // the shallow batches (measured: +6.5 % at 4096 envs, -18 % at 65536)
-  s->step_fat = deep ? 0 : 1;
+  // The instantiation that keeps per-contact Jacobian columns and line-search coefficients in local memory: at every batch
+  // size. Mid-round it lost 18 % at 65536 envs (its per-contact words did not fit the L1 of 8 resident warps); with 16-byte
+  // records, the cone constants in their spare words and shared memory sized per block it wins there too (measured at the
+  // end of round 2, tools/tune_fat2.sh, with lockstep pairs: +12 % at 8192 / 32768 envs, +11 % at 16384, +10 % at 65536).
+  // The lean instantiation stays selectable (OdgEnvConfig::launch_fat = 0): the GPU suite holds both to the same bits.
+  s->step_fat = 1;
   if (s->cfg_fat >= 0) s->step_fat = s->cfg_fat ? 1 : 0;
   s->step_grid = (int)(need < cap ? need : cap);
   return ODG_OK;

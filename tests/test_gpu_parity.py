@@ -12,12 +12,13 @@ pytestmark = pytest.mark.gpu
 
 from test_emu_parity import FLIP_M, assert_info_matches  # noqa: E402  (shared tolerances; importing runs nothing)
 
-# Launch shapes of the step kernel (OdgEnvConfig::launch_*). "auto" is what a small handle gets; "lockstep" is what every
+# Launch shapes of the step kernel (OdgEnvConfig::launch_*). "auto" is what a small handle gets; "large-batch" is what every
 # batch of more than one wave gets (>= ~8192 envs: BASELINE configs[2]/[3]); the others are the remaining code paths
 # (2 / 4 environments per warp, one- and four-warp blocks). Every oracle comparison below runs under each of them.
 SHAPES = {
     "auto": {},
-    "lockstep": dict(launch_lanes=32, launch_block=64, launch_lockstep=1, launch_fat=0),      # what every large batch gets
+    "large-batch": dict(launch_lanes=32, launch_block=128, launch_lockstep=2, launch_fat=1),  # what every batch of more than one wave gets
+    "lockstep": dict(launch_lanes=32, launch_block=64, launch_lockstep=1, launch_fat=0),      # lean instantiation, whole-block lockstep
     "lean": dict(launch_fat=0),
     "2-per-warp": dict(launch_lanes=8, launch_block=128, launch_lockstep=0),
     "4-per-warp-lockstep": dict(launch_lanes=16, launch_block=32, launch_lockstep=1),
@@ -350,7 +351,7 @@ def test_full_size_batches_equal_small_batches_and_hold_their_weight():
         g = torch.Generator(device="cuda").manual_seed(n)
         acts = torch.rand(6, n, 8, device="cuda", generator=g) * 2 - 1
         big = BatchedWalkEnv(n, seed=13, info_keys=None)
-        lo = BatchedWalkEnv(64, seed=13, info_keys=None)
+        lo = BatchedWalkEnv(64, seed=13, info_keys=None, launch_fat=(0 if n == 16384 else -1))     # (one of the small ones: the lean instantiation)
         hi = BatchedWalkEnv(64, seed=13, first_env_id=n - 64, info_keys=None)
         ob, ol, oh = big.reset(), lo.reset(), hi.reset()
         assert torch.equal(ob[:64], ol) and torch.equal(ob[-64:], oh)
