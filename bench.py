@@ -337,7 +337,9 @@ def run_gpu(args):
                              "bound, not HBM bound (see alu)",
                      "alu": {"lane_instr_per_s_peak": alu_peak_lane_ips}},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * 8 * 4,
-                "d2h_bytes_per_step": int(env._out_bytes), "ms_per_step": e2e_ms / e2e_steps},
+                "d2h_bytes_per_step": int(env._out_bytes), "ms_per_step": e2e_ms / e2e_steps,
+                "transfer": ("copy-engine H2D + D2H", "actions read in place from page-locked memory, D2H copy of the results",
+                             "actions read from and results written to page-locked host memory by the kernel itself")[env.host_zero_copy]},
         "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

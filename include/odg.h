@@ -141,7 +141,11 @@ int odg_step(OdgSim* sim, const float* action_dev, float* obs_dev, float* reward
  * NULL when action_host is page-locked itself) to action_dev, takes the step into obs_dev / reward_dev / terminated_dev /
  * truncated_dev (+ info), copies `out_bytes` bytes from out_dev to out_host (page-locked; the caller lays its output
  * tensors out in one device slab so that one copy brings all of them), and waits for the stream: when it returns, out_host
- * holds the step's results. out_dev / out_host may be NULL (no copy back). */
+ * holds the step's results. out_dev / out_host may be NULL (no copy back).
+ * Zero-copy forms (page-locked memory has the same address on the device under unified addressing): pass the page-locked
+ * source itself as action_dev and the kernel reads the actions in place over PCIe (no H2D copy is issued); pass
+ * page-locked obs_dev / reward_dev / terminated_dev / truncated_dev with out_dev = out_host = NULL and the kernel writes
+ * the results where the host reads them. Same results; saves the copy engine's launch latencies on small batches. */
 int odg_step_host(OdgSim* sim, const float* action_host, float* action_pinned, float* action_dev,
                   float* obs_dev, float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev,
                   const OdgInfoPtrs* info, const void* out_dev, void* out_host, size_t out_bytes, void* stream);

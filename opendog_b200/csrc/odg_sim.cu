@@ -351,7 +351,9 @@ int odg_step_host(OdgSim* s, const float* action_host, float* action_pinned, flo
   const size_t abytes = (size_t)s->N * s->prep.C.nu * sizeof(float);
   const float* src = action_host;
   if (action_pinned && action_pinned != action_host) { std::memcpy(action_pinned, action_host, abytes); src = action_pinned; }
-  CUDA_TRY(cudaMemcpyAsync(action_dev, src, abytes, cudaMemcpyHostToDevice, st));
+  // action_dev == the page-locked source: the kernel reads the actions in place over PCIe (unified addressing: page-locked
+  // memory has the same address on the device), which takes the copy engine's launch latency off the step's critical path
+  if (action_dev != src) CUDA_TRY(cudaMemcpyAsync(action_dev, src, abytes, cudaMemcpyHostToDevice, st));
   StepArgs A;
   fill_args(&A, action_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, info, 0);
   int rc = launch_step(s, A, st);

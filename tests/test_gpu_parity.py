@@ -453,14 +453,17 @@ def test_fat_and_lean_step_kernels_are_bit_identical(model):
         assert torch.equal(a_, b_)
 
 
-def test_step_host_equals_step_with_device_tensors():
+@pytest.mark.parametrize("zero_copy", [0, 1, 2])
+def test_step_host_equals_step_with_device_tensors(zero_copy):
     """`step_host` (include/odg.h: odg_step_host — host actions in, host results out, one C call) against `step` on
     CUDA tensors: same seeds, same actions, identical observations, rewards, flags and info through terminations and
-    auto-resets; pageable, page-locked and non-contiguous / float64 action tensors all take the same path."""
+    auto-resets; pageable, page-locked and non-contiguous / float64 action tensors all take the same path. With copies
+    (0), with the kernel reading the page-locked actions in place (1) and writing the results in place too (2)."""
     from opendog_b200.env import BatchedWalkEnv
     n = 300
     keys = ("x_position", "paw_contact_forces", "terminal_obs")
-    a_env = BatchedWalkEnv(n, seed=11, info_keys=keys, max_episode_steps=9)
+    a_env = BatchedWalkEnv(n, seed=11, info_keys=keys, max_episode_steps=9, host_zero_copy=zero_copy)
+    assert BatchedWalkEnv(n, info_keys=None).host_zero_copy == 2 and BatchedWalkEnv(16384, info_keys=None).host_zero_copy == 1
     b_env = BatchedWalkEnv(n, seed=11, info_keys=keys, max_episode_steps=9)
     assert torch.equal(a_env.reset(), b_env.reset())
     g = torch.Generator().manual_seed(3)
