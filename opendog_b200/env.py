@@ -71,10 +71,11 @@ class BatchedWalkEnv:
             self.cfg.obs_layout = 1        # 12-actuator models: the 48-value layout (landing_environment.py:116-136 + v_des)
         task = config.pop("task", "walk")
         # step_host: 0 = H2D copy of the actions and D2H copy of the output slab; 1 = the kernel reads the page-locked actions
-        # in place over PCIe; 2 = and writes obs / reward / terminated / truncated straight into the page-locked result
-        # buffer (calls without info). Same bits either way. Default: 2 up to 8192 envs, where the copy engine's two launch
-        # latencies are 3-5 % of a step (measured, tools/ab_e2e.py: 4096 envs 0.445 -> 0.428 ms), 1 beyond (16384 envs: +-0)
-        self.host_zero_copy = int(config.pop("host_zero_copy", 2 if int(num_envs) <= 8192 else 1))
+        # in place over PCIe; 2 (default) = and writes obs / reward / terminated / truncated straight into the page-locked
+        # result buffer (the info arrays too when the call asks for them). Same bits either way. Measured (tools/ab_e2e.py):
+        # 4096 envs 0.445 -> 0.428 ms per step (with the default info arrays 0.466 -> 0.453), 16384 envs +-0, 65536 envs
+        # 3.67 -> 3.54 ms (the results cross PCIe while the kernel's later tiles still run)
+        self.host_zero_copy = int(config.pop("host_zero_copy", 2))
         self.cfg.task = TASKS[task] if isinstance(task, str) else int(task)
         if self.cfg.task == TASKS["jump"]:
             # JumpEnvironmentV0 is not wrapped in ScaleActionWrapper: actions are ctrl targets; its reward calculator's
@@ -201,6 +202,12 @@ class BatchedWalkEnv:
             self._host["args"] = (_ptr(self._host["act"]), _ptr(self._host["dact"]), _ptr(self.obs), _ptr(self.reward),
                                   _ptr(self.terminated), _ptr(self.truncated), _ptr(self._slab), _ptr(h))
             self._host["args_inplace"] = tuple(_ptr(self._host[k]) for k in ("obs", "reward", "terminated", "truncated"))
+            self._host["info_inplace"] = None
+            if self.info:
+                hs = _lib.OdgInfoPtrs()                             # the same info arrays, in the page-locked slab
+                for k in self.info:
+                    setattr(hs, k, self._host[k].data_ptr())
+                self._host["info_inplace"] = hs
         H = self._host
         a = action_host
         if a.device.type != "cpu" or a.dtype != torch.float32 or not a.is_contiguous():
@@ -215,8 +222,10 @@ class BatchedWalkEnv:
         p_act, p_dact, p_obs, p_rew, p_term, p_trunc, p_slab, p_hslab = H["args"]
         if self.host_zero_copy >= 1:
             p_dact = _ptr(a) if staged else p_act                   # the kernel reads the page-locked actions in place
-        if self.host_zero_copy >= 2 and not with_info:
+        if self.host_zero_copy >= 2:
             p_obs, p_rew, p_term, p_trunc = H["args_inplace"]       # ... and writes its results into the page-locked buffer
+            if with_info and H["info_inplace"] is not None:
+                info = C.byref(H["info_inplace"])
             p_slab = p_hslab = None
             nb = 0
         _lib.check(self.L.odg_step_host(self._h, _ptr(a), None if staged else p_act, p_dact, p_obs, p_rew, p_term, p_trunc, info,

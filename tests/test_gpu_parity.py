@@ -463,7 +463,7 @@ def test_step_host_equals_step_with_device_tensors(zero_copy):
     n = 300
     keys = ("x_position", "paw_contact_forces", "terminal_obs")
     a_env = BatchedWalkEnv(n, seed=11, info_keys=keys, max_episode_steps=9, host_zero_copy=zero_copy)
-    assert BatchedWalkEnv(n, info_keys=None).host_zero_copy == 2 and BatchedWalkEnv(16384, info_keys=None).host_zero_copy == 1
+    assert BatchedWalkEnv(n, info_keys=None).host_zero_copy == 2                 # the default
     b_env = BatchedWalkEnv(n, seed=11, info_keys=keys, max_episode_steps=9)
     assert torch.equal(a_env.reset(), b_env.reset())
     g = torch.Generator().manual_seed(3)
