@@ -65,9 +65,10 @@ def _cpu_worker(conn, n_envs, seed, first_id):
         msg = conn.recv()
         if msg is None:
             break
-        a = rng.uniform(-1, 1, (n_envs, 8)).astype(np.float32)
-        L.odgo_walk_step_autoreset_batch(ptrs, n_envs, fp(a, C.c_float), fp(obs, C.c_double), fp(rew, C.c_double), fp(done, C.c_int))
-        conn.send(n_envs)
+        for _ in range(int(msg)):                        # msg = how many env-steps to advance before answering
+            a = rng.uniform(-1, 1, (n_envs, 8)).astype(np.float32)
+            L.odgo_walk_step_autoreset_batch(ptrs, n_envs, fp(a, C.c_float), fp(obs, C.c_double), fp(rew, C.c_double), fp(done, C.c_int))
+        conn.send(n_envs * int(msg))
     conn.close()
 
 
@@ -92,9 +93,9 @@ class CpuPool:
             c.recv()
         self.total = total_envs
 
-    def step(self):
+    def step(self, count=1):
         for c in self.conns:
-            c.send(1)
+            c.send(count)
         return sum(c.recv() for c in self.conns)
 
     def close(self):
@@ -104,27 +105,31 @@ class CpuPool:
             p.join(timeout=5)
 
 
-def cpu_throughput(sample_envs, steps, warmup, procs):
+def cpu_throughput(sample_envs, steps, warmup, procs, chunk=1):
+    """`steps` env-steps of every sample env, `chunk` of them per message to the workers."""
     pool = CpuPool(sample_envs, procs)
     for _ in range(warmup):
         pool.step()
     t0 = time.perf_counter()
     n = 0
-    for _ in range(steps):
-        n += pool.step()
+    for _ in range(max(1, steps // chunk)):
+        n += pool.step(chunk)
     dt = time.perf_counter() - t0
     pool.close()
     return n / dt, dt
 
 
-def cpu_baseline(all_core_steps, one_core_steps, envs_per_core=16, warmup=12):
+REFERENCE_ENV_STEPS_PER_STEP = 30     # --impl reference: one bench "step" advances every sample env by this many env-steps
+
+
+def cpu_baseline(all_core_steps, one_core_steps, envs_per_core=16, warmup=12, chunk=1):
     """The CPU arm on a bounded sample: all host cores (one process per core), then one core alone (SURVEY section 8d
     config 1 asks for both). Returns the `cpu_baseline` object of the bench line."""
     from oracle.oracle import build
     build()
     procs = os.cpu_count() or 1
-    v_all, dt_all = cpu_throughput(procs * envs_per_core, all_core_steps, warmup, procs)
-    v_one, dt_one = cpu_throughput(envs_per_core, one_core_steps, warmup, 1)
+    v_all, dt_all = cpu_throughput(procs * envs_per_core, all_core_steps, warmup, procs, chunk)
+    v_one, dt_one = cpu_throughput(envs_per_core, one_core_steps, warmup, 1, chunk)
     return {"value": v_all, "unit": "env-steps/s", "cores": procs, "kind": "port",
             "one_core": {"value": v_one, "unit": "env-steps/s", "physics_steps_per_s": v_one * FRAME_SKIP},
             "physics_steps_per_s_per_core": v_all * FRAME_SKIP / procs,
@@ -143,7 +148,8 @@ def workload_config(envs_per_gpu):
     return {"workload": workload_name(envs_per_gpu), "envs_per_gpu": envs_per_gpu, "frame_skip": FRAME_SKIP,
             "l2": "GPU arm: flushed (256 MiB memset) between timed steps, per-step CUDA events summed; CPU arm: host caches, wall clock",
             "actions": "U(-1,1), a fresh batch every step (GPU arm: pre-generated on the device; CPU arm: drawn in each worker)",
-            "cpu_arm": "every step advances a bounded sample of the workload (cpu_baseline.sample); throughput per env-step is what is compared"}
+            "cpu_arm": "every step advances a bounded sample of the workload (cpu_baseline.sample; with --impl reference by "
+                       f"{REFERENCE_ENV_STEPS_PER_STEP} env-steps per env); throughput per env-step is what is compared"}
 
 
 def workload_name(envs_per_gpu):
@@ -156,8 +162,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    # bounded sample: each "step" advances 16 envs per core (a 4096-env batch would cost ~0.25 s x 4096/16/cores per step)
-    cb, dt = cpu_baseline(all_core_steps=max(1, args.steps), one_core_steps=max(1, min(args.steps, 100)), warmup=max(args.warmup, 12))
+    # bounded sample: each "step" advances 16 envs per core by REFERENCE_ENV_STEPS_PER_STEP env-steps (a 4096-env batch would
+    # cost ~0.09 s x 4096/16/cores per env-step). Several seconds of steady-state stepping whatever --steps is: a 0.2 s
+    # sample right after the warm-up read 30 % low (round 2), which would flatter the GPU arm
+    R = REFERENCE_ENV_STEPS_PER_STEP
+    K = max(1, args.steps)
+    cb, dt = cpu_baseline(all_core_steps=K * R, one_core_steps=min(K * R, 600), warmup=max(args.warmup, 12), chunk=R)
     value = cb["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
