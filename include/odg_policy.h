@@ -71,6 +71,16 @@ int odg_gae(const float* reward_dev, const float* value_dev, const uint8_t* done
  * using the (possibly all-reduced) statistics. */
 int odg_normalize_advantages(float* adv_dev, long long count, const double* stats_dev, void* stream);
 
+/* PPO update phase (sim2real/train.py:566-585: `loss.backward()` through `nn.Tanh` + `nn.Linear` of the hidden layers):
+ * grad_x = grad_y * (1 - y*y) for a [rows][cols] bf16 activation gradient (torch's tanh_backward) AND, in the same pass
+ * over the data, bias_grad[cols] (f32) = the column sums of grad_x = the bias gradient of the Linear that produced the
+ * tanh's input. Deterministic (fixed summation order). cols = 8 x a power of two, <= 2048; grad_x must not overlap the inputs.
+ * scratch_dev: odg_tanh_backward_bias_scratch_floats(cols) floats of device memory, owned by the caller (so that the call
+ * can be captured in a CUDA graph). */
+int odg_tanh_backward_bias_scratch_floats(int cols);
+int odg_tanh_backward_bias(const void* grad_y_bf16, const void* y_bf16, void* grad_x_bf16, float* bias_grad_dev,
+                           float* scratch_dev, long long rows, int cols, void* stream);
+
 long long odg_policy_launch_count(const OdgPolicy* p);
 
 #ifdef __cplusplus

@@ -497,6 +497,79 @@ __global__ void k_adv_norm(float* __restrict__ adv, long long count, const doubl
   adv[i] = (float)(((double)adv[i] - mean) / (sqrt(var) + 1e-8));
 }
 
+// ---- PPO update phase: the backward of a hidden layer's tanh fused with the bias gradient of its Linear ----------------
+// g = gy * (1 - y*y) (bf16 in, fp32 arithmetic, bf16 out: torch's tanh_backward) and, in the same pass, the column sums of
+// the ROUNDED g (what grad_output.sum(0) of the Linear's backward adds up) as per-block fp32 partials in a fixed order.
+// torch runs these as two passes over the [rows, cols] gradient, the second one a bf16 column reduction at ~2 TB/s: 17 % of
+// a PPO epoch at 65536 envs x 24 (tools/prof_ppo2.py).
+constexpr int kTbGrid = 592;                        // 148 SMs x 4 blocks; also the row count of the partial-sum scratch
+constexpr int kTbBlock = 256;
+__device__ __forceinline__ void tb_unpack(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; k++) { const float2 t = __bfloat1622float2(h[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
+}
+__global__ void __launch_bounds__(kTbBlock) k_tanh_bwd_bias(const uint4* __restrict__ gy, const uint4* __restrict__ y,
+                                                            uint4* __restrict__ g, float* __restrict__ partial,
+                                                            long long rows, int cols) {
+  __shared__ float s_acc[kTbBlock * 8];
+  const int groups = cols >> 3;                     // 16-byte column groups per row (a power of two <= 256)
+  const int cg = threadIdx.x & (groups - 1), rl = threadIdx.x / groups, rp = kTbBlock / groups;
+  long long chunk = (rows + gridDim.x - 1) / gridDim.x;
+  chunk = (chunk + rp - 1) / rp * rp;
+  const long long r0 = (long long)blockIdx.x * chunk, r1 = r0 + chunk < rows ? r0 + chunk : rows;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc[k] = 0.f;
+  auto one = [&](const uint4& a, const uint4& b, long long r) {
+    float fa[8], fb[8];
+    tb_unpack(a, fa); tb_unpack(b, fb);
+    uint4 o; __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float g0 = fa[2 * k] * (1.f - fb[2 * k] * fb[2 * k]), g1 = fa[2 * k + 1] * (1.f - fb[2 * k + 1] * fb[2 * k + 1]);
+      oh[k] = __floats2bfloat162_rn(g0, g1);
+      const float2 q = __bfloat1622float2(oh[k]);
+      acc[2 * k] += q.x; acc[2 * k + 1] += q.y;
+    }
+    g[r * groups + cg] = o;
+  };
+  long long r = r0 + rl;
+  for (; r + 3LL * rp < r1; r += 4LL * rp) {        // four rows in flight per thread (8 x 16-byte loads)
+    uint4 a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { a[u] = __ldcs(gy + (r + (long long)u * rp) * groups + cg); b[u] = __ldcs(y + (r + (long long)u * rp) * groups + cg); }
+#pragma unroll
+    for (int u = 0; u < 4; u++) one(a[u], b[u], r + (long long)u * rp);
+  }
+  for (; r < r1; r += rp) one(__ldcs(gy + r * groups + cg), __ldcs(y + r * groups + cg), r);
+  // the block's column sums: row lanes added in lane order
+#pragma unroll
+  for (int k = 0; k < 8; k++) s_acc[rl * cols + cg * 8 + k] = acc[k];
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += kTbBlock) {
+    float t = 0.f;
+    for (int q = 0; q < rp; q++) t += s_acc[q * cols + c];
+    partial[(size_t)blockIdx.x * cols + c] = t;
+  }
+}
+// 32 columns per block, 8 threads per column: each adds every 8th block's partial, the 8 sums are added in slice order
+__global__ void __launch_bounds__(256) k_colsum_finish(const float* __restrict__ partial, int nblocks, int cols,
+                                                       float* __restrict__ out) {
+  __shared__ float s_t[8][32];
+  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5, c = blockIdx.x * 32 + cl;
+  float t = 0.f;
+  if (c < cols) for (int b = sl; b < nblocks; b += 8) t += partial[(size_t)b * cols + c];
+  s_t[sl][cl] = t;
+  __syncthreads();
+  if (sl == 0 && c < cols) {
+    float u = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; q++) u += s_t[q][cl];
+    out[c] = u;
+  }
+}
+
 }  // namespace
 
 struct OdgPolicy {
@@ -626,6 +699,25 @@ int odg_normalize_advantages(float* adv_dev, long long count, const double* stat
   if (dev < 0) return set_error(ODG_ERR_INVALID, "odg_normalize_advantages: adv_dev is not device memory");
   DevGuard guard(dev);
   k_adv_norm<<<(unsigned)((count + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(adv_dev, count, stats_dev);
+  CUDA_TRY(cudaGetLastError());
+  return ODG_OK;
+}
+
+int odg_tanh_backward_bias_scratch_floats(int cols) { return cols > 0 ? kTbGrid * cols : 0; }
+
+int odg_tanh_backward_bias(const void* grad_y_bf16, const void* y_bf16, void* grad_x_bf16, float* bias_grad_dev,
+                           float* scratch_dev, long long rows, int cols, void* stream) {
+  const int groups = cols >> 3;
+  if (!grad_y_bf16 || !y_bf16 || !grad_x_bf16 || !bias_grad_dev || !scratch_dev || rows < 1 || cols < 8 || (cols & 7) ||
+      groups > kTbBlock || (groups & (groups - 1)))
+    return set_error(ODG_ERR_INVALID, "odg_tanh_backward_bias: bad arguments (cols must be 8 x a power of two, <= 2048)");
+  const int dev = device_of(grad_y_bf16);
+  if (dev < 0) return set_error(ODG_ERR_INVALID, "odg_tanh_backward_bias: grad_y is not device memory");
+  DevGuard guard(dev);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  k_tanh_bwd_bias<<<kTbGrid, kTbBlock, 0, st>>>(static_cast<const uint4*>(grad_y_bf16), static_cast<const uint4*>(y_bf16),
+                                                static_cast<uint4*>(grad_x_bf16), scratch_dev, rows, cols);
+  k_colsum_finish<<<(cols + 31) / 32, 256, 0, st>>>(scratch_dev, kTbGrid, cols, bias_grad_dev);
   CUDA_TRY(cudaGetLastError());
   return ODG_OK;
 }

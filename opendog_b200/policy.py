@@ -159,14 +159,65 @@ class ActorCriticB200(nn.Module):
         F = torch.nn.functional
         k = state_padded.shape[-1] - self.state_dim
         def run(net):
-            x = torch.tanh(F.linear(state_padded, F.pad(net[0].weight, (0, k)), net[0].bias))
-            x = torch.tanh(F.linear(x, net[2].weight, net[2].bias))
-            return F.linear(x, net[4].weight, net[4].bias)
+            x = linear_tanh(state_padded, F.pad(net[0].weight, (0, k)), net[0].bias)
+            x = linear_tanh(x, net[2].weight, net[2].bias)
+            w3, b3 = net[4].weight, net[4].bias
+            n3 = w3.shape[0]
+            if n3 % 8 and x.is_cuda:
+                # a head narrower than 8 outputs (the critic's single value): zero rows up to 8, so that its backward GEMMs
+                # (K = out_features) are tensor-core aligned too — with K = 1 cuBLAS takes a legacy align-1 kernel
+                p3 = (-n3) % 8
+                return F.linear(x, F.pad(w3, (0, 0, 0, p3)), F.pad(b3, (0, p3)))[:, :n3]
+            return F.linear(x, w3, b3)
         mean = torch.tanh(run(self.actor))
         std = torch.exp(self.action_log_std.expand_as(mean))
         # (validate_args=False: the argument check reads a flag back to the host — a device sync per forward, and illegal
         #  inside a CUDA-graph capture)
         return torch.distributions.Normal(mean, std, validate_args=False), run(self.critic)
+
+
+class _LinearTanh(torch.autograd.Function):
+    """`tanh(linear(x, w, b))` of a hidden layer in the update phase, bf16 operands (what autocast makes of it), with a
+    backward whose tanh derivative and bias gradient are ONE pass over the activation gradient (include/odg_policy.h:
+    odg_tanh_backward_bias) instead of torch's two (tanh_backward, then a bf16 column reduction)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        with torch.autocast("cuda", enabled=False):
+            xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
+            y = torch.tanh(torch.nn.functional.linear(xb, wb, b.to(torch.bfloat16)))
+        ctx.save_for_backward(xb, wb, y)
+        ctx.dtypes = (x.dtype, w.dtype, b.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xb, wb, y = ctx.saved_tensors
+        L = _lib.load()
+        rows, cols = y.shape
+        gy = gy.to(torch.bfloat16).contiguous()
+        g = torch.empty_like(y)
+        gb = torch.empty(cols, device=y.device, dtype=torch.float32)
+        scratch = torch.empty(L.odg_tanh_backward_bias_scratch_floats(cols), device=y.device, dtype=torch.float32)
+        st = C.c_void_p(torch.cuda.current_stream(y.device).cuda_stream)
+        _lib.check(L.odg_tanh_backward_bias(_ptr(gy), _ptr(y), _ptr(g), _ptr(gb), _ptr(scratch), rows, cols, st),
+                   "odg_tanh_backward_bias")
+        dx, dw, db = ctx.dtypes
+        with torch.autocast("cuda", enabled=False):
+            gx = (g @ wb).to(dx) if ctx.needs_input_grad[0] else None
+            gw = (g.t() @ xb).to(dw) if ctx.needs_input_grad[1] else None
+        return gx, gw, (gb.to(db) if ctx.needs_input_grad[2] else None)
+
+
+def linear_tanh(x, w, b):
+    """Hidden layer of the update-phase forward: the fused-backward form on CUDA under bf16 autocast when the width allows
+    it (8 x a power of two, every ActorCritic of the reference: 512 / 256, 1024 / 512), plain torch otherwise (the TF32
+    path without autocast; CPU runs of the gloo tests)."""
+    n = w.shape[0]
+    if (x.is_cuda and torch.is_autocast_enabled() and x.dim() == 2 and n % 8 == 0 and n <= 2048
+            and ((n // 8) & (n // 8 - 1)) == 0):
+        return _LinearTanh.apply(x, w, b)
+    return torch.tanh(torch.nn.functional.linear(x, w, b))
 
 
 def gae(reward, value, done, gamma=0.99, lam=0.95, normalize=True, group=None):

@@ -255,3 +255,63 @@ def test_graphed_ppo_update_equals_the_eager_update():
     # the tensor-core copy of the weights was refreshed: the rollout-time forward sees the updated parameters
     m0 = pols[0].act(obs[:256], sample=False)[3]; m1 = pols[1].act(obs[:256], sample=False)[3]
     assert torch.allclose(m0, m1, atol=2e-2)
+
+
+@pytest.mark.parametrize("rows,cols", [(1000, 512), (4097, 256), (37, 1024), (600, 8), (5000, 2048)])
+def test_tanh_backward_with_bias_gradient_matches_torch(rows, cols):
+    """`odg_tanh_backward_bias` (include/odg_policy.h) against torch's two passes: gy * (1 - y*y) in fp32 rounded once to
+    bf16 (≤ 1 bf16 ulp: FMA contraction may differ; torch's own bf16 kernel, which rounds three times, within a few ulp) and
+    the column sums of the kernel's OWN rounded gradient in float64 (fp32 accumulation in a
+    fixed order: 1e-5 relative to the column's absolute sum); ragged row counts; deterministic."""
+    import ctypes as C
+    from opendog_b200 import lib as _lib
+    L = _lib.load()
+    g_ = torch.Generator(device="cuda").manual_seed(rows + cols)
+    gy = torch.randn(rows, cols, device="cuda", generator=g_).to(torch.bfloat16)
+    y = torch.tanh(torch.randn(rows, cols, device="cuda", generator=g_) * 2).to(torch.bfloat16)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    outs = []
+    for _ in range(2):
+        g = torch.zeros_like(y); gb = torch.zeros(cols, device="cuda")
+        scratch = torch.empty(L.odg_tanh_backward_bias_scratch_floats(cols), device="cuda")
+        _lib.check(L.odg_tanh_backward_bias(p(gy), p(y), p(g), p(gb), p(scratch), rows, cols,
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)), "odg_tanh_backward_bias")
+        outs.append((g, gb))
+    (g, gb), (g2, gb2) = outs
+    assert torch.equal(g, g2) and torch.equal(gb, gb2)                          # deterministic
+    ref = (gy.float() * (1.0 - y.float() * y.float())).to(torch.bfloat16)     # fp32 arithmetic, ONE rounding
+    d = (g.float() - ref.float()).abs()
+    assert bool((d <= 2 ** -7 * ref.float().abs() + 1e-30).all())               # within one bf16 ulp everywhere (FMA contraction)
+    assert float((g == ref).float().mean()) > 0.99
+    # torch's own bf16 kernel rounds y*y, 1 - y*y and the product separately: it sits within a few ulp of the above
+    tref = torch.ops.aten.tanh_backward(gy, y).float()
+    assert bool(((g.float() - tref).abs() <= 2 ** -5 * tref.abs() + 2 ** -9 * gy.float().abs() + 1e-30).all())
+    s64 = g.double().sum(0)
+    assert torch.allclose(gb.double(), s64, rtol=0, atol=1e-5 * float(g.double().abs().sum(0).max()) + 1e-12)
+    assert L.odg_tanh_backward_bias(p(gy), p(y), p(g), p(gb), p(scratch), rows, 24, None) == -1           # ODG_ERR_INVALID: 24 / 8 = 3
+    assert b"odg_tanh_backward_bias" in L.odg_last_error()
+
+
+def test_fused_hidden_layer_backward_matches_autocast_torch():
+    """`policy.linear_tanh` (custom backward: one pass for tanh' and the bias gradient) against the plain autocast
+    expression it replaces in the PPO update's forward: same output bits, gradients within bf16 rounding of each other."""
+    from opendog_b200.policy import linear_tanh
+    torch.manual_seed(5)
+    B, K, N = 3000, 48, 512
+    x0 = torch.randn(B, K, device="cuda"); w0 = torch.randn(N, K, device="cuda") * 0.1; b0 = torch.randn(N, device="cuda") * 0.1
+    go = torch.randn(B, N, device="cuda")
+    res = []
+    for fused in (False, True):
+        x, w, b = (t.clone().requires_grad_(True) for t in (x0, w0, b0))
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = linear_tanh(x, w, b) if fused else torch.tanh(torch.nn.functional.linear(x, w, b))
+        (y.float() * go).sum().backward()
+        res.append((y.detach(), x.grad, w.grad, b.grad))
+    (y0, gx0, gw0, gb0), (y1, gx1, gw1, gb1) = res
+    assert y1.dtype == torch.bfloat16 and torch.equal(y0, y1)
+    assert gx1.dtype == torch.float32 and gw1.dtype == torch.float32 and gb1.dtype == torch.float32
+    rel = lambda a, b_: float((a - b_).norm() / b_.norm())
+    assert rel(gx1, gx0) < 1e-2 and rel(gw1, gw0) < 1e-2 and rel(gb1, gb0) < 1e-2
+    # without autocast the plain fp32 / TF32 expression is what runs
+    x = x0.clone().requires_grad_(True)
+    assert linear_tanh(x, w0, b0).dtype == torch.float32
