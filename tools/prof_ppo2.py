@@ -24,4 +24,8 @@ print("graph replay only", timed(lambda: [gr.replay() for gr in g.graphs]))
 print({k: float(v) for k, v in g.out.items()})
 with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
     [gr.replay() for gr in g.graphs]; torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=90))
+rows = sorted(((e.self_device_time_total, e.count, e.key) for e in prof.key_averages() if e.self_device_time_total > 0), reverse=True)
+tot = sum(r[0] for r in rows)
+print("kernel time of one epoch: %.3f ms in %d launches" % (tot / 1e3, sum(r[1] for r in rows)))
+for t, n, k in rows[:70]:
+    print("%9.1f us %5.1f %% %4d x  %s" % (t, 100 * t / tot, n, k[:120]))
