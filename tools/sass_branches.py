@@ -8,7 +8,7 @@ cost branch_resolving stalls; in this latency-bound kernel removing them paid fa
 import os, re, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.environ.get("ODG_LIB_PATH", os.path.join(ROOT, "opendog_b200", "libodgsim.so"))
-kern = "k_stepILi2EE"
+kern = os.environ.get("ODG_KERNEL", "k_stepILi2ELb1")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 cubin = next(f for f in os.listdir(tmp) if f.endswith(".cubin") and "odg_sim." in f)
