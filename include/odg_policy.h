@@ -81,6 +81,19 @@ int odg_tanh_backward_bias_scratch_floats(int cols);
 int odg_tanh_backward_bias(const void* grad_y_bf16, const void* y_bf16, void* grad_x_bf16, float* bias_grad_dev,
                            float* scratch_dev, long long rows, int cols, void* stream);
 
+/* PPO update phase: the clipped-surrogate loss of one minibatch (train/train.py:117-130 hyper-parameters; the update of
+ * sim2real/train.py:566-585) and its gradients in one pass over the samples. Inputs f32: mean [B][A] (the actor's output),
+ * value [B], log_std [A], action [B][A], logp_old / adv / ret [B]. Outputs: loss_dev [1] = pg + vf_coef*vf - ent_coef*ent,
+ * terms_dev [4] = {loss, pg, vf, entropy} with pg = mean(-min(r*adv, clamp(r, 1-clip, 1+clip)*adv)), r = exp(logp - logp_old),
+ * vf = mean((value - ret)^2), entropy = sum_k(0.5 + 0.5 log 2pi + log_std[k]); grad_mean_dev [B][A], grad_value_dev [B],
+ * grad_log_std_dev [A] = d loss / d (those inputs), with torch.min's / torch.clamp's gradient conventions (ties split
+ * evenly, clamp ends pass). Deterministic. 1 <= A <= 16. scratch_dev: odg_ppo_loss_scratch_floats() floats, caller-owned. */
+int odg_ppo_loss_scratch_floats(void);
+int odg_ppo_loss(const float* mean_dev, const float* value_dev, const float* log_std_dev, const float* action_dev,
+                 const float* logp_old_dev, const float* adv_dev, const float* ret_dev, long long B, int A, float clip,
+                 float vf_coef, float ent_coef, float* loss_dev, float* terms_dev, float* grad_mean_dev,
+                 float* grad_value_dev, float* grad_log_std_dev, float* scratch_dev, void* stream);
+
 long long odg_policy_launch_count(const OdgPolicy* p);
 
 #ifdef __cplusplus

@@ -22,6 +22,7 @@ SYMBOLS = [
     # rollout / policy entry points (include/odg_policy.h)
     "odg_policy_create", "odg_policy_destroy", "odg_policy_load", "odg_policy_forward", "odg_gae",
     "odg_normalize_advantages", "odg_policy_launch_count", "odg_tanh_backward_bias", "odg_tanh_backward_bias_scratch_floats",
+    "odg_ppo_loss", "odg_ppo_loss_scratch_floats",
     # QuadrupedEnv surface (include/odg_sim2real.h)
     "odg_s2r_default_config", "odg_s2r_create", "odg_s2r_destroy", "odg_s2r_reset", "odg_s2r_step",
     "odg_s2r_set_bookkeeping", "odg_s2r_default_config_for", "odg_s2r_obs_dim", "odg_s2r_act_dim",
@@ -105,6 +106,8 @@ def load():
     L.odg_normalize_advantages.argtypes = [_vp, C.c_longlong, _vp, _vp]
     L.odg_tanh_backward_bias.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_longlong, C.c_int, _vp]
     L.odg_tanh_backward_bias_scratch_floats.argtypes = [C.c_int]
+    L.odg_ppo_loss_scratch_floats.argtypes = []
+    L.odg_ppo_loss.argtypes = [_vp] * 7 + [C.c_longlong, C.c_int, C.c_float, C.c_float, C.c_float] + [_vp] * 7
     L.odg_policy_launch_count.argtypes = [_vp]
     L.odg_policy_launch_count.restype = C.c_longlong
     L.odg_s2r_default_config.argtypes = [C.POINTER(OdgS2RConfig)]

@@ -220,6 +220,52 @@ def linear_tanh(x, w, b):
     return torch.tanh(torch.nn.functional.linear(x, w, b))
 
 
+class _PPOLoss(torch.autograd.Function):
+    """Clipped-surrogate loss of one minibatch with its gradients computed in the same pass (include/odg_policy.h:
+    odg_ppo_loss). Returns (loss, terms) with terms = [loss, pg, vf, entropy] (not differentiable)."""
+
+    @staticmethod
+    def forward(ctx, mean, value, log_std, action, logp_old, adv, ret, clip, vf_coef, ent_coef):
+        L = _lib.load()
+        dev = mean.device
+        B, A = mean.shape
+        f = lambda t: t.detach().to(torch.float32).contiguous()
+        m, v, ls = f(mean), f(value).reshape(-1), f(log_std).reshape(-1)
+        loss = torch.empty((), device=dev); terms = torch.empty(4, device=dev)
+        g_mean = torch.empty(B, A, device=dev); g_value = torch.empty(B, device=dev); g_ls = torch.empty(A, device=dev)
+        scratch = torch.empty(L.odg_ppo_loss_scratch_floats(), device=dev)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(L.odg_ppo_loss(_ptr(m), _ptr(v), _ptr(ls), _ptr(f(action)), _ptr(f(logp_old)), _ptr(f(adv)), _ptr(f(ret)),
+                                  B, A, float(clip), float(vf_coef), float(ent_coef), _ptr(loss), _ptr(terms), _ptr(g_mean),
+                                  _ptr(g_value), _ptr(g_ls), _ptr(scratch), st), "odg_ppo_loss")
+        ctx.save_for_backward(g_mean, g_value, g_ls)
+        ctx.meta = (mean.dtype, value.dtype, value.shape, log_std.dtype, log_std.shape)
+        ctx.mark_non_differentiable(terms)
+        return loss, terms
+
+    @staticmethod
+    def backward(ctx, gl, _gterms):
+        g_mean, g_value, g_ls = ctx.saved_tensors
+        md, vd, vs, ld, lshape = ctx.meta
+        return ((g_mean * gl).to(md), (g_value * gl).reshape(vs).to(vd), (g_ls * gl).reshape(lshape).to(ld),
+                None, None, None, None, None, None, None)
+
+
+def ppo_loss(mean, value, log_std, action, logp_old, adv, ret, clip, vf_coef, ent_coef):
+    """(loss, pg, vf, entropy) of the clipped-surrogate objective for a diagonal Normal(mean, exp(log_std)) policy: one fused
+    kernel on CUDA (forward and gradients), the plain torch expression elsewhere (CPU runs of the gloo tests; wider actions)."""
+    if mean.is_cuda and mean.dim() == 2 and mean.shape[1] <= 16:
+        loss, terms = _PPOLoss.apply(mean, value, log_std, action, logp_old, adv, ret, clip, vf_coef, ent_coef)
+        return loss, terms[1], terms[2], terms[3]
+    d = torch.distributions.Normal(mean, torch.exp(log_std.expand_as(mean)), validate_args=False)
+    logp = d.log_prob(action).float().sum(-1)
+    ratio = torch.exp(logp - logp_old)
+    pg = -torch.min(ratio * adv, torch.clamp(ratio, 1 - clip, 1 + clip) * adv).mean()
+    vf = torch.nn.functional.mse_loss(value.float().reshape(-1), ret)
+    ent = d.entropy().float().sum(-1).mean()
+    return pg + vf_coef * vf - ent_coef * ent, pg, vf, ent
+
+
 def gae(reward, value, done, gamma=0.99, lam=0.95, normalize=True, group=None):
     """GAE + advantage normalisation (sim2real/train.py:557-564) for [T, N] rollouts on the GPU.
 

@@ -60,6 +60,22 @@ def allreduce_flat_grads(params, group=None, world: int | None = None):
     return flat
 
 
+def _loss_terms(policy, d, v, action, logp_old, adv, ret, clip, vf_coef, ent_coef):
+    """Clipped-surrogate loss terms of one minibatch from the policy's (Normal, value) output: the fused kernel
+    (policy.ppo_loss) when the policy exposes its state-independent `action_log_std` (the reference's ActorCritic,
+    sim2real/train.py:132-149), the torch expression on the distribution otherwise."""
+    ls = getattr(policy, "action_log_std", None)
+    if ls is not None and d.loc.is_cuda and d.loc.dim() == 2:
+        from .policy import ppo_loss
+        return ppo_loss(d.loc, v, ls, action, logp_old, adv, ret, clip, vf_coef, ent_coef)
+    logp = d.log_prob(action).float().sum(-1)
+    ratio = torch.exp(logp - logp_old)
+    pg = -torch.min(ratio * adv, torch.clamp(ratio, 1 - clip, 1 + clip) * adv).mean()
+    vf = torch.nn.functional.mse_loss(v.float().squeeze(-1), ret)
+    ent = d.entropy().float().sum(-1).mean()
+    return pg + vf_coef * vf - ent_coef * ent, pg, vf, ent
+
+
 def ppo_update(policy, optimizer, obs, action, logp_old, adv, ret, clip: float = 0.2, vf_coef: float = 0.5,
                ent_coef: float = 0.005, max_grad_norm: float = 0.5, epochs: int = 1, minibatches: int = 4, group=None,
                autocast: bool = True, timing: dict | None = None):
@@ -89,13 +105,7 @@ def ppo_update(policy, optimizer, obs, action, logp_old, adv, ret, clip: float =
             sl = slice(i * mb, min(B, (i + 1) * mb))
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=use_ac):
                 d, v = policy.forward_padded(obs[sl]) if padded else policy(obs[sl])
-            logp = d.log_prob(action[sl]).float().sum(-1)
-            ratio = torch.exp(logp - logp_old[sl])
-            a = adv[sl]
-            pg = -torch.min(ratio * a, torch.clamp(ratio, 1 - clip, 1 + clip) * a).mean()
-            vf = torch.nn.functional.mse_loss(v.float().squeeze(-1), ret[sl])
-            ent = d.entropy().float().sum(-1).mean()
-            loss = pg + vf_coef * vf - ent_coef * ent
+            loss, pg, vf, ent = _loss_terms(policy, d, v, action[sl], logp_old[sl], adv[sl], ret[sl], clip, vf_coef, ent_coef)
             optimizer.zero_grad(set_to_none=True)
             loss.backward()
             if timing is not None and obs.is_cuda:
@@ -147,13 +157,8 @@ class GraphedPPOUpdate:
         hp = self.hp
         with torch.autocast("cuda", dtype=torch.bfloat16):
             d, v = self.policy.forward_padded(self.obs[sl]) if self.padded else self.policy(self.obs[sl])
-        logp = d.log_prob(self.action[sl]).float().sum(-1)
-        ratio = torch.exp(logp - self.logp_old[sl])
-        a = self.adv[sl]
-        pg = -torch.min(ratio * a, torch.clamp(ratio, 1 - hp["clip"], 1 + hp["clip"]) * a).mean()
-        vf = torch.nn.functional.mse_loss(v.float().squeeze(-1), self.ret[sl])
-        ent = d.entropy().float().sum(-1).mean()
-        loss = pg + hp["vf_coef"] * vf - hp["ent_coef"] * ent
+        loss, pg, vf, ent = _loss_terms(self.policy, d, v, self.action[sl], self.logp_old[sl], self.adv[sl], self.ret[sl],
+                                        hp["clip"], hp["vf_coef"], hp["ent_coef"])
         self.opt.zero_grad(set_to_none=False)
         loss.backward()
         allreduce_flat_grads(self.params, group=self.group)

@@ -315,3 +315,52 @@ def test_fused_hidden_layer_backward_matches_autocast_torch():
     # without autocast the plain fp32 / TF32 expression is what runs
     x = x0.clone().requires_grad_(True)
     assert linear_tanh(x, w0, b0).dtype == torch.float32
+
+
+@pytest.mark.parametrize("B,A", [(5000, 8), (333, 12), (70000, 4), (1, 16)])
+def test_fused_ppo_loss_matches_the_torch_expression(B, A):
+    """`policy.ppo_loss` on CUDA (odg_ppo_loss: loss terms and gradients in one pass) against the torch expression it
+    replaces (the objective of train/train.py:117-130 on the ActorCritic of sim2real/train.py:132-149), autograd in float64:
+    loss terms to 1e-5 relative, gradients to 1e-4 of their largest entry; ratios inside and outside the clip range, zero
+    advantages, and exact ties (ratio = 1)."""
+    from opendog_b200.policy import ppo_loss
+    g = torch.Generator(device="cuda").manual_seed(B + A)
+    r = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    mean0, value0, ls0 = torch.tanh(r(B, A)), r(B, 1), (r(1, A) * 0.3 - 0.9)
+    action = mean0 + torch.exp(ls0) * r(B, A)
+    with torch.no_grad():
+        lp = torch.distributions.Normal(mean0, torch.exp(ls0).expand_as(mean0)).log_prob(action).sum(-1)
+    logp_old = lp + r(B) * 0.25                     # ratios spread over ~[0.5, 2]
+    logp_old[::7] = lp[::7]                         # exact ties: ratio = 1
+    adv, ret = r(B), r(B)
+    adv[::11] = 0.0
+    clip, vf_coef, ent_coef = 0.2, 0.5, 0.005
+    # fused
+    m1, v1, l1 = (t.clone().requires_grad_(True) for t in (mean0, value0, ls0))
+    loss1, pg1, vf1, ent1 = ppo_loss(m1, v1, l1, action, logp_old, adv, ret, clip, vf_coef, ent_coef)
+    loss1.backward()
+    # torch, float64
+    m2, v2, l2 = (t.double().clone().requires_grad_(True) for t in (mean0, value0, ls0))
+    d = torch.distributions.Normal(m2, torch.exp(l2.expand_as(m2)), validate_args=False)
+    logp = d.log_prob(action.double()).sum(-1)
+    ratio = torch.exp(logp - logp_old.double())
+    a = adv.double()
+    pg2 = -torch.min(ratio * a, torch.clamp(ratio, 1 - clip, 1 + clip) * a).mean()
+    vf2 = torch.nn.functional.mse_loss(v2.squeeze(-1), ret.double())
+    ent2 = d.entropy().sum(-1).mean()
+    loss2 = pg2 + vf_coef * vf2 - ent_coef * ent2
+    loss2.backward()
+    for x, y in ((loss1, loss2), (pg1, pg2), (vf1, vf2), (ent1, ent2)):
+        x, y = float(x.detach()), float(y.detach())
+        assert abs(x - y) <= 1e-5 * (1 + abs(y)), (x, y)
+    # a sample whose float32 ratio lands on the other side of a clip boundary than the float64 one flips its gradient: leave
+    # those (ratio within 1e-5 of a boundary) out of the comparison
+    rt = ratio.detach()
+    near = ((rt - (1 - clip)).abs() < 1e-5) | ((rt - (1 + clip)).abs() < 1e-5)
+    keep = ~near
+    gm1, gm2 = m1.grad.double()[keep], m2.grad[keep]
+    assert float((gm1 - gm2).abs().max()) <= 1e-4 * float(gm2.abs().max()) + 1e-12
+    assert float((v1.grad.double() - v2.grad).abs().max()) <= 1e-5 * float(v2.grad.abs().max()) + 1e-12
+    if not bool(near.any()):
+        assert float((l1.grad.double() - l2.grad).abs().max()) <= 1e-4 * float(l2.grad.abs().max()) + 1e-9
+    assert m1.grad.shape == mean0.shape and v1.grad.shape == value0.shape and l1.grad.shape == ls0.shape
