@@ -94,6 +94,11 @@ int odg_ppo_loss(const float* mean_dev, const float* value_dev, const float* log
                  float vf_coef, float ent_coef, float* loss_dev, float* terms_dev, float* grad_mean_dev,
                  float* grad_value_dev, float* grad_log_std_dev, float* scratch_dev, void* stream);
 
+/* PPO update phase, forward: y = tanh(x) for `count` bf16 values (a multiple of 8; 16-byte aligned; y may be x) with the
+ * hardware tanh the rollout kernel's epilogue uses (odg_policy_forward), so that the update-time policy evaluates the same
+ * function as the policy that produced logp_old. Replaces nn.Tanh of sim2real/train.py:136-147 on bf16 activations. */
+int odg_tanh_bf16(const void* x_bf16, void* y_bf16, long long count, void* stream);
+
 long long odg_policy_launch_count(const OdgPolicy* p);
 
 #ifdef __cplusplus

@@ -657,6 +657,29 @@ __global__ void __launch_bounds__(256) k_ppo_finish(const float* __restrict__ pa
   if (threadIdx.x < A) g_log_std[threadIdx.x] = s_sum[2 + threadIdx.x] - ent_coef;
 }
 
+// tanh of a bf16 activation tensor in place (the update-phase forward): MUFU tanh.approx — the same function the rollout
+// kernel's epilogue applies, so the update-time policy is the rollout-time policy — at HBM speed (torch's tanhf-based
+// kernel is instruction-bound at ~4.8 TB/s for bf16)
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__global__ void __launch_bounds__(256) k_tanh_bf16(const uint4* x, uint4* y, long long n16) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  auto one = [](uint4 v) {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const float2 t = __bfloat1622float2(h[k]); h[k] = __floats2bfloat162_rn(tanh_approx(t.x), tanh_approx(t.y)); }
+    return v;
+  };
+  for (; i + 3 * stride < n16; i += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = __ldcs(x + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; u++) y[i + u * stride] = one(v[u]);
+  }
+  for (; i < n16; i += stride) y[i] = one(__ldcs(x + i));
+}
+
 }  // namespace
 
 struct OdgPolicy {
@@ -828,6 +851,18 @@ int odg_ppo_loss(const float* mean_dev, const float* value_dev, const float* log
                                         clip, vf_coef, grad_mean_dev, grad_value_dev, scratch_dev);
   k_ppo_finish<<<1, 256, 0, st>>>(scratch_dev, grid, A, log_std_dev, 1.f / (float)B, vf_coef, ent_coef, loss_dev, terms_dev,
                                   grad_log_std_dev);
+  CUDA_TRY(cudaGetLastError());
+  return ODG_OK;
+}
+
+int odg_tanh_bf16(const void* x_bf16, void* y_bf16, long long count, void* stream) {
+  if (!x_bf16 || !y_bf16 || count < 8 || (count & 7)) return set_error(ODG_ERR_INVALID, "odg_tanh_bf16: bad arguments (count must be a multiple of 8)");
+  const int dev = device_of(x_bf16);
+  if (dev < 0) return set_error(ODG_ERR_INVALID, "odg_tanh_bf16: x is not device memory");
+  DevGuard guard(dev);
+  const long long n16 = count >> 3, want = (n16 + 255) / 256;
+  k_tanh_bf16<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x_bf16), static_cast<uint4*>(y_bf16), n16);
   CUDA_TRY(cudaGetLastError());
   return ODG_OK;
 }

@@ -22,7 +22,7 @@ SYMBOLS = [
     # rollout / policy entry points (include/odg_policy.h)
     "odg_policy_create", "odg_policy_destroy", "odg_policy_load", "odg_policy_forward", "odg_gae",
     "odg_normalize_advantages", "odg_policy_launch_count", "odg_tanh_backward_bias", "odg_tanh_backward_bias_scratch_floats",
-    "odg_ppo_loss", "odg_ppo_loss_scratch_floats",
+    "odg_ppo_loss", "odg_ppo_loss_scratch_floats", "odg_tanh_bf16",
     # QuadrupedEnv surface (include/odg_sim2real.h)
     "odg_s2r_default_config", "odg_s2r_create", "odg_s2r_destroy", "odg_s2r_reset", "odg_s2r_step",
     "odg_s2r_set_bookkeeping", "odg_s2r_default_config_for", "odg_s2r_obs_dim", "odg_s2r_act_dim",
@@ -107,6 +107,7 @@ def load():
     L.odg_tanh_backward_bias.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_longlong, C.c_int, _vp]
     L.odg_tanh_backward_bias_scratch_floats.argtypes = [C.c_int]
     L.odg_ppo_loss_scratch_floats.argtypes = []
+    L.odg_tanh_bf16.argtypes = [_vp, _vp, C.c_longlong, _vp]
     L.odg_ppo_loss.argtypes = [_vp] * 7 + [C.c_longlong, C.c_int, C.c_float, C.c_float, C.c_float] + [_vp] * 7
     L.odg_policy_launch_count.argtypes = [_vp]
     L.odg_policy_launch_count.restype = C.c_longlong

@@ -185,7 +185,12 @@ class _LinearTanh(torch.autograd.Function):
     def forward(ctx, x, w, b):
         with torch.autocast("cuda", enabled=False):
             xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
-            y = torch.tanh(torch.nn.functional.linear(xb, wb, b.to(torch.bfloat16)))
+            y = torch.nn.functional.linear(xb, wb, b.to(torch.bfloat16))
+        if y.is_contiguous() and y.numel() % 8 == 0:
+            st = C.c_void_p(torch.cuda.current_stream(y.device).cuda_stream)        # in place, the rollout kernel's tanh
+            _lib.check(_lib.load().odg_tanh_bf16(_ptr(y), _ptr(y), y.numel(), st), "odg_tanh_bf16")
+        else:
+            y = torch.tanh(y)
         ctx.save_for_backward(xb, wb, y)
         ctx.dtypes = (x.dtype, w.dtype, b.dtype)
         return y

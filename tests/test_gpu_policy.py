@@ -294,7 +294,8 @@ def test_tanh_backward_with_bias_gradient_matches_torch(rows, cols):
 
 def test_fused_hidden_layer_backward_matches_autocast_torch():
     """`policy.linear_tanh` (custom backward: one pass for tanh' and the bias gradient) against the plain autocast
-    expression it replaces in the PPO update's forward: same output bits, gradients within bf16 rounding of each other."""
+    expression it replaces in the PPO update's forward: outputs within one bf16 ulp (hardware tanh), gradients within bf16
+    rounding of each other."""
     from opendog_b200.policy import linear_tanh
     torch.manual_seed(5)
     B, K, N = 3000, 48, 512
@@ -308,7 +309,11 @@ def test_fused_hidden_layer_backward_matches_autocast_torch():
         (y.float() * go).sum().backward()
         res.append((y.detach(), x.grad, w.grad, b.grad))
     (y0, gx0, gw0, gb0), (y1, gx1, gw1, gb1) = res
-    assert y1.dtype == torch.bfloat16 and torch.equal(y0, y1)
+    # forward: the hardware tanh of the rollout kernel (tanh.approx, rel. error 2^-11) rounded to bf16: within one bf16 ulp
+    # of torch's tanhf-based result, the same bits for most elements
+    assert y1.dtype == torch.bfloat16
+    assert bool(((y1.float() - y0.float()).abs() <= 2 ** -7 * y0.float().abs() + 1e-6).all())
+    assert float((y0 == y1).float().mean()) > 0.85
     assert gx1.dtype == torch.float32 and gw1.dtype == torch.float32 and gb1.dtype == torch.float32
     rel = lambda a, b_: float((a - b_).norm() / b_.norm())
     assert rel(gx1, gx0) < 1e-2 and rel(gw1, gw0) < 1e-2 and rel(gb1, gb0) < 1e-2
