@@ -81,8 +81,9 @@ int odg_tanh_backward_bias_scratch_floats(int cols);
 int odg_tanh_backward_bias(const void* grad_y_bf16, const void* y_bf16, void* grad_x_bf16, float* bias_grad_dev,
                            float* scratch_dev, long long rows, int cols, void* stream);
 
-/* PPO update phase: the clipped-surrogate loss of one minibatch (train/train.py:117-130 hyper-parameters; the update of
- * sim2real/train.py:566-585) and its gradients in one pass over the samples. Inputs f32: mean [B][A] (the actor's output),
+/* PPO update phase: the clipped-surrogate loss of one minibatch (stable-baselines3's PPO objective with the
+ * hyper-parameters of train/train.py:117-130; the update of sim2real/train.py:566-569, actor_loss = -(logp*adv).mean(), is
+ * its special case clip = +inf with logp_old = logp) and its gradients in one pass over the samples. Inputs f32: mean [B][A] (the actor's output),
  * value [B], log_std [A], action [B][A], logp_old / adv / ret [B]. Outputs: loss_dev [1] = pg + vf_coef*vf - ent_coef*ent,
  * terms_dev [4] = {loss, pg, vf, entropy} with pg = mean(-min(r*adv, clamp(r, 1-clip, 1+clip)*adv)), r = exp(logp - logp_old),
  * vf = mean((value - ret)^2), entropy = sum_k(0.5 + 0.5 log 2pi + log_std[k]); grad_mean_dev [B][A], grad_value_dev [B],

@@ -571,8 +571,8 @@ __global__ void __launch_bounds__(256) k_colsum_finish(const float* __restrict__
 }
 
 // ---- PPO update phase: the clipped-surrogate loss of one minibatch and its gradients in one pass ----------------------
-// (sim2real/train.py:566-585 / train/train.py:117-130: Normal log-prob, probability ratio, clipped surrogate, value MSE,
-// entropy bonus). torch evaluates this as ~170 element-wise / reduction launches per minibatch over [B, A] tensors
+// (SB3's PPO objective with the hyper-parameters of train/train.py:117-130; sim2real/train.py:566-569 is its special case
+// clip = +inf, logp_old = logp: Normal log-prob, probability ratio, clipped surrogate, value MSE, entropy bonus). torch evaluates this as ~170 element-wise / reduction launches per minibatch over [B, A] tensors
 // (1.5 ms of an 11.8 ms epoch at 65536 envs x 24); here one thread per sample computes its loss terms AND
 // d loss / d mean, d loss / d value, and its share of d loss / d log_std; block partials are added in a fixed order.
 constexpr int kPlBlock = 256, kPlMaxGrid = 1184, kPlCols = 32, kPlMaxA = 16;
