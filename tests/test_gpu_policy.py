@@ -369,3 +369,28 @@ def test_fused_ppo_loss_matches_the_torch_expression(B, A):
     if not bool(near.any()):
         assert float((l1.grad.double() - l2.grad).abs().max()) <= 1e-4 * float(l2.grad.abs().max()) + 1e-9
     assert m1.grad.shape == mean0.shape and v1.grad.shape == value0.shape and l1.grad.shape == ls0.shape
+
+
+def test_fused_ppo_loss_with_infinite_clip_is_the_sim2real_update():
+    """sim2real/train.py:566-569: actor_loss = -(log_prob * adv).mean(), critic MSE, entropy — the clipped objective with
+    clip = +inf and logp_old = logp (ratio 1): same loss gradients from `policy.ppo_loss`."""
+    from opendog_b200.policy import ppo_loss
+    g = torch.Generator(device="cuda").manual_seed(77)
+    r = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    B, A = 4000, 8
+    mean0, value0, ls0 = torch.tanh(r(B, A)), r(B, 1), (r(1, A) * 0.3 - 0.9)
+    action = mean0 + torch.exp(ls0) * r(B, A)
+    adv, ret = r(B), r(B)
+    VALUE_LOSS_COEF, ENT = 0.5, 0.01
+    m2, v2, l2 = (t.double().clone().requires_grad_(True) for t in (mean0, value0, ls0))
+    d = torch.distributions.Normal(m2, torch.exp(l2.expand_as(m2)), validate_args=False)
+    logp = d.log_prob(action.double()).sum(-1)
+    # (the reference takes entropy().mean() over [B, A]; per-dimension mean = the summed entropy / A)
+    loss2 = -(logp * adv.double()).mean() + VALUE_LOSS_COEF * torch.nn.functional.mse_loss(v2.squeeze(-1), ret.double()) \
+        - ENT * d.entropy().mean()
+    loss2.backward()
+    m1, v1, l1 = (t.clone().requires_grad_(True) for t in (mean0, value0, ls0))
+    loss1, _, _, _ = ppo_loss(m1, v1, l1, action, logp.detach().float(), adv, ret, float("inf"), VALUE_LOSS_COEF, ENT / A)
+    loss1.backward()
+    for a_, b_ in ((m1.grad, m2.grad), (v1.grad, v2.grad), (l1.grad, l2.grad)):
+        assert float((a_.double() - b_).abs().max()) <= 2e-4 * float(b_.abs().max()) + 1e-12
