@@ -97,6 +97,12 @@ def test_c_abi_error_behaviour():
     assert L.odg_policy_create(1000, 8, 0, C.byref(h)) < 0      # state_dim above ODG_POLICY_MAX_STATE
     assert L.odg_policy_forward(None, None, 16, None, None, None, None, 0, 0, None, 0, None) < 0
     L.odg_policy_destroy(None)
+    # update-phase entry points (include/odg_policy.h): argument checks come before any device work
+    assert L.odg_ppo_loss(*([None] * 7), 16, 8, 0.2, 0.5, 0.005, *([None] * 7)) == INVALID and b"odg_ppo_loss" in L.odg_last_error()
+    assert L.odg_tanh_bf16(None, None, 64, None) == INVALID and b"odg_tanh_bf16" in L.odg_last_error()
+    assert L.odg_tanh_backward_bias(None, None, None, None, None, 4, 512, None) == INVALID
+    assert L.odg_tanh_backward_bias_scratch_floats(512) >= 512 and L.odg_tanh_backward_bias_scratch_floats(0) == 0
+    assert L.odg_ppo_loss_scratch_floats() > 0
     assert L.odg_s2r_step(None, None, None, None, None, None, None, None, None) < 0
     L.odg_s2r_destroy(None)
     assert isinstance(L.odg_version(), bytes) and L.odg_version()
