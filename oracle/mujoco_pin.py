@@ -1,0 +1,88 @@
+"""Test infrastructure (oracle side): probes for the MuJoCo pin built from the reference's shipped (checkpoint, walk file)
+pairs — see tools/pin_walk_json.py for what the pin is and tests/test_mujoco_pin_walk_json.py for the gate. Follows
+/root/reference/Code/mujoco/sim2real/train.py: ActorCritic.actor (:132-149), the policy -> target mapping of
+`_apply_actions_and_step` (:235-277) and `convert_sim_rad_to_real_deg` (:120-130), reset (:209-233), `generate_walk_json`
+(:600-636). Only tests/ and tools/ import this module."""
+import copy
+
+import numpy as np
+
+from opendog_b200.model.compile import load_compiled
+
+from .oracle import Sim
+from .sim2real_oracle import AMP, QuadrupedEnvOracle
+
+MATCHING = (2600, 2700, 2800, 2900, 3000, 3100, 3200, 3300, 3500, 3700)    # step 0 within 0.5 degree (section 1 of the report)
+WIDE = dict(thigh_hi=3.2, knee_lo=-2.4)                                    # any range the 40-degree amplitude cannot reach
+REAL_HOME_DEG = np.array([-45.0, 45.0, 45.0, 45.0, 45.0, -45.0, 45.0, -45.0])   # train.py:95-101 in ORDERED order
+
+
+def actor_forward(w, x):
+    """The reference ActorCritic's actor (train.py:132-149: Linear-Tanh-Linear-Tanh-Linear-Tanh), float64 numpy."""
+    h = np.tanh(w[0] @ x + w[1]); h = np.tanh(w[2] @ h + w[3])
+    return np.tanh(w[4] @ h + w[5])
+
+
+def actor_weights(state_dict):
+    return [np.asarray(state_dict[k], dtype=np.float64) for k in
+            ("actor.0.weight", "actor.0.bias", "actor.2.weight", "actor.2.bias", "actor.4.weight", "actor.4.bias")]
+
+
+def model_desc(wide):
+    d = copy.deepcopy(load_compiled("our_robot"))
+    if wide:
+        for leg in range(4):
+            d["jnt_range"][leg][0] = [2.36, WIDE["thigh_hi"]]; d["jnt_range"][leg][1] = [WIDE["knee_lo"], -1.2]
+        for u in range(8):
+            d["act_ctrlrange"][u] = [2.36, WIDE["thigh_hi"]] if d["act_joint"][u] == 0 else [WIDE["knee_lo"], -1.2]
+    return d
+
+
+class Probe:
+    """QuadrupedEnvOracle on a given model description, with the policy -> targets mapping of train.py:235-277, 120-130."""
+
+    def __init__(self, desc):
+        self.e = QuadrupedEnvOracle(); self.e.sim = Sim(desc)
+        self.home = np.array(self.e.home)
+        self.cr = np.array([desc["act_ctrlrange"][u] for u in self.e.act_id])
+
+    def reset(self, settle=100):
+        e = self.e; s = e.sim
+        e.counter = 0; s.reset_keyframe(); s.ctrl[:] = e.initial_ctrl
+        for _ in range(settle):
+            s.ctrl[:] = e.initial_ctrl; s.step()
+        return e.obs().astype(np.float64)
+
+    def targets_deg(self, w, x):
+        fr, k1, fl, k2 = actor_forward(w, x) * AMP
+        d = np.array([fr, 0, fl, 0, fl, 0, fr, 0.0])
+        if self.e.counter % 2 == 0:
+            d[1], d[7] = k1, -k1
+        else:
+            d[3], d[5] = k2, -k2
+        return REAL_HOME_DEG + np.degrees(np.clip(self.home + d, self.cr[:, 0], self.cr[:, 1]) - self.home)
+
+    def apply_deg(self, deg):
+        e = self.e; cmd = np.zeros(8)
+        for o in range(8):
+            cmd[e.act_id[o]] = self.home[o] + np.radians(deg[o] - REAL_HOME_DEG[o])
+        e.sim.ctrl[:] = cmd
+        for _ in range(e.n_sub):
+            e.sim.step()
+        e.counter += 1
+        return e.obs().astype(np.float64)
+
+
+def teacher_forced(desc, w, shipped, nsteps):
+    p = Probe(desc); x = p.reset(); err = []
+    for t in range(min(nsteps, len(shipped))):
+        err.append(np.abs(np.round(p.targets_deg(w, x), 2) - shipped[t]).max())
+        x = p.apply_deg(shipped[t])
+    return np.array(err)
+
+
+def noise_floor(desc, w, nsteps):
+    p = Probe(desc); x = p.reset(); rec = []
+    for _ in range(nsteps):
+        m = p.targets_deg(w, x); rec.append(np.round(m, 2)); x = p.apply_deg(m)
+    return teacher_forced(desc, w, np.array(rec), nsteps)

@@ -1,4 +1,5 @@
-/* odg_oracle.c — CPU fp64 ORACLE (test infrastructure, see odg_oracle.h: PARITY UNPINNED).
+/* odg_oracle.c — CPU fp64 ORACLE (test infrastructure, see odg_oracle.h: PARITY UNPINNED at the single-step level,
+ * loosely pinned against the reference's shipped MuJoCo walk files).
  *
  * Restates, for "free trunk + hinge leg chains over a floor plane" models, what the reference's
  * hot path executes inside the third-party `mujoco==3.2.3` wheel and its own Python reward code:

@@ -3,9 +3,14 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library; the product path (opendog_b200/) never does.
  *
- * PARITY UNPINNED: the arithmetic being restated lives in the un-vendored third-party wheel
- * mujoco==3.2.3 (/root/reference/Code/mujoco/install.sh:27), which cannot be imported or built in
- * this environment, and the reference ships no tests / golden vectors for this path.
+ * PARITY: UNPINNED at the single-step level, LOOSELY PINNED at the trajectory level. The arithmetic being restated
+ * lives in the un-vendored third-party wheel mujoco==3.2.3 (/root/reference/Code/mujoco/install.sh:27), which cannot
+ * be imported or built in this environment, and the reference ships no tests / golden vectors of mj_step itself
+ * (SURVEY.md §4): no qpos / qvel / contact force of this file has ever been compared with MuJoCo's. What the reference
+ * does ship are ten (policy checkpoint, 50-step closed-loop walk recorded in real MuJoCo) pairs written by the revision
+ * of sim2real/train.py in the tree; under teacher forcing this file tracks them to 0.1 degree of policy output (of +-40)
+ * over the first 150 engine steps and to a few degrees afterwards, and resolves the reference's 100 settling steps to the
+ * step (tools/pin_walk_json.py, tests/test_mujoco_pin_walk_json.py, profiles/r02g_mujoco_pin.txt).
  * This file restates MuJoCo's published algorithm ("Computation" chapter of its documentation) for
  * the model class the reference uses, anchored on the reference's own call sites
  * (environments/WalkEnvironment.py:56-79, rewards/walk_environment_reward_calc.py, sim2real/train.py).

@@ -1,8 +1,8 @@
 """ctypes front-end of the CPU oracle (oracle/odg_oracle.c). TEST INFRASTRUCTURE ONLY.
 
 Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs; the product package `opendog_b200` never imports this module. PARITY UNPINNED (see
-odg_oracle.h).
+legs; the product package `opendog_b200` never imports this module. Physics parity: unpinned at the single-step
+level, loosely pinned against the reference's shipped MuJoCo walk files (see odg_oracle.h).
 """
 from __future__ import annotations
 

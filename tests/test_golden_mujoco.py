@@ -1,6 +1,7 @@
 """The physics oracle against REAL MuJoCo trajectories — skipped until someone runs tools/make_golden_mujoco.py on a
 machine that has `mujoco==3.2.3` and commits tests/golden/mj_<model>.npz. No such machine was available to this project
-(profiles/r02_mujoco_probe.txt), which is why oracle/ says PARITY UNPINNED for the physics; this file is the gate that
+(profiles/r02_mujoco_probe.txt), which is why oracle/ says PARITY UNPINNED at the single-step level for the physics (the shipped walk files pin it
+loosely at the trajectory level: tests/test_mujoco_pin_walk_json.py); this file is the gate that
 pins it the moment the fixture exists. Tolerances are the ones an exact restatement must meet in double precision with
 the oracle's tight solver settings; a failure here is a finding about the restatement (mesh inertia, invweight0,
 PlaneConvex support points, ...), not about the CUDA path."""
