@@ -86,3 +86,58 @@ def noise_floor(desc, w, nsteps):
     for _ in range(nsteps):
         m = p.targets_deg(w, x); rec.append(np.round(m, 2)); x = p.apply_deg(m)
     return teacher_forced(desc, w, np.array(rec), nsteps)
+
+
+class KernelProbe:
+    """The same probe on the PRODUCT's physics: an environment object with the walk-environment surface (`reset()`,
+    `step(ctrl)`, `get_state()`) created with `scale_actions=0, frame_skip=50, reset_noise_scale=0, auto_reset=0` — the
+    CUDA kernel through the C ABI (opendog_b200.env.BatchedWalkEnv) or its source run by the host lane emulator
+    (tests/emu) — stepped with the shipped targets as raw controls; the QuadrupedEnv observation (train.py:184-207) is
+    rebuilt from qpos / qvel. `to_np` converts what get_state returns to numpy, `ctrl_of` a numpy row to what step takes."""
+
+    def __init__(self, env, desc, to_np=np.asarray, ctrl_of=lambda a: a):
+        from .sim2real_oracle import quat_to_ypr
+        self.env, self.to_np, self.ctrl_of, self.ypr = env, to_np, ctrl_of, quat_to_ypr
+        ref = QuadrupedEnvOracle()                          # (index maps of the ordered actuators)
+        self.act_id, self.qidx, self.vidx = ref.act_id, ref.qidx, ref.vidx
+        self.home = np.array(ref.home)
+        self.cr = np.array([desc["act_ctrlrange"][u] for u in ref.act_id])
+        self.key_ctrl = np.array(desc["key_ctrl"], np.float32)
+        self.counter = 0
+
+    def obs(self):
+        st = self.env.get_state()
+        qpos, qvel = self.to_np(st[0])[0].astype(np.float64), self.to_np(st[1])[0].astype(np.float64)
+        yaw, pitch, roll = self.ypr(qpos[3:7])
+        jp = [qpos[q] - h for q, h in zip(self.qidx, self.home)]
+        jv = [qvel[v] for v in self.vidx]
+        ph = (self.counter % 2) / 1.0
+        return np.concatenate([[yaw, pitch, roll], jp, jv, [qvel[0]],
+                               [np.sin(ph * np.pi), np.cos(ph * np.pi)]]).astype(np.float32).astype(np.float64)
+
+    def reset(self):
+        self.env.reset(); self.counter = 0
+        for _ in range(2):                                  # 100 settling substeps with the keyframe's controls (train.py:218-221)
+            self.env.step(self.ctrl_of(self.key_ctrl[None, :]))
+        return self.obs()
+
+    targets_deg = Probe.targets_deg
+
+    @property
+    def e(self):                                            # (Probe.targets_deg reads self.e.counter)
+        return self
+
+    def apply_deg(self, deg):
+        cmd = np.zeros(8, np.float32)
+        for o in range(8):
+            cmd[self.act_id[o]] = self.home[o] + np.radians(deg[o] - REAL_HOME_DEG[o])
+        self.env.step(self.ctrl_of(cmd[None, :])); self.counter += 1
+        return self.obs()
+
+
+def teacher_forced_kernel(probe, w, shipped, nsteps):
+    x = probe.reset(); err = []
+    for t in range(min(nsteps, len(shipped))):
+        err.append(np.abs(np.round(probe.targets_deg(w, x), 2) - shipped[t]).max())
+        x = probe.apply_deg(shipped[t])
+    return np.array(err)

@@ -74,3 +74,45 @@ def test_fixture_records_all_ten_matching_episodes(pin):
     assert list(z["episodes"]) == [2600, 2700, 2800, 2900, 3000, 3100, 3200, 3300, 3500, 3700]
     Ew, Et = z["teacher_forced_wide"], z["teacher_forced_tree"]
     assert np.nanmedian(Ew[:, 0]) <= 0.2 and np.nanmedian(Ew[:, 1]) <= 0.2 and np.nanmedian(Et[:, 1]) >= 5.0
+
+
+PIN_CFG = dict(scale_actions=0, frame_skip=50, reset_noise_scale=0.0, auto_reset=0, max_episode_steps=100000)
+
+
+def test_kernel_source_tracks_the_shipped_mujoco_walks_like_the_oracle(pin):
+    """The PRODUCT's physics on the same pin: the step kernel's source (fp32) run by the host lane emulator (tests/emu),
+    stepped with the shipped targets as raw controls — the same differences from real MuJoCo as the fp64 oracle, to
+    0.05 degree, over 8 policy steps (400 substeps after the 100 settling ones)."""
+    from emu import EmuEnv
+    from oracle.mujoco_pin import KernelProbe, teacher_forced_kernel
+    W, S, _ = pin
+    wide = model_desc(True)
+    for ep in W:
+        probe = KernelProbe(EmuEnv(1, model=wide, **PIN_CFG), wide)
+        e = teacher_forced_kernel(probe, W[ep], S[ep], 8)
+        o = teacher_forced(wide, W[ep], S[ep], 8)
+        assert e[0] <= 0.5 and e[1] <= 0.5, (ep, e)
+        assert np.abs(e[:4] - o[:4]).max() <= 0.05, (ep, e, o)      # (later steps: chaotic, fp32 vs fp64 may part ways)
+
+
+@pytest.mark.gpu
+def test_cuda_kernel_tracks_the_shipped_mujoco_walks(pin, tmp_path):
+    """The same through the C ABI on the GPU: BatchedWalkEnv on a model file with the wide ranges, raw controls, 50
+    substeps per step. Steps 0 and 1 (150 engine steps: the drop onto the floor and the first swing) within 0.5 degree of
+    what the shipped policies output on real MuJoCo's states."""
+    torch = pytest.importorskip("torch")
+    from opendog_b200.env import BatchedWalkEnv
+    from opendog_b200.model.compile import save_compiled
+    from oracle.mujoco_pin import KernelProbe, teacher_forced_kernel
+    W, S, _ = pin
+    wide = model_desc(True)
+    path = str(tmp_path / "our_robot_wide.model.json")
+    save_compiled(wide, path)
+    for ep in W:
+        env = BatchedWalkEnv(1, model=path, info_keys=None, **PIN_CFG)
+        probe = KernelProbe(env, wide, to_np=lambda t: t.detach().cpu().numpy(),
+                            ctrl_of=lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda())
+        e = teacher_forced_kernel(probe, W[ep], S[ep], 6)
+        o = teacher_forced(wide, W[ep], S[ep], 6)
+        assert e[0] <= 0.5 and e[1] <= 0.5, (ep, e)
+        assert np.abs(e[:3] - o[:3]).max() <= 0.1, (ep, e, o)
